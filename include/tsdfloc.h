@@ -1,0 +1,179 @@
+/* include/tsdfloc.h — C ABI of the B200-native MCL sensor update (libtsdfloc.so).
+ *
+ * This is the drop-in boundary for ONE path of uos/tsdf_localization: particle poses + a LiDAR scan in,
+ * per-particle TSDF-likelihood weights, the weighted mean pose and systematically resampled particles out.
+ * Plain pointers and sizes only; no C++/torch types. Every entry point names the reference interface it
+ * replaces (paths relative to the reference repo).
+ *
+ * Two layers:
+ *   (A) host-buffer calls — what the reference's own call sites bind (INTEGRATION.md shows the C++ shim):
+ *         tsdfloc_sensor_update        <- CudaEvaluator::evaluate(vector<Particle>&, vector<CudaPoint>&, tf[16])
+ *                                         include/tsdf_localization/cuda/cuda_evaluator.h:119, src/cuda/cuda_evaluator.cu:118-428
+ *         tsdfloc_resample_systematic  <- SystematicResampler::resample(ParticleCloud&)
+ *                                         include/tsdf_localization/resampling/novel_resampling.h:38-74
+ *   (B) device-pointer stage calls — the same kernels on caller-owned device memory and a caller stream, so
+ *       a multi-GPU driver (one process per GPU) can put NCCL all-gathers between the stages.
+ *
+ * There is NO CPU fallback: every compute entry point needs a CUDA device and returns TSDFLOC_E_CUDA with a
+ * message if the device or the kernel image (sm_100a) is unavailable.
+ *
+ * Threading: calls on one ctx are not re-entrant; use one ctx per device / per caller thread.
+ */
+#ifndef TSDFLOC_H
+#define TSDFLOC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSDFLOC_ABI_VERSION 1
+
+typedef struct tsdfloc_ctx tsdfloc_ctx;
+
+/* Status codes. The reference signals the same conditions with std::runtime_error texts
+ * (src/cuda/cuda_util.cu:8-17; "No particle is valid!" src/cuda/cuda_evaluator.cu:366-369). */
+enum tsdfloc_status
+{
+  TSDFLOC_OK = 0,
+  TSDFLOC_E_BAD_ARG = 1,
+  TSDFLOC_E_CUDA = 2,
+  TSDFLOC_E_NO_VALID_PARTICLE = 3, /* sum of weights == 0 */
+  TSDFLOC_E_EMPTY_SCAN = 4,        /* P == 0: reference returns a default pose and leaves weights untouched (cuda_evaluator.cu:122-125) */
+  TSDFLOC_E_CAPACITY = 5,          /* resampling produced more particles than the output capacity */
+  TSDFLOC_E_STATE = 6              /* stage called out of order (e.g. resample before sensor_update) */
+};
+
+/* Geometry of the two-level sparse voxel map; field-for-field CudaSubVoxelMap<float,float>::MapCoef
+ * (include/tsdf_localization/cuda/cuda_sub_voxel_map.h:22-50) with fixed-width integers. */
+typedef struct tsdfloc_map_desc
+{
+  uint64_t dim[3];        /* ceil(|max-min| / resolution) per axis                 */
+  float min[3];
+  float max[3];
+  float resolution;
+  float init_value;       /* value returned for unmapped space                     */
+  uint64_t up_dim[3];     /* ceil(|max-min| / 1 m) per axis                        */
+  uint64_t up_dim_2;      /* up_dim[0] * up_dim[1]                                 */
+  uint64_t sub_dim;       /* ceil(1 m / resolution)                                */
+  uint64_t sub_dim_2;
+  uint64_t grid_occ_size; /* up_dim[0]*up_dim[1]*up_dim[2]                         */
+  uint64_t data_size;     /* number of fp32 voxels in data (bricks * sub_dim^3)    */
+} tsdfloc_map_desc;
+
+/* Sensor model; constructor arguments of CudaEvaluator (cuda_evaluator.h:112) / TSDFEvaluator (tsdf_evaluator.h:72). */
+typedef struct tsdfloc_params
+{
+  float a_hit;     /* default 0.9  (util.h:16) */
+  float a_range;   /* default 0.1  (util.h:17) */
+  float a_max;     /* default 0.0  (util.h:18) */
+  float max_range; /* default 100  (util.h:13); the range term uses 1/max_range like the CPU evaluator (tsdf_evaluator.cpp:60) */
+  int32_t per_point; /* accepted for signature parity; both reference variants compute the same weights, one kernel serves both */
+  int32_t reserved;
+} tsdfloc_params;
+
+void tsdfloc_default_params(tsdfloc_params* p);
+int tsdfloc_abi_version(void);
+const char* tsdfloc_status_string(int status);
+/* Message of the last failing call on this ctx (or of the last failing tsdfloc_create when ctx == NULL). */
+const char* tsdfloc_last_error(const tsdfloc_ctx* ctx);
+
+/* ---- host-side sparse map builder -----------------------------------------------------------------------------
+ * Stand-alone replacement for the host half of CudaSubVoxelMap<float,float>
+ * (include/tsdf_localization/cuda/cuda_sub_voxel_map.{h,tcc}): constructor geometry (tcc:4-48) and setData's brick
+ * allocation in increasing upper-cell order (tcc:170-230), producing the grid_occ / data arrays tsdfloc_create
+ * uploads. A caller that already owns a reference CudaSubVoxelMap passes coef()/rawGridOcc()/rawData() to
+ * tsdfloc_create instead and never needs these. Pure host code, no GPU required. */
+typedef struct tsdfloc_host_map tsdfloc_host_map;
+int tsdfloc_map_create(const float min[3], const float max[3], float resolution, float init_value, tsdfloc_host_map** out);
+/* cells: n x (x, y, z, value) fp32. Cells outside [min, max) on any axis are an error (the reference is undefined there). */
+int tsdfloc_map_set_data(tsdfloc_host_map* m, const float* cells, uint64_t n);
+const tsdfloc_map_desc* tsdfloc_map_get_desc(const tsdfloc_host_map* m);
+const int32_t* tsdfloc_map_grid_occ(const tsdfloc_host_map* m);
+const float* tsdfloc_map_data(const tsdfloc_host_map* m);
+void tsdfloc_map_destroy(tsdfloc_host_map* m);
+/* TSDF (mm) -> likelihood^3 LUT value and the value for unmapped space, createTSDFMap's transform
+ * (include/tsdf_localization/map/map_util.h:68-71, 124-126). */
+float tsdfloc_likelihood_value(float tsdf_mm, float sigma);
+float tsdfloc_likelihood_init(float sigma);
+
+/* ---- lifetime -------------------------------------------------------------------------------------------
+ * Replaces CudaEvaluator::CudaEvaluator(map, per_point, a_hit, a_range, a_max, max_range)
+ * (src/cuda/cuda_evaluator.cu:21-59): deep-copies the map's host arrays to the device (grid_occ = brick table,
+ * data = bricks). Host arrays are only read during the call. No process-wide globals: any number of ctx. */
+int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const float* data, const tsdfloc_params* params,
+                   int device, tsdfloc_ctx** out);
+void tsdfloc_destroy(tsdfloc_ctx* ctx);
+
+/* ---- (A) host-buffer calls ------------------------------------------------------------------------------ */
+
+/* One sensor update on host buffers.
+ *   particles : n x 7 fp32, the reference's `Particle` layout (x y z roll pitch yaw weight; particle.h:50-53).
+ *               Poses are read; slot [6] of every particle is overwritten with the NORMALISED weight
+ *               (cuda_eval_particles.h:556, cuda_evaluator.cu:405-408). Order is preserved.
+ *   points    : p x 3 fp32 sensor-frame points, the reference's `CudaPoint` (cuda_evaluator.h:22-39).
+ *   tf        : 16 fp32 row-major scanner->robot matrix; rows 0-2 are used (tsdf_evaluator.cpp:132-145).
+ *   mean_pose : out, x y z roll pitch yaw of the weighted mean (atan2 of weighted sin/cos sums, cuda_evaluator.cu:387-392).
+ * The particle set stays resident on the device for tsdfloc_resample_systematic. */
+int tsdfloc_sensor_update(tsdfloc_ctx* ctx, float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],
+                          float mean_pose[6]);
+
+/* Systematic resampling of the particle set left on the device by tsdfloc_sensor_update, with the random
+ * offset u0 in [0, 1/n) supplied by the caller (the reference draws it from std::mt19937, novel_resampling.h:49).
+ * Reproduces the reference's fp32 running-U / fp64 running-sum recurrence exactly, including output lengths
+ * != n. particles_out: capacity `cap` x 7 fp32; copies keep the parent's normalised weight. parents (optional):
+ * index of the source particle per output slot. */
+int tsdfloc_resample_systematic(tsdfloc_ctx* ctx, float u0, float* particles_out, uint64_t cap, uint64_t* n_out,
+                                uint32_t* parents);
+
+/* Parity/debug: per-(particle, point) flat voxel index (data_size = miss) and per-particle hit counts for the
+ * given inputs, computed by the same device index function the evaluation kernel uses.
+ * idx (optional): n*p uint32, particle-major. hits (optional): n uint32. raw_weights (optional): n un-normalised. */
+int tsdfloc_debug_eval(tsdfloc_ctx* ctx, const float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],
+                       uint32_t* idx, uint32_t* hits, float* raw_weights);
+
+/* ---- (B) device-pointer stage calls ---------------------------------------------------------------------
+ * All pointers are device pointers on ctx's device; `stream` is a cudaStream_t passed as void* (NULL = the
+ * ctx's own stream). Calls enqueue work and return without synchronising unless stated. */
+
+/* Scan upload + preparation: packs xyz into float4 with the per-point range term
+ * (a_range/max_range inside max_range, else a_max; cuda_eval_particles.h:200-209) and reduces their sum. */
+int tsdfloc_set_scan_device(tsdfloc_ctx* ctx, const float* d_points_xyz, uint64_t p, void* stream);
+int tsdfloc_set_scan_host(tsdfloc_ctx* ctx, const float* points_xyz, uint64_t p, void* stream);
+
+/* Evaluation of particles [first, first+count) of a pose array of n_total particles.
+ *   d_particles : n_total x 7 fp32 (Particle layout); only poses are read.
+ *   d_raw_weights: n_total fp32; entries [first, first+count) are written with the un-normalised weight
+ *                 sum_p (a_hit * tsdf(T_i p) + range_term(p)) (cuda_eval_particles.h:167-215). */
+int tsdfloc_eval_device(tsdfloc_ctx* ctx, const float* d_particles, uint64_t n_total, uint64_t first, uint64_t count,
+                        const float tf[16], float* d_raw_weights, void* stream);
+
+/* Normalisation + weighted mean + CDF over ALL n_total particles (redundantly on every rank in a multi-GPU run):
+ * writes normalised weights into d_particles[:,6], the mean pose (6 fp32) into d_mean_pose, and builds the fp64
+ * running-sum CDF kept inside ctx. Sets a device-side flag if the weight sum is 0 (query with tsdfloc_check). */
+int tsdfloc_normalize_device(tsdfloc_ctx* ctx, float* d_particles, uint64_t n_total, const float* d_raw_weights,
+                             float* d_mean_pose, void* stream);
+
+/* Draw output slots [first_out, first_out+count_out) from the CDF: d_particles_out[j] = d_particles[parent(j)].
+ * Slots >= n_out (see tsdfloc_check) are filled with parent = last valid parent so buffers stay defined.
+ * d_parents optional (uint32 per output slot, indexed from first_out). */
+int tsdfloc_draw_device(tsdfloc_ctx* ctx, const float* d_particles, uint64_t n_total, float u0, uint64_t first_out,
+                        uint64_t count_out, float* d_particles_out, uint32_t* d_parents, void* stream);
+
+/* Synchronises `stream` and reports what the device recorded for the last normalize/draw:
+ * n_out = number of particles the reference recurrence emits; returns TSDFLOC_E_NO_VALID_PARTICLE if sum == 0. */
+int tsdfloc_check(tsdfloc_ctx* ctx, uint64_t* n_out, double* weight_sum, void* stream);
+
+/* Host-only test hook: the reference's fp32 U recurrence U_{j+1} = (float)((double)U_j + 1/n) evaluated through the
+ * same segment-table code the device uses; writes U_j for all j with U_j < limit (at most cap) and returns their count. */
+uint64_t tsdfloc_host_u_sequence(float u0, uint64_t n, double limit, float* out, uint64_t cap, uint32_t* n_segs, uint32_t* flags);
+
+/* Number of kernels this library has launched on this ctx so far (for bench accounting). */
+uint64_t tsdfloc_kernel_launches(const tsdfloc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSDFLOC_H */

@@ -1,0 +1,305 @@
+// oracle/ref_harness.cpp — C ABI over the UNMODIFIED reference classes (test infrastructure only).
+//
+// This translation unit is compiled together with the reference's own sources, taken by path from
+// /root/reference (never copied into this repo):
+//   src/evaluation/tsdf_evaluator.cpp            (TSDFEvaluator::evaluate / evaluatePose, CPU/OpenMP)
+//   src/evaluation/model/likelihood_evaluation.cpp
+//   include/tsdf_localization/cuda/cuda_sub_voxel_map.{h,tcc}   (two-level sparse map)
+//   include/tsdf_localization/resampling/novel_resampling.h     (SystematicResampler)
+// against the stub ROS headers in oracle/ref_stubs/. The result (oracle/_ref/libtsdf_ref*.so) is
+// used ONLY by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs,
+// as the checker and the timed CPU baseline. Nothing in the product path links or loads it.
+//
+// What is verbatim and what is glue:
+//   * map build (setData), host getEntry, evaluate(), evaluatePose(), SystematicResampler::resample()
+//     run the reference's own code, bit for bit.
+//   * ParticleCloud's three trivial accessors (default ctor, operator[], size) are defined here because
+//     src/particle_cloud.cpp drags in tf2/ROS-time code unrelated to this path
+//     (reference: src/particle_cloud.cpp:11-15, 619-632).
+//   * CudaEvaluator's four symbols are defined as "no CUDA" stubs unless TSDF_REF_WITH_B200_SHIM is set,
+//     in which case the B200 drop-in shim provides them (tsdf_evaluator.h:78 constructs it unconditionally).
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include <tsdf_localization/cuda/cuda_sub_voxel_map.h>
+#include <tsdf_localization/evaluation/tsdf_evaluator.h>
+#include <tsdf_localization/evaluation/model/likelihood_evaluation.h>
+#include <tsdf_localization/resampling/novel_resampling.h>
+#include <tsdf_localization/util/constant.h>
+
+namespace tsdf_localization
+{
+
+// --- glue: trivial ParticleCloud members (see header comment) ---------------------------------
+ParticleCloud::ParticleCloud()
+{
+  m_generator_ptr.reset(new std::mt19937(0u));
+}
+Particle& ParticleCloud::operator[](unsigned int index)
+{
+  if (index >= size())
+  {
+    throw std::out_of_range("Index exceeds number of particles");
+  }
+  return m_particles[index];
+}
+std::size_t ParticleCloud::size() const
+{
+  return m_particles.size();
+}
+
+#ifndef TSDF_REF_WITH_B200_SHIM
+// --- glue: CPU-only build has no CUDA back-end; mirror the base class behaviour ----------------
+CudaEvaluator::CudaEvaluator(CudaSubVoxelMap<FLOAT_T, FLOAT_T>&, bool per_point, FLOAT_T a_hit, FLOAT_T a_range, FLOAT_T a_max, FLOAT_T max_range)
+: d_map_(nullptr), per_point_(per_point), d_grid_occ_(nullptr), d_data_(nullptr), d_particles_(nullptr), d_particles_ordered_(nullptr),
+  particles_reserved_(0), d_points_(nullptr), d_points_ordered_(nullptr), points_reserved_(0), d_transform_(nullptr), d_new_weights_(nullptr),
+  d_point_weights_(nullptr), point_weights_size_(0), p_x_(nullptr), p_y_(nullptr), p_z_(nullptr), sin_a_(nullptr), cos_a_(nullptr),
+  sin_b_(nullptr), cos_b_(nullptr), sin_c_(nullptr), cos_c_(nullptr), a_hit_(a_hit), a_range_(a_range), a_max_(a_max), max_range_(max_range),
+  inv_max_range_(1.0 / max_range), max_range_squared_(max_range * max_range)
+{
+}
+CudaEvaluator::~CudaEvaluator() {}
+geometry_msgs::PoseWithCovariance CudaEvaluator::evaluate(std::vector<Particle>&, const sensor_msgs::PointCloud2&, FLOAT_T*)
+{
+  throw std::runtime_error("CUDA acceleration is not supported. Please install CUDA!");
+}
+geometry_msgs::PoseWithCovariance CudaEvaluator::evaluate(std::vector<Particle>&, const std::vector<CudaPoint>&, FLOAT_T*)
+{
+  throw std::runtime_error("CUDA acceleration is not supported. Please install CUDA!");
+}
+#endif
+
+namespace
+{
+
+using RefMap = CudaSubVoxelMap<FLOAT_T, FLOAT_T>;
+
+// evaluatePose is protected virtual (tsdf_evaluator.h:59) — expose it unchanged.
+struct ExposedEvaluator : public TSDFEvaluator
+{
+  using TSDFEvaluator::TSDFEvaluator;
+  FLOAT_T pose_weight(FLOAT_T* pose, const std::vector<CudaPoint>& cloud)
+  {
+    LikelihoodEvaluation eval(10000);
+    return evaluatePose(pose, cloud, eval);
+  }
+};
+
+// m_generator_ptr is protected (resampler.h:28) — reseed it so U0 is reproducible.
+struct SeededSystematic : public SystematicResampler
+{
+  void seed(uint32_t s) { m_generator_ptr.reset(new std::mt19937(s)); }
+};
+
+struct MapHandle
+{
+  std::shared_ptr<RefMap> map;
+};
+
+struct EvalHandle
+{
+  std::shared_ptr<RefMap> map;
+  std::unique_ptr<ExposedEvaluator> eval;
+  std::string last_error;
+};
+
+thread_local std::string g_last_error;
+
+}  // namespace
+}  // namespace tsdf_localization
+
+using namespace tsdf_localization;
+
+extern "C"
+{
+
+// POD mirror of CudaSubVoxelMap::MapCoef (cuda_sub_voxel_map.h:22-50) with fixed-width fields.
+struct ref_map_coef
+{
+  uint64_t dim[3];
+  float min[3];
+  float max[3];
+  float resolution;
+  float init_value;
+  uint64_t up_dim[3];
+  uint64_t up_dim_2;
+  uint64_t sub_dim;
+  uint64_t sub_dim_2;
+  uint64_t grid_occ_size;
+  uint64_t data_size;
+};
+
+const char* ref_last_error() { return g_last_error.c_str(); }
+unsigned ref_omp_threads() { return OMP_THREADS; }
+
+void* ref_map_create(const float mn[3], const float mx[3], float resolution, float init_value)
+{
+  try
+  {
+    auto* h = new MapHandle;
+    h->map = std::make_shared<RefMap>(RefMap(mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], resolution, init_value));
+    return h;
+  }
+  catch (std::exception& e)
+  {
+    g_last_error = e.what();
+    return nullptr;
+  }
+}
+
+// NOTE: std::make_shared<RefMap>(RefMap(...)) move-constructs from a temporary exactly as
+// map_util.h:73 does (the class is move-only, cuda_sub_voxel_map.h:121-137).
+
+void ref_map_destroy(void* h) { delete static_cast<MapHandle*>(h); }
+
+// cells: n × (x, y, z, value) fp32 — the tuple list createTSDFMap hands to setData (map_util.h:129,152).
+int ref_map_set_data(void* h, const float* cells, uint64_t n)
+{
+  try
+  {
+    std::vector<std::tuple<FLOAT_T, FLOAT_T, FLOAT_T, FLOAT_T>> data;
+    data.reserve(n);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+      data.push_back(std::make_tuple(cells[4 * i], cells[4 * i + 1], cells[4 * i + 2], cells[4 * i + 3]));
+    }
+    static_cast<MapHandle*>(h)->map->setData(data);
+    return 0;
+  }
+  catch (std::exception& e)
+  {
+    g_last_error = e.what();
+    return 1;
+  }
+}
+
+void ref_map_get_coef(void* h, ref_map_coef* out)
+{
+  const auto& c = static_cast<MapHandle*>(h)->map->coef();
+  out->dim[0] = c.dim_x_; out->dim[1] = c.dim_y_; out->dim[2] = c.dim_z_;
+  out->min[0] = c.min_x_; out->min[1] = c.min_y_; out->min[2] = c.min_z_;
+  out->max[0] = c.max_x_; out->max[1] = c.max_y_; out->max[2] = c.max_z_;
+  out->resolution = c.resolution_;
+  out->init_value = c.init_value_;
+  out->up_dim[0] = c.up_dim_x_; out->up_dim[1] = c.up_dim_y_; out->up_dim[2] = c.up_dim_z_;
+  out->up_dim_2 = c.up_dim_2_;
+  out->sub_dim = c.sub_dim_;
+  out->sub_dim_2 = c.sub_dim_2_;
+  out->grid_occ_size = c.grid_occ_size_;
+  out->data_size = c.data_size_;
+}
+
+const int* ref_map_grid_occ(void* h) { return static_cast<MapHandle*>(h)->map->rawGridOcc(); }
+const float* ref_map_data(void* h) { return static_cast<MapHandle*>(h)->map->rawData(); }
+
+// Host getEntry (cuda_sub_voxel_map.tcc:139-157) on n query points.
+void ref_map_get_entries(void* h, const float* xyz, uint64_t n, float* out)
+{
+  auto& map = *static_cast<MapHandle*>(h)->map;
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    out[i] = map.getEntry(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  }
+}
+
+void* ref_eval_create(void* map_h, float a_hit, float a_range, float a_max, float max_range)
+{
+  try
+  {
+    auto* e = new EvalHandle;
+    e->map = static_cast<MapHandle*>(map_h)->map;
+    e->eval.reset(new ExposedEvaluator(e->map, false, a_hit, a_range, a_max, max_range));
+    return e;
+  }
+  catch (std::exception& ex)
+  {
+    g_last_error = ex.what();
+    return nullptr;
+  }
+}
+
+void ref_eval_destroy(void* e) { delete static_cast<EvalHandle*>(e); }
+
+// TSDFEvaluator::evaluate(particles, points, tf, use_cuda) (tsdf_evaluator.cpp:78-245).
+// particles: N × 7 fp32 (x y z roll pitch yaw weight), weights overwritten with the NORMALISED weights.
+// pose_out: x y z qx qy qz qw (doubles).  Returns 0, or 1 on an exception (e.g. "No particle is valid!").
+int ref_evaluate(void* eh, float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16], int use_cuda, double pose_out[7])
+{
+  auto* e = static_cast<EvalHandle*>(eh);
+  static_assert(sizeof(Particle) == 7 * sizeof(float), "Particle must be 7 packed floats");
+  static_assert(sizeof(CudaPoint) == 3 * sizeof(float), "CudaPoint must be 3 packed floats");
+  try
+  {
+    std::vector<Particle> ps(n);
+    std::memcpy(static_cast<void*>(ps.data()), particles, n * sizeof(Particle));
+    std::vector<CudaPoint> pts(p);
+    std::memcpy(static_cast<void*>(pts.data()), points, p * sizeof(CudaPoint));
+    FLOAT_T tfm[16];
+    std::memcpy(tfm, tf, sizeof(tfm));
+    auto pose = e->eval->evaluate(ps, pts, tfm, use_cuda != 0);
+    std::memcpy(particles, static_cast<void*>(ps.data()), n * sizeof(Particle));
+    if (pose_out)
+    {
+      pose_out[0] = pose.pose.position.x; pose_out[1] = pose.pose.position.y; pose_out[2] = pose.pose.position.z;
+      pose_out[3] = pose.pose.orientation.x; pose_out[4] = pose.pose.orientation.y;
+      pose_out[5] = pose.pose.orientation.z; pose_out[6] = pose.pose.orientation.w;
+    }
+    return 0;
+  }
+  catch (std::exception& ex)
+  {
+    g_last_error = ex.what();
+    return 1;
+  }
+}
+
+// evaluatePose (tsdf_evaluator.cpp:27-76) for n pre-built 3x4 (row-major, 12 floats) sensor→map matrices:
+// the un-normalised per-particle weight.
+void ref_pose_weights(void* eh, const float* matrices12, uint64_t n, const float* points, uint64_t p, float* weights_out)
+{
+  auto* e = static_cast<EvalHandle*>(eh);
+  std::vector<CudaPoint> pts(p);
+  std::memcpy(static_cast<void*>(pts.data()), points, p * sizeof(CudaPoint));
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    FLOAT_T pose[16] = {0};
+    std::memcpy(pose, matrices12 + 12 * i, 12 * sizeof(float));
+    pose[15] = 1;
+    weights_out[i] = e->eval->pose_weight(pose, pts);
+  }
+}
+
+// SystematicResampler::resample (novel_resampling.h:41-72) with a seeded generator.
+// u0_out receives the U the resampler drew (same generator state, same distribution type).
+// Returns the number of particles the reference produced (may differ from n); at most cap are copied out.
+uint64_t ref_systematic_resample(const float* particles, uint64_t n, uint32_t seed, float* particles_out, uint64_t cap, float* u0_out)
+{
+  ParticleCloud cloud;
+  cloud.particles().resize(n);
+  std::memcpy(static_cast<void*>(cloud.particles().data()), particles, n * sizeof(Particle));
+  if (u0_out)
+  {
+    std::mt19937 gen(seed);
+    auto inverse_M = 1.0 / n;
+    std::uniform_real_distribution<FLOAT_T> uniform_distribution(0.0, inverse_M);
+    *u0_out = uniform_distribution(gen);
+  }
+  SeededSystematic rs;
+  rs.seed(seed);
+  rs.resample(cloud);
+  const uint64_t m = cloud.size();
+  const uint64_t c = m < cap ? m : cap;
+  if (particles_out && c)
+  {
+    std::memcpy(particles_out, static_cast<void*>(cloud.particles().data()), c * sizeof(Particle));
+  }
+  return m;
+}
+
+}  // extern "C"

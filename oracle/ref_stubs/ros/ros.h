@@ -1,0 +1,36 @@
+// Stub of <ros/ros.h> for building the reference's CPU evaluator WITHOUT ROS.
+// TEST INFRASTRUCTURE ONLY (oracle/_ref build). Written from scratch: just enough
+// surface for the reference headers to parse; nothing here runs on the hot path.
+#pragma once
+#include <chrono>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <cstdint>
+#include <stdexcept>
+#include <cmath>
+#include <algorithm>
+namespace ros {
+struct Duration {
+  double sec_ = 0.0;
+  Duration() = default;
+  explicit Duration(double s) : sec_(s) {}
+  double toSec() const { return sec_; }
+};
+struct Time {
+  double sec_ = 0.0;
+  Time() = default;
+  explicit Time(double s) : sec_(s) {}
+  static Time now() {
+    using namespace std::chrono;
+    return Time(duration<double>(steady_clock::now().time_since_epoch()).count());
+  }
+  double toSec() const { return sec_; }
+  Duration operator-(const Time& o) const { return Duration(sec_ - o.sec_); }
+};
+}  // namespace ros
+#define TSDF_STUB_LOG(x) do { std::ostringstream _s; _s << x; std::cerr << _s.str() << std::endl; } while (0)
+#define ROS_INFO_STREAM(x)  TSDF_STUB_LOG(x)
+#define ROS_WARN_STREAM(x)  TSDF_STUB_LOG(x)
+#define ROS_ERROR_STREAM(x) TSDF_STUB_LOG(x)
+#define ROS_DEBUG_STREAM(x) do {} while (0)

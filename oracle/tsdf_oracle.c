@@ -1,0 +1,365 @@
+/* oracle/tsdf_oracle.c — CPU restatement of the reference's MCL sensor-update path (plain C).
+ * TEST INFRASTRUCTURE ONLY — see tsdf_oracle.h for who may use it and for the parity-pinning status.
+ * Build: oracle/Makefile (gcc -O2 -ffp-contract=off, no -march=native: every a*b+c rounds twice,
+ * exactly like the reference CPU build on baseline x86-64). */
+#define _GNU_SOURCE
+#include "tsdf_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ---- float -> unsigned conversions under the three policies ------------------------------------- */
+
+/* What gcc emits for (size_t)f on x86-64 without AVX-512: cvttss2si on f when f < 2^63 (negative values
+ * wrap modulo 2^64, NaN gives 0x8000...0), else cvttss2si(f - 2^63) ^ 2^63 (out of range gives 0). */
+static uint64_t cvt_u64_x86(float f)
+{
+  const float two63 = 9223372036854775808.0f;
+  if (f != f) return 0x8000000000000000ull;
+  if (f < two63)
+  {
+    if (f <= -two63) return 0x8000000000000000ull;
+    return (uint64_t)(int64_t)f;
+  }
+  {
+    float g = f - two63;
+    if (!(g < two63)) return 0ull; /* indefinite ^ 2^63 */
+    return ((uint64_t)(int64_t)g) ^ 0x8000000000000000ull;
+  }
+}
+
+/* CUDA cvt.rzi.u32.f32: saturating, NaN -> 0 */
+static uint64_t cvt_u32_sat(float f)
+{
+  if (!(f > 0.0f)) return 0u;
+  if (f >= 4294967296.0f) return 0xffffffffu;
+  return (uint32_t)f;
+}
+
+/* ---- map ------------------------------------------------------------------------------------------ */
+
+oracle_map* oracle_map_create(const float mn[3], const float mx[3], float resolution, float init_value)
+{
+  /* cuda_sub_voxel_map.tcc:16-34; sub_voxel_size = 1.0 (cuda_sub_voxel_map.h:15) */
+  oracle_map* m = (oracle_map*)calloc(1, sizeof(oracle_map));
+  oracle_map_coef* c = &m->coef;
+  for (int a = 0; a < 3; ++a)
+  {
+    c->dim[a] = (uint64_t)ceilf(fabsf(mx[a] - mn[a]) / resolution);
+    c->min[a] = mn[a];
+    c->max[a] = mx[a];
+    c->up_dim[a] = (uint64_t)ceilf(fabsf(mx[a] - mn[a]) / 1.0f);
+  }
+  c->resolution = resolution;
+  c->init_value = init_value;
+  c->up_dim_2 = c->up_dim[0] * c->up_dim[1];
+  c->sub_dim = (uint64_t)ceilf(1.0f / resolution);
+  c->sub_dim_2 = c->sub_dim * c->sub_dim;
+  c->grid_occ_size = c->up_dim[0] * c->up_dim[1] * c->up_dim[2];
+  c->data_size = 0;
+  m->grid_occ = (int32_t*)malloc(sizeof(int32_t) * (c->grid_occ_size ? c->grid_occ_size : 1));
+  for (uint64_t i = 0; i < c->grid_occ_size; ++i) m->grid_occ[i] = -1;
+  m->data = NULL;
+  return m;
+}
+
+void oracle_map_destroy(oracle_map* m)
+{
+  if (!m) return;
+  free(m->grid_occ);
+  free(m->data);
+  free(m);
+}
+
+oracle_map* oracle_map_from_arrays(const oracle_map_coef* coef, const int32_t* grid_occ, const float* data)
+{
+  oracle_map* m = (oracle_map*)calloc(1, sizeof(oracle_map));
+  m->coef = *coef;
+  m->grid_occ = (int32_t*)malloc(sizeof(int32_t) * (coef->grid_occ_size ? coef->grid_occ_size : 1));
+  memcpy(m->grid_occ, grid_occ, sizeof(int32_t) * coef->grid_occ_size);
+  m->data = (float*)malloc(sizeof(float) * (coef->data_size ? coef->data_size : 1));
+  memcpy(m->data, data, sizeof(float) * coef->data_size);
+  return m;
+}
+
+uint64_t oracle_get_index(const oracle_map* m, float x, float y, float z, int neg_mode)
+{
+  /* cuda_sub_voxel_map.tcc:50-137 (host, size_t) == cuda_eval_particles.h:12-67 (device, unsigned int) for
+   * non-negative offsets; they differ only in how negative/NaN offsets convert (neg_mode). */
+  const oracle_map_coef* c = &m->coef;
+  const float p[3] = {x, y, z};
+  float off[3];
+  uint64_t up[3];
+  float sub_pos[3];
+  for (int a = 0; a < 3; ++a)
+  {
+    off[a] = p[a] - c->min[a];
+    if (neg_mode == ORACLE_NEG_AS_MISS && !(off[a] >= 0.0f)) return c->data_size;
+  }
+  for (int a = 0; a < 3; ++a)
+  {
+    /* tcc:53-60: metre-truncated offset, then "/= resolution" through float */
+    uint64_t g = (neg_mode == ORACLE_NEG_REF_DEVICE_SAT) ? cvt_u32_sat(off[a]) : cvt_u64_x86(off[a]);
+    float q = (neg_mode == ORACLE_NEG_REF_DEVICE_SAT) ? (float)(uint32_t)g / c->resolution : (float)g / c->resolution;
+    g = (neg_mode == ORACLE_NEG_REF_DEVICE_SAT) ? cvt_u32_sat(q) : cvt_u64_x86(q);
+    if (g >= c->dim[a]) return c->data_size; /* tcc:62-65 */
+  }
+  for (int a = 0; a < 3; ++a)
+  {
+    /* tcc:74-84 */
+    float t = off[a] / 1.0f;
+    if (neg_mode == ORACLE_NEG_REF_DEVICE_SAT)
+    {
+      up[a] = cvt_u32_sat(t);
+      sub_pos[a] = off[a] - (float)(uint32_t)up[a] * 1.0f;
+    }
+    else
+    {
+      up[a] = cvt_u64_x86(t);
+      sub_pos[a] = off[a] - (float)up[a] * 1.0f;
+    }
+  }
+  uint64_t up_index = up[0] + up[1] * c->up_dim[0] + up[2] * c->up_dim_2; /* tcc:86 */
+  if (neg_mode == ORACLE_NEG_REF_DEVICE_SAT) up_index = (uint32_t)up_index;
+  if (up_index >= c->grid_occ_size) return c->data_size; /* tcc:108-111 */
+  int32_t sub_index = m->grid_occ[up_index];
+  if (sub_index < 0) return c->data_size; /* tcc:120-128 */
+  uint64_t sub[3];
+  for (int a = 0; a < 3; ++a)
+  {
+    float q = sub_pos[a] / c->resolution; /* tcc:132-134 */
+    sub[a] = (neg_mode == ORACLE_NEG_REF_DEVICE_SAT) ? cvt_u32_sat(q) : cvt_u64_x86(q);
+  }
+  uint64_t r = (uint64_t)(int64_t)sub_index + sub[0] + sub[1] * c->sub_dim + sub[2] * c->sub_dim_2; /* tcc:136 */
+  if (neg_mode == ORACLE_NEG_REF_DEVICE_SAT) r = (uint32_t)r;
+  return r;
+}
+
+float oracle_get_entry(const oracle_map* m, float x, float y, float z, int neg_mode)
+{
+  /* tcc:139-157 */
+  if (!m->data || !m->grid_occ) return m->coef.init_value;
+  uint64_t idx = oracle_get_index(m, x, y, z, neg_mode);
+  return idx < m->coef.data_size ? m->data[idx] : m->coef.init_value;
+}
+
+void oracle_get_entries(const oracle_map* m, const float* xyz, uint64_t n, int neg_mode, float* out)
+{
+  for (uint64_t i = 0; i < n; ++i) out[i] = oracle_get_entry(m, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], neg_mode);
+}
+
+int oracle_map_set_data(oracle_map* m, const float* cells, uint64_t n)
+{
+  /* cuda_sub_voxel_map.tcc:170-230 */
+  oracle_map_coef* c = &m->coef;
+  if (n == 0) return 0;
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    uint64_t up[3];
+    for (int a = 0; a < 3; ++a)
+    {
+      float off = cells[4 * i + a] - c->min[a];
+      up[a] = cvt_u64_x86(off / 1.0f);
+    }
+    uint64_t up_index = up[0] + up[1] * c->up_dim[0] + up[2] * c->up_dim[0] * c->up_dim[1];
+    if (up_index >= c->grid_occ_size) return 1; /* "Upper voxel index overflow!" */
+    m->grid_occ[up_index] = 0;
+  }
+  int32_t current = 0;
+  const uint64_t sub_size = c->sub_dim * c->sub_dim * c->sub_dim;
+  for (uint64_t i = 0; i < c->grid_occ_size; ++i)
+  {
+    if (m->grid_occ[i] >= 0)
+    {
+      m->grid_occ[i] = current;
+      current += (int32_t)sub_size;
+    }
+  }
+  free(m->data);
+  c->data_size = (uint64_t)(int64_t)current;
+  m->data = (float*)malloc(sizeof(float) * (c->data_size ? c->data_size : 1));
+  for (uint64_t i = 0; i < c->data_size; ++i) m->data[i] = c->init_value;
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    /* setEntry, tcc:159-168: writes data_[getIndex()] unguarded; a cell whose getIndex misses would write
+     * data_[data_size] (out of bounds) in the reference. Cells handed to setData come from inside the
+     * bounding box, so this does not happen for valid maps; the oracle skips such a write. */
+    uint64_t idx = oracle_get_index(m, cells[4 * i], cells[4 * i + 1], cells[4 * i + 2], ORACLE_NEG_REF_HOST_X86);
+    if (idx < c->data_size) m->data[idx] = cells[4 * i + 3];
+  }
+  return 0;
+}
+
+/* ---- likelihood LUT -------------------------------------------------------------------------------- */
+
+float oracle_likelihood_init(float sigma)
+{
+  /* map_util.h:68-71: sigma_quad float; expf(double expr -> float); sqrtf(double expr -> float) */
+  float sigma_quad = sigma * sigma;
+  float init = expf((float)(-(10.0 * 10.0) / sigma_quad / 2)) / (sqrtf((float)(2 * sigma_quad * M_PI)));
+  init = init * init * init;
+  return init;
+}
+
+float oracle_likelihood_value(float tsdf_mm, float sigma)
+{
+  /* map_util.h:124-126: value is double (float * 0.001); expf/sqrtf take float arguments; the quotient and
+   * the cube are evaluated in double because value is double, then stored into the float tuple (:129). */
+  float sigma_quad = sigma * sigma;
+  double value = tsdf_mm * 0.001;
+  value = expf((float)(-(value * value) / sigma_quad / 2)) / (sqrtf((float)(2 * sigma_quad * M_PI)));
+  value = value * value * value;
+  return (float)value;
+}
+
+/* ---- pose -> matrix -------------------------------------------------------------------------------- */
+
+void oracle_pose_matrix(const float pose6[6], const float tf[16], float out[12])
+{
+  /* tsdf_evaluator.cpp:102-145. sin/cos are the double versions, rounded to float on assignment. */
+  float tp[16];
+  float alpha = pose6[3], beta = pose6[4], gamma = pose6[5];
+  float sin_alpha = (float)sin((double)alpha);
+  float cos_alpha = (float)cos((double)alpha);
+  float sin_beta = (float)sin((double)beta);
+  float cos_beta = (float)cos((double)beta);
+  float sin_gamma = (float)sin((double)gamma);
+  float cos_gamma = (float)cos((double)gamma);
+
+  tp[0] = cos_beta * cos_gamma;
+  tp[4] = cos_beta * sin_gamma;
+  tp[8] = -sin_beta;
+  tp[3] = pose6[0];
+
+  tp[1] = sin_alpha * sin_beta * cos_gamma - cos_alpha * sin_gamma;
+  tp[5] = sin_alpha * sin_beta * sin_gamma + cos_alpha * cos_gamma;
+  tp[9] = sin_alpha * cos_beta;
+  tp[7] = pose6[1];
+
+  tp[2] = cos_alpha * sin_beta * cos_gamma + sin_alpha * sin_gamma;
+  tp[6] = cos_alpha * sin_beta * sin_gamma - sin_alpha * cos_gamma;
+  tp[10] = cos_alpha * cos_beta;
+  tp[11] = pose6[2];
+
+  for (int r = 0; r < 3; ++r)
+  {
+    const float a = tp[4 * r], b = tp[4 * r + 1], c = tp[4 * r + 2], d = tp[4 * r + 3];
+    out[4 * r + 0] = a * tf[0] + b * tf[4] + c * tf[8];
+    out[4 * r + 1] = a * tf[1] + b * tf[5] + c * tf[9];
+    out[4 * r + 2] = a * tf[2] + b * tf[6] + c * tf[10];
+    out[4 * r + 3] = a * tf[3] + b * tf[7] + c * tf[11] + d;
+  }
+}
+
+/* ---- evaluatePose ---------------------------------------------------------------------------------- */
+
+float oracle_pose_weight(const oracle_map* m, const oracle_params* prm, const float pose[12], const float* pts, uint64_t np,
+                         int neg_mode, uint32_t* idx_out, uint32_t* hits_out, double* w64_out)
+{
+  /* tsdf_evaluator.cpp:27-76 */
+  const float inv_max_range = (float)(1.0 / prm->max_range);            /* tsdf_evaluator.h:75 */
+  const float max_range_squared = prm->max_range * prm->max_range;      /* tsdf_evaluator.h:75 */
+  float eval_sum = 0.0f;
+  double eval_sum64 = 0.0;
+  uint32_t hits = 0;
+  for (uint64_t i = 0; i < np; ++i)
+  {
+    float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    float tx = pose[0] * x + pose[1] * y + pose[2] * z + pose[3];
+    float ty = pose[4] * x + pose[5] * y + pose[6] * z + pose[7];
+    float tz = pose[8] * x + pose[9] * y + pose[10] * z + pose[11];
+    uint64_t idx = oracle_get_index(m, tx, ty, tz, neg_mode);
+    float value = (m->data && idx < m->coef.data_size) ? m->data[idx] : m->coef.init_value;
+    if (idx < m->coef.data_size) ++hits;
+    if (idx_out) idx_out[i] = (uint32_t)(idx < m->coef.data_size ? idx : m->coef.data_size);
+    float square_dist = x * x + y * y + z * z;
+    if (square_dist < max_range_squared)
+      value = prm->a_hit * value + prm->a_range * inv_max_range;
+    else
+      value = prm->a_hit * value + prm->a_max;
+    eval_sum += value;
+    eval_sum64 += (double)value;
+  }
+  if (hits_out) *hits_out = hits;
+  if (w64_out) *w64_out = eval_sum64;
+  return eval_sum;
+}
+
+/* ---- evaluate -------------------------------------------------------------------------------------- */
+
+int oracle_evaluate(const oracle_map* m, const oracle_params* prm, float* P, uint64_t n, const float* pts, uint64_t np,
+                    const float tf[16], int neg_mode, float* raw_out, float mean_pose6[6], uint32_t* idx_out,
+                    uint32_t* hits_out, float* weight_sum_out)
+{
+  /* tsdf_evaluator.cpp:85-157 */
+  int64_t i;
+#pragma omp parallel for schedule(dynamic)
+  for (i = 0; i < (int64_t)n; ++i)
+  {
+    float mat[12];
+    oracle_pose_matrix(&P[7 * i], tf, mat);
+    P[7 * i + 6] = oracle_pose_weight(m, prm, mat, pts, np, neg_mode, idx_out ? idx_out + (uint64_t)i * np : NULL,
+                                      hits_out ? hits_out + i : NULL, NULL);
+  }
+  float weight_sum = 0.0f;
+  for (uint64_t k = 0; k < n; ++k)
+  {
+    if (raw_out) raw_out[k] = P[7 * k + 6];
+    weight_sum += P[7 * k + 6];
+  }
+  if (weight_sum_out) *weight_sum_out = weight_sum;
+  if (weight_sum == 0.0f) return 1; /* :159-162 "No particle is valid!" */
+
+  /* :198-221 */
+  float avg[3] = {0, 0, 0};
+  float ss[3] = {0, 0, 0}, sc[3] = {0, 0, 0};
+  for (uint64_t k = 0; k < n; ++k)
+  {
+    float* p = &P[7 * k];
+    p[6] /= weight_sum;
+    avg[0] += p[0] * p[6];
+    avg[1] += p[1] * p[6];
+    avg[2] += p[2] * p[6];
+    for (int a = 0; a < 3; ++a)
+    {
+      ss[a] += (float)(sin((double)p[3 + a]) * p[6]);
+      sc[a] += (float)(cos((double)p[3 + a]) * p[6]);
+    }
+  }
+  if (mean_pose6)
+  {
+    mean_pose6[0] = avg[0];
+    mean_pose6[1] = avg[1];
+    mean_pose6[2] = avg[2];
+    for (int a = 0; a < 3; ++a) mean_pose6[3 + a] = (float)atan2((double)ss[a], (double)sc[a]);
+  }
+  return 0;
+}
+
+/* ---- systematic resampling ------------------------------------------------------------------------- */
+
+uint64_t oracle_systematic_resample(const float* w, uint64_t n, float u0, uint32_t* parents_out, uint64_t cap)
+{
+  /* novel_resampling.h:41-72: inverse_M double, U float (float += double rounds to float every step),
+   * s double running sum, strict s > U. */
+  const double inverse_M = 1.0 / (double)n;
+  float U = u0;
+  double s = 0.0;
+  uint64_t out = 0;
+  for (uint64_t mi = 0; mi < n; ++mi)
+  {
+    s += w[mi];
+    while (s > U)
+    {
+      if (parents_out && out < cap) parents_out[out] = (uint32_t)mi;
+      ++out;
+      U += inverse_M;
+    }
+  }
+  return out;
+}

@@ -1,0 +1,109 @@
+/* oracle/tsdf_oracle.h — CPU restatement of the reference's MCL sensor-update path in plain C.
+ *
+ * TEST INFRASTRUCTURE ONLY. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may build, load or call this; the product (libtsdfloc.so) never does and
+ * fails loudly without its CUDA code.
+ *
+ * Parity status: PINNED against the unmodified reference compiled here (oracle/_ref/libtsdf_ref.so,
+ * built by oracle/Makefile from /root/reference sources): tests/test_oracle_vs_ref.py runs both on the
+ * same seeded inputs in this container, and tests/golden/ holds vectors minted from the verbatim build
+ * (oracle/gen_golden.py) that travel to the GPU box. The reference itself ships no tests or goldens
+ * (SURVEY §4).
+ *
+ * Every function cites the reference file:line it restates (paths relative to /root/reference).
+ */
+#ifndef TSDF_ORACLE_H
+#define TSDF_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* How a NEGATIVE (or NaN) axis offset x - min is converted to an unsigned integer. The reference code is
+ * undefined behaviour there; three behaviours exist in the wild: */
+enum oracle_neg_mode
+{
+  ORACLE_NEG_AS_MISS = 0,      /* product policy: any axis offset not >= 0 -> miss (init_value)           */
+  ORACLE_NEG_REF_HOST_X86 = 1, /* what the reference CPU build does on x86-64 (cvttss2si wrap-around)      */
+  ORACLE_NEG_REF_DEVICE_SAT = 2 /* what the reference CUDA build does (cvt.rzi.u32.f32 saturates to 0)    */
+};
+
+/* CudaSubVoxelMap<float,float>::MapCoef, include/tsdf_localization/cuda/cuda_sub_voxel_map.h:22-50 */
+typedef struct oracle_map_coef
+{
+  uint64_t dim[3];
+  float min[3];
+  float max[3];
+  float resolution;
+  float init_value;
+  uint64_t up_dim[3];
+  uint64_t up_dim_2;
+  uint64_t sub_dim;
+  uint64_t sub_dim_2;
+  uint64_t grid_occ_size;
+  uint64_t data_size;
+} oracle_map_coef;
+
+typedef struct oracle_map
+{
+  oracle_map_coef coef;
+  int32_t* grid_occ; /* [grid_occ_size]  -1 or element offset of the brick in data */
+  float* data;       /* [data_size] */
+} oracle_map;
+
+/* ctor, cuda_sub_voxel_map.tcc:4-48 */
+oracle_map* oracle_map_create(const float min[3], const float max[3], float resolution, float init_value);
+void oracle_map_destroy(oracle_map* m);
+/* setData, cuda_sub_voxel_map.tcc:170-230. cells = n x (x,y,z,value). Returns 0, or 1 on "Upper voxel index overflow!" */
+int oracle_map_set_data(oracle_map* m, const float* cells, uint64_t n);
+/* Adopt arrays built elsewhere (e.g. by the verbatim reference) without rebuilding. Copies. */
+oracle_map* oracle_map_from_arrays(const oracle_map_coef* coef, const int32_t* grid_occ, const float* data);
+
+/* getIndex, cuda_sub_voxel_map.tcc:50-137 (host) / cuda_eval_particles.h:12-67 (device). Returns the flat
+ * element offset into data, or coef.data_size for a miss. */
+uint64_t oracle_get_index(const oracle_map* m, float x, float y, float z, int neg_mode);
+/* getEntry, cuda_sub_voxel_map.tcc:139-157 */
+float oracle_get_entry(const oracle_map* m, float x, float y, float z, int neg_mode);
+void oracle_get_entries(const oracle_map* m, const float* xyz, uint64_t n, int neg_mode, float* out);
+
+/* createTSDFMap value transform, include/tsdf_localization/map/map_util.h:68-71,124-126 */
+float oracle_likelihood_value(float tsdf_mm, float sigma);
+float oracle_likelihood_init(float sigma);
+
+/* Pose (x y z roll pitch yaw) o tf_matrix -> 3x4 row-major sensor->map matrix,
+ * src/evaluation/tsdf_evaluator.cpp:102-145 */
+void oracle_pose_matrix(const float pose6[6], const float tf[16], float out12[12]);
+
+typedef struct oracle_params
+{
+  float a_hit, a_range, a_max, max_range; /* inv_max_range = 1/max_range, max_range_squared as tsdf_evaluator.h:72-76 */
+} oracle_params;
+
+/* evaluatePose, src/evaluation/tsdf_evaluator.cpp:27-76: sequential fp32 sum over points.
+ * Optional outputs: idx_out[p] flat index per point (data_size = miss); *hits_out = #points with idx < data_size;
+ * *w64_out = the same sum accumulated in double (for the tolerance analysis of SURVEY §7.3(3)). */
+float oracle_pose_weight(const oracle_map* m, const oracle_params* prm, const float mat12[12], const float* points_xyz,
+                         uint64_t n_points, int neg_mode, uint32_t* idx_out, uint32_t* hits_out, double* w64_out);
+
+/* evaluate (CPU branch), src/evaluation/tsdf_evaluator.cpp:85-221.
+ * particles: N x 7 (x y z r p y w). On return w holds the NORMALISED weight; raw_out (optional, N) the
+ * un-normalised one; mean_pose6 = weighted mean xyz + atan2 of weighted sin/cos sums; idx_out optional N*P
+ * uint32; hits_out optional N. weight_sum is accumulated in particle order in fp32 (one legal ordering of
+ * the reference's OpenMP reduction). Returns 0, or 1 when weight_sum == 0 ("No particle is valid!"). */
+int oracle_evaluate(const oracle_map* m, const oracle_params* prm, float* particles7, uint64_t n, const float* points_xyz,
+                    uint64_t n_points, const float tf[16], int neg_mode, float* raw_out, float mean_pose6[6],
+                    uint32_t* idx_out, uint32_t* hits_out, float* weight_sum_out);
+
+/* SystematicResampler::resample, include/tsdf_localization/resampling/novel_resampling.h:41-72, with the
+ * random offset U0 injected. weights = N normalised fp32 weights. parents_out[j] = index of the particle
+ * copied into output slot j. Returns the number of output particles the reference loop produces (can differ
+ * from N); at most cap parents are written. */
+uint64_t oracle_systematic_resample(const float* weights, uint64_t n, float u0, uint32_t* parents_out, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

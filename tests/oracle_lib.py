@@ -1,0 +1,249 @@
+"""ctypes access to the CPU checkers under oracle/ (TEST INFRASTRUCTURE; never imported by the product package).
+
+  Oracle  — oracle/_build/libtsdf_oracle.so, the plain-C restatement (always available, built by oracle/Makefile)
+  Ref     — oracle/_ref/libtsdf_ref*.so, the UNMODIFIED reference CPU evaluator/map/resampler compiled against stub ROS
+            headers (built in the container that has /root/reference; the prebuilt .so travels to the GPU box)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_DIR = ROOT / "oracle"
+
+NEG_AS_MISS, NEG_REF_HOST_X86, NEG_REF_DEVICE_SAT = 0, 1, 2
+
+
+class Coef(C.Structure):
+    _fields_ = [
+        ("dim", C.c_uint64 * 3), ("min", C.c_float * 3), ("max", C.c_float * 3), ("resolution", C.c_float),
+        ("init_value", C.c_float), ("up_dim", C.c_uint64 * 3), ("up_dim_2", C.c_uint64), ("sub_dim", C.c_uint64),
+        ("sub_dim_2", C.c_uint64), ("grid_occ_size", C.c_uint64), ("data_size", C.c_uint64),
+    ]
+
+
+class OracleMapStruct(C.Structure):
+    _fields_ = [("coef", Coef), ("grid_occ", C.POINTER(C.c_int32)), ("data", C.POINTER(C.c_float))]
+
+
+class OParams(C.Structure):
+    _fields_ = [("a_hit", C.c_float), ("a_range", C.c_float), ("a_max", C.c_float), ("max_range", C.c_float)]
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def build_oracle():
+    so = ORACLE_DIR / "_build" / "libtsdf_oracle.so"
+    src = [ORACLE_DIR / "tsdf_oracle.c", ORACLE_DIR / "tsdf_oracle.h"]
+    if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in src):
+        subprocess.run(["make", "-C", str(ORACLE_DIR), "oracle"], check=True, capture_output=True)
+    return so
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(str(build_oracle()))
+        L = self.lib
+        L.oracle_map_create.restype = C.POINTER(OracleMapStruct)
+        L.oracle_map_create.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float]
+        L.oracle_map_from_arrays.restype = C.POINTER(OracleMapStruct)
+        L.oracle_map_from_arrays.argtypes = [C.POINTER(Coef), C.c_void_p, C.c_void_p]
+        L.oracle_map_destroy.argtypes = [C.c_void_p]
+        L.oracle_map_set_data.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.oracle_get_index.restype = C.c_uint64
+        L.oracle_get_index.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int]
+        L.oracle_get_entries.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        L.oracle_likelihood_value.restype = C.c_float
+        L.oracle_likelihood_value.argtypes = [C.c_float, C.c_float]
+        L.oracle_likelihood_init.restype = C.c_float
+        L.oracle_likelihood_init.argtypes = [C.c_float]
+        L.oracle_pose_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_pose_weight.restype = C.c_float
+        L.oracle_pose_weight.argtypes = [C.c_void_p, C.POINTER(OParams), C.c_void_p, C.c_void_p, C.c_uint64, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_evaluate.argtypes = [C.c_void_p, C.POINTER(OParams), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                      C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_systematic_resample.restype = C.c_uint64
+        L.oracle_systematic_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_uint64]
+
+    # -- map --
+    def map_create(self, mn, mx, res, init):
+        a = np.asarray(mn, dtype=np.float32)
+        b = np.asarray(mx, dtype=np.float32)
+        return self.lib.oracle_map_create(_fp(a), _fp(b), C.c_float(res), C.c_float(init))
+
+    def map_from_arrays(self, coef, grid_occ, data):
+        c = Coef()
+        C.memmove(C.byref(c), C.byref(coef), C.sizeof(Coef))
+        g = np.ascontiguousarray(grid_occ, dtype=np.int32)
+        d = np.ascontiguousarray(data, dtype=np.float32)
+        return self.lib.oracle_map_from_arrays(C.byref(c), _fp(g), _fp(d))
+
+    def map_set_data(self, m, cells):
+        cells = np.ascontiguousarray(cells, dtype=np.float32)
+        return self.lib.oracle_map_set_data(m, _fp(cells), cells.shape[0])
+
+    def map_arrays(self, m):
+        c = m.contents.coef
+        occ = np.ctypeslib.as_array(m.contents.grid_occ, shape=(int(c.grid_occ_size),)).copy()
+        data = (np.ctypeslib.as_array(m.contents.data, shape=(int(c.data_size),)).copy() if c.data_size
+                else np.zeros(0, dtype=np.float32))
+        return c, occ, data
+
+    def map_destroy(self, m):
+        self.lib.oracle_map_destroy(m)
+
+    def get_entries(self, m, xyz, mode):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        out = np.empty(xyz.shape[0], dtype=np.float32)
+        self.lib.oracle_get_entries(m, _fp(xyz), xyz.shape[0], mode, _fp(out))
+        return out
+
+    def get_index(self, m, x, y, z, mode):
+        return int(self.lib.oracle_get_index(m, C.c_float(x), C.c_float(y), C.c_float(z), mode))
+
+    def pose_matrices(self, particles, tf):
+        particles = np.ascontiguousarray(particles, dtype=np.float32)
+        tf = np.ascontiguousarray(tf, dtype=np.float32)
+        out = np.empty((particles.shape[0], 12), dtype=np.float32)
+        for i in range(particles.shape[0]):
+            pose = np.ascontiguousarray(particles[i, :6])
+            row = np.empty(12, dtype=np.float32)
+            self.lib.oracle_pose_matrix(_fp(pose), _fp(tf), _fp(row))
+            out[i] = row
+        return out
+
+    def evaluate(self, m, params, particles, points, tf, mode=NEG_AS_MISS, want_idx=False, want_hits=True):
+        """Returns dict(status, normalised particles, raw, mean, idx, hits, weight_sum)."""
+        ps = np.array(particles, dtype=np.float32, copy=True, order="C")
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        tf = np.ascontiguousarray(tf, dtype=np.float32)
+        n, p = ps.shape[0], pts.shape[0]
+        raw = np.empty(n, dtype=np.float32)
+        mean = np.zeros(6, dtype=np.float32)
+        idx = np.empty((n, p), dtype=np.uint32) if want_idx else None
+        hits = np.empty(n, dtype=np.uint32) if want_hits else None
+        wsum = C.c_float(0)
+        prm = OParams(*params)
+        rc = self.lib.oracle_evaluate(m, C.byref(prm), _fp(ps), n, _fp(pts), p, _fp(tf), mode, _fp(raw), _fp(mean),
+                                      _fp(idx) if want_idx else None, _fp(hits) if want_hits else None, C.byref(wsum))
+        return dict(status=rc, particles=ps, raw=raw, mean=mean, idx=idx, hits=hits, weight_sum=wsum.value)
+
+    def pose_weight64(self, m, params, mat12, points, mode=NEG_AS_MISS):
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        mat = np.ascontiguousarray(mat12, dtype=np.float32)
+        w64 = C.c_double(0)
+        prm = OParams(*params)
+        w32 = self.lib.oracle_pose_weight(m, C.byref(prm), _fp(mat), _fp(pts), pts.shape[0], mode, None, None, C.byref(w64))
+        return float(w32), w64.value
+
+    def systematic_resample(self, weights, u0, cap=None):
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        n = w.shape[0]
+        cap = cap or (n + n // 8 + 64)
+        parents = np.empty(cap, dtype=np.uint32)
+        m = int(self.lib.oracle_systematic_resample(_fp(w), n, C.c_float(u0), _fp(parents), cap))
+        return m, parents[:min(m, cap)]
+
+
+def ref_lib_path(threads: int | None = None) -> Path:
+    name = "libtsdf_ref.so" if threads is None else f"libtsdf_ref_t{threads}.so"
+    return ORACLE_DIR / "_ref" / name
+
+
+def ref_available() -> bool:
+    return ref_lib_path().exists()
+
+
+class Ref:
+    """The verbatim reference (oracle/ref_harness.cpp)."""
+
+    def __init__(self, threads: int | None = None):
+        self.lib = C.CDLL(str(ref_lib_path(threads)))
+        L = self.lib
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_omp_threads.restype = C.c_uint
+        L.ref_map_create.restype = C.c_void_p
+        L.ref_map_create.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float]
+        L.ref_map_destroy.argtypes = [C.c_void_p]
+        L.ref_map_set_data.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.ref_map_get_coef.argtypes = [C.c_void_p, C.POINTER(Coef)]
+        L.ref_map_grid_occ.restype = C.POINTER(C.c_int32)
+        L.ref_map_grid_occ.argtypes = [C.c_void_p]
+        L.ref_map_data.restype = C.POINTER(C.c_float)
+        L.ref_map_data.argtypes = [C.c_void_p]
+        L.ref_map_get_entries.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.ref_eval_create.restype = C.c_void_p
+        L.ref_eval_create.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.ref_eval_destroy.argtypes = [C.c_void_p]
+        L.ref_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_pose_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.ref_systematic_resample.restype = C.c_uint64
+        L.ref_systematic_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+
+    def omp_threads(self):
+        return int(self.lib.ref_omp_threads())
+
+    def map_create(self, mn, mx, res, init):
+        a = np.asarray(mn, dtype=np.float32)
+        b = np.asarray(mx, dtype=np.float32)
+        return self.lib.ref_map_create(_fp(a), _fp(b), C.c_float(res), C.c_float(init))
+
+    def map_set_data(self, m, cells):
+        cells = np.ascontiguousarray(cells, dtype=np.float32)
+        return self.lib.ref_map_set_data(m, _fp(cells), cells.shape[0])
+
+    def map_arrays(self, m):
+        c = Coef()
+        self.lib.ref_map_get_coef(m, C.byref(c))
+        occ = np.ctypeslib.as_array(self.lib.ref_map_grid_occ(m), shape=(int(c.grid_occ_size),)).copy()
+        data = (np.ctypeslib.as_array(self.lib.ref_map_data(m), shape=(int(c.data_size),)).copy() if c.data_size
+                else np.zeros(0, dtype=np.float32))
+        return c, occ, data
+
+    def map_destroy(self, m):
+        self.lib.ref_map_destroy(m)
+
+    def get_entries(self, m, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        out = np.empty(xyz.shape[0], dtype=np.float32)
+        self.lib.ref_map_get_entries(m, _fp(xyz), xyz.shape[0], _fp(out))
+        return out
+
+    def eval_create(self, m, a_hit=0.9, a_range=0.1, a_max=0.0, max_range=100.0):
+        return self.lib.ref_eval_create(m, a_hit, a_range, a_max, max_range)
+
+    def eval_destroy(self, e):
+        self.lib.ref_eval_destroy(e)
+
+    def evaluate(self, e, particles, points, tf):
+        ps = np.array(particles, dtype=np.float32, copy=True, order="C")
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        tf = np.ascontiguousarray(tf, dtype=np.float32)
+        pose = np.zeros(7, dtype=np.float64)
+        rc = self.lib.ref_evaluate(e, _fp(ps), ps.shape[0], _fp(pts), pts.shape[0], _fp(tf), 0, _fp(pose))
+        err = self.lib.ref_last_error().decode() if rc else ""
+        return rc, ps, pose, err
+
+    def pose_weights(self, e, mats12, points):
+        mats = np.ascontiguousarray(mats12, dtype=np.float32)
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        out = np.empty(mats.shape[0], dtype=np.float32)
+        self.lib.ref_pose_weights(e, _fp(mats), mats.shape[0], _fp(pts), pts.shape[0], _fp(out))
+        return out
+
+    def systematic_resample(self, particles, seed, cap=None):
+        ps = np.ascontiguousarray(particles, dtype=np.float32)
+        n = ps.shape[0]
+        cap = cap or (n + n // 8 + 64)
+        out = np.empty((cap, 7), dtype=np.float32)
+        u0 = C.c_float(0)
+        m = int(self.lib.ref_systematic_resample(_fp(ps), n, seed, _fp(out), cap, C.byref(u0)))
+        return m, out[:min(m, cap)], u0.value

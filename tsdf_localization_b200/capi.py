@@ -1,0 +1,100 @@
+"""ctypes binding of include/tsdfloc.h. Fails loudly when the CUDA library is missing — there is no fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+
+OK, E_BAD_ARG, E_CUDA, E_NO_VALID_PARTICLE, E_EMPTY_SCAN, E_CAPACITY, E_STATE = range(7)
+
+
+class LibraryNotBuilt(RuntimeError):
+    pass
+
+
+class TsdflocError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+
+
+class MapDesc(C.Structure):
+    """tsdfloc_map_desc == CudaSubVoxelMap::MapCoef (cuda_sub_voxel_map.h:22-50)."""
+    _fields_ = [
+        ("dim", C.c_uint64 * 3), ("min", C.c_float * 3), ("max", C.c_float * 3), ("resolution", C.c_float),
+        ("init_value", C.c_float), ("up_dim", C.c_uint64 * 3), ("up_dim_2", C.c_uint64), ("sub_dim", C.c_uint64),
+        ("sub_dim_2", C.c_uint64), ("grid_occ_size", C.c_uint64), ("data_size", C.c_uint64),
+    ]
+
+
+class Params(C.Structure):
+    _fields_ = [("a_hit", C.c_float), ("a_range", C.c_float), ("a_max", C.c_float), ("max_range", C.c_float),
+                ("per_point", C.c_int32), ("reserved", C.c_int32)]
+
+
+def lib_path() -> Path:
+    return PKG / "lib" / "libtsdfloc.so"
+
+
+_LIB = None
+
+_vp, _u64, _u32p, _fp, _i32p = C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+
+# name -> (restype, argtypes): every symbol include/tsdfloc.h declares
+SIGNATURES = {
+    "tsdfloc_default_params": (None, [C.POINTER(Params)]),
+    "tsdfloc_abi_version": (C.c_int, []),
+    "tsdfloc_status_string": (C.c_char_p, [C.c_int]),
+    "tsdfloc_last_error": (C.c_char_p, [_vp]),
+    "tsdfloc_map_create": (C.c_int, [_fp, _fp, C.c_float, C.c_float, C.POINTER(_vp)]),
+    "tsdfloc_map_set_data": (C.c_int, [_vp, _fp, _u64]),
+    "tsdfloc_map_get_desc": (C.POINTER(MapDesc), [_vp]),
+    "tsdfloc_map_grid_occ": (_i32p, [_vp]),
+    "tsdfloc_map_data": (_fp, [_vp]),
+    "tsdfloc_map_destroy": (None, [_vp]),
+    "tsdfloc_likelihood_value": (C.c_float, [C.c_float, C.c_float]),
+    "tsdfloc_likelihood_init": (C.c_float, [C.c_float]),
+    "tsdfloc_create": (C.c_int, [C.POINTER(MapDesc), _vp, _vp, C.POINTER(Params), C.c_int, C.POINTER(_vp)]),
+    "tsdfloc_destroy": (None, [_vp]),
+    "tsdfloc_sensor_update": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _fp, _fp]),
+    "tsdfloc_resample_systematic": (C.c_int, [_vp, C.c_float, _vp, _u64, C.POINTER(_u64), _vp]),
+    "tsdfloc_debug_eval": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _fp, _vp, _vp, _vp]),
+    "tsdfloc_set_scan_device": (C.c_int, [_vp, _vp, _u64, _vp]),
+    "tsdfloc_set_scan_host": (C.c_int, [_vp, _vp, _u64, _vp]),
+    "tsdfloc_eval_device": (C.c_int, [_vp, _vp, _u64, _u64, _u64, _fp, _vp, _vp]),
+    "tsdfloc_normalize_device": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp]),
+    "tsdfloc_draw_device": (C.c_int, [_vp, _vp, _u64, C.c_float, _u64, _u64, _vp, _vp, _vp]),
+    "tsdfloc_check": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double), _vp]),
+    "tsdfloc_host_u_sequence": (_u64, [C.c_float, _u64, C.c_double, _vp, _u64, _u32p, _u32p]),
+    "tsdfloc_kernel_launches": (_u64, [_vp]),
+}
+
+
+def load_library():
+    """dlopen lib/libtsdfloc.so and type every entry point. Raises LibraryNotBuilt if it is not there."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not path.exists():
+        raise LibraryNotBuilt(
+            f"{path} is missing: build it with `python -m tsdf_localization_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback for the sensor update.")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(lib, ctx, status: int) -> None:
+    if status == OK:
+        return
+    msg = lib.tsdfloc_last_error(ctx)
+    text = msg.decode() if msg else ""
+    if not text:
+        text = lib.tsdfloc_status_string(status).decode()
+    raise TsdflocError(status, text)

@@ -1,0 +1,143 @@
+// host_map.cpp — host-side two-level sparse TSDF map builder and likelihood LUT of libtsdfloc.so.
+//
+// Stand-alone counterpart of the reference's CudaSubVoxelMap<float,float> constructor / setData
+// (include/tsdf_localization/cuda/cuda_sub_voxel_map.tcc:4-48, 170-230) and of createTSDFMap's value transform
+// (include/tsdf_localization/map/map_util.h:68-71, 124-126). It produces exactly the arrays the reference class
+// would (1 m upper cells -> dense sub_dim^3 bricks, bricks laid out in increasing upper-cell index), because the flat
+// voxel numbering of that layout is what parity is measured in. Unlike the reference it rejects cells outside the
+// bounding box instead of invoking undefined float->unsigned conversions.
+#include "../../include/tsdfloc.h"
+
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+struct tsdfloc_host_map
+{
+  tsdfloc_map_desc desc{};
+  std::vector<int32_t> grid_occ;
+  std::vector<float> data;
+};
+
+namespace
+{
+
+// every division below must be a single IEEE fp32 operation, like the reference's
+inline float div32(float a, float b)
+{
+  volatile float q = a / b;
+  return q;
+}
+
+// upper cell / in-cell voxel of one axis offset, same arithmetic as cuda_sub_voxel_map.tcc:74-84,132-134
+inline void split_axis(float off, float res, uint64_t& up, uint64_t& sub)
+{
+  up = static_cast<uint64_t>(off);  // off >= 0 checked by the caller
+  volatile float pos = off - static_cast<float>(up);
+  sub = static_cast<uint64_t>(div32(pos, res));
+}
+
+}  // namespace
+
+extern "C"
+{
+
+int tsdfloc_map_create(const float mn[3], const float mx[3], float res, float init_value, tsdfloc_host_map** out)
+{
+  if (!out || !mn || !mx) return TSDFLOC_E_BAD_ARG;
+  *out = nullptr;
+  if (!(res > 0.0f) || !std::isfinite(res)) return TSDFLOC_E_BAD_ARG;
+  tsdfloc_host_map* m = new (std::nothrow) tsdfloc_host_map;
+  if (!m) return TSDFLOC_E_BAD_ARG;
+  tsdfloc_map_desc& d = m->desc;
+  for (int a = 0; a < 3; ++a)
+  {
+    if (!std::isfinite(mn[a]) || !std::isfinite(mx[a])) { delete m; return TSDFLOC_E_BAD_ARG; }
+    volatile float extent = std::fabs(mx[a] - mn[a]);
+    d.dim[a] = static_cast<uint64_t>(std::ceil(div32(extent, res)));
+    d.up_dim[a] = static_cast<uint64_t>(std::ceil(extent));  // 1 m upper cells (cuda_sub_voxel_map.h:15)
+    d.min[a] = mn[a];
+    d.max[a] = mx[a];
+  }
+  d.resolution = res;
+  d.init_value = init_value;
+  d.up_dim_2 = d.up_dim[0] * d.up_dim[1];
+  d.sub_dim = static_cast<uint64_t>(std::ceil(div32(1.0f, res)));
+  d.sub_dim_2 = d.sub_dim * d.sub_dim;
+  d.grid_occ_size = d.up_dim[0] * d.up_dim[1] * d.up_dim[2];
+  d.data_size = 0;
+  if (d.grid_occ_size == 0 || d.grid_occ_size >= (1ull << 31)) { delete m; return TSDFLOC_E_BAD_ARG; }
+  m->grid_occ.assign(d.grid_occ_size, -1);
+  *out = m;
+  return TSDFLOC_OK;
+}
+
+int tsdfloc_map_set_data(tsdfloc_host_map* m, const float* cells, uint64_t n)
+{
+  if (!m || (n && !cells)) return TSDFLOC_E_BAD_ARG;
+  if (n == 0) return TSDFLOC_OK;
+  tsdfloc_map_desc& d = m->desc;
+  std::fill(m->grid_occ.begin(), m->grid_occ.end(), -1);
+  std::vector<uint64_t> upper(n), inner(n);
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    uint64_t up[3], sub[3];
+    for (int a = 0; a < 3; ++a)
+    {
+      volatile float off = cells[4 * i + a] - d.min[a];
+      if (!(off >= 0.0f)) return TSDFLOC_E_BAD_ARG;
+      split_axis(off, d.resolution, up[a], sub[a]);
+      if (up[a] >= d.up_dim[a]) return TSDFLOC_E_BAD_ARG;
+    }
+    upper[i] = up[0] + up[1] * d.up_dim[0] + up[2] * d.up_dim_2;
+    inner[i] = sub[0] + sub[1] * d.sub_dim + sub[2] * d.sub_dim_2;
+    m->grid_occ[upper[i]] = 0;
+  }
+  const uint64_t brick = d.sub_dim * d.sub_dim * d.sub_dim;
+  uint64_t offset = 0;
+  for (uint64_t u = 0; u < d.grid_occ_size; ++u)
+  {
+    if (m->grid_occ[u] < 0) continue;
+    if (offset + brick >= (1ull << 31)) return TSDFLOC_E_BAD_ARG;  // reference offsets are int
+    m->grid_occ[u] = static_cast<int32_t>(offset);
+    offset += brick;
+  }
+  d.data_size = offset;
+  m->data.assign(offset, d.init_value);
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    const uint64_t idx = static_cast<uint64_t>(m->grid_occ[upper[i]]) + inner[i];
+    if (idx < offset) m->data[idx] = cells[4 * i + 3];
+  }
+  return TSDFLOC_OK;
+}
+
+const tsdfloc_map_desc* tsdfloc_map_get_desc(const tsdfloc_host_map* m) { return m ? &m->desc : nullptr; }
+const int32_t* tsdfloc_map_grid_occ(const tsdfloc_host_map* m) { return m ? m->grid_occ.data() : nullptr; }
+const float* tsdfloc_map_data(const tsdfloc_host_map* m) { return m ? m->data.data() : nullptr; }
+void tsdfloc_map_destroy(tsdfloc_host_map* m) { delete m; }
+
+float tsdfloc_likelihood_init(float sigma)
+{
+  // N(10 m; 0, sigma)^3 — the value of unmapped space (0 in fp32 for sigma = 0.1)
+  const float s2 = sigma * sigma;
+  const float e = std::exp(static_cast<float>(-(10.0 * 10.0) / s2 / 2));
+  const float nrm = std::sqrt(static_cast<float>(2 * s2 * 3.14159265358979323846));
+  const float v = e / nrm;
+  return v * v * v;
+}
+
+float tsdfloc_likelihood_value(float tsdf_mm, float sigma)
+{
+  // metres in double, exp/sqrt in fp32, the cube in double, stored as fp32 — the reference's mixed precision
+  const float s2 = sigma * sigma;
+  const double metres = tsdf_mm * 0.001;
+  const float e = std::exp(static_cast<float>(-(metres * metres) / s2 / 2));
+  const float nrm = std::sqrt(static_cast<float>(2 * s2 * 3.14159265358979323846));
+  const double v = e / nrm;
+  return static_cast<float>(v * v * v);
+}
+
+}  // extern "C"

@@ -1,0 +1,716 @@
+// tsdfloc_api.cu — context, map upload and the C ABI of libtsdfloc.so (see include/tsdfloc.h).
+//
+// Host orchestration that replaces src/cuda/cuda_evaluator.cu:21-59 (constructor: map upload) and :118-428
+// (evaluate) of the reference, and hosts the GPU systematic resampler that replaces
+// include/tsdf_localization/resampling/novel_resampling.h:41-72. No file-scope device globals (the reference keeps
+// the map pointers in cuda_data.h:25-26): everything lives in the ctx, one per device, any number per process.
+// No CPU fallback anywhere: without a CUDA device every compute entry point fails with TSDFLOC_E_CUDA.
+#include "../../include/tsdfloc.h"
+#include "tsdfloc_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace tsdfloc;
+
+namespace
+{
+
+thread_local std::string g_create_error;
+
+struct DevBuf
+{
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct tsdfloc_ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  tsdfloc_params prm{};
+  tsdfloc_map_desc desc{};
+  MapDev map{};
+  int sm_count = 148;
+  uint64_t launches = 0;
+
+  // map
+  int32_t* d_table = nullptr;
+  float* d_voxels = nullptr;
+
+  // scan
+  DevBuf d_xyz_stage, d_pts, d_blocksums;
+  double* d_term_sum = nullptr;
+  uint64_t n_points = 0;
+
+  // particles / scratch
+  DevBuf d_particles, d_particles_out, d_mats, d_partial, d_raw, d_cdf, d_tile_total, d_tile_offset, d_tile_moments, d_parents,
+      d_idx, d_hits;
+  float* d_mean = nullptr;
+  USeg* d_segs = nullptr;
+  Status* d_status = nullptr;
+  uint64_t n_resident = 0;  // particles left on the device by tsdfloc_sensor_update
+  bool have_cdf = false;
+
+  // pinned staging
+  void* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+  Status* h_status = nullptr;
+  float* h_mean = nullptr;
+};
+
+namespace
+{
+
+int fail(tsdfloc_ctx* c, int code, const std::string& msg)
+{
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define CU_TRY(c, expr, what)                                                                                       \
+  do                                                                                                                \
+  {                                                                                                                 \
+    cudaError_t _e = (expr);                                                                                        \
+    if (_e != cudaSuccess)                                                                                          \
+      return fail((c), TSDFLOC_E_CUDA, std::string(what) + ": " + cudaGetErrorName(_e) + " (" + cudaGetErrorString(_e) + ")"); \
+  } while (0)
+
+int ensure(tsdfloc_ctx* c, DevBuf& b, size_t bytes, const char* what)
+{
+  if (bytes <= b.bytes) return TSDFLOC_OK;
+  if (b.p)
+  {
+    CU_TRY(c, cudaStreamSynchronize(c->stream), "sync before regrow");
+    CU_TRY(c, cudaDeviceSynchronize(), "device sync before regrow");
+    CU_TRY(c, cudaFree(b.p), what);
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  size_t want = bytes + bytes / 4 + 256;
+  CU_TRY(c, cudaMalloc(&b.p, want), what);
+  b.bytes = want;
+  return TSDFLOC_OK;
+}
+
+int ensure_host(tsdfloc_ctx* c, size_t bytes)
+{
+  if (bytes <= c->h_stage_bytes) return TSDFLOC_OK;
+  if (c->h_stage)
+  {
+    CU_TRY(c, cudaStreamSynchronize(c->stream), "sync before host regrow");
+    CU_TRY(c, cudaFreeHost(c->h_stage), "cudaFreeHost");
+    c->h_stage = nullptr;
+    c->h_stage_bytes = 0;
+  }
+  size_t want = bytes + bytes / 4 + 4096;
+  CU_TRY(c, cudaMallocHost(&c->h_stage, want), "cudaMallocHost(staging)");
+  c->h_stage_bytes = want;
+  return TSDFLOC_OK;
+}
+
+cudaStream_t pick(tsdfloc_ctx* c, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : c->stream; }
+
+struct DeviceGuard
+{
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev)
+  {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+    if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard()
+  {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// Smallest whole-metre offset m for which the reference's bound test rejects the point:
+//   (unsigned)((float)m / resolution) >= dim     (cuda_eval_particles.h:14-25, cuda_sub_voxel_map.tcc:53-65)
+uint32_t bound_threshold(uint64_t dim, float res)
+{
+  uint32_t m = 0;
+  for (;;)
+  {
+    const volatile float q = static_cast<float>(m) / res;
+    const double qd = q;
+    const uint64_t g = qd >= 18446744073709551615.0 ? ~0ull : static_cast<uint64_t>(qd);
+    if (g >= dim) return m;
+    ++m;
+    if (m == (1u << 22)) return m;
+  }
+}
+
+int launch_check(tsdfloc_ctx* c, const char* what)
+{
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(c, TSDFLOC_E_CUDA, std::string("launch of ") + what + " failed: " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+  ++c->launches;
+  return TSDFLOC_OK;
+}
+
+// ---- stages (device pointers) ----------------------------------------------------------------------------
+
+int stage_prep_scan(tsdfloc_ctx* c, const float* d_xyz, uint64_t p, cudaStream_t s)
+{
+  if (p > 0x7fffffffull) return fail(c, TSDFLOC_E_BAD_ARG, "scan larger than 2^31 points");
+  int rc;
+  if ((rc = ensure(c, c->d_pts, sizeof(float4) * (p + 64), "cudaMalloc(scan)"))) return rc;
+  const int nb = 64;
+  if ((rc = ensure(c, c->d_blocksums, sizeof(double) * 4096, "cudaMalloc(block sums)"))) return rc;
+  c->n_points = p;
+  if (p == 0) return TSDFLOC_OK;
+  const float a_range_term = c->prm.a_range * static_cast<float>(1.0 / c->prm.max_range);
+  k_prep_scan<<<nb, 256, 0, s>>>(d_xyz, static_cast<uint32_t>(p), static_cast<float4*>(c->d_pts.p), a_range_term, c->prm.a_max,
+                                 c->prm.max_range * c->prm.max_range, static_cast<double*>(c->d_blocksums.p));
+  if ((rc = launch_check(c, "k_prep_scan"))) return rc;
+  k_prep_scan_finish<<<1, 1, 0, s>>>(static_cast<double*>(c->d_blocksums.p), nb, c->d_term_sum);
+  return launch_check(c, "k_prep_scan_finish");
+}
+
+// Launch geometry of the evaluation kernel for `count` particles.
+struct EvalPlan
+{
+  int ppw;
+  uint32_t tiles;      // gridDim.x
+  uint32_t chunks;     // gridDim.y
+  uint32_t chunk_len;  // points per chunk (multiple of 32)
+};
+
+EvalPlan plan_eval(const tsdfloc_ctx* c, uint64_t count, uint64_t p)
+{
+  EvalPlan pl{};
+  // particles per warp: 2 once there are enough particles to fill the machine with 2-particle warps
+  const uint64_t warps_needed_1 = count;
+  pl.ppw = (warps_needed_1 >= static_cast<uint64_t>(c->sm_count) * kEvalWarps * 4) ? 2 : 1;
+  const uint64_t per_cta = static_cast<uint64_t>(kEvalWarps) * pl.ppw;
+  pl.tiles = static_cast<uint32_t>((count + per_cta - 1) / per_cta);
+  // split the scan so that the grid has at least ~8 CTAs per SM, in chunks of >= 1024 points
+  const uint64_t want_ctas = static_cast<uint64_t>(c->sm_count) * 8;
+  uint64_t chunks = (want_ctas + pl.tiles - 1) / pl.tiles;
+  const uint64_t max_chunks = std::max<uint64_t>(1, p / 1024);
+  chunks = std::max<uint64_t>(1, std::min<uint64_t>(chunks, std::min<uint64_t>(max_chunks, 256)));
+  uint64_t len = (p + chunks - 1) / chunks;
+  len = (len + 31) & ~31ull;
+  if (len == 0) len = 32;
+  pl.chunk_len = static_cast<uint32_t>(len);
+  pl.chunks = static_cast<uint32_t>((p + len - 1) / len);
+  if (pl.chunks == 0) pl.chunks = 1;
+  return pl;
+}
+
+template <int kPPW>
+void launch_eval(const tsdfloc_ctx* c, const EvalPlan& pl, uint32_t count, cudaStream_t s)
+{
+  dim3 grid(pl.tiles, pl.chunks);
+  if (c->map.fast_div)
+    k_eval<kPPW, true><<<grid, kEvalThreads, 0, s>>>(c->map, static_cast<const float4*>(c->d_pts.p), static_cast<uint32_t>(c->n_points),
+                                                      pl.chunk_len, static_cast<const float*>(c->d_mats.p), count,
+                                                      static_cast<float*>(c->d_partial.p));
+  else
+    k_eval<kPPW, false><<<grid, kEvalThreads, 0, s>>>(c->map, static_cast<const float4*>(c->d_pts.p), static_cast<uint32_t>(c->n_points),
+                                                       pl.chunk_len, static_cast<const float*>(c->d_mats.p), count,
+                                                       static_cast<float*>(c->d_partial.p));
+}
+
+int stage_matrices(tsdfloc_ctx* c, const float* d_particles, uint64_t first, uint64_t count, const float tf[16], cudaStream_t s)
+{
+  int rc;
+  if ((rc = ensure(c, c->d_mats, sizeof(float) * 12 * count, "cudaMalloc(matrices)"))) return rc;
+  Tf12 t;
+  std::memcpy(t.m, tf, sizeof(t.m));
+  k_pose_matrices<<<static_cast<unsigned>((count + 127) / 128), 128, 0, s>>>(d_particles, static_cast<uint32_t>(first),
+                                                                            static_cast<uint32_t>(count), t,
+                                                                            static_cast<float*>(c->d_mats.p));
+  return launch_check(c, "k_pose_matrices");
+}
+
+int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint64_t first, uint64_t count, const float tf[16],
+               float* d_raw, cudaStream_t s)
+{
+  if (first + count > n_total) return fail(c, TSDFLOC_E_BAD_ARG, "particle slice exceeds n_total");
+  if (n_total > (1ull << 24)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 2^24 particles: the reference's fp32 U recurrence stalls");
+  if (c->n_points == 0) return fail(c, TSDFLOC_E_EMPTY_SCAN, "empty scan");
+  if (count == 0) return TSDFLOC_OK;
+  int rc;
+  if ((rc = stage_matrices(c, d_particles, first, count, tf, s))) return rc;
+  const EvalPlan pl = plan_eval(c, count, c->n_points);
+  if ((rc = ensure(c, c->d_partial, sizeof(float) * static_cast<size_t>(pl.chunks) * count, "cudaMalloc(partials)"))) return rc;
+  if (pl.ppw == 2)
+    launch_eval<2>(c, pl, static_cast<uint32_t>(count), s);
+  else
+    launch_eval<1>(c, pl, static_cast<uint32_t>(count), s);
+  if ((rc = launch_check(c, "k_eval"))) return rc;
+  k_finish_raw<<<static_cast<unsigned>((count + 255) / 256), 256, 0, s>>>(static_cast<const float*>(c->d_partial.p), pl.chunks,
+                                                                         static_cast<uint32_t>(count), c->prm.a_hit, c->d_term_sum,
+                                                                         d_raw + first);
+  return launch_check(c, "k_finish_raw");
+}
+
+int stage_normalize(tsdfloc_ctx* c, float* d_particles, uint64_t n, const float* d_raw, float* d_mean, cudaStream_t s)
+{
+  if (n == 0) return fail(c, TSDFLOC_E_BAD_ARG, "no particles");
+  if (n > (1ull << 24)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 2^24 particles: the reference's fp32 U recurrence stalls");
+  const uint32_t tiles = static_cast<uint32_t>((n + kScanTile - 1) / kScanTile);
+  int rc;
+  if ((rc = ensure(c, c->d_cdf, sizeof(double) * n, "cudaMalloc(cdf)"))) return rc;
+  if ((rc = ensure(c, c->d_tile_total, sizeof(double) * tiles, "cudaMalloc(tile totals)"))) return rc;
+  if ((rc = ensure(c, c->d_tile_offset, sizeof(double) * tiles, "cudaMalloc(tile offsets)"))) return rc;
+  if ((rc = ensure(c, c->d_tile_moments, sizeof(double) * 9 * tiles, "cudaMalloc(tile moments)"))) return rc;
+  const uint32_t n32 = static_cast<uint32_t>(n);
+  k_weight_sum<<<tiles, kScanThreads, 0, s>>>(d_raw, n32, static_cast<double*>(c->d_tile_total.p), c->d_status);
+  if ((rc = launch_check(c, "k_weight_sum"))) return rc;
+  k_normalise_scan<<<tiles, kScanThreads, 0, s>>>(d_particles, d_raw, n32, c->d_status, static_cast<double*>(c->d_cdf.p),
+                                                  static_cast<double*>(c->d_tile_total.p), static_cast<double*>(c->d_tile_moments.p));
+  if ((rc = launch_check(c, "k_normalise_scan"))) return rc;
+  k_scan_tiles<<<1, 32, 0, s>>>(static_cast<const double*>(c->d_tile_total.p), static_cast<double*>(c->d_tile_offset.p), tiles,
+                                static_cast<const double*>(c->d_tile_moments.p), d_mean, c->d_status);
+  if ((rc = launch_check(c, "k_scan_tiles"))) return rc;
+  k_cdf_finalize<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(static_cast<double*>(c->d_cdf.p),
+                                                                       static_cast<const double*>(c->d_tile_offset.p), n32, c->d_status);
+  if ((rc = launch_check(c, "k_cdf_finalize"))) return rc;
+  c->have_cdf = true;
+  return TSDFLOC_OK;
+}
+
+int stage_draw(tsdfloc_ctx* c, const float* d_particles, uint64_t n, float u0, uint64_t first_out, uint64_t count_out, float* d_out,
+               uint32_t* d_parents, cudaStream_t s)
+{
+  if (!c->have_cdf) return fail(c, TSDFLOC_E_STATE, "draw before normalize");
+  if (!(u0 >= 0.0f)) return fail(c, TSDFLOC_E_BAD_ARG, "u0 must be >= 0");
+  k_finish_cdf_utable<<<1, 32, 0, s>>>(d_particles, static_cast<double*>(c->d_cdf.p), static_cast<uint32_t>(n), u0, c->d_segs, c->d_status);
+  int rc;
+  if ((rc = launch_check(c, "k_finish_cdf_utable"))) return rc;
+  if (count_out == 0) return TSDFLOC_OK;
+  k_draw<<<static_cast<unsigned>((count_out + 255) / 256), 256, 0, s>>>(d_particles, static_cast<const double*>(c->d_cdf.p),
+                                                                       static_cast<uint32_t>(n), c->d_segs, c->d_status, first_out,
+                                                                       static_cast<uint32_t>(count_out), d_out, d_parents);
+  return launch_check(c, "k_draw");
+}
+
+int read_status(tsdfloc_ctx* c, cudaStream_t s)
+{
+  CU_TRY(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s), "status readback");
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  return TSDFLOC_OK;
+}
+
+bool valid_desc(const tsdfloc_map_desc* m, std::string& why)
+{
+  if (!(m->resolution > 0.0f) || !std::isfinite(m->resolution)) { why = "resolution must be positive"; return false; }
+  for (int a = 0; a < 3; ++a)
+  {
+    if (!std::isfinite(m->min[a]) || !std::isfinite(m->max[a])) { why = "non-finite bounds"; return false; }
+    if (m->up_dim[a] == 0 || m->up_dim[a] >= (1u << 20)) { why = "up_dim out of range"; return false; }
+  }
+  if (m->up_dim_2 != m->up_dim[0] * m->up_dim[1]) { why = "up_dim_2 != up_dim[0]*up_dim[1]"; return false; }
+  if (m->grid_occ_size != m->up_dim[0] * m->up_dim[1] * m->up_dim[2]) { why = "grid_occ_size mismatch"; return false; }
+  if (m->grid_occ_size >= (1ull << 31)) { why = "brick table too large"; return false; }
+  if (m->sub_dim == 0 || m->sub_dim > 4096) { why = "sub_dim out of range"; return false; }
+  if (m->sub_dim_2 != m->sub_dim * m->sub_dim) { why = "sub_dim_2 != sub_dim^2"; return false; }
+  if (m->data_size >= (1ull << 31)) { why = "data_size exceeds the reference's int offsets (OCC_T = int)"; return false; }
+  return true;
+}
+
+}  // namespace
+
+// ---- C ABI ---------------------------------------------------------------------------------------------------
+
+extern "C"
+{
+
+void tsdfloc_default_params(tsdfloc_params* p)
+{
+  if (!p) return;
+  p->a_hit = 0.9f;
+  p->a_range = 0.1f;
+  p->a_max = 0.0f;
+  p->max_range = 100.0f;
+  p->per_point = 0;
+  p->reserved = 0;
+}
+
+int tsdfloc_abi_version(void) { return TSDFLOC_ABI_VERSION; }
+
+const char* tsdfloc_status_string(int status)
+{
+  switch (status)
+  {
+    case TSDFLOC_OK: return "ok";
+    case TSDFLOC_E_BAD_ARG: return "bad argument";
+    case TSDFLOC_E_CUDA: return "CUDA error";
+    case TSDFLOC_E_NO_VALID_PARTICLE: return "No particle is valid!";
+    case TSDFLOC_E_EMPTY_SCAN: return "empty scan";
+    case TSDFLOC_E_CAPACITY: return "output capacity exceeded";
+    case TSDFLOC_E_STATE: return "call out of order";
+    default: return "unknown status";
+  }
+}
+
+const char* tsdfloc_last_error(const tsdfloc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+uint64_t tsdfloc_kernel_launches(const tsdfloc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const float* data, const tsdfloc_params* params, int device,
+                   tsdfloc_ctx** out)
+{
+  if (!out) return fail(nullptr, TSDFLOC_E_BAD_ARG, "out is NULL");
+  *out = nullptr;
+  if (!map || !grid_occ || (!data && map->data_size)) return fail(nullptr, TSDFLOC_E_BAD_ARG, "map, grid_occ and data are required");
+  std::string why;
+  if (!valid_desc(map, why)) return fail(nullptr, TSDFLOC_E_BAD_ARG, "invalid map description: " + why);
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, TSDFLOC_E_CUDA,
+                std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                    "); libtsdfloc has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(nullptr, TSDFLOC_E_BAD_ARG, "device index out of range");
+
+  tsdfloc_ctx* c = new (std::nothrow) tsdfloc_ctx;
+  if (!c) return fail(nullptr, TSDFLOC_E_BAD_ARG, "out of host memory");
+  c->device = device;
+  DeviceGuard guard(device);
+  auto bail = [&](int code, const std::string& msg) {
+    g_create_error = msg;
+    tsdfloc_destroy(c);
+    return code;
+  };
+#define CU_CREATE(expr, what)                                                                             \
+  do                                                                                                      \
+  {                                                                                                       \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess) return bail(TSDFLOC_E_CUDA, std::string(what) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+  if (!guard.ok) return bail(TSDFLOC_E_CUDA, "cudaSetDevice failed");
+  cudaDeviceProp prop{};
+  CU_CREATE(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return bail(TSDFLOC_E_CUDA, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                    "; libtsdfloc is built for sm_100a (B200) only");
+  c->sm_count = prop.multiProcessorCount;
+  if (params) c->prm = *params; else tsdfloc_default_params(&c->prm);
+  if (!(c->prm.max_range > 0.0f)) return bail(TSDFLOC_E_BAD_ARG, "max_range must be positive");
+  c->desc = *map;
+  CU_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+
+  // ---- padded brick table ------------------------------------------------------------------------------------
+  uint32_t thr[3];
+  for (int a = 0; a < 3; ++a)
+  {
+    thr[a] = bound_threshold(map->dim[a], map->resolution);
+    if (thr[a] >= (1u << 22)) return bail(TSDFLOC_E_BAD_ARG, "map extent too large");
+  }
+  const uint64_t px = thr[0] + 2ull, py = thr[1] + 2ull, pz = thr[2] + 2ull;
+  const uint64_t table_n = px * py * pz;
+  if (table_n >= (1ull << 31)) return bail(TSDFLOC_E_BAD_ARG, "padded brick table too large");
+  const uint64_t sub_n = map->sub_dim * map->sub_dim * map->sub_dim;
+  // miss brick: large enough for the largest in-brick offset the index arithmetic can produce (sub coordinate == sub_dim)
+  const uint64_t miss_n = map->sub_dim * (1 + map->sub_dim + map->sub_dim_2) + 1;
+  const uint64_t miss_offset = map->data_size;
+  if (miss_offset + miss_n + sub_n >= (1ull << 32)) return bail(TSDFLOC_E_BAD_ARG, "voxel array too large");
+  std::vector<int32_t> table(table_n, static_cast<int32_t>(miss_offset));
+  uint64_t bricks = 0;
+  for (uint64_t z = 0; z < thr[2]; ++z)
+    for (uint64_t y = 0; y < thr[1]; ++y)
+      for (uint64_t x = 0; x < thr[0]; ++x)
+      {
+        // the reference's own (aliasing) upper index, cuda_eval_particles.h:44-58
+        const uint64_t up_index = x + y * map->up_dim[0] + z * map->up_dim_2;
+        if (up_index >= map->grid_occ_size) continue;
+        const int32_t off = grid_occ[up_index];
+        if (off < 0) continue;
+        if (static_cast<uint64_t>(off) + sub_n > map->data_size) return bail(TSDFLOC_E_BAD_ARG, "grid_occ entry points outside data");
+        table[(x + 1) + (y + 1) * px + (z + 1) * px * py] = off;
+        ++bricks;
+      }
+  (void)bricks;
+  CU_CREATE(cudaMalloc(&c->d_table, sizeof(int32_t) * table_n), "cudaMalloc(brick table)");
+  CU_CREATE(cudaMemcpy(c->d_table, table.data(), sizeof(int32_t) * table_n, cudaMemcpyHostToDevice), "upload brick table");
+  CU_CREATE(cudaMalloc(&c->d_voxels, sizeof(float) * (miss_offset + miss_n)), "cudaMalloc(voxels)");
+  if (map->data_size)
+    CU_CREATE(cudaMemcpy(c->d_voxels, data, sizeof(float) * map->data_size, cudaMemcpyHostToDevice), "upload voxels");
+  {
+    std::vector<float> miss(miss_n, map->init_value);
+    CU_CREATE(cudaMemcpy(c->d_voxels + miss_offset, miss.data(), sizeof(float) * miss_n, cudaMemcpyHostToDevice), "upload miss brick");
+  }
+
+  MapDev& M = c->map;
+  M.table = c->d_table;
+  M.voxels = c->d_voxels;
+  for (int a = 0; a < 3; ++a)
+  {
+    M.min[a] = map->min[a];
+    M.clamp_hi[a] = static_cast<float>(thr[a]);
+  }
+  M.res = map->resolution;
+  {
+    const volatile float inv = 1.0f / map->resolution;
+    M.inv_res = inv;
+  }
+  M.pad_x = static_cast<uint32_t>(px);
+  M.pad_xy = static_cast<uint32_t>(px * py);
+  M.sub_dim = static_cast<uint32_t>(map->sub_dim);
+  M.sub_dim_2 = static_cast<uint32_t>(map->sub_dim_2);
+  M.data_size = static_cast<uint32_t>(map->data_size);
+  M.table_bias = kMagicBits * (1u + M.pad_x + M.pad_xy);
+  M.sub_bias = kMagicBits * (1u + M.sub_dim + M.sub_dim_2);
+
+  // ---- small fixed buffers -------------------------------------------------------------------------------------
+  CU_CREATE(cudaMalloc(&c->d_term_sum, sizeof(double)), "cudaMalloc(term sum)");
+  CU_CREATE(cudaMalloc(&c->d_mean, sizeof(float) * 8), "cudaMalloc(mean pose)");
+  CU_CREATE(cudaMalloc(&c->d_segs, sizeof(USeg) * kMaxUSegs), "cudaMalloc(U table)");
+  CU_CREATE(cudaMalloc(&c->d_status, sizeof(Status)), "cudaMalloc(status)");
+  CU_CREATE(cudaMemset(c->d_status, 0, sizeof(Status)), "memset(status)");
+  CU_CREATE(cudaMallocHost(&c->h_status, sizeof(Status)), "cudaMallocHost(status)");
+  CU_CREATE(cudaMallocHost(&c->h_mean, sizeof(float) * 8), "cudaMallocHost(mean)");
+
+  // ---- verify the 3-instruction division for this resolution (exhaustive over [0,1)) --------------------------
+  {
+    unsigned long long* d_bad = nullptr;
+    CU_CREATE(cudaMalloc(&d_bad, sizeof(unsigned long long)), "cudaMalloc(div check)");
+    CU_CREATE(cudaMemset(d_bad, 0, sizeof(unsigned long long)), "memset(div check)");
+    k_check_div<<<c->sm_count * 8, 256, 0, c->stream>>>(M.res, M.inv_res, d_bad);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess)
+    {
+      cudaFree(d_bad);
+      return bail(TSDFLOC_E_CUDA, std::string("kernel image not loadable on this device (built for sm_100a): ") + cudaGetErrorString(le));
+    }
+    ++c->launches;
+    unsigned long long bad = 0;
+    cudaError_t ce = cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, c->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+    cudaFree(d_bad);
+    if (ce != cudaSuccess) return bail(TSDFLOC_E_CUDA, std::string("division self-check failed to run: ") + cudaGetErrorString(ce));
+    M.fast_div = (bad == 0) ? 1 : 0;
+  }
+#undef CU_CREATE
+  *out = c;
+  return TSDFLOC_OK;
+}
+
+void tsdfloc_destroy(tsdfloc_ctx* c)
+{
+  if (!c) return;
+  DeviceGuard guard(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->d_xyz_stage, &c->d_pts, &c->d_blocksums, &c->d_particles, &c->d_particles_out, &c->d_mats, &c->d_partial,
+                    &c->d_raw, &c->d_cdf, &c->d_tile_total, &c->d_tile_offset, &c->d_tile_moments, &c->d_parents, &c->d_idx, &c->d_hits};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (c->d_table) cudaFree(c->d_table);
+  if (c->d_voxels) cudaFree(c->d_voxels);
+  if (c->d_term_sum) cudaFree(c->d_term_sum);
+  if (c->d_mean) cudaFree(c->d_mean);
+  if (c->d_segs) cudaFree(c->d_segs);
+  if (c->d_status) cudaFree(c->d_status);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->h_status) cudaFreeHost(c->h_status);
+  if (c->h_mean) cudaFreeHost(c->h_mean);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+// ---- (B) device-pointer stages ----------------------------------------------------------------------------------
+
+int tsdfloc_set_scan_device(tsdfloc_ctx* c, const float* d_points_xyz, uint64_t p, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (p && !d_points_xyz) return fail(c, TSDFLOC_E_BAD_ARG, "points is NULL");
+  DeviceGuard guard(c->device);
+  return stage_prep_scan(c, d_points_xyz, p, pick(c, stream));
+}
+
+int tsdfloc_set_scan_host(tsdfloc_ctx* c, const float* points_xyz, uint64_t p, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (p && !points_xyz) return fail(c, TSDFLOC_E_BAD_ARG, "points is NULL");
+  DeviceGuard guard(c->device);
+  cudaStream_t s = pick(c, stream);
+  int rc;
+  if ((rc = ensure(c, c->d_xyz_stage, sizeof(float) * 3 * (p + 1), "cudaMalloc(scan staging)"))) return rc;
+  if (p) CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, points_xyz, sizeof(float) * 3 * p, cudaMemcpyHostToDevice, s), "H2D scan");
+  return stage_prep_scan(c, static_cast<const float*>(c->d_xyz_stage.p), p, s);
+}
+
+int tsdfloc_eval_device(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint64_t first, uint64_t count, const float tf[16],
+                        float* d_raw_weights, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!d_particles || !tf || !d_raw_weights) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  DeviceGuard guard(c->device);
+  return stage_eval(c, d_particles, n_total, first, count, tf, d_raw_weights, pick(c, stream));
+}
+
+int tsdfloc_normalize_device(tsdfloc_ctx* c, float* d_particles, uint64_t n_total, const float* d_raw_weights, float* d_mean_pose,
+                             void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!d_particles || !d_raw_weights) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  DeviceGuard guard(c->device);
+  return stage_normalize(c, d_particles, n_total, d_raw_weights, d_mean_pose ? d_mean_pose : c->d_mean, pick(c, stream));
+}
+
+int tsdfloc_draw_device(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, float u0, uint64_t first_out, uint64_t count_out,
+                        float* d_particles_out, uint32_t* d_parents, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!d_particles || (count_out && !d_particles_out)) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  DeviceGuard guard(c->device);
+  return stage_draw(c, d_particles, n_total, u0, first_out, count_out, d_particles_out, d_parents, pick(c, stream));
+}
+
+int tsdfloc_check(tsdfloc_ctx* c, uint64_t* n_out, double* weight_sum, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  DeviceGuard guard(c->device);
+  int rc = read_status(c, pick(c, stream));
+  if (rc) return rc;
+  if (n_out) *n_out = c->h_status->n_out;
+  if (weight_sum) *weight_sum = c->h_status->weight_sum;
+  if (c->h_status->zero_sum) return fail(c, TSDFLOC_E_NO_VALID_PARTICLE, "No particle is valid!");
+  if (c->h_status->table_overflow & 3u) return fail(c, TSDFLOC_E_CAPACITY, "U recurrence table overflow or stalled recurrence");
+  return TSDFLOC_OK;
+}
+
+// ---- (A) host-buffer calls ---------------------------------------------------------------------------------------
+
+int tsdfloc_sensor_update(tsdfloc_ctx* c, float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],
+                          float mean_pose[6])
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!particles || !tf || (p && !points)) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (p == 0) return fail(c, TSDFLOC_E_EMPTY_SCAN, "empty scan: weights left untouched");
+  if (n == 0) return fail(c, TSDFLOC_E_BAD_ARG, "no particles");
+  DeviceGuard guard(c->device);
+  cudaStream_t s = c->stream;
+  int rc;
+  const size_t pbytes = sizeof(float) * 7 * n;
+  if ((rc = ensure(c, c->d_particles, pbytes, "cudaMalloc(particles)"))) return rc;
+  if ((rc = ensure(c, c->d_raw, sizeof(float) * n, "cudaMalloc(raw weights)"))) return rc;
+  if ((rc = ensure_host(c, std::max(pbytes, sizeof(float) * 3 * p)))) return rc;
+  c->have_cdf = false;
+  c->n_resident = 0;
+
+  // scan: host -> pinned -> device, then prep
+  std::memcpy(c->h_stage, points, sizeof(float) * 3 * p);
+  if ((rc = ensure(c, c->d_xyz_stage, sizeof(float) * 3 * (p + 1), "cudaMalloc(scan staging)"))) return rc;
+  CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, c->h_stage, sizeof(float) * 3 * p, cudaMemcpyHostToDevice, s), "H2D scan");
+  if ((rc = stage_prep_scan(c, static_cast<const float*>(c->d_xyz_stage.p), p, s))) return rc;
+  // the pinned buffer is reused for the particles: wait for the scan copy to leave it
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  std::memcpy(c->h_stage, particles, pbytes);
+  float* d_p = static_cast<float*>(c->d_particles.p);
+  CU_TRY(c, cudaMemcpyAsync(d_p, c->h_stage, pbytes, cudaMemcpyHostToDevice, s), "H2D particles");
+
+  if ((rc = stage_eval(c, d_p, n, 0, n, tf, static_cast<float*>(c->d_raw.p), s))) return rc;
+  if ((rc = stage_normalize(c, d_p, n, static_cast<const float*>(c->d_raw.p), c->d_mean, s))) return rc;
+  CU_TRY(c, cudaMemcpyAsync(c->h_stage, d_p, pbytes, cudaMemcpyDeviceToHost, s), "D2H particles");
+  CU_TRY(c, cudaMemcpyAsync(c->h_mean, c->d_mean, sizeof(float) * 6, cudaMemcpyDeviceToHost, s), "D2H mean pose");
+  if ((rc = read_status(c, s))) return rc;
+  if (c->h_status->zero_sum) return fail(c, TSDFLOC_E_NO_VALID_PARTICLE, "No particle is valid!");
+  // only the weight slot is written back: the caller's poses are untouched (cuda_evaluator.cu:405-408)
+  const float* h = static_cast<const float*>(c->h_stage);
+  for (uint64_t i = 0; i < n; ++i) particles[7 * i + 6] = h[7 * i + 6];
+  if (mean_pose) std::memcpy(mean_pose, c->h_mean, sizeof(float) * 6);
+  c->n_resident = n;
+  return TSDFLOC_OK;
+}
+
+int tsdfloc_resample_systematic(tsdfloc_ctx* c, float u0, float* particles_out, uint64_t cap, uint64_t* n_out, uint32_t* parents)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!particles_out || !n_out) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (c->n_resident == 0 || !c->have_cdf) return fail(c, TSDFLOC_E_STATE, "resample_systematic needs a preceding successful sensor_update");
+  DeviceGuard guard(c->device);
+  cudaStream_t s = c->stream;
+  const uint64_t n = c->n_resident;
+  int rc;
+  if ((rc = ensure(c, c->d_particles_out, sizeof(float) * 7 * cap, "cudaMalloc(resampled particles)"))) return rc;
+  if (parents && (rc = ensure(c, c->d_parents, sizeof(uint32_t) * cap, "cudaMalloc(parents)"))) return rc;
+  if ((rc = ensure_host(c, sizeof(float) * 7 * cap + sizeof(uint32_t) * cap))) return rc;
+  float* d_p = static_cast<float*>(c->d_particles.p);
+  if ((rc = stage_draw(c, d_p, n, u0, 0, cap, static_cast<float*>(c->d_particles_out.p), parents ? static_cast<uint32_t*>(c->d_parents.p) : nullptr, s)))
+    return rc;
+  CU_TRY(c, cudaMemcpyAsync(c->h_stage, c->d_particles_out.p, sizeof(float) * 7 * cap, cudaMemcpyDeviceToHost, s), "D2H resampled particles");
+  uint32_t* h_par = reinterpret_cast<uint32_t*>(static_cast<char*>(c->h_stage) + sizeof(float) * 7 * cap);
+  if (parents) CU_TRY(c, cudaMemcpyAsync(h_par, c->d_parents.p, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, s), "D2H parents");
+  if ((rc = read_status(c, s))) return rc;
+  if (c->h_status->table_overflow & 3u) return fail(c, TSDFLOC_E_CAPACITY, "U recurrence table overflow or stalled recurrence");
+  const uint64_t m = c->h_status->n_out;
+  *n_out = m;
+  if (m > cap) return fail(c, TSDFLOC_E_CAPACITY, "resampling emits " + std::to_string(m) + " particles, capacity is " + std::to_string(cap));
+  std::memcpy(particles_out, c->h_stage, sizeof(float) * 7 * m);
+  if (parents) std::memcpy(parents, h_par, sizeof(uint32_t) * m);
+  return TSDFLOC_OK;
+}
+
+int tsdfloc_debug_eval(tsdfloc_ctx* c, const float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],
+                       uint32_t* idx, uint32_t* hits, float* raw_weights)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!particles || !points || !tf || n == 0 || p == 0) return fail(c, TSDFLOC_E_BAD_ARG, "NULL or empty argument");
+  if (n * p >= (1ull << 32)) return fail(c, TSDFLOC_E_BAD_ARG, "debug dump limited to n*p < 2^32 pairs");
+  DeviceGuard guard(c->device);
+  cudaStream_t s = c->stream;
+  int rc;
+  if ((rc = ensure(c, c->d_particles, sizeof(float) * 7 * n, "cudaMalloc(particles)"))) return rc;
+  if ((rc = ensure(c, c->d_raw, sizeof(float) * n, "cudaMalloc(raw weights)"))) return rc;
+  if ((rc = ensure(c, c->d_xyz_stage, sizeof(float) * 3 * (p + 1), "cudaMalloc(scan staging)"))) return rc;
+  if (idx && (rc = ensure(c, c->d_idx, sizeof(uint32_t) * n * p, "cudaMalloc(index dump)"))) return rc;
+  if ((rc = ensure(c, c->d_hits, sizeof(uint32_t) * n, "cudaMalloc(hit counts)"))) return rc;
+  c->have_cdf = false;
+  c->n_resident = 0;
+  CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, points, sizeof(float) * 3 * p, cudaMemcpyHostToDevice, s), "H2D scan");
+  if ((rc = stage_prep_scan(c, static_cast<const float*>(c->d_xyz_stage.p), p, s))) return rc;
+  float* d_p = static_cast<float*>(c->d_particles.p);
+  CU_TRY(c, cudaMemcpyAsync(d_p, particles, sizeof(float) * 7 * n, cudaMemcpyHostToDevice, s), "H2D particles");
+  if ((rc = stage_eval(c, d_p, n, 0, n, tf, static_cast<float*>(c->d_raw.p), s))) return rc;
+  CU_TRY(c, cudaMemsetAsync(c->d_hits.p, 0, sizeof(uint32_t) * n, s), "memset hits");
+  const unsigned long long total = n * p;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (c->map.fast_div)
+    k_debug_pairs<true><<<blocks, 256, 0, s>>>(c->map, static_cast<const float4*>(c->d_pts.p), static_cast<uint32_t>(p),
+                                               static_cast<const float*>(c->d_mats.p), static_cast<uint32_t>(n),
+                                               idx ? static_cast<uint32_t*>(c->d_idx.p) : nullptr, static_cast<uint32_t*>(c->d_hits.p));
+  else
+    k_debug_pairs<false><<<blocks, 256, 0, s>>>(c->map, static_cast<const float4*>(c->d_pts.p), static_cast<uint32_t>(p),
+                                                static_cast<const float*>(c->d_mats.p), static_cast<uint32_t>(n),
+                                                idx ? static_cast<uint32_t*>(c->d_idx.p) : nullptr, static_cast<uint32_t*>(c->d_hits.p));
+  if ((rc = launch_check(c, "k_debug_pairs"))) return rc;
+  if (idx) CU_TRY(c, cudaMemcpyAsync(idx, c->d_idx.p, sizeof(uint32_t) * n * p, cudaMemcpyDeviceToHost, s), "D2H index dump");
+  if (hits) CU_TRY(c, cudaMemcpyAsync(hits, c->d_hits.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s), "D2H hits");
+  if (raw_weights) CU_TRY(c, cudaMemcpyAsync(raw_weights, c->d_raw.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s), "D2H raw weights");
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  return TSDFLOC_OK;
+}
+
+// Host-only test hook (no GPU needed): the U recurrence table evaluated on the host, for unit tests of the
+// __host__ __device__ table builder against the plain loop. Writes min(count, cap) values; returns count.
+uint64_t tsdfloc_host_u_sequence(float u0, uint64_t n, double limit, float* out, uint64_t cap, uint32_t* n_segs, uint32_t* flags)
+{
+  std::vector<USeg> segs(kMaxUSegs);
+  unsigned long long below = 0;
+  uint32_t fl = 0;
+  const uint32_t ns = build_u_table(u0, 1.0 / static_cast<double>(n), limit, segs.data(), kMaxUSegs, &below, 2ull * n + 64ull, &fl);
+  if (n_segs) *n_segs = ns;
+  if (flags) *flags = fl;
+  for (uint64_t j = 0; j < below && j < cap; ++j) out[j] = u_at(segs.data(), ns, j);
+  return below;
+}
+
+}  // extern "C"

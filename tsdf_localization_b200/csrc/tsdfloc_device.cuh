@@ -1,0 +1,92 @@
+// tsdfloc_device.cuh — device-side data layout and the voxel index function of the B200 sensor update.
+//
+// Replaces (does not port) include/tsdf_localization/cuda/cuda_eval_particles.h:12-164 (getIndex/getEntry) of the
+// reference. The index ARITHMETIC must be bit-identical to the reference's for every non-negative offset
+// (SURVEY §2.5(3)); the way it is evaluated is new:
+//   * the metre-truncated bound test and the `up_index >= grid_occ_size` test are folded, at map-upload time,
+//     into a PADDED BRICK TABLE with a one-cell border of "miss" entries, so the kernel clamps each axis
+//     offset into the padded range instead of branching;
+//   * misses (border, unallocated upper cells, negative/NaN offsets — policy NEG_AS_MISS) point at a
+//     MISS BRICK filled with init_value appended behind the real bricks: the gather is branch-free;
+//   * floor() is a round-down add of 2^23 (FADD.RM) instead of F2I/I2F;
+//   * x / resolution uses a verified 3-instruction correctly-rounded sequence (FMUL, FFMA, FFMA); tsdfloc_create
+//     checks it exhaustively against IEEE division for the map's resolution and falls back to __fdiv_rn.
+// All fp32 arithmetic that feeds an index uses explicit _rn/_rd intrinsics: nvcc never contracts those into FMAs.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tsdfloc
+{
+
+constexpr float kMagic = 8388608.0f;        // 2^23
+constexpr float kMagicP1 = 8388609.0f;      // 2^23 + 1: floor(x)+1 lands in the mantissa
+constexpr uint32_t kMagicBits = 0x4B000000u;  // bit pattern of 2^23
+
+// Device view of the map. 96 bytes, passed by value as a kernel parameter (constant bank).
+struct MapDev
+{
+  const int32_t* __restrict__ table;  // padded brick table [pz][py][px]: element offset of the brick in voxels
+  const float* __restrict__ voxels;   // bricks in reference order + one miss brick at miss_offset
+  float min[3];
+  float clamp_hi[3];   // (float)thr[a]: offsets are clamped into [-1, thr]
+  float res;
+  float inv_res;       // RN(1/res)
+  uint32_t pad_x;      // thr[0] + 2
+  uint32_t pad_xy;     // (thr[0]+2)*(thr[1]+2)
+  uint32_t sub_dim;
+  uint32_t sub_dim_2;
+  uint32_t data_size;  // reference data_size; every index >= data_size is a miss
+  uint32_t table_bias; // kMagicBits * (1 + pad_x + pad_xy)   (mod 2^32)
+  uint32_t sub_bias;   // kMagicBits * (1 + sub_dim + sub_dim_2) (mod 2^32)
+  int32_t fast_div;    // 1: the 3-instruction division is exact for this resolution
+};
+
+// q = trunc-able quotient a / res for a in [0, 1). Bit-identical to IEEE a / res when fast_div was verified.
+template <bool kFastDiv>
+__device__ __forceinline__ float div_res(float a, float res, float inv_res)
+{
+  if (kFastDiv)
+  {
+    const float q0 = __fmul_rn(a, inv_res);
+    const float e = __fmaf_rn(-res, q0, a);
+    return __fmaf_rn(e, inv_res, q0);
+  }
+  return __fdiv_rn(a, res);
+}
+
+// Flat voxel offset (reference numbering: brick offset + sx + sy*sub_dim + sz*sub_dim^2) of world point t.
+// Returns a value >= M.data_size (inside the miss brick) for every miss.
+template <bool kFastDiv>
+__device__ __forceinline__ uint32_t voxel_index(const MapDev& M, float tx, float ty, float tz)
+{
+  // offsets x - min (cuda_eval_particles.h:27-29), clamped into the padded table's range
+  const float ox = fminf(fmaxf(__fsub_rn(tx, M.min[0]), -1.0f), M.clamp_hi[0]);
+  const float oy = fminf(fmaxf(__fsub_rn(ty, M.min[1]), -1.0f), M.clamp_hi[1]);
+  const float oz = fminf(fmaxf(__fsub_rn(tz, M.min[2]), -1.0f), M.clamp_hi[2]);
+  // 2^23 + 1 + floor(o): the low mantissa bits are the padded upper-cell coordinate (:34-36)
+  const float bx = __fadd_rd(ox, kMagicP1);
+  const float by = __fadd_rd(oy, kMagicP1);
+  const float bz = __fadd_rd(oz, kMagicP1);
+  // position inside the 1 m upper cell (:40-42); exact
+  const float px = __fsub_rn(ox, __fsub_rn(bx, kMagicP1));
+  const float py = __fsub_rn(oy, __fsub_rn(by, kMagicP1));
+  const float pz = __fsub_rn(oz, __fsub_rn(bz, kMagicP1));
+  // padded table index; the three 2^23 biases are removed by one pre-computed constant
+  const uint32_t ti = __float_as_uint(bx) + __float_as_uint(by) * M.pad_x + __float_as_uint(bz) * M.pad_xy - M.table_bias;
+  const uint32_t brick = static_cast<uint32_t>(__ldg(M.table + ti));
+  // sub-voxel coordinates (:62-64)
+  const float qx = __fadd_rd(div_res<kFastDiv>(px, M.res, M.inv_res), kMagic);
+  const float qy = __fadd_rd(div_res<kFastDiv>(py, M.res, M.inv_res), kMagic);
+  const float qz = __fadd_rd(div_res<kFastDiv>(pz, M.res, M.inv_res), kMagic);
+  return brick + __float_as_uint(qx) + __float_as_uint(qy) * M.sub_dim + __float_as_uint(qz) * M.sub_dim_2 - M.sub_bias;
+}
+
+// p' = M * p with the reference's operation order, every product and sum rounded separately
+// (cuda_eval_particles.h:182-184 as the CPU build evaluates it, tsdf_evaluator.cpp:44-46).
+__device__ __forceinline__ float row_apply(float a, float b, float c, float d, float x, float y, float z)
+{
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, x), __fmul_rn(b, y)), __fmul_rn(c, z)), d);
+}
+
+}  // namespace tsdfloc

@@ -1,0 +1,599 @@
+// tsdfloc_kernels.cuh — kernels of the B200 sensor update (K0 pose->matrix, K1 evaluation, K2 normalise +
+// moments + CDF, K3 U-table, K4 draw). Included once by tsdfloc_api.cu. sm_100a only.
+//
+// Reference functions these replace (paths relative to the reference repo):
+//   K0/K1  cudaEvaluateParticlesOrdered + cudaEvaluatePose   include/tsdf_localization/cuda/cuda_eval_particles.h:167-215, 273-333
+//   K2     weightSum / chunk_sums_kernel / weight_particles   src/cuda/cuda_sum.cu:18-173, cuda_eval_particles.h:521-557
+//   K3/K4  SystematicResampler::resample (CPU, serial)        include/tsdf_localization/resampling/novel_resampling.h:41-72
+#pragma once
+#include "tsdfloc_device.cuh"
+#include <cstring>
+
+namespace tsdfloc
+{
+
+constexpr int kEvalThreads = 256;                 // 8 warps per CTA
+constexpr int kEvalWarps = kEvalThreads / 32;
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;  // particles per scan tile
+constexpr int kMaxUSegs = 192;
+
+// Device-side status block, read back by tsdfloc_check.
+struct Status
+{
+  double weight_sum;      // sum of raw weights (fp64, fixed order)
+  double s_last;          // last CDF entry (sum of normalised weights, fp64 running sum)
+  float weight_sum_f;     // (float)weight_sum: the divisor of the normalisation
+  uint32_t zero_sum;      // 1: weight_sum == 0 -> "No particle is valid!"
+  uint32_t inexact;       // 1: a parallel fp64 add was inexact -> sequential fallback ran
+  uint32_t n_segs;
+  unsigned long long n_out;  // particles the reference recurrence emits
+  uint32_t ticket;        // last-block-done counter of k_weight_sum (self-resetting)
+  uint32_t table_overflow;   // build_u_table flags: 1 table full, 2 stalled recurrence, 4 max_j reached
+};
+
+// One linear run of the reference's fp32 U recurrence: U_j = u_start + (j - j0) * step, exact, for j0 <= j < next j0.
+struct USeg
+{
+  unsigned long long j0;
+  float u_start;
+  float step;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Scan preparation: xyz -> float4 (w = range term) and the fp64 sum of the range terms.
+// Range term per point: |p|^2 < max_range^2 ? a_range * (1/max_range) : a_max  (tsdf_evaluator.cpp:56-65).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_prep_scan(const float* __restrict__ xyz, uint32_t p, float4* __restrict__ out, float a_range_term, float a_max,
+                            float max_range_sq, double* __restrict__ block_sums)
+{
+  __shared__ double s_part[32];
+  double acc = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p; i += gridDim.x * blockDim.x)
+  {
+    const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    const float sq = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    const float term = sq < max_range_sq ? a_range_term : a_max;
+    out[i] = make_float4(x, y, z, term);
+    acc += static_cast<double>(term);
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += s_part[w];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void k_prep_scan_finish(const double* __restrict__ block_sums, int nb, double* __restrict__ term_sum)
+{
+  double t = 0.0;
+  for (int i = 0; i < nb; ++i) t += block_sums[i];
+  *term_sum = t;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K0: pose (x y z roll pitch yaw) o tf -> 3x4 sensor->map matrix, rounded exactly like the reference CPU build:
+// sin/cos in fp64 rounded to fp32, every product/sum separately rounded (tsdf_evaluator.cpp:102-145).
+// ------------------------------------------------------------------------------------------------------------
+struct Tf12
+{
+  float m[12];
+};
+
+__global__ void k_pose_matrices(const float* __restrict__ particles, uint32_t first, uint32_t count, Tf12 tf, float* __restrict__ mats)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float* p = particles + 7ull * (first + i);
+  double sd, cd;
+  sincos(static_cast<double>(p[3]), &sd, &cd);
+  const float sa = static_cast<float>(sd), ca = static_cast<float>(cd);
+  sincos(static_cast<double>(p[4]), &sd, &cd);
+  const float sb = static_cast<float>(sd), cb = static_cast<float>(cd);
+  sincos(static_cast<double>(p[5]), &sd, &cd);
+  const float sg = static_cast<float>(sd), cg = static_cast<float>(cd);
+
+  float r[3][4];
+  r[0][0] = __fmul_rn(cb, cg);
+  r[1][0] = __fmul_rn(cb, sg);
+  r[2][0] = -sb;
+  r[0][3] = p[0];
+  r[0][1] = __fsub_rn(__fmul_rn(__fmul_rn(sa, sb), cg), __fmul_rn(ca, sg));
+  r[1][1] = __fadd_rn(__fmul_rn(__fmul_rn(sa, sb), sg), __fmul_rn(ca, cg));
+  r[2][1] = __fmul_rn(sa, cb);
+  r[1][3] = p[1];
+  r[0][2] = __fadd_rn(__fmul_rn(__fmul_rn(ca, sb), cg), __fmul_rn(sa, sg));
+  r[1][2] = __fsub_rn(__fmul_rn(__fmul_rn(ca, sb), sg), __fmul_rn(sa, cg));
+  r[2][2] = __fmul_rn(ca, cb);
+  r[2][3] = p[2];
+
+  float* o = mats + 12ull * i;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+  {
+    const float a = r[k][0], b = r[k][1], c = r[k][2], d = r[k][3];
+    o[4 * k + 0] = __fadd_rn(__fadd_rn(__fmul_rn(a, tf.m[0]), __fmul_rn(b, tf.m[4])), __fmul_rn(c, tf.m[8]));
+    o[4 * k + 1] = __fadd_rn(__fadd_rn(__fmul_rn(a, tf.m[1]), __fmul_rn(b, tf.m[5])), __fmul_rn(c, tf.m[9]));
+    o[4 * k + 2] = __fadd_rn(__fadd_rn(__fmul_rn(a, tf.m[2]), __fmul_rn(b, tf.m[6])), __fmul_rn(c, tf.m[10]));
+    o[4 * k + 3] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, tf.m[3]), __fmul_rn(b, tf.m[7])), __fmul_rn(c, tf.m[11])), d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1: evaluation. CTA = kEvalWarps warps; a warp owns kPPW particles (their 3x4 matrices live in registers) and
+// its 32 lanes walk CONSECUTIVE scan points, so the 32 voxel gathers of one warp instruction land on neighbouring
+// voxels of the same surface (few 128 B lines) instead of 32 unrelated particles' voxels as in the reference's
+// one-thread-per-particle kernel. blockIdx.y selects a chunk of the scan; each (chunk, particle) partial sum is
+// written once and reduced in fixed order by k_finish_raw -> deterministic weights.
+// ------------------------------------------------------------------------------------------------------------
+template <int kPPW, bool kFastDiv>
+__global__ void __launch_bounds__(kEvalThreads) k_eval(const MapDev M, const float4* __restrict__ pts, uint32_t n_points, uint32_t chunk_len,
+                                                        const float* __restrict__ mats, uint32_t n_local, float* __restrict__ partial)
+{
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t part0 = (blockIdx.x * kEvalWarps + warp) * kPPW;
+  if (part0 >= n_local) return;
+
+  float m[kPPW][12];
+#pragma unroll
+  for (int k = 0; k < kPPW; ++k)
+  {
+    const uint32_t pi = min(part0 + k, n_local - 1);
+#pragma unroll
+    for (int e = 0; e < 12; ++e) m[k][e] = __ldg(mats + 12ull * pi + e);
+  }
+
+  const uint32_t p0 = blockIdx.y * chunk_len;
+  const uint32_t p1 = min(n_points, p0 + chunk_len);
+  const uint32_t n_full = p0 + ((p1 - p0) & ~31u);
+
+  float acc[kPPW];
+#pragma unroll
+  for (int k = 0; k < kPPW; ++k) acc[k] = 0.0f;
+
+#pragma unroll 2
+  for (uint32_t i = p0 + lane; i < n_full; i += 32)
+  {
+    const float4 p = __ldg(pts + i);
+#pragma unroll
+    for (int k = 0; k < kPPW; ++k)
+    {
+      const float tx = row_apply(m[k][0], m[k][1], m[k][2], m[k][3], p.x, p.y, p.z);
+      const float ty = row_apply(m[k][4], m[k][5], m[k][6], m[k][7], p.x, p.y, p.z);
+      const float tz = row_apply(m[k][8], m[k][9], m[k][10], m[k][11], p.x, p.y, p.z);
+      acc[k] += __ldg(M.voxels + voxel_index<kFastDiv>(M, tx, ty, tz));
+    }
+  }
+  if (n_full + lane < p1)
+  {
+    const float4 p = __ldg(pts + n_full + lane);
+#pragma unroll
+    for (int k = 0; k < kPPW; ++k)
+    {
+      const float tx = row_apply(m[k][0], m[k][1], m[k][2], m[k][3], p.x, p.y, p.z);
+      const float ty = row_apply(m[k][4], m[k][5], m[k][6], m[k][7], p.x, p.y, p.z);
+      const float tz = row_apply(m[k][8], m[k][9], m[k][10], m[k][11], p.x, p.y, p.z);
+      acc[k] += __ldg(M.voxels + voxel_index<kFastDiv>(M, tx, ty, tz));
+    }
+  }
+
+#pragma unroll
+  for (int k = 0; k < kPPW; ++k)
+  {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && part0 + k < n_local) partial[static_cast<size_t>(blockIdx.y) * n_local + part0 + k] = v;
+  }
+}
+
+// raw weight = a_hit * sum_chunks(partial) + sum_points(range term)
+//   (= sum_p (a_hit * v_p + term_p), cuda_eval_particles.h:200-211, regrouped; within 1e-5 rel. of the fp32-sequential sum)
+__global__ void k_finish_raw(const float* __restrict__ partial, uint32_t n_chunks, uint32_t n_local, float a_hit,
+                             const double* __restrict__ term_sum, float* __restrict__ raw_out)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_local) return;
+  float s = 0.0f;
+  for (uint32_t c = 0; c < n_chunks; ++c) s += partial[static_cast<size_t>(c) * n_local + i];
+  raw_out[i] = __fmaf_rn(a_hit, s, static_cast<float>(*term_sum));
+}
+
+// Parity/debug kernel: one thread per (particle, point) pair, same index function as k_eval.
+template <bool kFastDiv>
+__global__ void k_debug_pairs(const MapDev M, const float4* __restrict__ pts, uint32_t n_points, const float* __restrict__ mats, uint32_t n,
+                              uint32_t* __restrict__ idx_out, uint32_t* __restrict__ hits)
+{
+  const unsigned long long t = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned long long total = static_cast<unsigned long long>(n) * n_points;
+  if (t >= total) return;
+  const uint32_t pi = static_cast<uint32_t>(t / n_points);
+  const uint32_t qi = static_cast<uint32_t>(t % n_points);
+  const float* m = mats + 12ull * pi;
+  const float4 p = pts[qi];
+  const float tx = row_apply(m[0], m[1], m[2], m[3], p.x, p.y, p.z);
+  const float ty = row_apply(m[4], m[5], m[6], m[7], p.x, p.y, p.z);
+  const float tz = row_apply(m[8], m[9], m[10], m[11], p.x, p.y, p.z);
+  uint32_t idx = voxel_index<kFastDiv>(M, tx, ty, tz);
+  if (idx >= M.data_size) idx = M.data_size;
+  if (idx_out) idx_out[t] = idx;
+  if (hits && idx < M.data_size) atomicAdd(hits + pi, 1u);
+}
+
+// Exhaustive check of the 3-instruction division against IEEE division for every float in [0, 1).
+__global__ void k_check_div(float res, float inv_res, unsigned long long* __restrict__ mismatches)
+{
+  unsigned long long bad = 0;
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < 0x3F800000u; b += gridDim.x * blockDim.x)
+  {
+    const float a = __uint_as_float(b);
+    const uint32_t fast = __float_as_uint(__fadd_rd(div_res<true>(a, res, inv_res), kMagic));
+    const uint32_t ieee = __float_as_uint(__fadd_rd(__fdiv_rn(a, res), kMagic));
+    bad += (fast != ieee);
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2a: sum of raw weights in fp64, fixed order (block tree, then the last block adds the block sums in index order).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_weight_sum(const float* __restrict__ raw, uint32_t n, double* __restrict__ block_sums, Status* __restrict__ st)
+{
+  __shared__ double s_part[kScanThreads / 32];
+  __shared__ bool s_last;
+  const uint32_t base = blockIdx.x * kScanTile;
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+  {
+    const uint32_t i = base + threadIdx.x * kScanItems + k;
+    if (i < n) acc += static_cast<double>(raw[i]);
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    double t = 0.0;
+    for (int w = 0; w < kScanThreads / 32; ++w) t += s_part[w];
+    block_sums[blockIdx.x] = t;
+    __threadfence();
+    const uint32_t ticket = atomicAdd(&st->ticket, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0)
+  {
+    __threadfence();
+    double t = 0.0;
+    for (uint32_t b = 0; b < gridDim.x; ++b) t += reinterpret_cast<volatile double*>(block_sums)[b];
+    st->weight_sum = t;
+    st->weight_sum_f = static_cast<float>(t);
+    st->zero_sum = (t == 0.0) ? 1u : 0u;
+    st->inexact = 0u;
+    st->table_overflow = 0u;
+    st->ticket = 0u;
+  }
+}
+
+// exact-add check: returns a+b and sets `bad` if the fp64 addition rounded.
+__device__ __forceinline__ double add_checked(double a, double b, bool& bad)
+{
+  const double s = a + b;
+  const double bb = s - a;
+  const double err = (a - (s - bb)) + (b - bb);
+  bad |= (err != 0.0);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2b: normalise (w /= (float)sum, cuda_eval_particles.h:556), per-tile fp64 inclusive scan of the normalised
+// weights, per-tile weighted moments (x y z, sin/cos of the three angles; tsdf_evaluator.cpp:203-217).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScanThreads) k_normalise_scan(float* __restrict__ particles, const float* __restrict__ raw, uint32_t n,
+                                                                 Status* __restrict__ st, double* __restrict__ cdf,
+                                                                 double* __restrict__ tile_total, double* __restrict__ tile_moments)
+{
+  __shared__ double s_warp[kScanThreads / 32];
+  __shared__ double s_mom[kScanThreads / 32][9];
+  const float inv_den = st->weight_sum_f;
+  const bool dead = st->zero_sum != 0u;
+  const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  bool bad = false;
+
+  double loc[kScanItems];
+  double mom[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) mom[q] = 0.0;
+  double run = 0.0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+  {
+    const uint32_t i = base + k;
+    float w = 0.0f;
+    if (i < n)
+    {
+      float* p = particles + 7ull * i;
+      w = dead ? 0.0f : __fdiv_rn(raw[i], inv_den);
+      p[6] = w;
+      const float x = p[0], y = p[1], z = p[2];
+      mom[0] += static_cast<double>(__fmul_rn(x, w));
+      mom[1] += static_cast<double>(__fmul_rn(y, w));
+      mom[2] += static_cast<double>(__fmul_rn(z, w));
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+      {
+        double sd, cd;
+        sincos(static_cast<double>(p[3 + a]), &sd, &cd);
+        mom[3 + 2 * a] += sd * static_cast<double>(w);
+        mom[4 + 2 * a] += cd * static_cast<double>(w);
+      }
+    }
+    run = add_checked(run, static_cast<double>(w), bad);
+    loc[k] = run;
+  }
+
+  // inclusive scan of the per-thread totals across the warp, then across warps
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  double incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const double up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= static_cast<uint32_t>(o)) incl = add_checked(incl, up, bad);
+  }
+  double lane_excl = __shfl_up_sync(0xffffffffu, incl, 1);  // exclusive prefix over lanes: an already-checked sum
+  if (lane == 0) lane_excl = 0.0;
+  if (lane == 31) s_warp[warp] = incl;
+#pragma unroll
+  for (int q = 0; q < 9; ++q)
+  {
+    double v = mom[q];
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s_mom[warp][q] = v;
+  }
+  __syncthreads();
+  double warp_off = 0.0;
+  for (uint32_t w = 0; w < warp; ++w) warp_off = add_checked(warp_off, s_warp[w], bad);
+  const double excl = add_checked(warp_off, lane_excl, bad);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+  {
+    const uint32_t i = base + k;
+    if (i < n) cdf[i] = add_checked(excl, loc[k], bad);
+  }
+  if (threadIdx.x == kScanThreads - 1) tile_total[blockIdx.x] = add_checked(excl, run, bad);
+  if (threadIdx.x < 9)
+  {
+    double v = 0.0;
+    for (int w = 0; w < kScanThreads / 32; ++w) v += s_mom[w][threadIdx.x];
+    tile_moments[static_cast<size_t>(blockIdx.x) * 9 + threadIdx.x] = v;
+  }
+  if (bad) atomicOr(&st->inexact, 1u);
+}
+
+// K2c: one block. Exclusive scan of the tile totals (fp64, exactness-checked), moments -> mean pose.
+__global__ void k_scan_tiles(const double* __restrict__ tile_total, double* __restrict__ tile_offset, uint32_t n_tiles,
+                             const double* __restrict__ tile_moments, float* __restrict__ mean_pose, Status* __restrict__ st)
+{
+  __shared__ double s_mom[9];
+  if (threadIdx.x == 0)
+  {
+    bool bad = false;
+    double run = 0.0;
+    for (uint32_t t = 0; t < n_tiles; ++t)
+    {
+      tile_offset[t] = run;
+      run = add_checked(run, tile_total[t], bad);
+    }
+    if (bad) atomicOr(&st->inexact, 1u);
+  }
+  if (threadIdx.x < 9)
+  {
+    double v = 0.0;
+    for (uint32_t t = 0; t < n_tiles; ++t) v += tile_moments[static_cast<size_t>(t) * 9 + threadIdx.x];
+    s_mom[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && mean_pose)
+  {
+    mean_pose[0] = static_cast<float>(s_mom[0]);
+    mean_pose[1] = static_cast<float>(s_mom[1]);
+    mean_pose[2] = static_cast<float>(s_mom[2]);
+    mean_pose[3] = static_cast<float>(atan2(s_mom[3], s_mom[4]));
+    mean_pose[4] = static_cast<float>(atan2(s_mom[5], s_mom[6]));
+    mean_pose[5] = static_cast<float>(atan2(s_mom[7], s_mom[8]));
+  }
+}
+
+// K2d: add the tile offsets (exactness-checked) -> global fp64 CDF s_m = sum_{i<=m} w_i.
+__global__ void k_cdf_finalize(double* __restrict__ cdf, const double* __restrict__ tile_offset, uint32_t n, Status* __restrict__ st)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool bad = false;
+  const uint32_t tile = i / kScanTile;
+  if (tile) cdf[i] = add_checked(tile_offset[tile], cdf[i], bad);
+  if (bad) atomicOr(&st->inexact, 1u);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The reference's U recurrence: U_{j+1} = (float)((double)U_j + 1/N)  (novel_resampling.h:61-64, float += double).
+// Inside one binade the rounded step is constant after the first element (DESIGN.md "U recurrence"), so the whole
+// sequence is a short list of exact linear runs. Built by one thread; unit-tested on the host against the loop.
+// ------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t f32_bits(float f)
+{
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, sizeof(u));
+  return u;
+#endif
+}
+
+__host__ __device__ inline float u_next(float u, double inv_m)
+{
+  return static_cast<float>(static_cast<double>(u) + inv_m);
+}
+
+// Walks the recurrence from U_0 = u0 and records it as segments until U_j >= limit (so every j with U_j < limit is
+// covered), max_j elements were produced, the recurrence stalls (U stops growing), or max_segs is exhausted.
+// Returns the number of segments. *n_below = #{j : U_j < limit} = the reference's output length for limit = s_last.
+// *flags: bit0 = table full, bit1 = stalled recurrence, bit2 = max_j reached.
+//
+// Why linear runs are exact: write U = k*u with u = ulp of U's binade, k in [2^23, 2^24). While U + 1/N stays inside
+// the binade, (double)U + 1/N rounds (fp64) to U + d' with d' independent of k, and the fp32 rounding of that adds
+// q or q+1 ulps depending only on d' — except on an exact tie, where round-half-even makes k even after one step and
+// the step constant from then on. So within a binade the step is constant from the second element on; a run is
+// opened only where two consecutive measured steps agree, and it stops early enough (k + q <= 2^24 - 2) that every
+// transition it covers stays inside the binade.
+__host__ __device__ inline uint32_t build_u_table(float u0, double inv_m, double limit, USeg* segs, uint32_t max_segs,
+                                                  unsigned long long* n_below, unsigned long long max_j, uint32_t* flags)
+{
+  uint32_t ns = 0;
+  unsigned long long j = 0, below = 0;
+  float u = u0;
+  uint32_t fl = 0;
+  while (static_cast<double>(u) < limit)
+  {
+    if (j >= max_j) { fl |= 4u; break; }
+    if (ns >= max_segs) { fl |= 1u; break; }
+    const float n1 = u_next(u, inv_m);
+    if (!(n1 > u)) { fl |= 2u; ++below; break; }
+    const uint32_t b0 = f32_bits(u);
+    const uint32_t e0 = (b0 >> 23) & 0xffu;
+    if (u > 0.0f && e0 != 0u && e0 != 0xffu)
+    {
+      const float n2 = u_next(n1, inv_m);
+      const uint32_t b1 = f32_bits(n1), b2 = f32_bits(n2);
+      if (((b1 >> 23) & 0xffu) == e0 && ((b2 >> 23) & 0xffu) == e0)
+      {
+        const uint32_t k0 = (b0 & 0x7fffffu) | 0x800000u;
+        const uint32_t q1 = b1 - b0, q2 = b2 - b1;  // same binade: bit patterns differ by the ulp count
+        if (q1 == q2 && q1 != 0u && k0 + q1 <= 0xfffffeu)
+        {
+          unsigned long long len = (0xfffffeull - k0) / q1;  // elements i = 0..len-1; element len is still in-binade
+          if (len >= 2)
+          {
+            if (j + len > max_j) len = max_j - j;
+            const double start = static_cast<double>(u);
+            const double step = static_cast<double>(n1) - start;  // exact
+            unsigned long long cnt = len;
+            if (!(start + static_cast<double>(len - 1) * step < limit))
+            {
+              const double di = (limit - start) / step;
+              unsigned long long i = di > 0.0 ? static_cast<unsigned long long>(di) : 0ull;
+              if (i > len) i = len;
+              while (i > 0 && !(start + static_cast<double>(i - 1) * step < limit)) --i;
+              while (i < len && (start + static_cast<double>(i) * step < limit)) ++i;
+              cnt = i;
+            }
+            segs[ns].j0 = j;
+            segs[ns].u_start = u;
+            segs[ns].step = static_cast<float>(step);
+            ++ns;
+            below += cnt;
+            j += len;
+            if (cnt < len) { *n_below = below; *flags = fl; return ns; }
+            u = static_cast<float>(start + static_cast<double>(len) * step);
+            continue;
+          }
+        }
+      }
+    }
+    segs[ns].j0 = j;
+    segs[ns].u_start = u;
+    segs[ns].step = 0.0f;
+    ++ns;
+    ++below;
+    ++j;
+    u = n1;
+  }
+  *n_below = below;
+  *flags = fl;
+  return ns;
+}
+
+// U_j from the table (exact).
+__host__ __device__ inline float u_at(const USeg* segs, uint32_t n_segs, unsigned long long j)
+{
+  uint32_t lo = 0, hi = n_segs;  // last segment with j0 <= j
+  while (hi - lo > 1)
+  {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (segs[mid].j0 <= j) lo = mid; else hi = mid;
+  }
+  const USeg s = segs[lo];
+  return static_cast<float>(static_cast<double>(s.u_start) + static_cast<double>(j - s.j0) * static_cast<double>(s.step));
+}
+
+// K3: one warp. If the parallel scan was inexact, thread 0 redoes the CDF sequentially (the reference's own
+// order of fp64 additions); then builds the U table and n_out.
+__global__ void k_finish_cdf_utable(const float* __restrict__ particles, double* __restrict__ cdf, uint32_t n, float u0,
+                                    USeg* __restrict__ segs, Status* __restrict__ st)
+{
+  if (threadIdx.x != 0) return;
+  if (st->inexact)
+  {
+    double s = 0.0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+      s += static_cast<double>(particles[7ull * i + 6]);
+      cdf[i] = s;
+    }
+  }
+  const double s_last = n ? cdf[n - 1] : 0.0;
+  st->s_last = s_last;
+  unsigned long long n_below = 0;
+  const double inv_m = 1.0 / static_cast<double>(n);
+  // the recurrence cannot emit more than ~ s_last * N + 1 elements; 2N + 64 bounds any sane weight vector
+  const unsigned long long max_j = 2ull * n + 64ull;
+  uint32_t flags = 0;
+  const uint32_t ns = build_u_table(u0, inv_m, s_last, segs, kMaxUSegs, &n_below, max_j, &flags);
+  st->n_segs = ns;
+  st->n_out = st->zero_sum ? 0ull : n_below;
+  st->table_overflow = flags;
+}
+
+// K4: draw. Output slot j copies the first particle m with s_m > U_j (strict, novel_resampling.h:59).
+__global__ void k_draw(const float* __restrict__ particles, const double* __restrict__ cdf, uint32_t n, const USeg* __restrict__ segs,
+                       const Status* __restrict__ st, unsigned long long first_out, uint32_t count_out, float* __restrict__ out,
+                       uint32_t* __restrict__ parents)
+{
+  __shared__ USeg s_segs[kMaxUSegs];
+  const uint32_t ns = st->n_segs;
+  for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) s_segs[i] = segs[i];
+  __syncthreads();
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count_out) return;
+  const unsigned long long n_out = st->n_out;
+  unsigned long long j = first_out + t;
+  uint32_t parent = 0;
+  if (n_out != 0ull && ns != 0u)
+  {
+    if (j >= n_out) j = n_out - 1;  // padding slots repeat the last valid draw
+    const double u = static_cast<double>(u_at(s_segs, ns, j));
+    uint32_t lo = 0, hi = n;  // first m in [0, n) with cdf[m] > u
+    while (lo < hi)
+    {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (cdf[mid] > u) hi = mid; else lo = mid + 1;
+    }
+    parent = lo < n ? lo : n - 1;
+  }
+  const float* src = particles + 7ull * parent;
+  float* dst = out + 7ull * t;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) dst[k] = src[k];
+  if (parents) parents[t] = parent;
+}
+
+}  // namespace tsdfloc

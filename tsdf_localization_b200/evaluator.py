@@ -1,0 +1,262 @@
+"""Host-side mirror of the reference's evaluator / resampler interface, on top of the C ABI (include/tsdfloc.h).
+
+Same names, argument meaning and error behaviour as the reference classes (paths relative to the reference repo):
+
+  CudaSubVoxelMap      include/tsdf_localization/cuda/cuda_sub_voxel_map.h:17-342   (host half: geometry + setData)
+  CudaEvaluator        include/tsdf_localization/cuda/cuda_evaluator.h:109-169, src/cuda/cuda_evaluator.cu:21-59,118-428
+  TSDFEvaluator        include/tsdf_localization/evaluation/tsdf_evaluator.h:38-115 (facade; evaluate(..., use_cuda))
+  SystematicResampler  include/tsdf_localization/resampling/novel_resampling.h:38-74
+
+Particles are ``float32[N, 7]`` arrays in the reference's ``Particle`` layout (x y z roll pitch yaw weight), points
+``float32[P, 3]`` (``CudaPoint``). Everything numeric happens in libtsdfloc.so on the GPU; nothing here computes
+weights on the CPU, and every call raises if the library or a B200 is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+
+
+def _f32(a, shape_tail: int, name: str) -> np.ndarray:
+    arr = np.ascontiguousarray(a, dtype=np.float32)
+    if arr.ndim != 2 or arr.shape[1] != shape_tail:
+        raise ValueError(f"{name} must have shape [n, {shape_tail}]")
+    return arr
+
+
+def likelihood_value(tsdf_mm: float, sigma: float = 0.1) -> float:
+    """TSDF value in mm -> N(d; 0, sigma)^3, createTSDFMap's transform (map_util.h:124-126)."""
+    return float(capi.load_library().tsdfloc_likelihood_value(C.c_float(tsdf_mm), C.c_float(sigma)))
+
+
+def likelihood_init(sigma: float = 0.1) -> float:
+    """Value of unmapped space, N(10 m; 0, sigma)^3 (map_util.h:70-71)."""
+    return float(capi.load_library().tsdfloc_likelihood_init(C.c_float(sigma)))
+
+
+@dataclass
+class PoseWithCovariance:
+    """What the reference returns as geometry_msgs::PoseWithCovariance (cuda_evaluator.cu:410-423)."""
+    position: tuple = (0.0, 0.0, 0.0)
+    orientation: tuple = (0.0, 0.0, 0.0, 0.0)          # x y z w, from setRPY(roll, pitch, yaw)
+    covariance: list = field(default_factory=lambda: [0.0] * 36)
+    rpy: tuple = (0.0, 0.0, 0.0)
+
+    @staticmethod
+    def from_mean(mean6: Sequence[float]) -> "PoseWithCovariance":
+        x, y, z, roll, pitch, yaw = (float(v) for v in mean6)
+        hr, hp, hy = roll * 0.5, pitch * 0.5, yaw * 0.5
+        cr, sr, cp, sp, cy, sy = math.cos(hr), math.sin(hr), math.cos(hp), math.sin(hp), math.cos(hy), math.sin(hy)
+        q = (sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy)
+        return PoseWithCovariance((x, y, z), q, [0.0] * 36, (roll, pitch, yaw))
+
+
+class CudaSubVoxelMap:
+    """Two-level sparse voxel map: 1 m upper cells -> dense sub_dim^3 fp32 bricks (host arrays)."""
+
+    def __init__(self, min_x, min_y, min_z, max_x, max_y, max_z, resolution, init_value=0.0):
+        self._lib = capi.load_library()
+        self._h = C.c_void_p()
+        mn = (C.c_float * 3)(min_x, min_y, min_z)
+        mx = (C.c_float * 3)(max_x, max_y, max_z)
+        rc = self._lib.tsdfloc_map_create(mn, mx, C.c_float(resolution), C.c_float(init_value), C.byref(self._h))
+        if rc != capi.OK:
+            raise ValueError("invalid map geometry")
+        self._adopted = None
+
+    @classmethod
+    def from_arrays(cls, desc: capi.MapDesc, grid_occ: np.ndarray, data: np.ndarray) -> "CudaSubVoxelMap":
+        """Adopt coef()/rawGridOcc()/rawData() of an existing (e.g. reference-built) map."""
+        self = cls.__new__(cls)
+        self._lib = capi.load_library()
+        self._h = None
+        d = capi.MapDesc()
+        C.memmove(C.byref(d), C.byref(desc), C.sizeof(capi.MapDesc))
+        self._adopted = (d, np.ascontiguousarray(grid_occ, dtype=np.int32), np.ascontiguousarray(data, dtype=np.float32))
+        return self
+
+    def setData(self, cells) -> None:
+        """cells: [n, 4] (x, y, z, value) — the tuple list createTSDFMap hands to setData (map_util.h:129,152)."""
+        if self._h is None:
+            raise RuntimeError("map adopted from arrays is read-only")
+        arr = _f32(cells, 4, "cells")
+        rc = self._lib.tsdfloc_map_set_data(self._h, arr.ctypes.data_as(C.POINTER(C.c_float)), arr.shape[0])
+        if rc != capi.OK:
+            raise ValueError("cell outside the map bounds (or map too large)")
+
+    def coef(self) -> capi.MapDesc:
+        if self._adopted is not None:
+            return self._adopted[0]
+        return self._lib.tsdfloc_map_get_desc(self._h).contents
+
+    def rawGridOcc(self) -> np.ndarray:
+        if self._adopted is not None:
+            return self._adopted[1]
+        n = int(self.coef().grid_occ_size)
+        return np.ctypeslib.as_array(self._lib.tsdfloc_map_grid_occ(self._h), shape=(n,))
+
+    def rawData(self) -> np.ndarray:
+        if self._adopted is not None:
+            return self._adopted[2]
+        n = int(self.coef().data_size)
+        if n == 0:
+            return np.zeros(0, dtype=np.float32)
+        return np.ctypeslib.as_array(self._lib.tsdfloc_map_data(self._h), shape=(n,))
+
+    def dataBytes(self) -> int:
+        return int(self.coef().data_size) * 4
+
+    def gridOccBytes(self) -> int:
+        return int(self.coef().grid_occ_size) * 4
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.tsdfloc_map_destroy(h)
+            self._h = None
+
+
+class CudaEvaluator:
+    """GPU sensor update. Constructor uploads the map once (cuda_evaluator.cu:21-59)."""
+
+    def __init__(self, map: CudaSubVoxelMap, per_point: bool = False, a_hit: float = 0.9, a_range: float = 0.1,
+                 a_max: float = 0.0, max_range: float = 100.0, device: int = 0):
+        self._lib = capi.load_library()
+        self._ctx = C.c_void_p()
+        prm = capi.Params(a_hit, a_range, a_max, max_range, int(per_point), 0)
+        desc = map.coef()
+        occ = np.ascontiguousarray(map.rawGridOcc(), dtype=np.int32)
+        data = np.ascontiguousarray(map.rawData(), dtype=np.float32)
+        rc = self._lib.tsdfloc_create(C.byref(desc), occ.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p),
+                                      C.byref(prm), int(device), C.byref(self._ctx))
+        if rc != capi.OK:
+            msg = self._lib.tsdfloc_last_error(None).decode()
+            # the reference wraps every constructor failure in this text (cuda_evaluator.cu:52-55)
+            raise RuntimeError("Error while creating the CUDA context for the map! " + msg)
+        self.device = device
+        self.data_size = int(desc.data_size)
+
+    # -- reference interface -------------------------------------------------------------------------------------
+    def evaluate(self, particles: np.ndarray, points, tf_matrix) -> PoseWithCovariance:
+        """evaluate(std::vector<Particle>&, const std::vector<CudaPoint>&, FLOAT_T tf_matrix[16]).
+
+        Writes the NORMALISED weights into ``particles[:, 6]`` in place and returns the weighted mean pose.
+        An empty scan returns a default pose and leaves the weights untouched (cuda_evaluator.cu:122-125).
+        Raises RuntimeError("No particle is valid!") when all weights are zero (cuda_evaluator.cu:366-369).
+        """
+        if not (isinstance(particles, np.ndarray) and particles.dtype == np.float32 and particles.ndim == 2
+                and particles.shape[1] == 7 and particles.flags.c_contiguous):
+            raise ValueError("particles must be a C-contiguous float32[n, 7] array (it is updated in place)")
+        pts = _f32(np.asarray(points).reshape(-1, 3), 3, "points")
+        if pts.shape[0] == 0:
+            return PoseWithCovariance()
+        tf = (C.c_float * 16)(*[float(v) for v in np.asarray(tf_matrix, dtype=np.float32).reshape(-1)[:16]])
+        mean = (C.c_float * 6)()
+        rc = self._lib.tsdfloc_sensor_update(self._ctx, particles.ctypes.data_as(C.c_void_p), particles.shape[0],
+                                             pts.ctypes.data_as(C.c_void_p), pts.shape[0], tf, mean)
+        if rc == capi.E_NO_VALID_PARTICLE:
+            raise RuntimeError("No particle is valid!")
+        capi.check(self._lib, self._ctx, rc)
+        return PoseWithCovariance.from_mean(list(mean))
+
+    # -- resampling on the particle set the last evaluate() left on the device -------------------------------------
+    def resample_systematic(self, u0: float, capacity: Optional[int] = None, want_parents: bool = False):
+        n = capacity if capacity is not None else 0
+        if n <= 0:
+            raise ValueError("capacity must be positive")
+        out = np.empty((n, 7), dtype=np.float32)
+        parents = np.empty(n, dtype=np.uint32) if want_parents else None
+        n_out = C.c_uint64(0)
+        rc = self._lib.tsdfloc_resample_systematic(self._ctx, C.c_float(u0), out.ctypes.data_as(C.c_void_p), n, C.byref(n_out),
+                                                   parents.ctypes.data_as(C.c_void_p) if want_parents else None)
+        capi.check(self._lib, self._ctx, rc)
+        m = int(n_out.value)
+        return (out[:m], parents[:m]) if want_parents else out[:m]
+
+    # -- parity/debug -------------------------------------------------------------------------------------------------
+    def debug_eval(self, particles, points, tf_matrix, want_idx: bool = True):
+        """Per-pair flat voxel indices (data_size = miss), per-particle hit counts and un-normalised weights."""
+        ps = _f32(particles, 7, "particles")
+        pts = _f32(points, 3, "points")
+        n, p = ps.shape[0], pts.shape[0]
+        tf = (C.c_float * 16)(*[float(v) for v in np.asarray(tf_matrix, dtype=np.float32).reshape(-1)[:16]])
+        idx = np.empty((n, p), dtype=np.uint32) if want_idx else None
+        hits = np.empty(n, dtype=np.uint32)
+        raw = np.empty(n, dtype=np.float32)
+        rc = self._lib.tsdfloc_debug_eval(self._ctx, ps.ctypes.data_as(C.c_void_p), n, pts.ctypes.data_as(C.c_void_p), p, tf,
+                                          idx.ctypes.data_as(C.c_void_p) if want_idx else None,
+                                          hits.ctypes.data_as(C.c_void_p), raw.ctypes.data_as(C.c_void_p))
+        capi.check(self._lib, self._ctx, rc)
+        return idx, hits, raw
+
+    @property
+    def ctx(self) -> C.c_void_p:
+        return self._ctx
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.tsdfloc_kernel_launches(self._ctx))
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._lib.tsdfloc_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        self.close()
+
+
+class TSDFEvaluator:
+    """Sensor-update facade with the reference's constructor and evaluate() signature (tsdf_evaluator.h:72-114).
+
+    The reference dispatches ``use_cuda`` between its CUDA evaluator and a CPU/OpenMP loop; this build ships only the
+    GPU path, so ``use_cuda=False`` raises instead of silently computing on the host.
+    """
+
+    def __init__(self, map_ptr: CudaSubVoxelMap, per_point: bool = False, a_hit: float = 0.9, a_range: float = 0.1,
+                 a_max: float = 0.0, max_range: float = 100.0, reduction_cell_size: float = 0.064, device: int = 0):
+        self.map_ptr_ = map_ptr
+        self.cuda_evaluator_ = CudaEvaluator(map_ptr, per_point, a_hit, a_range, a_max, max_range, device=device)
+        self.map_res_ = reduction_cell_size
+
+    def evaluate(self, particles: np.ndarray, points, tf_matrix, use_cuda: bool = True) -> PoseWithCovariance:
+        if not use_cuda:
+            raise RuntimeError("tsdf_localization_b200 has no CPU evaluator: call evaluate(..., use_cuda=True)")
+        return self.cuda_evaluator_.evaluate(particles, points, tf_matrix)
+
+
+class SystematicResampler:
+    """Systematic resampling on the GPU with the reference's recurrence (novel_resampling.h:41-72).
+
+    The reference draws U0 ~ uniform_real_distribution<float>(0, 1/N) from its own std::mt19937; here U0 comes from a
+    seeded numpy Generator or is passed explicitly (parity is defined "given the same weights and the same U0").
+    """
+
+    def __init__(self, seed: Optional[int] = None):
+        self._rng = np.random.default_rng(seed)
+
+    def draw_u0(self, n: int) -> float:
+        inv_m = 1.0 / n
+        u = np.float32(self._rng.random() * inv_m)
+        if float(u) >= inv_m:   # rounding up to the open bound
+            u = np.nextafter(u, np.float32(0.0))
+        return float(u)
+
+    def resample(self, evaluator, n: Optional[int] = None, u0: Optional[float] = None, want_parents: bool = False):
+        """Resample the particle set that ``evaluator``'s last evaluate() left on the device.
+
+        Returns the new ``float32[n_out, 7]`` particle array (n_out is whatever the reference recurrence emits —
+        usually n); copies keep the parent's normalised weight.
+        """
+        ev = evaluator.cuda_evaluator_ if isinstance(evaluator, TSDFEvaluator) else evaluator
+        if n is None:
+            raise ValueError("n (current particle count) is required")
+        if u0 is None:
+            u0 = self.draw_u0(n)
+        cap = n + n // 8 + 64
+        return ev.resample_systematic(u0, capacity=cap, want_parents=want_parents)
