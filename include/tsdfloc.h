@@ -170,6 +170,11 @@ int tsdfloc_check(tsdfloc_ctx* ctx, uint64_t* n_out, double* weight_sum, void* s
  * same segment-table code the device uses; writes U_j for all j with U_j < limit (at most cap) and returns their count. */
 uint64_t tsdfloc_host_u_sequence(float u0, uint64_t n, double limit, float* out, uint64_t cap, uint32_t* n_segs, uint32_t* flags);
 
+/* Cumulative statistics of the evaluation kernel's summation blocks (synchronises the device):
+ * out[0] = (particle, block) pairs processed, out[1] = of those folded sequentially (binade crossing, early phase or tie),
+ * out[2] = of those caused by an exact rounding tie, out[3] reserved. */
+int tsdfloc_eval_stats(tsdfloc_ctx* ctx, uint64_t out[4]);
+
 /* Number of kernels this library has launched on this ctx so far (for bench accounting). */
 uint64_t tsdfloc_kernel_launches(const tsdfloc_ctx* ctx);
 

@@ -42,7 +42,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not _stale(LIB, deps):
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, sources)]
+    extra = os.environ.get("TSDFLOC_NVCC_DEFS", "").split()   # e.g. "-DTSDFLOC_BLOCK_STEPS=8" for tuning experiments
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, sources)]
     env = dict(os.environ)
     # the image's CC/CXX wrappers point at a gcc without libgomp specs; nvcc is fine with the system one
     if Path("/usr/bin/g++").exists():

@@ -67,6 +67,7 @@ SIGNATURES = {
     "tsdfloc_draw_device": (C.c_int, [_vp, _vp, _u64, C.c_float, _u64, _u64, _vp, _vp, _vp]),
     "tsdfloc_check": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double), _vp]),
     "tsdfloc_host_u_sequence": (_u64, [C.c_float, _u64, C.c_double, _vp, _u64, _u32p, _u32p]),
+    "tsdfloc_eval_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "tsdfloc_kernel_launches": (_u64, [_vp]),
 }
 

@@ -41,6 +41,8 @@ struct tsdfloc_ctx
   tsdfloc_map_desc desc{};
   MapDev map{};
   int sm_count = 148;
+  float x_bound = 0.0f;     // upper bound of one point's contribution a_hit*v + term (k_eval block planning)
+  uint32_t force_seq = 0;   // 1: contributions may be negative / non-finite -> always fold sequentially
   uint64_t launches = 0;
 
   // map
@@ -48,15 +50,15 @@ struct tsdfloc_ctx
   float* d_voxels = nullptr;
 
   // scan
-  DevBuf d_xyz_stage, d_pts, d_blocksums;
-  double* d_term_sum = nullptr;
+  DevBuf d_xyz_stage, d_pts;
   uint64_t n_points = 0;
 
   // particles / scratch
-  DevBuf d_particles, d_particles_out, d_mats, d_partial, d_raw, d_cdf, d_tile_total, d_tile_offset, d_tile_moments, d_parents,
+  DevBuf d_particles, d_particles_out, d_mats, d_raw, d_cdf, d_tile_total, d_tile_offset, d_tile_moments, d_parents,
       d_idx, d_hits;
   float* d_mean = nullptr;
   USeg* d_segs = nullptr;
+  unsigned long long* d_eval_stats = nullptr;  // k_eval block statistics (cumulative)
   Status* d_status = nullptr;
   uint64_t n_resident = 0;  // particles left on the device by tsdfloc_sensor_update
   bool have_cdf = false;
@@ -167,61 +169,41 @@ int stage_prep_scan(tsdfloc_ctx* c, const float* d_xyz, uint64_t p, cudaStream_t
   if (p > 0x7fffffffull) return fail(c, TSDFLOC_E_BAD_ARG, "scan larger than 2^31 points");
   int rc;
   if ((rc = ensure(c, c->d_pts, sizeof(float4) * (p + 64), "cudaMalloc(scan)"))) return rc;
-  const int nb = 64;
-  if ((rc = ensure(c, c->d_blocksums, sizeof(double) * 4096, "cudaMalloc(block sums)"))) return rc;
   c->n_points = p;
   if (p == 0) return TSDFLOC_OK;
+  // the evaluation kernel reads whole 32-point steps: keep the tail of the last step defined
+  {
+    cudaError_t me = cudaMemsetAsync(static_cast<float4*>(c->d_pts.p) + p, 0, sizeof(float4) * 64, s);
+    if (me != cudaSuccess) return fail(c, TSDFLOC_E_CUDA, std::string("memset(scan pad): ") + cudaGetErrorString(me));
+  }
   const float a_range_term = c->prm.a_range * static_cast<float>(1.0 / c->prm.max_range);
+  const unsigned nb = static_cast<unsigned>(std::min<uint64_t>((p + 255) / 256, 1024));
   k_prep_scan<<<nb, 256, 0, s>>>(d_xyz, static_cast<uint32_t>(p), static_cast<float4*>(c->d_pts.p), a_range_term, c->prm.a_max,
-                                 c->prm.max_range * c->prm.max_range, static_cast<double*>(c->d_blocksums.p));
-  if ((rc = launch_check(c, "k_prep_scan"))) return rc;
-  k_prep_scan_finish<<<1, 1, 0, s>>>(static_cast<double*>(c->d_blocksums.p), nb, c->d_term_sum);
-  return launch_check(c, "k_prep_scan_finish");
+                                 c->prm.max_range * c->prm.max_range);
+  return launch_check(c, "k_prep_scan");
 }
 
-// Launch geometry of the evaluation kernel for `count` particles.
-struct EvalPlan
+// Particles per warp: two once there are enough particles to keep every SM busy with 2-particle warps
+// (the point load, loop and planning overhead is shared); overridable for experiments with TSDFLOC_PPW=1|2.
+int pick_ppw(const tsdfloc_ctx* c, uint64_t count)
 {
-  int ppw;
-  uint32_t tiles;      // gridDim.x
-  uint32_t chunks;     // gridDim.y
-  uint32_t chunk_len;  // points per chunk (multiple of 32)
-};
-
-EvalPlan plan_eval(const tsdfloc_ctx* c, uint64_t count, uint64_t p)
-{
-  EvalPlan pl{};
-  // particles per warp: 2 once there are enough particles to fill the machine with 2-particle warps
-  const uint64_t warps_needed_1 = count;
-  pl.ppw = (warps_needed_1 >= static_cast<uint64_t>(c->sm_count) * kEvalWarps * 4) ? 2 : 1;
-  const uint64_t per_cta = static_cast<uint64_t>(kEvalWarps) * pl.ppw;
-  pl.tiles = static_cast<uint32_t>((count + per_cta - 1) / per_cta);
-  // split the scan so that the grid has at least ~8 CTAs per SM, in chunks of >= 1024 points
-  const uint64_t want_ctas = static_cast<uint64_t>(c->sm_count) * 8;
-  uint64_t chunks = (want_ctas + pl.tiles - 1) / pl.tiles;
-  const uint64_t max_chunks = std::max<uint64_t>(1, p / 1024);
-  chunks = std::max<uint64_t>(1, std::min<uint64_t>(chunks, std::min<uint64_t>(max_chunks, 256)));
-  uint64_t len = (p + chunks - 1) / chunks;
-  len = (len + 31) & ~31ull;
-  if (len == 0) len = 32;
-  pl.chunk_len = static_cast<uint32_t>(len);
-  pl.chunks = static_cast<uint32_t>((p + len - 1) / len);
-  if (pl.chunks == 0) pl.chunks = 1;
-  return pl;
+  if (const char* e = std::getenv("TSDFLOC_PPW"))
+  {
+    const int v = std::atoi(e);
+    if (v == 1 || v == 2) return v;
+  }
+  return count >= static_cast<uint64_t>(c->sm_count) * 32 ? 2 : 1;
 }
 
 template <int kPPW>
-void launch_eval(const tsdfloc_ctx* c, const EvalPlan& pl, uint32_t count, cudaStream_t s)
+void launch_eval(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s)
 {
-  dim3 grid(pl.tiles, pl.chunks);
+  const uint32_t per_cta = kEvalWarps * kPPW;
+  const uint32_t grid = (a.n_local + per_cta - 1) / per_cta;
   if (c->map.fast_div)
-    k_eval<kPPW, true><<<grid, kEvalThreads, 0, s>>>(c->map, static_cast<const float4*>(c->d_pts.p), static_cast<uint32_t>(c->n_points),
-                                                      pl.chunk_len, static_cast<const float*>(c->d_mats.p), count,
-                                                      static_cast<float*>(c->d_partial.p));
+    k_eval<kPPW, true><<<grid, kEvalThreads, 0, s>>>(c->map, a);
   else
-    k_eval<kPPW, false><<<grid, kEvalThreads, 0, s>>>(c->map, static_cast<const float4*>(c->d_pts.p), static_cast<uint32_t>(c->n_points),
-                                                       pl.chunk_len, static_cast<const float*>(c->d_mats.p), count,
-                                                       static_cast<float*>(c->d_partial.p));
+    k_eval<kPPW, false><<<grid, kEvalThreads, 0, s>>>(c->map, a);
 }
 
 int stage_matrices(tsdfloc_ctx* c, const float* d_particles, uint64_t first, uint64_t count, const float tf[16], cudaStream_t s)
@@ -245,17 +227,22 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   if (count == 0) return TSDFLOC_OK;
   int rc;
   if ((rc = stage_matrices(c, d_particles, first, count, tf, s))) return rc;
-  const EvalPlan pl = plan_eval(c, count, c->n_points);
-  if ((rc = ensure(c, c->d_partial, sizeof(float) * static_cast<size_t>(pl.chunks) * count, "cudaMalloc(partials)"))) return rc;
-  if (pl.ppw == 2)
-    launch_eval<2>(c, pl, static_cast<uint32_t>(count), s);
+  EvalArgs a{};
+  a.pts = static_cast<const float4*>(c->d_pts.p);
+  a.mats = static_cast<const float*>(c->d_mats.p);
+  a.raw_out = d_raw + first;
+  a.n_points = static_cast<uint32_t>(c->n_points);
+  a.n_local = static_cast<uint32_t>(count);
+  a.a_hit = c->prm.a_hit;
+  a.one = 1.0f;
+  a.s_min = 32.0f * c->x_bound;
+  a.stats = c->d_eval_stats;
+  a.force_seq = c->force_seq;
+  if (pick_ppw(c, count) == 2)
+    launch_eval<2>(c, a, s);
   else
-    launch_eval<1>(c, pl, static_cast<uint32_t>(count), s);
-  if ((rc = launch_check(c, "k_eval"))) return rc;
-  k_finish_raw<<<static_cast<unsigned>((count + 255) / 256), 256, 0, s>>>(static_cast<const float*>(c->d_partial.p), pl.chunks,
-                                                                         static_cast<uint32_t>(count), c->prm.a_hit, c->d_term_sum,
-                                                                         d_raw + first);
-  return launch_check(c, "k_finish_raw");
+    launch_eval<1>(c, a, s);
+  return launch_check(c, "k_eval");
 }
 
 int stage_normalize(tsdfloc_ctx* c, float* d_particles, uint64_t n, const float* d_raw, float* d_mean, cudaStream_t s)
@@ -469,10 +456,31 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
   M.table_bias = kMagicBits * (1u + M.pad_x + M.pad_xy);
   M.sub_bias = kMagicBits * (1u + M.sub_dim + M.sub_dim_2);
 
+  // ---- bound of one point's contribution, for the evaluation kernel's binade planning ---------------------------
+  {
+    float vmax = map->init_value, vmin = map->init_value;
+    bool finite = std::isfinite(map->init_value);
+    for (uint64_t i = 0; i < map->data_size; ++i)
+    {
+      const float v = data[i];
+      if (!std::isfinite(v)) { finite = false; break; }
+      vmax = std::max(vmax, v);
+      vmin = std::min(vmin, v);
+    }
+    const float c_in = c->prm.a_range * static_cast<float>(1.0 / c->prm.max_range);
+    const float c_out = c->prm.a_max;
+    const bool nonneg = finite && vmin >= 0.0f && c->prm.a_hit >= 0.0f && c_in >= 0.0f && c_out >= 0.0f &&
+                        std::isfinite(c->prm.a_hit) && std::isfinite(c_in) && std::isfinite(c_out);
+    c->force_seq = nonneg ? 0u : 1u;
+    const float xmax = c->prm.a_hit * std::max(vmax, 0.0f) + std::max(c_in, c_out);
+    c->x_bound = nonneg ? xmax * 1.0001f + 1e-30f : 0.0f;
+  }
+
   // ---- small fixed buffers -------------------------------------------------------------------------------------
-  CU_CREATE(cudaMalloc(&c->d_term_sum, sizeof(double)), "cudaMalloc(term sum)");
   CU_CREATE(cudaMalloc(&c->d_mean, sizeof(float) * 8), "cudaMalloc(mean pose)");
   CU_CREATE(cudaMalloc(&c->d_segs, sizeof(USeg) * kMaxUSegs), "cudaMalloc(U table)");
+  CU_CREATE(cudaMalloc(&c->d_eval_stats, sizeof(unsigned long long) * 4), "cudaMalloc(eval stats)");
+  CU_CREATE(cudaMemset(c->d_eval_stats, 0, sizeof(unsigned long long) * 4), "memset(eval stats)");
   CU_CREATE(cudaMalloc(&c->d_status, sizeof(Status)), "cudaMalloc(status)");
   CU_CREATE(cudaMemset(c->d_status, 0, sizeof(Status)), "memset(status)");
   CU_CREATE(cudaMallocHost(&c->h_status, sizeof(Status)), "cudaMallocHost(status)");
@@ -508,15 +516,15 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
   if (!c) return;
   DeviceGuard guard(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  DevBuf* bufs[] = {&c->d_xyz_stage, &c->d_pts, &c->d_blocksums, &c->d_particles, &c->d_particles_out, &c->d_mats, &c->d_partial,
+  DevBuf* bufs[] = {&c->d_xyz_stage, &c->d_pts, &c->d_particles, &c->d_particles_out, &c->d_mats,
                     &c->d_raw, &c->d_cdf, &c->d_tile_total, &c->d_tile_offset, &c->d_tile_moments, &c->d_parents, &c->d_idx, &c->d_hits};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->d_table) cudaFree(c->d_table);
   if (c->d_voxels) cudaFree(c->d_voxels);
-  if (c->d_term_sum) cudaFree(c->d_term_sum);
   if (c->d_mean) cudaFree(c->d_mean);
   if (c->d_segs) cudaFree(c->d_segs);
+  if (c->d_eval_stats) cudaFree(c->d_eval_stats);
   if (c->d_status) cudaFree(c->d_status);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_status) cudaFreeHost(c->h_status);
@@ -696,6 +704,17 @@ int tsdfloc_debug_eval(tsdfloc_ctx* c, const float* particles, uint64_t n, const
   if (hits) CU_TRY(c, cudaMemcpyAsync(hits, c->d_hits.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s), "D2H hits");
   if (raw_weights) CU_TRY(c, cudaMemcpyAsync(raw_weights, c->d_raw.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s), "D2H raw weights");
   CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  return TSDFLOC_OK;
+}
+
+int tsdfloc_eval_stats(tsdfloc_ctx* c, uint64_t out[4])
+{
+  if (!c || !out) return TSDFLOC_E_BAD_ARG;
+  DeviceGuard guard(c->device);
+  CU_TRY(c, cudaDeviceSynchronize(), "device sync");
+  unsigned long long h[4];
+  CU_TRY(c, cudaMemcpy(h, c->d_eval_stats, sizeof(h), cudaMemcpyDeviceToHost), "D2H eval stats");
+  for (int i = 0; i < 4; ++i) out[i] = h[i];
   return TSDFLOC_OK;
 }
 

@@ -89,4 +89,76 @@ __device__ __forceinline__ float row_apply(float a, float b, float c, float d, f
   return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, x), __fmul_rn(b, y)), __fmul_rn(c, z)), d);
 }
 
+// ---- packed fp32x2 path (Blackwell FMUL2 / FADD2 / FFMA2): two particles per instruction ----------------------------
+//
+// ptxas (12.9) contracts mul.rn.f32x2 feeding add.rn.f32x2 into one FFMA2 even though both carry .rn and even with
+// --fmad=false, which would break bit-parity with the reference's separately rounded products and sums. Every
+// "sum of a product" is therefore written as fma(product, one, addend) with `one` = 1.0f read from a kernel
+// parameter the compiler cannot see through: the product feeds the MULTIPLICAND slot, where no contraction exists,
+// and fma(p, 1, q) rounds p + q exactly once — the same value as an unfused add.
+struct Pair
+{
+  float2 v;
+};
+
+__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+
+// {A, B} rows applied to one point: ((a*x + b*y) + c*z) + d per half, each product and sum rounded separately.
+__device__ __forceinline__ float2 row_apply2(float2 a, float2 b, float2 c, float2 d, float2 xx, float2 yy, float2 zz, float2 one)
+{
+  const float2 p1 = __fmul2_rn(a, xx);
+  const float2 p2 = __fmul2_rn(b, yy);
+  const float2 p3 = __fmul2_rn(c, zz);
+  const float2 s1 = __ffma2_rn(p1, one, p2);
+  const float2 s2 = __ffma2_rn(s1, one, p3);
+  return __fadd2_rn(s2, d);
+}
+
+__device__ __forceinline__ float2 clamp2(float2 o, float hi)
+{
+  return make_float2(fminf(fmaxf(o.x, -1.0f), hi), fminf(fmaxf(o.y, -1.0f), hi));
+}
+
+template <bool kFastDiv>
+__device__ __forceinline__ float2 div_res2(float2 a, float res, float inv_res)
+{
+  if (kFastDiv)
+  {
+    const float2 ir = dup2(inv_res);
+    const float2 q0 = __fmul2_rn(a, ir);
+    const float2 e = __ffma2_rn(dup2(-res), q0, a);
+    return __ffma2_rn(e, ir, q0);
+  }
+  return make_float2(__fdiv_rn(a.x, res), __fdiv_rn(a.y, res));
+}
+
+// voxel_index for two particles at once; same arithmetic per half as voxel_index<>.
+template <bool kFastDiv>
+__device__ __forceinline__ void voxel_index2(const MapDev& M, float2 tx, float2 ty, float2 tz, uint32_t& ia, uint32_t& ib)
+{
+  const float2 ox = clamp2(__fadd2_rn(tx, dup2(-M.min[0])), M.clamp_hi[0]);
+  const float2 oy = clamp2(__fadd2_rn(ty, dup2(-M.min[1])), M.clamp_hi[1]);
+  const float2 oz = clamp2(__fadd2_rn(tz, dup2(-M.min[2])), M.clamp_hi[2]);
+  const float2 kp = dup2(kMagicP1), kn = dup2(-kMagicP1);
+  const float2 bx = __fadd2_rd(ox, kp);
+  const float2 by = __fadd2_rd(oy, kp);
+  const float2 bz = __fadd2_rd(oz, kp);
+  const float2 fx = __fadd2_rn(bx, kn);
+  const float2 fy = __fadd2_rn(by, kn);
+  const float2 fz = __fadd2_rn(bz, kn);
+  const float2 px = __fadd2_rn(ox, make_float2(-fx.x, -fx.y));
+  const float2 py = __fadd2_rn(oy, make_float2(-fy.x, -fy.y));
+  const float2 pz = __fadd2_rn(oz, make_float2(-fz.x, -fz.y));
+  const uint32_t ta = __float_as_uint(bx.x) + __float_as_uint(by.x) * M.pad_x + __float_as_uint(bz.x) * M.pad_xy - M.table_bias;
+  const uint32_t tb = __float_as_uint(bx.y) + __float_as_uint(by.y) * M.pad_x + __float_as_uint(bz.y) * M.pad_xy - M.table_bias;
+  const uint32_t brick_a = static_cast<uint32_t>(__ldg(M.table + ta));
+  const uint32_t brick_b = static_cast<uint32_t>(__ldg(M.table + tb));
+  const float2 km = dup2(kMagic);
+  const float2 qx = __fadd2_rd(div_res2<kFastDiv>(px, M.res, M.inv_res), km);
+  const float2 qy = __fadd2_rd(div_res2<kFastDiv>(py, M.res, M.inv_res), km);
+  const float2 qz = __fadd2_rd(div_res2<kFastDiv>(pz, M.res, M.inv_res), km);
+  ia = brick_a + __float_as_uint(qx.x) + __float_as_uint(qy.x) * M.sub_dim + __float_as_uint(qz.x) * M.sub_dim_2 - M.sub_bias;
+  ib = brick_b + __float_as_uint(qx.y) + __float_as_uint(qy.y) * M.sub_dim + __float_as_uint(qz.y) * M.sub_dim_2 - M.sub_bias;
+}
+
 }  // namespace tsdfloc

@@ -12,8 +12,15 @@
 namespace tsdfloc
 {
 
-constexpr int kEvalThreads = 256;                 // 8 warps per CTA
-constexpr int kEvalWarps = kEvalThreads / 32;
+#ifndef TSDFLOC_EVAL_WARPS
+#define TSDFLOC_EVAL_WARPS 1
+#endif
+#ifndef TSDFLOC_BLOCK_STEPS
+#define TSDFLOC_BLOCK_STEPS 16
+#endif
+constexpr int kEvalWarps = TSDFLOC_EVAL_WARPS;    // independent warps per CTA (1: finest granularity for the block scheduler)
+constexpr int kEvalThreads = kEvalWarps * 32;
+constexpr int kBlockSteps = TSDFLOC_BLOCK_STEPS;  // 32-point steps summed as integers between two warp reductions
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 4;
 constexpr int kScanTile = kScanThreads * kScanItems;  // particles per scan tile
@@ -42,38 +49,18 @@ struct USeg
 };
 
 // ------------------------------------------------------------------------------------------------------------
-// Scan preparation: xyz -> float4 (w = range term) and the fp64 sum of the range terms.
-// Range term per point: |p|^2 < max_range^2 ? a_range * (1/max_range) : a_max  (tsdf_evaluator.cpp:56-65).
+// Scan preparation: xyz -> float4 with w = the point's range term
+//   |p|^2 < max_range^2 ? a_range * (1/max_range) : a_max     (tsdf_evaluator.cpp:56-65, cuda_eval_particles.h:200-209)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_prep_scan(const float* __restrict__ xyz, uint32_t p, float4* __restrict__ out, float a_range_term, float a_max,
-                            float max_range_sq, double* __restrict__ block_sums)
+                            float max_range_sq)
 {
-  __shared__ double s_part[32];
-  double acc = 0.0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p; i += gridDim.x * blockDim.x)
   {
     const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
     const float sq = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
-    const float term = sq < max_range_sq ? a_range_term : a_max;
-    out[i] = make_float4(x, y, z, term);
-    acc += static_cast<double>(term);
+    out[i] = make_float4(x, y, z, sq < max_range_sq ? a_range_term : a_max);
   }
-  for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0)
-  {
-    double t = 0.0;
-    for (int w = 0; w < (blockDim.x >> 5); ++w) t += s_part[w];
-    block_sums[blockIdx.x] = t;
-  }
-}
-
-__global__ void k_prep_scan_finish(const double* __restrict__ block_sums, int nb, double* __restrict__ term_sum)
-{
-  double t = 0.0;
-  for (int i = 0; i < nb; ++i) t += block_sums[i];
-  *term_sum = t;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -125,84 +112,202 @@ __global__ void k_pose_matrices(const float* __restrict__ particles, uint32_t fi
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K1: evaluation. CTA = kEvalWarps warps; a warp owns kPPW particles (their 3x4 matrices live in registers) and
-// its 32 lanes walk CONSECUTIVE scan points, so the 32 voxel gathers of one warp instruction land on neighbouring
-// voxels of the same surface (few 128 B lines) instead of 32 unrelated particles' voxels as in the reference's
-// one-thread-per-particle kernel. blockIdx.y selects a chunk of the scan; each (chunk, particle) partial sum is
-// written once and reduced in fixed order by k_finish_raw -> deterministic weights.
+// K1: evaluation. A warp owns kPPW particles (their 3x4 matrices live in registers) and its 32 lanes walk
+// CONSECUTIVE scan points, so the 32 voxel gathers of one warp instruction land on neighbouring voxels of the same
+// surface (few 128 B lines) instead of 32 unrelated particles' voxels as in the reference's one-thread-per-particle
+// kernel.
+//
+// The weight is the reference's fp32 SEQUENTIAL sum over the points in scan order, bit for bit
+// (eval_sum += a_hit*v + term, cuda_eval_particles.h:200-211 / tsdf_evaluator.cpp:56-67, unfused like the CPU
+// build). A tree reduction would be more accurate but differs from the reference by up to 1e-3 relative at
+// P = 131k, because a sequential fp32 sum absorbs addends below half an ulp of the running sum. The sequential sum
+// is reproduced in parallel with this identity: while the running sum s stays inside one binade (ulp u) and the
+// addends are >= 0,  RN(s + x) = s + RN_u(x)  unless x lies exactly between two multiples of u. So a block of
+// steps whose total provably cannot leave the binade is summed as exact integers q = RN(x/u) (magic-number
+// rounding, per-lane int32 accumulators, one warp reduction per block) and accepted only if, checked afterwards, no
+// lane saw an exact tie and the sum stayed below the top of the binade; otherwise (binade crossing, tie, or the first
+// few steps while s is still small) the block is folded truly sequentially from a shared-memory copy of its x values.
 // ------------------------------------------------------------------------------------------------------------
-template <int kPPW, bool kFastDiv>
-__global__ void __launch_bounds__(kEvalThreads) k_eval(const MapDev M, const float4* __restrict__ pts, uint32_t n_points, uint32_t chunk_len,
-                                                        const float* __restrict__ mats, uint32_t n_local, float* __restrict__ partial)
+constexpr float kRoundMagic = 12582912.0f;       // 1.5 * 2^23: x + magic rounds x to an integer (RN-even) for 0 <= x < 2^22
+constexpr uint32_t kRoundMagicBits = 0x4B400000u;
+
+struct EvalArgs
 {
+  const float4* __restrict__ pts;   // x y z term, padded to a multiple of 32 points
+  const float* __restrict__ mats;   // [n_local][12]
+  float* __restrict__ raw_out;      // [n_local] un-normalised weights
+  unsigned long long* __restrict__ stats;  // [4]: blocks, blocks folded sequentially (binade crossing / early phase), tie folds, -
+  uint32_t n_points;
+  uint32_t n_local;
+  float a_hit;
+  float one;                        // 1.0f, opaque to the compiler (see tsdfloc_device.cuh, packed path)
+  float s_min;                      // integer-block summation is used once s >= s_min (= 32 * bound of one addend)
+  uint32_t force_seq;               // 1: negative/non-finite addends possible -> always fold sequentially
+};
+
+// One point against one particle: transform, voxel gather, x = a_hit * v + term (two roundings, like the CPU build).
+template <bool kFastDiv>
+__device__ __forceinline__ float eval_point(const MapDev& M, const float (&m)[12], const float4& p, float a_hit)
+{
+  const float tx = row_apply(m[0], m[1], m[2], m[3], p.x, p.y, p.z);
+  const float ty = row_apply(m[4], m[5], m[6], m[7], p.x, p.y, p.z);
+  const float tz = row_apply(m[8], m[9], m[10], m[11], p.x, p.y, p.z);
+  const float v = __ldg(M.voxels + voxel_index<kFastDiv>(M, tx, ty, tz));
+  return __fadd_rn(__fmul_rn(a_hit, v), p.w);
+}
+
+template <int kPPW, bool kFastDiv>
+__global__ void __launch_bounds__(kEvalThreads) k_eval(const MapDev M, const EvalArgs A)
+{
+  __shared__ __align__(16) float xs[kEvalWarps][kPPW][kBlockSteps * 32];
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t part0 = (blockIdx.x * kEvalWarps + warp) * kPPW;
-  if (part0 >= n_local) return;
+  if (part0 >= A.n_local) return;
 
   float m[kPPW][12];
+  float s[kPPW];
 #pragma unroll
   for (int k = 0; k < kPPW; ++k)
   {
-    const uint32_t pi = min(part0 + k, n_local - 1);
+    const uint32_t pi = min(part0 + k, A.n_local - 1);
 #pragma unroll
-    for (int e = 0; e < 12; ++e) m[k][e] = __ldg(mats + 12ull * pi + e);
+    for (int e = 0; e < 12; ++e) m[k][e] = __ldg(A.mats + 12ull * pi + e);
+    s[k] = 0.0f;
   }
 
-  const uint32_t p0 = blockIdx.y * chunk_len;
-  const uint32_t p1 = min(n_points, p0 + chunk_len);
-  const uint32_t n_full = p0 + ((p1 - p0) & ~31u);
-
-  float acc[kPPW];
+  float2 mm[12];  // {A, B} matrix entries for the packed path
 #pragma unroll
-  for (int k = 0; k < kPPW; ++k) acc[k] = 0.0f;
+  for (int e = 0; e < 12; ++e) mm[e] = make_float2(m[0][e], m[kPPW - 1][e]);
 
+  uint32_t n_blocks = 0, n_fold = 0, n_tie = 0;
+  const uint32_t n_full = A.n_points >> 5;
+  const uint32_t rem = A.n_points & 31u;
+  uint32_t step = 0;
+  while (step < n_full)
+  {
+    const uint32_t nb = min(static_cast<uint32_t>(kBlockSteps), n_full - step);
+    // plan: binade of the running sum -> ulp u, 1/u, and the largest sum that still lies safely inside the binade
+    float u[kPPW], inv_u[kPPW], limit[kPPW];
+    bool fast[kPPW];
+    uint32_t acc[kPPW];
+    bool tie[kPPW];
+#pragma unroll
+    for (int k = 0; k < kPPW; ++k)
+    {
+      const uint32_t e = __float_as_uint(s[k]) >> 23;  // s >= 0
+      fast[k] = !A.force_seq && s[k] >= A.s_min && e > 24u && e < 253u;
+      const uint32_t ec = min(max(e, 25u), 252u);
+      u[k] = __uint_as_float((ec - 23u) << 23);
+      inv_u[k] = __uint_as_float((277u - ec) << 23);
+      limit[k] = __fsub_rn(__uint_as_float((ec + 1u) << 23), u[k]);  // top of the binade minus one ulp (exact)
+      acc[k] = 0u;
+      tie[k] = false;
+    }
+    const float4* __restrict__ pp = A.pts + (static_cast<size_t>(step) << 5) + lane;
+    if (kPPW == 2)
+    {
+      // two particles per instruction: matrices, offsets, quotients and rounding all as fp32x2 pairs {A, B}
+      const float2 one = dup2(A.one);
+      const float2 iu = make_float2(inv_u[0], inv_u[kPPW - 1]);
+      const float2 ah = dup2(A.a_hit);
 #pragma unroll 2
-  for (uint32_t i = p0 + lane; i < n_full; i += 32)
-  {
-    const float4 p = __ldg(pts + i);
+      for (uint32_t b = 0; b < nb; ++b)
+      {
+        const float4 p = __ldg(pp + (b << 5));
+        const float2 xx = dup2(p.x), yy = dup2(p.y), zz = dup2(p.z);
+        const float2 tx = row_apply2(mm[0], mm[1], mm[2], mm[3], xx, yy, zz, one);
+        const float2 ty = row_apply2(mm[4], mm[5], mm[6], mm[7], xx, yy, zz, one);
+        const float2 tz = row_apply2(mm[8], mm[9], mm[10], mm[11], xx, yy, zz, one);
+        uint32_t ia, ib;
+        voxel_index2<kFastDiv>(M, tx, ty, tz, ia, ib);
+        const float2 v = make_float2(__ldg(M.voxels + ia), __ldg(M.voxels + ib));
+        const float2 x = __ffma2_rn(__fmul2_rn(ah, v), one, dup2(p.w));         // fl(fl(a_hit*v) + term)
+        xs[warp][0][(b << 5) + lane] = x.x;
+        xs[warp][kPPW - 1][(b << 5) + lane] = x.y;
+        const float2 t = __ffma2_rn(x, iu, dup2(kRoundMagic));
+        acc[0] += __float_as_uint(t.x) - kRoundMagicBits;
+        acc[kPPW - 1] += __float_as_uint(t.y) - kRoundMagicBits;
+        const float2 tm = __fadd2_rn(t, dup2(-kRoundMagic));
+        const float2 r = __ffma2_rn(x, iu, make_float2(-tm.x, -tm.y));
+        tie[0] |= (fabsf(r.x) == 0.5f);
+        tie[kPPW - 1] |= (fabsf(r.y) == 0.5f);
+      }
+    }
+    else
+    {
+#pragma unroll 2
+      for (uint32_t b = 0; b < nb; ++b)
+      {
+        const float4 p = __ldg(pp + (b << 5));
+#pragma unroll
+        for (int k = 0; k < kPPW; ++k)
+        {
+          const float x = eval_point<kFastDiv>(M, m[k], p, A.a_hit);
+          xs[warp][k][(b << 5) + lane] = x;
+          const float t = __fmaf_rn(x, inv_u[k], kRoundMagic);                 // RN-even(x/u) in the low mantissa bits
+          acc[k] += __float_as_uint(t) - kRoundMagicBits;
+          const float r = __fmaf_rn(x, inv_u[k], -__fsub_rn(t, kRoundMagic));   // exact rounding residue
+          tie[k] |= (fabsf(r) == 0.5f);
+        }
+      }
+    }
+    __syncwarp();
+    ++n_blocks;
 #pragma unroll
     for (int k = 0; k < kPPW; ++k)
     {
-      const float tx = row_apply(m[k][0], m[k][1], m[k][2], m[k][3], p.x, p.y, p.z);
-      const float ty = row_apply(m[k][4], m[k][5], m[k][6], m[k][7], p.x, p.y, p.z);
-      const float tz = row_apply(m[k][8], m[k][9], m[k][10], m[k][11], p.x, p.y, p.z);
-      acc[k] += __ldg(M.voxels + voxel_index<kFastDiv>(M, tx, ty, tz));
+      // s + sum(q) * u is the sequential fp32 sum iff no addend was an exact tie and the result stays below the top
+      // of the binade (then every partial sum did, the addends being >= 0).
+      const uint32_t tot = __reduce_add_sync(0xffffffffu, acc[k]);
+      const bool any_tie = __any_sync(0xffffffffu, tie[k]);
+      const float cand = __fadd_rn(s[k], __fmul_rn(static_cast<float>(tot), u[k]));
+      if (fast[k] && !any_tie && tot < (1u << 24) && cand <= limit[k])
+      {
+        s[k] = cand;
+      }
+      else
+      {
+        const float4* __restrict__ q = reinterpret_cast<const float4*>(xs[warp][k]);
+        float a = s[k];
+        const uint32_t cnt = nb << 3;
+#pragma unroll 2
+        for (uint32_t j = 0; j < cnt; ++j)
+        {
+          const float4 w = q[j];
+          a = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(a, w.x), w.y), w.z), w.w);
+        }
+        s[k] = a;
+        ++n_fold;
+        n_tie += (fast[k] && any_tie) ? 1u : 0u;
+      }
     }
+    __syncwarp();
+    step += nb;
   }
-  if (n_full + lane < p1)
+  if (rem)
   {
-    const float4 p = __ldg(pts + n_full + lane);
+    const float4 p = __ldg(A.pts + (static_cast<size_t>(n_full) << 5) + lane);  // padded: reading past n_points is safe
+#pragma unroll
+    for (int k = 0; k < kPPW; ++k) xs[warp][k][lane] = eval_point<kFastDiv>(M, m[k], p, A.a_hit);
+    __syncwarp();
 #pragma unroll
     for (int k = 0; k < kPPW; ++k)
     {
-      const float tx = row_apply(m[k][0], m[k][1], m[k][2], m[k][3], p.x, p.y, p.z);
-      const float ty = row_apply(m[k][4], m[k][5], m[k][6], m[k][7], p.x, p.y, p.z);
-      const float tz = row_apply(m[k][8], m[k][9], m[k][10], m[k][11], p.x, p.y, p.z);
-      acc[k] += __ldg(M.voxels + voxel_index<kFastDiv>(M, tx, ty, tz));
+      float a = s[k];
+      for (uint32_t j = 0; j < rem; ++j) a = __fadd_rn(a, xs[warp][k][j]);
+      s[k] = a;
     }
   }
-
 #pragma unroll
   for (int k = 0; k < kPPW; ++k)
+    if (lane == 0 && part0 + k < A.n_local) A.raw_out[part0 + k] = s[k];
+  if (lane == 0 && A.stats)
   {
-    float v = acc[k];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0 && part0 + k < n_local) partial[static_cast<size_t>(blockIdx.y) * n_local + part0 + k] = v;
+    atomicAdd(A.stats + 0, static_cast<unsigned long long>(n_blocks) * kPPW);
+    atomicAdd(A.stats + 1, static_cast<unsigned long long>(n_fold));
+    atomicAdd(A.stats + 2, static_cast<unsigned long long>(n_tie));
   }
-}
-
-// raw weight = a_hit * sum_chunks(partial) + sum_points(range term)
-//   (= sum_p (a_hit * v_p + term_p), cuda_eval_particles.h:200-211, regrouped; within 1e-5 rel. of the fp32-sequential sum)
-__global__ void k_finish_raw(const float* __restrict__ partial, uint32_t n_chunks, uint32_t n_local, float a_hit,
-                             const double* __restrict__ term_sum, float* __restrict__ raw_out)
-{
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_local) return;
-  float s = 0.0f;
-  for (uint32_t c = 0; c < n_chunks; ++c) s += partial[static_cast<size_t>(c) * n_local + i];
-  raw_out[i] = __fmaf_rn(a_hit, s, static_cast<float>(*term_sum));
 }
 
 // Parity/debug kernel: one thread per (particle, point) pair, same index function as k_eval.
