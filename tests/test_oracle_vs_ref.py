@@ -1,0 +1,177 @@
+"""Pins the plain-C oracle (oracle/tsdf_oracle.c) against the UNMODIFIED reference compiled here (oracle/_ref).
+
+The reference ships no tests or golden vectors, so the oracle is pinned on outputs of the reference's own
+code: map arrays from CudaSubVoxelMap::setData, host getEntry, TSDFEvaluator::evaluatePose / evaluate, and
+SystematicResampler::resample (with its own std::mt19937-drawn U0). Runs on CPU; skipped where oracle/_ref was not built
+(it is built wherever /root/reference exists, and the prebuilt .so travels to the GPU box).
+"""
+import numpy as np
+import pytest
+
+import common
+from oracle_lib import NEG_AS_MISS, NEG_REF_HOST_X86
+from tsdf_localization_b200 import synthetic as syn
+
+
+@pytest.fixture(scope="module")
+def small_spec():
+    spec, _ = common.box_room(small=True)
+    return spec
+
+
+@pytest.fixture(scope="module")
+def maps(oracle, ref, small_spec):
+    s = small_spec
+    om = oracle.map_create(s.min, s.max, s.resolution, s.init_value)
+    assert oracle.map_set_data(om, s.cells) == 0
+    rm = ref.map_create(s.min, s.max, s.resolution, s.init_value)
+    assert rm, "reference map constructor failed"
+    assert ref.map_set_data(rm, s.cells) == 0
+    yield om, rm
+    oracle.map_destroy(om)
+    ref.map_destroy(rm)
+
+
+def _coef_tuple(c):
+    return (tuple(c.dim), tuple(c.min), tuple(c.max), c.resolution, c.init_value, tuple(c.up_dim), c.up_dim_2, c.sub_dim,
+            c.sub_dim_2, c.grid_occ_size, c.data_size)
+
+
+def test_map_arrays_identical(oracle, ref, maps):
+    om, rm = maps
+    oc, oocc, odata = oracle.map_arrays(om)
+    rc, rocc, rdata = ref.map_arrays(rm)
+    assert _coef_tuple(oc) == _coef_tuple(rc)
+    assert np.array_equal(oocc, rocc)
+    assert odata.tobytes() == rdata.tobytes()
+    assert oc.data_size > 0 and (oocc >= 0).sum() * oc.sub_dim ** 3 == oc.data_size
+
+
+@pytest.mark.parametrize("res", [0.05, 0.064, 0.1])
+def test_map_geometry_other_resolutions(oracle, ref, res):
+    mn, mx = (-3.3, -2.0, -0.5), (4.1, 2.7, 2.2)
+    rng = np.random.default_rng(3)
+    cells = np.empty((4000, 4), dtype=np.float32)
+    cells[:, :3] = rng.uniform(np.asarray(mn) + 0.01, np.asarray(mx) - 0.01, size=(4000, 3))
+    cells[:, 3] = rng.uniform(0.1, 60.0, size=4000)
+    om = oracle.map_create(mn, mx, res, 0.0)
+    rm = ref.map_create(mn, mx, res, 0.0)
+    assert oracle.map_set_data(om, cells) == 0 and ref.map_set_data(rm, cells) == 0
+    oc, oocc, odata = oracle.map_arrays(om)
+    rc, rocc, rdata = ref.map_arrays(rm)
+    assert _coef_tuple(oc) == _coef_tuple(rc)
+    assert np.array_equal(oocc, rocc) and odata.tobytes() == rdata.tobytes()
+    q = rng.uniform(np.asarray(mn) - 0.0, np.asarray(mx) + 3.0, size=(200000, 3)).astype(np.float32)
+    assert ref.get_entries(rm, q).tobytes() == oracle.get_entries(om, q, NEG_REF_HOST_X86).tobytes()
+    oracle.map_destroy(om)
+    ref.map_destroy(rm)
+
+
+def test_get_entry_random_and_adversarial(oracle, ref, maps, small_spec):
+    om, rm = maps
+    s = small_spec
+    rng = np.random.default_rng(11)
+    lo, hi = np.asarray(s.min), np.asarray(s.max)
+    # inside the box and beyond max on every axis (offsets >= 0): all three negative-offset policies agree
+    q = rng.uniform(lo, hi + 2.5, size=(400000, 3)).astype(np.float32)
+    r = ref.get_entries(rm, q)
+    assert r.tobytes() == oracle.get_entries(om, q, NEG_REF_HOST_X86).tobytes()
+    assert r.tobytes() == oracle.get_entries(om, q, NEG_AS_MISS).tobytes()
+    # voxel faces, brick faces and the map's max face: coordinates that are exact multiples of the resolution / 1 m
+    k = rng.integers(0, 140, size=(100000, 3))
+    faces = (lo[None, :] + k * np.float32(s.resolution)).astype(np.float32)
+    faces[::3] = (lo[None, :] + rng.integers(0, 8, size=(len(faces[::3]), 3))).astype(np.float32)
+    faces[1::7] = np.nextafter(faces[1::7], np.float32(-np.inf))
+    faces = faces[(faces >= lo.astype(np.float32)).all(axis=1)]
+    assert ref.get_entries(rm, faces).tobytes() == oracle.get_entries(om, faces, NEG_REF_HOST_X86).tobytes()
+    assert ref.get_entries(rm, faces).tobytes() == oracle.get_entries(om, faces, NEG_AS_MISS).tobytes()
+    # the negative band: the oracle's x86 mode restates what this container's build of the reference does
+    neg = rng.uniform(lo - 2.0, hi, size=(200000, 3)).astype(np.float32)
+    assert ref.get_entries(rm, neg).tobytes() == oracle.get_entries(om, neg, NEG_REF_HOST_X86).tobytes()
+
+
+def _workload(n=96, p=700):
+    gt = (0.4, -0.3, 1.2, 0.01, -0.02, 0.4)
+    pts, _ = syn.make_scan("vlp16", gt, room_lo=(-3.0, -2.5, 0.0), room_hi=(3.0, 2.5, 3.0), n_points=p)
+    ps = syn.tracking_particles(n, gt, sigma_xy=0.2)
+    return ps, pts
+
+
+@pytest.mark.parametrize("tf", [syn.IDENTITY_TF, syn.CALIB_TF], ids=["identity_tf", "calib_tf"])
+def test_pose_weights_bit_exact(oracle, ref, maps, tf):
+    om, rm = maps
+    ps, pts = _workload()
+    mats = oracle.pose_matrices(ps, tf)
+    ev = ref.eval_create(rm)
+    w_ref = ref.pose_weights(ev, mats, pts)
+    w_or = np.array([oracle.pose_weight64(om, common.DEFAULT_PARAMS, mats[i], pts, NEG_REF_HOST_X86)[0] for i in range(len(ps))],
+                    dtype=np.float32)
+    assert w_ref.tobytes() == w_or.tobytes()
+    ref.eval_destroy(ev)
+
+
+@pytest.mark.parametrize("params", [common.DEFAULT_PARAMS, (0.7, 0.2, 0.05, 4.0)], ids=["default", "short_range"])
+def test_evaluate_matches_reference(oracle, ref, maps, params):
+    """Full TSDFEvaluator::evaluate (CPU/OpenMP): normalised weights + mean pose. The reference's weight_sum is an OpenMP
+    reduction in scheduling order (tsdf_evaluator.cpp:97), so normalised weights are compared to 2 ulp, the raw ones
+    (weight * sum) are covered bit-exactly by test_pose_weights_bit_exact."""
+    om, rm = maps
+    ps, pts = _workload()
+    ev = ref.eval_create(rm, *params)
+    rc, ps_ref, pose_ref, err = ref.evaluate(ev, ps, pts, syn.CALIB_TF)
+    assert rc == 0, err
+    out = oracle.evaluate(om, params, ps, pts, syn.CALIB_TF, mode=NEG_REF_HOST_X86)
+    assert out["status"] == 0
+    assert np.array_equal(out["particles"][:, :6], ps_ref[:, :6])
+    np.testing.assert_allclose(out["particles"][:, 6], ps_ref[:, 6], rtol=3e-7, atol=0)
+    np.testing.assert_allclose(out["mean"][:3], pose_ref[:3], atol=2e-6)
+    # orientation: reference returns the setRPY quaternion of the mean angles
+    r, p, y = (float(v) * 0.5 for v in out["mean"][3:])
+    q = np.array([np.sin(r) * np.cos(p) * np.cos(y) - np.cos(r) * np.sin(p) * np.sin(y),
+                  np.cos(r) * np.sin(p) * np.cos(y) + np.sin(r) * np.cos(p) * np.sin(y),
+                  np.cos(r) * np.cos(p) * np.sin(y) - np.sin(r) * np.sin(p) * np.cos(y),
+                  np.cos(r) * np.cos(p) * np.cos(y) + np.sin(r) * np.sin(p) * np.sin(y)])
+    np.testing.assert_allclose(q, pose_ref[3:], atol=2e-6)
+    ref.eval_destroy(ev)
+
+
+def test_evaluate_no_valid_particle(oracle, ref, maps):
+    om, rm = maps
+    ps, pts = _workload(8, 64)
+    ps[:, :3] += 500.0      # far outside the map: every lookup misses; a_range = 0 -> all weights 0
+    params = (0.9, 0.0, 0.0, 100.0)
+    ev = ref.eval_create(rm, *params)
+    rc, _, _, err = ref.evaluate(ev, ps, pts, syn.IDENTITY_TF)
+    assert rc == 1 and "No particle is valid" in err
+    assert oracle.evaluate(om, params, ps, pts, syn.IDENTITY_TF, mode=NEG_REF_HOST_X86)["status"] == 1
+    ref.eval_destroy(ev)
+
+
+@pytest.mark.parametrize("n", [1, 7, 500, 4096, 100000])
+@pytest.mark.parametrize("seed", [1, 2, 12345])
+def test_systematic_resample_matches_reference(oracle, ref, n, seed):
+    rng = np.random.default_rng(seed + n)
+    ps = np.zeros((n, 7), dtype=np.float32)
+    ps[:, :6] = rng.normal(size=(n, 6))
+    w = rng.exponential(size=n) ** 3
+    if n > 10:
+        w[rng.integers(0, n, size=n // 5)] = 0.0     # particles that must never be drawn
+    ps[:, 6] = (w / w.sum()).astype(np.float32)
+    m_ref, out_ref, u0 = ref.systematic_resample(ps, seed)
+    m_or, parents = oracle.systematic_resample(ps[:, 6], u0)
+    assert m_or == m_ref
+    assert np.array_equal(ps[parents], out_ref)
+
+
+def test_systematic_resample_short_output_drift(oracle, ref):
+    """for N not a power of two the fp32 U drifts and the reference emits != N particles."""
+    n = 1_000_000
+    rng = np.random.default_rng(5)
+    ps = np.zeros((n, 7), dtype=np.float32)
+    ps[:, 0] = np.arange(n)
+    w = rng.exponential(size=n)
+    ps[:, 6] = (w / w.sum()).astype(np.float32)
+    m_ref, out_ref, u0 = ref.systematic_resample(ps, 99, cap=n + n // 8)
+    m_or, parents = oracle.systematic_resample(ps[:, 6], u0, cap=n + n // 8)
+    assert m_or == m_ref and m_ref != n
+    assert np.array_equal(parents.astype(np.float32), out_ref[:, 0])
