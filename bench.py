@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — MCL sensor-update benchmark (BASELINE.json metric: particle-point evaluations/s + update latency).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A STEP is one full sensor update on one scan: scan preparation, particle x point TSDF evaluation, weight normalisation +
+weighted mean pose + CDF, systematic resampling (and, at N > 1 GPUs, the two NCCL all-gathers). Workloads are the
+BASELINE.json configs built by tsdf_localization_b200/synthetic.py (seeds fixed):
+  c3 (default)  OS1-128 scan (131,072 points) x 65,536 particles, box room 20x20x5 m @ 5 cm — the config the north star's
+                <5 ms target is quoted on; STRONG scaling: the 65,536 particles are sharded over the N ranks
+  c2            VLP-16 scan (30,000 points) x 5,000 particles
+  c1            1,024 points x 500 particles (the parity config)
+`value`  : whole-job particle-point evaluations/s, inputs already resident in HBM, CUDA events around each step on the
+           launching stream, L2 flushed (256 MiB memset) between steps outside the timed events, max over ranks.
+`e2e`    : the same update through the reference-facing host-buffer calls (tsdfloc_sensor_update +
+           tsdfloc_resample_systematic at N = 1; pinned-host -> device copies + the sharded update + device -> pinned-host
+           copies at N > 1), host<->device copies inside the timed region.
+`roofline`: the evaluation kernel k_eval alone (tsdfloc_last_eval_ms: CUDA events on its stream), algorithmic bytes =
+           8 B per particle-point evaluation (4 B brick-table entry + 4 B voxel) over the measured HBM copy peak.
+`cpu_baseline` / --impl reference: the UNMODIFIED reference CPU/OpenMP evaluator + SystematicResampler (oracle/_ref,
+           compiled from /root/reference in the build container) on this box's host cores, on a bounded particle sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "particle_point_evals_per_s"
+UNIT = "evals/s"
+ALG_BYTES_PER_EVAL = 8          # 4 B brick-table entry + 4 B voxel
+L2_FLUSH_BYTES = 256 << 20
+
+WORKLOADS = {
+    "c3": dict(scan="os1-128", particles=65536, desc="OS1-128 scan (131,072 pts) x 65,536 particles, box room 20x20x5 m @ 5 cm"),
+    "c2": dict(scan="vlp16", particles=5000, desc="VLP-16 scan (30,000 pts) x 5,000 particles, box room 20x20x5 m @ 5 cm"),
+    "c1": dict(scan="vlp16", particles=500, n_points=1024, desc="1,024 pts x 500 particles, box room 20x20x5 m @ 5 cm"),
+}
+
+
+def build_workload(name: str):
+    import common
+    from tsdf_localization_b200 import synthetic as syn
+    w = WORKLOADS[name]
+    spec, m = common.box_room()
+    pts, _ = syn.make_scan(w["scan"], syn.GT_POSE, n_points=w.get("n_points"))
+    ps = syn.tracking_particles(w["particles"], syn.GT_POSE)
+    return spec, m, ps, pts, syn.IDENTITY_TF
+
+
+# ---- clocks sampler ---------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- reference arm / cpu baseline ---------------------------------------------------------------------------------------
+
+def pick_ref_threads():
+    """The reference hard-codes OMP_THREADS = 8 (util/constant.h:4); oracle/_ref holds variants rebuilt with the constant
+    shadowed. Use the largest variant that does not exceed this host's cores."""
+    from oracle_lib import ref_lib_path
+    cores = os.cpu_count() or 8
+    best = None
+    for t in (8, 12, 16, 24, 32, 48, 64, 96, 128, 192, 256):
+        path = ref_lib_path(None if t == 8 else t)
+        if t <= max(cores, 8) and path.exists():
+            best = t
+    return best
+
+
+def reference_runner(spec, ps, pts, tf, sample: int):
+    """Returns (run_once() -> seconds for evaluate + resample on the sample, cores, description)."""
+    from oracle_lib import Ref, ref_available
+    if not ref_available():
+        raise RuntimeError("oracle/_ref not built: run `make -C oracle` in the container that has /root/reference")
+    t = pick_ref_threads()
+    ref = Ref(None if t == 8 else t)
+    rm = ref.map_create(spec.min, spec.max, spec.resolution, spec.init_value)
+    if not rm or ref.map_set_data(rm, spec.cells) != 0:
+        raise RuntimeError("reference map build failed")
+    ev = ref.eval_create(rm)
+    sub = np.ascontiguousarray(ps[:sample])
+
+    def run_once():
+        t0 = time.perf_counter()
+        rc, out, _, err = ref.evaluate(ev, sub, pts, tf)
+        if rc != 0:
+            raise RuntimeError("reference evaluate failed: " + err)
+        ref.systematic_resample(out, 1)
+        return time.perf_counter() - t0
+
+    return run_once, ref.omp_threads(), f"first {sample} of {len(ps)} particles x full {len(pts)}-point scan"
+
+
+def cpu_sample_size(n_particles: int, n_points: int) -> int:
+    """~3e8 evaluations per run (about a second on 16 cores), capped by the workload."""
+    return int(max(16, min(n_particles, 3.0e8 // max(n_points, 1))))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    try:
+        spec, m, ps, pts, tf = build_workload(args.workload)
+        sample = cpu_sample_size(len(ps), len(pts))
+        run_once, cores, what = reference_runner(spec, ps, pts, tf, sample)
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps({"impl": "reference", "unavailable": str(e).splitlines()[0]}))
+        return
+    for _ in range(args.warmup):
+        run_once()
+    times = [run_once() for _ in range(args.steps)]
+    total = sum(times)
+    value = sample * len(pts) * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + WORKLOADS[args.workload]["desc"], "particles": len(ps), "points": len(pts),
+                   "sample": what, "step": "TSDFEvaluator::evaluate(use_cuda=false) + SystematicResampler::resample on the sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": what},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---- B200 arm ----------------------------------------------------------------------------------------------------------
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from tsdf_localization_b200 import CudaEvaluator, capi
+    from tsdf_localization_b200.dist import GpuStages, ShardedSensorUpdate, shard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nproc-per-node {args.gpus} bench.py ...")
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: the sensor update has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    spec, m, ps, pts, tf = build_workload(args.workload)
+    n, p = len(ps), len(pts)
+    ev = CudaEvaluator(m, device=local)
+    lib = capi.load_library()
+    stages = GpuStages(ev)
+    upd = ShardedSensorUpdate(stages, world=world, rank=rank, device=dev, max_particles=n)
+    stream = torch.cuda.Stream(device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    d_ps = torch.from_numpy(ps).to(dev)
+    d_pts = torch.from_numpy(pts).to(dev)
+    h_ps = torch.from_numpy(ps).pin_memory()
+    h_pts = torch.from_numpy(pts).pin_memory()
+    u0 = 0.37 / n
+    _, _, n_local = shard(n, world, rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def device_step():
+        upd.set_scan(d_pts)
+        return upd.step(d_ps, n, tf, u0)
+
+    # e2e at N = 1: the reference-facing host-buffer C-ABI calls; at N > 1: pinned copies around the sharded update
+    cap = n + n // 8 + 64
+    h_out = torch.empty((cap, 7), dtype=torch.float32).pin_memory()
+    h_mean = torch.empty(6, dtype=torch.float32).pin_memory()
+    e2e_ps = h_ps.clone().pin_memory()
+    tfc = (C.c_float * 16)(*[float(v) for v in tf])
+
+    def e2e_step():
+        if world == 1:
+            mean = (C.c_float * 6)()
+            n_out = C.c_uint64(0)
+            capi.check(lib, ev.ctx, lib.tsdfloc_sensor_update(ev.ctx, C.c_void_p(e2e_ps.data_ptr()), n, C.c_void_p(h_pts.data_ptr()), p, tfc, mean))
+            capi.check(lib, ev.ctx, lib.tsdfloc_resample_systematic(ev.ctx, C.c_float(u0), C.c_void_p(h_out.data_ptr()), cap, C.byref(n_out), None))
+            return int(n_out.value)
+        d_ps.copy_(h_ps, non_blocking=True)
+        d_pts.copy_(h_pts, non_blocking=True)
+        upd.set_scan(d_pts)
+        out, mean, n_out, _ = upd.step(d_ps, n, tf, u0)
+        h_out[:n_out].copy_(out, non_blocking=True)
+        h_mean.copy_(mean, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return n_out
+
+    with torch.cuda.stream(stream):
+        # ---- device-resident timing -------------------------------------------------------------------------------------
+        for _ in range(args.warmup):
+            device_step()
+        barrier()
+        launches0 = stages.kernel_launches()
+        sampler = ClockSampler(local) if rank == 0 else None
+        step_ms, eval_ms = [], []
+        wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.zero_()                                   # L2 flush, outside the timed events
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            _, _, n_out, wsum = device_step()
+            e1.record(stream)
+            e1.synchronize()
+            step_ms.append(e0.elapsed_time(e1))
+            eval_ms.append(stages.last_eval_ms())
+        barrier()
+        wall = time.perf_counter() - wall0
+        launches = stages.kernel_launches() - launches0
+        clocks = sampler.stop() if sampler else None
+
+        # ---- end-to-end timing (host buffers) -----------------------------------------------------------------------------
+        for _ in range(max(1, min(args.warmup, 3))):
+            e2e_step()
+        barrier()
+        e2e_ms = []
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            e2e_step()
+            e2e_ms.append(1e3 * (time.perf_counter() - t0))
+        barrier()
+
+    t = torch.tensor([sum(step_ms), sum(e2e_ms), float(np.mean(eval_ms)), wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_total_ms, eval_mean_ms, wall_ms = (float(v) for v in t.cpu())
+    K = args.steps
+    ms_per_step = total_ms / K
+    value = n * p / (ms_per_step * 1e-3)
+    e2e_value = n * p / (e2e_total_ms / K * 1e-3)
+
+    if rank == 0:
+        peaks_path = ROOT / "MEASURED_PEAKS.json"
+        if peaks_path.exists():
+            peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = ALG_BYTES_PER_EVAL * n_local * p / (eval_mean_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = ROOT / "profiles" / "k_eval_traffic.json"
+        if tpath.exists():
+            try:
+                traffic = json.loads(tpath.read_text()).get(args.workload, {}).get("dram_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": "k_eval", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel_ms": eval_mean_ms,
+                    "algorithmic_bytes_per_launch": ALG_BYTES_PER_EVAL * n_local * p,
+                    "note": "8 B per particle-point evaluation; the 77 MB map is L2-resident, so DRAM traffic is far below the algorithmic bytes"}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                sample = cpu_sample_size(n, p)
+                run_once, cores, what = reference_runner(spec, ps, pts, tf, sample)
+                run_once()
+                best = min(run_once() for _ in range(5))
+                cpu = {"value": sample * p / best, "unit": UNIT, "cores": cores, "kind": "reference", "sample": what + ", best of 5",
+                       "ms_per_update_extrapolated": 1e3 * best * n / sample}
+            except Exception as e:  # noqa: BLE001
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: " + str(e).splitlines()[0]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload + ": " + WORKLOADS[args.workload]["desc"], "particles": n, "points": p,
+                       "particles_per_gpu": n_local, "map_mb": m.dataBytes() / 1e6, "sharding": f"particles/{world}, map replicated",
+                       "step": "scan prep + eval + normalise/mean/CDF + systematic resample" + (" + 2 NCCL all-gathers" if world > 1 else ""),
+                       "l2": "flushed (256 MiB memset) between timed steps, outside the CUDA-event pairs",
+                       "n_out": int(n_out), "weight_sum": wsum},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_total_ms / K,
+                    "h2d_bytes_per_step": world * (n * 28 + p * 12), "d2h_bytes_per_step": world * (int(n_out) * 28 + 24) + (n * 28 if world == 1 else 0),
+                    "api": "tsdfloc_sensor_update + tsdfloc_resample_systematic (host buffers)" if world == 1
+                           else "pinned H2D + ShardedSensorUpdate.step + pinned D2H, per rank"},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step_incl_flush": wall_ms / K,
+        }
+        print(json.dumps(line))
+    ev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--workload", choices=tuple(WORKLOADS), default="c3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

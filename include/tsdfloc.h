@@ -128,6 +128,13 @@ int tsdfloc_sensor_update(tsdfloc_ctx* ctx, float* particles, uint64_t n, const 
 int tsdfloc_resample_systematic(tsdfloc_ctx* ctx, float u0, float* particles_out, uint64_t cap, uint64_t* n_out,
                                 uint32_t* parents);
 
+/* Systematic resampling of a weighted particle set in host memory — the drop-in for
+ * SystematicResampler::resample(ParticleCloud&) (novel_resampling.h:41-72) as mcl_3d calls it (src/mcl_3d.cpp:424-426),
+ * independent of any preceding sensor update. particles: n x 7 fp32 whose slot [6] holds the (normalised) weights; they
+ * are used as they are, exactly like the reference's running sum `s += particle.second`. Outputs as above. */
+int tsdfloc_resample_particles(tsdfloc_ctx* ctx, const float* particles, uint64_t n, float u0, float* particles_out, uint64_t cap,
+                               uint64_t* n_out, uint32_t* parents);
+
 /* Parity/debug: per-(particle, point) flat voxel index (data_size = miss) and per-particle hit counts for the
  * given inputs, computed by the same device index function the evaluation kernel uses.
  * idx (optional): n*p uint32, particle-major. hits (optional): n uint32. raw_weights (optional): n un-normalised. */
@@ -156,6 +163,10 @@ int tsdfloc_eval_device(tsdfloc_ctx* ctx, const float* d_particles, uint64_t n_t
 int tsdfloc_normalize_device(tsdfloc_ctx* ctx, float* d_particles, uint64_t n_total, const float* d_raw_weights,
                              float* d_mean_pose, void* stream);
 
+/* Same CDF build for particles that already carry their weights in slot [6] (no normalisation, nothing rewritten):
+ * the device half of tsdfloc_resample_particles. */
+int tsdfloc_cdf_device(tsdfloc_ctx* ctx, float* d_particles, uint64_t n_total, float* d_mean_pose, void* stream);
+
 /* Draw output slots [first_out, first_out+count_out) from the CDF: d_particles_out[j] = d_particles[parent(j)].
  * Slots >= n_out (see tsdfloc_check) are filled with parent = last valid parent so buffers stay defined.
  * d_parents optional (uint32 per output slot, indexed from first_out). */
@@ -174,6 +185,10 @@ uint64_t tsdfloc_host_u_sequence(float u0, uint64_t n, double limit, float* out,
  * out[0] = (particle, block) pairs processed, out[1] = of those folded sequentially (binade crossing, early phase or tie),
  * out[2] = of those caused by an exact rounding tie, out[3] reserved. */
 int tsdfloc_eval_stats(tsdfloc_ctx* ctx, uint64_t out[4]);
+
+/* Device time of the most recent evaluation-kernel launch (k_eval alone, CUDA events recorded on the stream it was
+ * launched on); waits for that launch to finish. This is the figure bench.py's roofline is computed from. */
+int tsdfloc_last_eval_ms(tsdfloc_ctx* ctx, float* ms);
 
 /* Number of kernels this library has launched on this ctx so far (for bench accounting). */
 uint64_t tsdfloc_kernel_launches(const tsdfloc_ctx* ctx);

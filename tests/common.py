@@ -12,7 +12,7 @@ DEFAULT_PARAMS = (0.9, 0.1, 0.0, 100.0)   # a_hit, a_range, a_max, max_range (ut
 
 
 @functools.lru_cache(maxsize=4)
-def box_room(resolution: float = 0.05, margin: float = 0.0, small: bool = False):
+def box_room(resolution: float = 0.05, margin=None, small: bool = False):
     """(spec, product map). small=True: a 6x5x3 m room for fast CPU tests."""
     if small:
         spec = syn.box_room_map(likelihood_value, likelihood_init(syn.SIGMA), room_lo=(-3.0, -2.5, 0.0), room_hi=(3.0, 2.5, 3.0),

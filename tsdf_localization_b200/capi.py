@@ -59,6 +59,8 @@ SIGNATURES = {
     "tsdfloc_destroy": (None, [_vp]),
     "tsdfloc_sensor_update": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _fp, _fp]),
     "tsdfloc_resample_systematic": (C.c_int, [_vp, C.c_float, _vp, _u64, C.POINTER(_u64), _vp]),
+    "tsdfloc_resample_particles": (C.c_int, [_vp, _vp, _u64, C.c_float, _vp, _u64, C.POINTER(_u64), _vp]),
+    "tsdfloc_cdf_device": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
     "tsdfloc_debug_eval": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _fp, _vp, _vp, _vp]),
     "tsdfloc_set_scan_device": (C.c_int, [_vp, _vp, _u64, _vp]),
     "tsdfloc_set_scan_host": (C.c_int, [_vp, _vp, _u64, _vp]),
@@ -68,6 +70,7 @@ SIGNATURES = {
     "tsdfloc_check": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double), _vp]),
     "tsdfloc_host_u_sequence": (_u64, [C.c_float, _u64, C.c_double, _vp, _u64, _u32p, _u32p]),
     "tsdfloc_eval_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "tsdfloc_last_eval_ms": (C.c_int, [_vp, _fp]),
     "tsdfloc_kernel_launches": (_u64, [_vp]),
 }
 

@@ -44,6 +44,8 @@ struct tsdfloc_ctx
   float x_bound = 0.0f;     // upper bound of one point's contribution a_hit*v + term (k_eval block planning)
   uint32_t force_seq = 0;   // 1: contributions may be negative / non-finite -> always fold sequentially
   uint64_t launches = 0;
+  cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;  // bracket the last k_eval launch (tsdfloc_last_eval_ms)
+  bool eval_timed = false;
 
   // map
   int32_t* d_table = nullptr;
@@ -238,11 +240,15 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   a.s_min = 32.0f * c->x_bound;
   a.stats = c->d_eval_stats;
   a.force_seq = c->force_seq;
+  CU_TRY(c, cudaEventRecord(c->ev_eval0, s), "event record");
   if (pick_ppw(c, count) == 2)
     launch_eval<2>(c, a, s);
   else
     launch_eval<1>(c, a, s);
-  return launch_check(c, "k_eval");
+  if ((rc = launch_check(c, "k_eval"))) return rc;
+  CU_TRY(c, cudaEventRecord(c->ev_eval1, s), "event record");
+  c->eval_timed = true;
+  return TSDFLOC_OK;
 }
 
 int stage_normalize(tsdfloc_ctx* c, float* d_particles, uint64_t n, const float* d_raw, float* d_mean, cudaStream_t s)
@@ -256,7 +262,9 @@ int stage_normalize(tsdfloc_ctx* c, float* d_particles, uint64_t n, const float*
   if ((rc = ensure(c, c->d_tile_offset, sizeof(double) * tiles, "cudaMalloc(tile offsets)"))) return rc;
   if ((rc = ensure(c, c->d_tile_moments, sizeof(double) * 9 * tiles, "cudaMalloc(tile moments)"))) return rc;
   const uint32_t n32 = static_cast<uint32_t>(n);
-  k_weight_sum<<<tiles, kScanThreads, 0, s>>>(d_raw, n32, static_cast<double*>(c->d_tile_total.p), c->d_status);
+  // d_raw == nullptr: scan the weights the particles already carry (slot 6, stride 7) without normalising them
+  k_weight_sum<<<tiles, kScanThreads, 0, s>>>(d_raw ? d_raw : d_particles + 6, d_raw ? 1u : 7u, n32,
+                                              static_cast<double*>(c->d_tile_total.p), c->d_status);
   if ((rc = launch_check(c, "k_weight_sum"))) return rc;
   k_normalise_scan<<<tiles, kScanThreads, 0, s>>>(d_particles, d_raw, n32, c->d_status, static_cast<double*>(c->d_cdf.p),
                                                   static_cast<double*>(c->d_tile_total.p), static_cast<double*>(c->d_tile_moments.p));
@@ -393,6 +401,8 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
   if (!(c->prm.max_range > 0.0f)) return bail(TSDFLOC_E_BAD_ARG, "max_range must be positive");
   c->desc = *map;
   CU_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  CU_CREATE(cudaEventCreate(&c->ev_eval0), "cudaEventCreate");
+  CU_CREATE(cudaEventCreate(&c->ev_eval1), "cudaEventCreate");
 
   // ---- padded brick table ------------------------------------------------------------------------------------
   uint32_t thr[3];
@@ -529,6 +539,8 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->h_mean) cudaFreeHost(c->h_mean);
+  if (c->ev_eval0) cudaEventDestroy(c->ev_eval0);
+  if (c->ev_eval1) cudaEventDestroy(c->ev_eval1);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -571,6 +583,14 @@ int tsdfloc_normalize_device(tsdfloc_ctx* c, float* d_particles, uint64_t n_tota
   if (!d_particles || !d_raw_weights) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
   DeviceGuard guard(c->device);
   return stage_normalize(c, d_particles, n_total, d_raw_weights, d_mean_pose ? d_mean_pose : c->d_mean, pick(c, stream));
+}
+
+int tsdfloc_cdf_device(tsdfloc_ctx* c, float* d_particles, uint64_t n_total, float* d_mean_pose, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!d_particles) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  DeviceGuard guard(c->device);
+  return stage_normalize(c, d_particles, n_total, nullptr, d_mean_pose ? d_mean_pose : c->d_mean, pick(c, stream));
 }
 
 int tsdfloc_draw_device(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, float u0, uint64_t first_out, uint64_t count_out,
@@ -667,6 +687,29 @@ int tsdfloc_resample_systematic(tsdfloc_ctx* c, float u0, float* particles_out, 
   return TSDFLOC_OK;
 }
 
+int tsdfloc_resample_particles(tsdfloc_ctx* c, const float* particles, uint64_t n, float u0, float* particles_out, uint64_t cap,
+                               uint64_t* n_out, uint32_t* parents)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!particles || !particles_out || !n_out) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (n == 0) return fail(c, TSDFLOC_E_BAD_ARG, "no particles");
+  DeviceGuard guard(c->device);
+  cudaStream_t s = c->stream;
+  int rc;
+  const size_t pbytes = sizeof(float) * 7 * n;
+  if ((rc = ensure(c, c->d_particles, pbytes, "cudaMalloc(particles)"))) return rc;
+  if ((rc = ensure_host(c, pbytes))) return rc;
+  c->have_cdf = false;
+  c->n_resident = 0;
+  std::memcpy(c->h_stage, particles, pbytes);
+  float* d_p = static_cast<float*>(c->d_particles.p);
+  CU_TRY(c, cudaMemcpyAsync(d_p, c->h_stage, pbytes, cudaMemcpyHostToDevice, s), "H2D particles");
+  if ((rc = stage_normalize(c, d_p, n, nullptr, c->d_mean, s))) return rc;
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");  // the pinned buffer is reused for the output
+  c->n_resident = n;
+  return tsdfloc_resample_systematic(c, u0, particles_out, cap, n_out, parents);
+}
+
 int tsdfloc_debug_eval(tsdfloc_ctx* c, const float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],
                        uint32_t* idx, uint32_t* hits, float* raw_weights)
 {
@@ -715,6 +758,16 @@ int tsdfloc_eval_stats(tsdfloc_ctx* c, uint64_t out[4])
   unsigned long long h[4];
   CU_TRY(c, cudaMemcpy(h, c->d_eval_stats, sizeof(h), cudaMemcpyDeviceToHost), "D2H eval stats");
   for (int i = 0; i < 4; ++i) out[i] = h[i];
+  return TSDFLOC_OK;
+}
+
+int tsdfloc_last_eval_ms(tsdfloc_ctx* c, float* ms)
+{
+  if (!c || !ms) return TSDFLOC_E_BAD_ARG;
+  if (!c->eval_timed) return fail(c, TSDFLOC_E_STATE, "no evaluation kernel has been launched yet");
+  DeviceGuard guard(c->device);
+  CU_TRY(c, cudaEventSynchronize(c->ev_eval1), "event sync");
+  CU_TRY(c, cudaEventElapsedTime(ms, c->ev_eval0, c->ev_eval1), "event elapsed");
   return TSDFLOC_OK;
 }
 

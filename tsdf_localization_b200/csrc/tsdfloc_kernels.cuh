@@ -348,7 +348,8 @@ __global__ void k_check_div(float res, float inv_res, unsigned long long* __rest
 // ------------------------------------------------------------------------------------------------------------
 // K2a: sum of raw weights in fp64, fixed order (block tree, then the last block adds the block sums in index order).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_weight_sum(const float* __restrict__ raw, uint32_t n, double* __restrict__ block_sums, Status* __restrict__ st)
+__global__ void k_weight_sum(const float* __restrict__ raw, uint32_t stride, uint32_t n, double* __restrict__ block_sums,
+                             Status* __restrict__ st)
 {
   __shared__ double s_part[kScanThreads / 32];
   __shared__ bool s_last;
@@ -358,7 +359,7 @@ __global__ void k_weight_sum(const float* __restrict__ raw, uint32_t n, double* 
   for (int k = 0; k < kScanItems; ++k)
   {
     const uint32_t i = base + threadIdx.x * kScanItems + k;
-    if (i < n) acc += static_cast<double>(raw[i]);
+    if (i < n) acc += static_cast<double>(raw[static_cast<size_t>(i) * stride]);
   }
   for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
@@ -400,6 +401,8 @@ __device__ __forceinline__ double add_checked(double a, double b, bool& bad)
 // ------------------------------------------------------------------------------------------------------------
 // K2b: normalise (w /= (float)sum, cuda_eval_particles.h:556), per-tile fp64 inclusive scan of the normalised
 // weights, per-tile weighted moments (x y z, sin/cos of the three angles; tsdf_evaluator.cpp:203-217).
+// raw == nullptr: the particles already carry their weights (Resampler::resample on a weighted cloud): they are
+// scanned as they are and not rewritten.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads) k_normalise_scan(float* __restrict__ particles, const float* __restrict__ raw, uint32_t n,
                                                                  Status* __restrict__ st, double* __restrict__ cdf,
@@ -425,8 +428,15 @@ __global__ void __launch_bounds__(kScanThreads) k_normalise_scan(float* __restri
     if (i < n)
     {
       float* p = particles + 7ull * i;
-      w = dead ? 0.0f : __fdiv_rn(raw[i], inv_den);
-      p[6] = w;
+      if (raw)
+      {
+        w = dead ? 0.0f : __fdiv_rn(raw[i], inv_den);
+        p[6] = w;
+      }
+      else
+      {
+        w = p[6];
+      }
       const float x = p[0], y = p[1], z = p[2];
       mom[0] += static_cast<double>(__fmul_rn(x, w));
       mom[1] += static_cast<double>(__fmul_rn(y, w));

@@ -1,0 +1,153 @@
+"""One-process-per-GPU driver of the sensor update: particles sharded, TSDF map replicated.
+
+Rank r evaluates the contiguous particle slice [r*ceil(N/R), ...) against the full scan; the un-normalised weights are
+all-gathered (NCCL over NVLink; N fp32); every rank then normalises and scans the GLOBAL weight vector redundantly —
+same kernels, same fixed summation order, so all ranks hold bit-identical CDFs and the result is independent of R —
+draws only ITS contiguous slice of output slots, and the resampled particles are all-gathered (7*N fp32) so the next
+update again finds the full particle set on every GPU. One host sync per update (status read-back: n_out, zero-sum).
+
+The reference has no multi-GPU path at all (single process, default stream); this is the north star's
+item (4). ``torch`` is plumbing here: device buffers, the stream, ``torch.distributed`` collectives. The stage
+implementation is injectable so the slicing / padding / collective logic is testable on CPU with gloo (tests/ plug the
+CPU oracle in; the product class ``GpuStages`` only ever calls libtsdfloc.so).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import capi
+
+
+def shard(n: int, world: int, rank: int) -> Tuple[int, int, int]:
+    """(chunk, first, count): contiguous slices of ceil(n / world); trailing ranks may get a short or empty slice."""
+    chunk = (n + world - 1) // world
+    first = min(rank * chunk, n)
+    return chunk, first, min(chunk, n - first)
+
+
+def output_capacity(n: int, world: int) -> int:
+    """Output slots reserved for resampling n particles. The reference recurrence emits exactly n particles when n is a
+    power of two (1/n exact in fp32) and drifts by up to a few per cent otherwise."""
+    cap = n if (n & (n - 1)) == 0 else n + n // 8 + 64
+    return ((cap + world - 1) // world) * world
+
+
+class GpuStages:
+    """The device-pointer stage calls of include/tsdfloc.h on torch CUDA tensors and the current torch stream."""
+
+    def __init__(self, evaluator):
+        self.ev = evaluator
+        self.lib = capi.load_library()
+        self.ctx = evaluator.ctx
+
+    @staticmethod
+    def _stream() -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def set_scan(self, d_points: torch.Tensor) -> None:
+        assert d_points.is_cuda and d_points.dtype == torch.float32 and d_points.is_contiguous()
+        capi.check(self.lib, self.ctx, self.lib.tsdfloc_set_scan_device(self.ctx, C.c_void_p(d_points.data_ptr()), d_points.shape[0],
+                                                                       self._stream()))
+
+    def eval(self, d_particles, n, first, count, tf, d_raw) -> None:
+        tfc = (C.c_float * 16)(*[float(v) for v in tf])
+        capi.check(self.lib, self.ctx, self.lib.tsdfloc_eval_device(self.ctx, C.c_void_p(d_particles.data_ptr()), n, first, count, tfc,
+                                                                   C.c_void_p(d_raw.data_ptr()), self._stream()))
+
+    def normalize(self, d_particles, n, d_raw, d_mean) -> None:
+        capi.check(self.lib, self.ctx, self.lib.tsdfloc_normalize_device(self.ctx, C.c_void_p(d_particles.data_ptr()), n,
+                                                                        C.c_void_p(d_raw.data_ptr()), C.c_void_p(d_mean.data_ptr()),
+                                                                        self._stream()))
+
+    def draw(self, d_particles, n, u0, first_out, count_out, d_out) -> None:
+        capi.check(self.lib, self.ctx, self.lib.tsdfloc_draw_device(self.ctx, C.c_void_p(d_particles.data_ptr()), n, C.c_float(u0),
+                                                                   first_out, count_out, C.c_void_p(d_out.data_ptr()), None,
+                                                                   self._stream()))
+
+    def check(self) -> Tuple[int, float]:
+        n_out, wsum = C.c_uint64(0), C.c_double(0.0)
+        rc = self.lib.tsdfloc_check(self.ctx, C.byref(n_out), C.byref(wsum), self._stream())
+        if rc == capi.E_NO_VALID_PARTICLE:
+            raise RuntimeError("No particle is valid!")
+        capi.check(self.lib, self.ctx, rc)
+        return int(n_out.value), float(wsum.value)
+
+    def last_eval_ms(self) -> float:
+        ms = C.c_float(0.0)
+        capi.check(self.lib, self.ctx, self.lib.tsdfloc_last_eval_ms(self.ctx, C.byref(ms)))
+        return float(ms.value)
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.tsdfloc_kernel_launches(self.ctx))
+
+
+class ShardedSensorUpdate:
+    """Full sensor update (evaluation + normalisation + systematic resampling) over ``world`` ranks.
+
+    All ranks hold the full particle set ``particles[:n]`` (float32[cap, 7], Particle layout) and the scan; after
+    ``step`` they all hold the full resampled set. With world == 1 no collective is issued.
+    """
+
+    def __init__(self, stages, world: int = 1, rank: int = 0, group=None, device: Optional[torch.device] = None,
+                 max_particles: int = 0):
+        self.stages = stages
+        self.world, self.rank, self.group = int(world), int(rank), group
+        self.device = device if device is not None else torch.device("cpu")
+        self._cap = 0
+        self._reserve(max_particles)
+
+    def _reserve(self, n: int) -> None:
+        if n <= self._cap:
+            return
+        W = self.world
+        chunk = (n + W - 1) // W
+        ocap = output_capacity(n, W)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.raw = torch.zeros(W * chunk, **f32)              # un-normalised weights, slice r at [r*chunk, (r+1)*chunk)
+        self.out = torch.zeros((ocap, 7), **f32)              # resampled particles, slice r at [r*ochunk, (r+1)*ochunk)
+        self.mean = torch.zeros(8, **f32)
+        self._cap = n
+
+    def set_scan(self, d_points: torch.Tensor) -> None:
+        self.stages.set_scan(d_points)
+
+    def step(self, particles: torch.Tensor, n: int, tf, u0: float):
+        """particles: float32[>= n, 7] on this rank's device, identical on every rank. Returns (resampled particles
+        float32[n_out, 7] — a view into an internal buffer, valid until the next step —, mean pose float32[6] tensor,
+        n_out, weight_sum). particles[:, 6] is overwritten with the normalised weights (cuda_eval_particles.h:556)."""
+        import torch.distributed as dist
+        W, r = self.world, self.rank
+        self._reserve(n)
+        chunk, first, count = shard(n, W, r)
+        self.stages.eval(particles, n, first, count, tf, self.raw)
+        if W > 1:
+            dist.all_gather_into_tensor(self.raw[:W * chunk], self.raw[r * chunk:(r + 1) * chunk], group=self.group)
+        self.stages.normalize(particles, n, self.raw, self.mean)
+        ocap = output_capacity(n, W)
+        ochunk = ocap // W
+        out = self.out[:ocap]
+        self.stages.draw(particles, n, u0, r * ochunk, ochunk, out[r * ochunk:(r + 1) * ochunk])
+        if W > 1:
+            dist.all_gather_into_tensor(out.view(-1), out[r * ochunk:(r + 1) * ochunk].reshape(-1), group=self.group)
+        n_out, wsum = self.stages.check()
+        if n_out > ocap:
+            raise RuntimeError(f"resampling emits {n_out} particles, capacity is {ocap}")
+        return out[:n_out], self.mean[:6], n_out, wsum
+
+    def evaluate_only(self, particles: torch.Tensor, n: int, tf):
+        """Evaluation + normalisation without resampling (what the reference's evaluate() covers). Returns
+        (mean pose tensor, weight_sum); normalised weights are left in particles[:, 6] on every rank."""
+        import torch.distributed as dist
+        W, r = self.world, self.rank
+        self._reserve(n)
+        chunk, first, count = shard(n, W, r)
+        self.stages.eval(particles, n, first, count, tf, self.raw)
+        if W > 1:
+            dist.all_gather_into_tensor(self.raw[:W * chunk], self.raw[r * chunk:(r + 1) * chunk], group=self.group)
+        self.stages.normalize(particles, n, self.raw, self.mean)
+        _, wsum = self.stages.check()
+        return self.mean[:6], wsum

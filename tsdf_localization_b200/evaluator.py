@@ -233,11 +233,15 @@ class TSDFEvaluator:
 class SystematicResampler:
     """Systematic resampling on the GPU with the reference's recurrence (novel_resampling.h:41-72).
 
-    The reference draws U0 ~ uniform_real_distribution<float>(0, 1/N) from its own std::mt19937; here U0 comes from a
-    seeded numpy Generator or is passed explicitly (parity is defined "given the same weights and the same U0").
+    ``resample(particle_cloud)`` mirrors ``Resampler::resample(ParticleCloud&)`` (resampler.h:26): a weighted particle set
+    in, the resampled set out (its length is whatever the reference recurrence emits — usually n, SURVEY §2.5(11));
+    copies keep the parent's weight. The reference draws U0 ~ uniform_real_distribution<float>(0, 1/N) from its own
+    std::mt19937; here U0 comes from a seeded numpy Generator or is passed explicitly (parity is defined "given the
+    same weights and the same U0"). The GPU context (device, stream, scratch) is borrowed from an evaluator.
     """
 
-    def __init__(self, seed: Optional[int] = None):
+    def __init__(self, evaluator, seed: Optional[int] = None):
+        self._ev = evaluator.cuda_evaluator_ if isinstance(evaluator, TSDFEvaluator) else evaluator
         self._rng = np.random.default_rng(seed)
 
     def draw_u0(self, n: int) -> float:
@@ -247,16 +251,25 @@ class SystematicResampler:
             u = np.nextafter(u, np.float32(0.0))
         return float(u)
 
-    def resample(self, evaluator, n: Optional[int] = None, u0: Optional[float] = None, want_parents: bool = False):
-        """Resample the particle set that ``evaluator``'s last evaluate() left on the device.
-
-        Returns the new ``float32[n_out, 7]`` particle array (n_out is whatever the reference recurrence emits —
-        usually n); copies keep the parent's normalised weight.
-        """
-        ev = evaluator.cuda_evaluator_ if isinstance(evaluator, TSDFEvaluator) else evaluator
-        if n is None:
-            raise ValueError("n (current particle count) is required")
+    def resample(self, particle_cloud: np.ndarray, u0: Optional[float] = None, want_parents: bool = False):
+        ps = _f32(particle_cloud, 7, "particle_cloud")
+        n = ps.shape[0]
         if u0 is None:
             u0 = self.draw_u0(n)
         cap = n + n // 8 + 64
-        return ev.resample_systematic(u0, capacity=cap, want_parents=want_parents)
+        out = np.empty((cap, 7), dtype=np.float32)
+        parents = np.empty(cap, dtype=np.uint32) if want_parents else None
+        n_out = C.c_uint64(0)
+        lib = self._ev._lib
+        rc = lib.tsdfloc_resample_particles(self._ev.ctx, ps.ctypes.data_as(C.c_void_p), n, C.c_float(u0),
+                                            out.ctypes.data_as(C.c_void_p), cap, C.byref(n_out),
+                                            parents.ctypes.data_as(C.c_void_p) if want_parents else None)
+        capi.check(lib, self._ev.ctx, rc)
+        m = int(n_out.value)
+        return (out[:m], parents[:m]) if want_parents else out[:m]
+
+    def resample_resident(self, n: int, u0: Optional[float] = None, want_parents: bool = False):
+        """Resample the particle set the evaluator's last evaluate() left on the device (no re-upload)."""
+        if u0 is None:
+            u0 = self.draw_u0(n)
+        return self._ev.resample_systematic(u0, capacity=n + n // 8 + 64, want_parents=want_parents)

@@ -41,11 +41,30 @@ def box_sdf(p: np.ndarray, lo: np.ndarray, hi: np.ndarray) -> np.ndarray:
     return -(outside + inside)
 
 
+CHUNK_VOXELS = 64      # grid_map.h:18 CHUNK_SIZE: the real pipeline's maps are unions of 64^3-voxel HDF5 chunks
+
+
+def chunk_aligned_bounds(room_lo, room_hi, resolution: float):
+    """Bounding box createTSDFMap would compute for this room (map_util.h:27-66): the union of the 64^3-voxel chunks that
+    hold any stored voxel, i.e. the room grown by the truncation band and rounded outwards to chunk edges."""
+    edge = CHUNK_VOXELS * resolution
+    band = TRUNCATION_MM * 1e-3
+    lo = np.floor((np.asarray(room_lo, dtype=np.float64) - band) / edge + 1e-9) * edge
+    hi = np.ceil((np.asarray(room_hi, dtype=np.float64) + band) / edge - 1e-9) * edge
+    return lo, hi
+
+
 def box_room_map(value_fn, init_value: float, room_lo=(-10.0, -10.0, 0.0), room_hi=(10.0, 10.0, 5.0), resolution: float = 0.05,
-                 margin: float = 0.0) -> MapSpec:
-    """Config C1–C3 map: an empty box room; bounding box = room (+ margin). 20x20x5 m @ 5 cm -> 1,028 bricks (margin 0)."""
-    lo = np.asarray(room_lo, dtype=np.float64) - margin
-    hi = np.asarray(room_hi, dtype=np.float64) + margin
+                 margin: float | None = None) -> MapSpec:
+    """Config C1–C3 map: an empty box room with the +-0.6 m truncation band stored around all six faces.
+    margin=None (default): chunk-aligned bounding box like the real pipeline's (20x20x5 m @ 5 cm -> 25.6x25.6x9.6 m box);
+    margin=m: bounding box = room grown by m on every side (m = 0 puts the walls ON the box faces, which makes a quarter
+    of all lookups land at negative offsets — the reference's undefined-behaviour band, used by the policy tests)."""
+    if margin is None:
+        lo, hi = chunk_aligned_bounds(room_lo, room_hi, resolution)
+    else:
+        lo = np.asarray(room_lo, dtype=np.float64) - margin
+        hi = np.asarray(room_hi, dtype=np.float64) + margin
     dims = np.ceil((hi - lo) / resolution - 1e-9).astype(np.int64)
     lut = _likelihood_lut(value_fn)
     rlo, rhi = np.asarray(room_lo, dtype=np.float64), np.asarray(room_hi, dtype=np.float64)
