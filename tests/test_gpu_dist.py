@@ -1,0 +1,107 @@
+"""GPU tests of the particle-sharded update (north star item 4): R-rank results must be IDENTICAL to the 1-rank result.
+
+* On one GPU the ranks are emulated by threads, each with its own tsdfloc ctx + stream on cuda:0, and an all-gather that
+  copies between the ranks' buffers at a thread barrier — the product's GpuStages / ShardedSensorUpdate code is what runs.
+* With >= 2 GPUs (gpurun --gpus 2) a real torchrun/NCCL run of the same check is launched as a subprocess.
+"""
+import os
+import subprocess
+import sys
+import threading
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import common
+from tsdf_localization_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _single(m, ps, pts, tf, u0):
+    import torch
+    from tsdf_localization_b200 import CudaEvaluator
+    from tsdf_localization_b200.dist import GpuStages, ShardedSensorUpdate
+    dev = torch.device("cuda", 0)
+    ev = CudaEvaluator(m)
+    upd = ShardedSensorUpdate(GpuStages(ev), device=dev)
+    upd.set_scan(torch.from_numpy(pts).to(dev))
+    d = torch.from_numpy(ps).to(dev)
+    out, mean, n_out, wsum = upd.step(d, len(ps), tf, u0)
+    res = (out.cpu().numpy().copy(), d.cpu().numpy().copy(), mean.cpu().numpy().copy(), n_out, wsum)
+    ev.close()
+    return res
+
+
+@pytest.mark.parametrize("world,n", [(2, 4096), (3, 1000), (8, 5000)])
+def test_thread_emulated_ranks_equal_single_rank(world, n):
+    import torch
+    from tsdf_localization_b200 import CudaEvaluator
+    from tsdf_localization_b200.dist import GpuStages, ShardedSensorUpdate
+
+    _, m = common.box_room()
+    pts, _ = syn.make_scan("vlp16", syn.GT_POSE, n_points=4000)
+    ps = syn.tracking_particles(n, syn.GT_POSE)
+    tf, u0 = syn.CALIB_TF, 0.37 / n
+    single = _single(m, ps, pts, tf, u0)
+
+    dev = torch.device("cuda", 0)
+    bar = threading.Barrier(world)
+    pending = {}
+    results, errors = {}, []
+
+    def make_all_gather(rank):
+        def all_gather(out, inp):
+            # publish my slice, wait for everyone, copy the peers' slices into my output buffer
+            torch.cuda.current_stream().synchronize()
+            pending[rank] = inp
+            bar.wait()
+            k = inp.numel()
+            for r in range(world):
+                if r != rank:
+                    out[r * k:(r + 1) * k].copy_(pending[r])
+            torch.cuda.current_stream().synchronize()
+            bar.wait()
+        return all_gather
+
+    def run(rank):
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+                ev = CudaEvaluator(m)
+                upd = ShardedSensorUpdate(GpuStages(ev), world=world, rank=rank, device=dev, all_gather=make_all_gather(rank))
+                upd.set_scan(torch.from_numpy(pts).to(dev))
+                d = torch.from_numpy(ps).to(dev)
+                out, mean, n_out, wsum = upd.step(d, n, tf, u0)
+                results[rank] = (out.cpu().numpy().copy(), d.cpu().numpy().copy(), mean.cpu().numpy().copy(), n_out, wsum)
+                ev.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((rank, repr(e)))
+            bar.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not errors, errors
+    for r in range(world):
+        out, d, mean, n_out, wsum = results[r]
+        assert n_out == single[3] and wsum == single[4]
+        assert d.tobytes() == single[1].tobytes(), f"rank {r}: normalised weights differ from the 1-rank run"
+        assert out.tobytes() == single[0].tobytes(), f"rank {r}: resampled particles differ from the 1-rank run"
+        assert mean.tobytes() == single[2].tobytes()
+
+
+def test_nccl_two_ranks_equal_single_rank():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", str(ROOT / "tests" / "dist_nccl_check.py")]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "NCCL_CHECK_OK" in res.stdout

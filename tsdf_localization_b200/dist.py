@@ -93,12 +93,18 @@ class ShardedSensorUpdate:
     """
 
     def __init__(self, stages, world: int = 1, rank: int = 0, group=None, device: Optional[torch.device] = None,
-                 max_particles: int = 0):
+                 max_particles: int = 0, all_gather=None):
         self.stages = stages
         self.world, self.rank, self.group = int(world), int(rank), group
+        # all_gather(out_flat, in_flat): torch.distributed (NCCL on GPUs, gloo in the CPU tests) unless injected
+        self._all_gather = all_gather if all_gather is not None else self._dist_all_gather
         self.device = device if device is not None else torch.device("cpu")
         self._cap = 0
         self._reserve(max_particles)
+
+    def _dist_all_gather(self, out: torch.Tensor, inp: torch.Tensor) -> None:
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(out, inp, group=self.group)
 
     def _reserve(self, n: int) -> None:
         if n <= self._cap:
@@ -119,20 +125,19 @@ class ShardedSensorUpdate:
         """particles: float32[>= n, 7] on this rank's device, identical on every rank. Returns (resampled particles
         float32[n_out, 7] — a view into an internal buffer, valid until the next step —, mean pose float32[6] tensor,
         n_out, weight_sum). particles[:, 6] is overwritten with the normalised weights (cuda_eval_particles.h:556)."""
-        import torch.distributed as dist
         W, r = self.world, self.rank
         self._reserve(n)
         chunk, first, count = shard(n, W, r)
         self.stages.eval(particles, n, first, count, tf, self.raw)
         if W > 1:
-            dist.all_gather_into_tensor(self.raw[:W * chunk], self.raw[r * chunk:(r + 1) * chunk], group=self.group)
+            self._all_gather(self.raw[:W * chunk], self.raw[r * chunk:(r + 1) * chunk])
         self.stages.normalize(particles, n, self.raw, self.mean)
         ocap = output_capacity(n, W)
         ochunk = ocap // W
         out = self.out[:ocap]
         self.stages.draw(particles, n, u0, r * ochunk, ochunk, out[r * ochunk:(r + 1) * ochunk])
         if W > 1:
-            dist.all_gather_into_tensor(out.view(-1), out[r * ochunk:(r + 1) * ochunk].reshape(-1), group=self.group)
+            self._all_gather(out.view(-1), out[r * ochunk:(r + 1) * ochunk].reshape(-1))
         n_out, wsum = self.stages.check()
         if n_out > ocap:
             raise RuntimeError(f"resampling emits {n_out} particles, capacity is {ocap}")
@@ -141,13 +146,12 @@ class ShardedSensorUpdate:
     def evaluate_only(self, particles: torch.Tensor, n: int, tf):
         """Evaluation + normalisation without resampling (what the reference's evaluate() covers). Returns
         (mean pose tensor, weight_sum); normalised weights are left in particles[:, 6] on every rank."""
-        import torch.distributed as dist
         W, r = self.world, self.rank
         self._reserve(n)
         chunk, first, count = shard(n, W, r)
         self.stages.eval(particles, n, first, count, tf, self.raw)
         if W > 1:
-            dist.all_gather_into_tensor(self.raw[:W * chunk], self.raw[r * chunk:(r + 1) * chunk], group=self.group)
+            self._all_gather(self.raw[:W * chunk], self.raw[r * chunk:(r + 1) * chunk])
         self.stages.normalize(particles, n, self.raw, self.mean)
         _, wsum = self.stages.check()
         return self.mean[:6], wsum
