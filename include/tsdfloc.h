@@ -143,7 +143,8 @@ int tsdfloc_debug_eval(tsdfloc_ctx* ctx, const float* particles, uint64_t n, con
 
 /* ---- (B) device-pointer stage calls ---------------------------------------------------------------------
  * All pointers are device pointers on ctx's device; `stream` is a cudaStream_t passed as void* (NULL = the
- * ctx's own stream). Calls enqueue work and return without synchronising unless stated. */
+ * ctx's own non-blocking stream; pass cudaStreamLegacy / cudaStreamPerThread explicitly for the default streams).
+ * Calls enqueue work and return without synchronising unless stated. */
 
 /* Scan upload + preparation: packs xyz into float4 with the per-point range term
  * (a_range/max_range inside max_range, else a_max; cuda_eval_particles.h:200-209) and reduces their sum. */

@@ -32,6 +32,9 @@
 #include <tsdf_localization/evaluation/model/likelihood_evaluation.h>
 #include <tsdf_localization/resampling/novel_resampling.h>
 #include <tsdf_localization/util/constant.h>
+#ifdef TSDF_REF_WITH_B200_SHIM
+#include "tsdfloc_shim.h"
+#endif
 
 namespace tsdf_localization
 {
@@ -301,5 +304,35 @@ uint64_t ref_systematic_resample(const float* particles, uint64_t n, uint32_t se
   }
   return m;
 }
+
+#ifdef TSDF_REF_WITH_B200_SHIM
+// GpuSystematicResampler (the product's Resampler subclass) through the reference's Resampler interface, same seed
+// handling as ref_systematic_resample. Needs a live evaluator created by ref_eval_create (it owns the GPU context).
+uint64_t ref_gpu_systematic_resample(const float* particles, uint64_t n, uint32_t seed, float* particles_out, uint64_t cap)
+{
+  try
+  {
+    ParticleCloud cloud;
+    cloud.particles().resize(n);
+    std::memcpy(static_cast<void*>(cloud.particles().data()), particles, n * sizeof(Particle));
+    GpuSystematicResampler rs;
+    rs.seed(seed);
+    Resampler& base = rs;
+    base.resample(cloud);
+    const uint64_t m = cloud.size();
+    const uint64_t c = m < cap ? m : cap;
+    if (particles_out && c) std::memcpy(particles_out, static_cast<void*>(cloud.particles().data()), c * sizeof(Particle));
+    return m;
+  }
+  catch (std::exception& ex)
+  {
+    g_last_error = ex.what();
+    return ~0ull;
+  }
+}
+int ref_has_b200_shim() { return 1; }
+#else
+int ref_has_b200_shim() { return 0; }
+#endif
 
 }  // extern "C"

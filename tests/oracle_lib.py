@@ -162,12 +162,21 @@ def ref_available() -> bool:
     return ref_lib_path().exists()
 
 
+def ref_shim_path() -> Path:
+    return ORACLE_DIR / "_ref" / "libtsdf_ref_shim.so"
+
+
 class Ref:
     """The verbatim reference (oracle/ref_harness.cpp)."""
 
-    def __init__(self, threads: int | None = None):
-        self.lib = C.CDLL(str(ref_lib_path(threads)))
+    def __init__(self, threads: int | None = None, shim: bool = False):
+        """shim=True: the same reference classes linked against the product's drop-in CudaEvaluator shim + libtsdfloc.so
+        (evaluate(use_cuda=True) and GpuSystematicResampler then run on the B200)."""
+        self.lib = C.CDLL(str(ref_shim_path() if shim else ref_lib_path(threads)))
         L = self.lib
+        if shim:
+            L.ref_gpu_systematic_resample.restype = C.c_uint64
+            L.ref_gpu_systematic_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64]
         L.ref_last_error.restype = C.c_char_p
         L.ref_omp_threads.restype = C.c_uint
         L.ref_map_create.restype = C.c_void_p
@@ -223,12 +232,25 @@ class Ref:
     def eval_destroy(self, e):
         self.lib.ref_eval_destroy(e)
 
-    def evaluate(self, e, particles, points, tf):
+    def last_error(self) -> str:
+        return self.lib.ref_last_error().decode()
+
+    def gpu_systematic_resample(self, particles, seed, cap=None):
+        ps = np.ascontiguousarray(particles, dtype=np.float32)
+        n = ps.shape[0]
+        cap = cap or (n + n // 8 + 64)
+        out = np.empty((cap, 7), dtype=np.float32)
+        m = int(self.lib.ref_gpu_systematic_resample(_fp(ps), n, seed, _fp(out), cap))
+        if m == 2 ** 64 - 1:
+            raise RuntimeError(self.last_error())
+        return m, out[:min(m, cap)]
+
+    def evaluate(self, e, particles, points, tf, use_cuda: bool = False):
         ps = np.array(particles, dtype=np.float32, copy=True, order="C")
         pts = np.ascontiguousarray(points, dtype=np.float32)
         tf = np.ascontiguousarray(tf, dtype=np.float32)
         pose = np.zeros(7, dtype=np.float64)
-        rc = self.lib.ref_evaluate(e, _fp(ps), ps.shape[0], _fp(pts), pts.shape[0], _fp(tf), 0, _fp(pose))
+        rc = self.lib.ref_evaluate(e, _fp(ps), ps.shape[0], _fp(pts), pts.shape[0], _fp(tf), 1 if use_cuda else 0, _fp(pose))
         err = self.lib.ref_last_error().decode() if rc else ""
         return rc, ps, pose, err
 

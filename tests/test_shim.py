@@ -1,0 +1,94 @@
+"""The drop-in seam itself: the reference's OWN TSDFEvaluator / Resampler classes (compiled unmodified from /root/reference
+into oracle/_ref/libtsdf_ref_shim.so) linked against the product's C++ shim (tsdf_localization_b200/shim) + libtsdfloc.so.
+`TSDFEvaluator::evaluate(particles, points, tf, use_cuda=true)` (tsdf_evaluator.cpp:82) then runs on the B200, and its result
+is compared with the same object's CPU/OpenMP branch (use_cuda=false) — the reference checking its replacement."""
+import numpy as np
+import pytest
+
+import common
+from oracle_lib import Ref, ref_shim_path
+from tsdf_localization_b200 import synthetic as syn
+
+pytestmark = pytest.mark.skipif(not ref_shim_path().exists(), reason="oracle/_ref/libtsdf_ref_shim.so not built")
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+@pytest.fixture(scope="module")
+def shim():
+    return Ref(shim=True)
+
+
+@pytest.fixture(scope="module")
+def small_map(shim):
+    spec, _ = common.box_room(small=True)
+    rm = shim.map_create(spec.min, spec.max, spec.resolution, spec.init_value)
+    assert shim.map_set_data(rm, spec.cells) == 0
+    yield rm
+    shim.map_destroy(rm)
+
+
+def _workload(n=512, p=3000):
+    gt = (0.4, -0.3, 1.2, 0.01, -0.02, 0.4)
+    pts, _ = syn.make_scan("vlp16", gt, room_lo=(-3.0, -2.5, 0.0), room_hi=(3.0, 2.5, 3.0), n_points=p)
+    ps = syn.tracking_particles(n, gt, sigma_xy=0.2)
+    return ps, pts
+
+
+def test_constructor_fails_loudly_without_gpu(shim, small_map):
+    if _has_gpu():
+        pytest.skip("a GPU is present")
+    ev = shim.eval_create(small_map)     # TSDFEvaluator's ctor constructs CudaEvaluator unconditionally (tsdf_evaluator.h:78)
+    assert not ev
+    err = shim.last_error()
+    assert "Error while creating the CUDA context for the map!" in err and "no CPU fallback" in err
+
+
+@pytest.mark.gpu
+def test_reference_facade_gpu_branch_matches_its_cpu_branch(shim, small_map):
+    ev = shim.eval_create(small_map)
+    assert ev, shim.last_error()
+    ps, pts = _workload()
+    rc_c, cpu, pose_c, err_c = shim.evaluate(ev, ps, pts, syn.CALIB_TF, use_cuda=False)
+    rc_g, gpu, pose_g, err_g = shim.evaluate(ev, ps, pts, syn.CALIB_TF, use_cuda=True)
+    assert rc_c == 0 and rc_g == 0, (err_c, err_g)
+    assert np.array_equal(gpu[:, :6], ps[:, :6])
+    rel = common.rel_err(gpu[:, 6], cpu[:, 6])
+    assert rel.max() <= 1e-5, f"normalised weights: max rel err {rel.max():.2e}"      # north-star tolerance
+    np.testing.assert_allclose(pose_g, pose_c, atol=1e-5)
+    shim.eval_destroy(ev)
+
+
+@pytest.mark.gpu
+def test_reference_facade_gpu_branch_errors(shim, small_map):
+    ev = shim.eval_create(small_map, 0.9, 0.0, 0.0, 100.0)
+    ps, pts = _workload(16, 64)
+    far = ps.copy()
+    far[:, :3] += 500.0
+    rc, _, _, err = shim.evaluate(ev, far, pts, syn.IDENTITY_TF, use_cuda=True)
+    assert rc == 1 and err == "No particle is valid!"
+    # empty scan: default pose, weights untouched (cuda_evaluator.cu:122-125)
+    ps[:, 6] = 0.25
+    rc, out, pose, _ = shim.evaluate(ev, ps, np.zeros((0, 3), dtype=np.float32), syn.IDENTITY_TF, use_cuda=True)
+    assert rc == 0 and np.array_equal(out, ps) and not pose.any()
+    shim.eval_destroy(ev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [500, 4096, 100000])
+def test_gpu_resampler_subclass_matches_reference_resampler(shim, small_map, n):
+    ev = shim.eval_create(small_map)      # owns the GPU context the resampler borrows
+    rng = np.random.default_rng(n)
+    ps = np.zeros((n, 7), dtype=np.float32)
+    ps[:, :6] = rng.normal(size=(n, 6))
+    w = rng.exponential(size=n) ** 2
+    ps[:, 6] = (w / w.sum()).astype(np.float32)
+    for seed in (1, 7):
+        m_ref, out_ref, _ = shim.systematic_resample(ps, seed)
+        m_gpu, out_gpu = shim.gpu_systematic_resample(ps, seed)
+        assert m_gpu == m_ref
+        assert np.array_equal(out_gpu, out_ref)
+    shim.eval_destroy(ev)

@@ -46,7 +46,10 @@ class GpuStages:
 
     @staticmethod
     def _stream() -> C.c_void_p:
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        # NULL means "the ctx's own stream" in the C ABI; torch's default stream has handle 0, which is CUDA's legacy
+        # default stream -> pass cudaStreamLegacy (0x1) so the kernels are ordered with torch's and NCCL's work on it.
+        h = torch.cuda.current_stream().cuda_stream
+        return C.c_void_p(h if h else 1)
 
     def set_scan(self, d_points: torch.Tensor) -> None:
         assert d_points.is_cuda and d_points.dtype == torch.float32 and d_points.is_contiguous()

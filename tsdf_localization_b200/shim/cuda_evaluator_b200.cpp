@@ -1,0 +1,168 @@
+// cuda_evaluator_b200.cpp — drop-in replacement for the reference's src/cuda/cuda_evaluator.cu.
+//
+// Compiled INTO the reference package in place of src/cuda/cuda_evaluator.cu (+ cuda_sum.cu, cuda_util.cu) and linked
+// against libtsdfloc.so: it defines the four CudaEvaluator symbols the reference's own header declares
+// (include/tsdf_localization/cuda/cuda_evaluator.h:109-121), so TSDFEvaluator (evaluation/tsdf_evaluator.h:78),
+// mcl_3d (src/mcl_3d.cpp:749) and num_particles_eval (src/num_particles_eval.cpp:206) compile and link UNCHANGED.
+// All numeric work happens behind the C ABI (include/tsdfloc.h); this file only adapts types and error behaviour:
+//
+//   reference behaviour                                                         here
+//   ctor uploads the map, wraps failures in "Error while creating ..."          tsdfloc_create            (cuda_evaluator.cu:21-59)
+//   evaluate(): empty scan -> default pose, weights untouched                   same                      (:122-125)
+//   evaluate(): normalised weights written to particles[i].second, in order     tsdfloc_sensor_update     (:397-408)
+//   evaluate(): "No particle is valid!" when the weight sum is 0                TSDFLOC_E_NO_VALID_PARTICLE -> same text (:366-369)
+//   evaluate(): pose = weighted mean xyz + setRPY(atan2 means), covariance 0     same                      (:410-423)
+//   any CUDA failure -> std::runtime_error                                      TSDFLOC_E_CUDA -> std::runtime_error(last_error)
+//
+// The header's private data members stay as they are (binary layout unchanged); the tsdfloc context handle is kept
+// in the otherwise unused `d_transform_` pointer.
+#include <tsdf_localization/cuda/cuda_evaluator.h>
+
+#include <sensor_msgs/point_cloud2_iterator.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "tsdfloc.h"
+#include "tsdfloc_shim.h"
+
+namespace tsdf_localization
+{
+
+static_assert(sizeof(Particle) == 7 * sizeof(float), "Particle must be 7 packed floats (particle.h:26-55)");
+static_assert(sizeof(CudaPoint) == 3 * sizeof(float), "CudaPoint must be 3 packed floats (cuda_evaluator.h:22-39)");
+
+namespace
+{
+std::mutex g_ctx_mutex;
+tsdfloc_ctx* g_last_ctx = nullptr;
+
+inline tsdfloc_ctx* ctx_of(FLOAT_T* slot) { return reinterpret_cast<tsdfloc_ctx*>(slot); }
+}  // namespace
+
+tsdfloc_ctx* tsdfloc_shim_context()
+{
+  std::lock_guard<std::mutex> lock(g_ctx_mutex);
+  return g_last_ctx;
+}
+
+CudaEvaluator::CudaEvaluator(CudaSubVoxelMap<FLOAT_T, FLOAT_T>& map, bool per_point, FLOAT_T a_hit, FLOAT_T a_range, FLOAT_T a_max, FLOAT_T max_range)
+: d_map_(nullptr), per_point_(per_point), d_grid_occ_(nullptr), d_data_(nullptr), d_particles_(nullptr), d_particles_ordered_(nullptr),
+  particles_reserved_(0), d_points_(nullptr), d_points_ordered_(nullptr), points_reserved_(0), d_transform_(nullptr), d_new_weights_(nullptr),
+  d_point_weights_(nullptr), point_weights_size_(0), p_x_(nullptr), p_y_(nullptr), p_z_(nullptr), sin_a_(nullptr), cos_a_(nullptr),
+  sin_b_(nullptr), cos_b_(nullptr), sin_c_(nullptr), cos_c_(nullptr), a_hit_(a_hit), a_range_(a_range), a_max_(a_max), max_range_(max_range),
+  inv_max_range_(1.0 / max_range), max_range_squared_(max_range * max_range)
+{
+  const auto& c = map.coef();
+  tsdfloc_map_desc d{};
+  d.dim[0] = c.dim_x_; d.dim[1] = c.dim_y_; d.dim[2] = c.dim_z_;
+  d.min[0] = c.min_x_; d.min[1] = c.min_y_; d.min[2] = c.min_z_;
+  d.max[0] = c.max_x_; d.max[1] = c.max_y_; d.max[2] = c.max_z_;
+  d.resolution = c.resolution_;
+  d.init_value = c.init_value_;
+  d.up_dim[0] = c.up_dim_x_; d.up_dim[1] = c.up_dim_y_; d.up_dim[2] = c.up_dim_z_;
+  d.up_dim_2 = c.up_dim_2_;
+  d.sub_dim = c.sub_dim_;
+  d.sub_dim_2 = c.sub_dim_2_;
+  d.grid_occ_size = c.grid_occ_size_;
+  d.data_size = c.data_size_;
+
+  tsdfloc_params prm{};
+  tsdfloc_default_params(&prm);
+  prm.a_hit = a_hit;
+  prm.a_range = a_range;
+  prm.a_max = a_max;
+  prm.max_range = max_range;
+  prm.per_point = per_point ? 1 : 0;
+
+  int device = 0;
+  if (const char* e = std::getenv("TSDFLOC_DEVICE")) device = std::atoi(e);
+  tsdfloc_ctx* ctx = nullptr;
+  static_assert(sizeof(OCC_T) == sizeof(int32_t), "OCC_T must be a 32-bit int (cuda_sub_voxel_map.h:13)");
+  const int rc = tsdfloc_create(&d, reinterpret_cast<const int32_t*>(map.rawGridOcc()), map.rawData(), &prm, device, &ctx);
+  if (rc != TSDFLOC_OK)
+  {
+    // same wrapper text as cuda_evaluator.cu:52-55, with the cause appended
+    throw std::runtime_error(std::string("Error while creating the CUDA context for the map! ") + tsdfloc_last_error(nullptr));
+  }
+  d_map_ = &map;
+  d_transform_ = reinterpret_cast<FLOAT_T*>(ctx);
+  std::lock_guard<std::mutex> lock(g_ctx_mutex);
+  g_last_ctx = ctx;
+}
+
+CudaEvaluator::~CudaEvaluator()
+{
+  tsdfloc_ctx* ctx = ctx_of(d_transform_);
+  {
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    if (g_last_ctx == ctx) g_last_ctx = nullptr;
+  }
+  tsdfloc_destroy(ctx);
+  d_transform_ = nullptr;
+}
+
+// PointCloud2 overload (cuda_evaluator.cu:78-116): ring-major ordering, then the ring-agnostic 6.4 cm cell-centre
+// reduction, then the vector overload. No caller in the reference; kept for interface completeness.
+geometry_msgs::PoseWithCovariance CudaEvaluator::evaluate(std::vector<Particle>& particles, const sensor_msgs::PointCloud2& real_cloud, FLOAT_T tf_matrix[16])
+{
+  sensor_msgs::PointCloud2ConstIterator<float> iter_x(real_cloud, "x");
+  sensor_msgs::PointCloud2ConstIterator<int> iter_ring(real_cloud, "ring");
+  std::multimap<int, CudaPoint> by_ring;
+  for (; iter_x != iter_x.end(); ++iter_x, ++iter_ring)
+  {
+    by_ring.insert(std::pair<int, CudaPoint>(iter_ring[0], CudaPoint(iter_x[0], iter_x[1], iter_x[2])));
+  }
+  std::unordered_set<CudaPoint, hash> cells;
+  for (const auto& entry : by_ring)
+  {
+    const CudaPoint& p = entry.second;
+    cells.insert(CudaPoint(static_cast<float>(std::floor(p.x / 0.064) * 0.064 + 0.032),
+                           static_cast<float>(std::floor(p.y / 0.064) * 0.064 + 0.032),
+                           static_cast<float>(std::floor(p.z / 0.064) * 0.064 + 0.032)));
+  }
+  std::vector<CudaPoint> reduced(cells.begin(), cells.end());
+  return evaluate(particles, reduced, tf_matrix);
+}
+
+geometry_msgs::PoseWithCovariance CudaEvaluator::evaluate(std::vector<Particle>& particles, const std::vector<CudaPoint>& points, FLOAT_T tf_matrix[16])
+{
+  if (points.size() == 0)
+  {
+    return geometry_msgs::PoseWithCovariance();
+  }
+  tsdfloc_ctx* ctx = ctx_of(d_transform_);
+  float mean[6] = {0, 0, 0, 0, 0, 0};
+  const int rc = tsdfloc_sensor_update(ctx, reinterpret_cast<float*>(particles.data()), particles.size(),
+                                       reinterpret_cast<const float*>(points.data()), points.size(), tf_matrix, mean);
+  if (rc == TSDFLOC_E_NO_VALID_PARTICLE)
+  {
+    throw std::runtime_error("No particle is valid!");
+  }
+  if (rc != TSDFLOC_OK)
+  {
+    throw std::runtime_error(std::string("Error occured during the sensor update on the gpu! ") + tsdfloc_last_error(ctx));
+  }
+
+  geometry_msgs::PoseWithCovariance average_pose;
+  average_pose.pose.position.x = mean[0];
+  average_pose.pose.position.y = mean[1];
+  average_pose.pose.position.z = mean[2];
+  // tf2::Quaternion::setRPY(roll, pitch, yaw) written out (ZYX half-angle formula), as cuda_evaluator.cu:414-416 uses it
+  const double hr = 0.5 * mean[3], hp = 0.5 * mean[4], hy = 0.5 * mean[5];
+  const double cr = std::cos(hr), sr = std::sin(hr), cp = std::cos(hp), sp = std::sin(hp), cy = std::cos(hy), sy = std::sin(hy);
+  average_pose.pose.orientation.x = sr * cp * cy - cr * sp * sy;
+  average_pose.pose.orientation.y = cr * sp * cy + sr * cp * sy;
+  average_pose.pose.orientation.z = cr * cp * sy - sr * sp * cy;
+  average_pose.pose.orientation.w = cr * cp * cy + sr * sp * sy;
+  for (auto& v : average_pose.covariance) v = 0.0;  // the reference leaves all six variances at 0 (cuda_evaluator.cu:418-423)
+  return average_pose;
+}
+
+}  // namespace tsdf_localization
