@@ -32,9 +32,11 @@ def small_map(shim):
 
 
 def _workload(n=512, p=3000):
+    """Tight tracking cloud: no lookup lands at a negative axis offset (the small room's box is only 0.7 m wider than the room
+    in y), so the reference's CPU branch is well defined everywhere and must agree with the GPU branch."""
     gt = (0.4, -0.3, 1.2, 0.01, -0.02, 0.4)
     pts, _ = syn.make_scan("vlp16", gt, room_lo=(-3.0, -2.5, 0.0), room_hi=(3.0, 2.5, 3.0), n_points=p)
-    ps = syn.tracking_particles(n, gt, sigma_xy=0.2)
+    ps = syn.tracking_particles(n, gt, sigma_xy=0.05, sigma_z=0.05, sigma_yaw=0.03)
     return ps, pts
 
 
@@ -58,7 +60,10 @@ def test_reference_facade_gpu_branch_matches_its_cpu_branch(shim, small_map):
     assert np.array_equal(gpu[:, :6], ps[:, :6])
     rel = common.rel_err(gpu[:, 6], cpu[:, 6])
     assert rel.max() <= 1e-5, f"normalised weights: max rel err {rel.max():.2e}"      # north-star tolerance
-    np.testing.assert_allclose(pose_g, pose_c, atol=1e-5)
+    np.testing.assert_allclose(pose_g[3:], pose_c[3:], atol=1e-5)       # orientation (race-free in the reference)
+    # position: the reference's CPU xyz mean is racy (lost updates, see test_oracle_vs_ref); check against the weights instead
+    xyz = (gpu[:, :3].astype(np.float64) * gpu[:, 6:7].astype(np.float64)).sum(0)
+    np.testing.assert_allclose(pose_g[:3], xyz, atol=1e-5)
     shim.eval_destroy(ev)
 
 
