@@ -51,6 +51,10 @@ def main():
             st = (C.c_uint64 * 4)()
             lib.tsdfloc_eval_stats(ev.ctx, st)
             print(f"eval blocks {st[0]} folded {st[1]} ({100.0 * st[1] / max(st[0], 1):.2f}%) tie-folds {st[2]}")
+        if it == reps + 1:
+            import hashlib
+            print("raw sha", hashlib.sha256(d_raw.cpu().numpy().tobytes()).hexdigest()[:16], "variant",
+                  {k: v for k, v in __import__("os").environ.items() if k.startswith("TSDFLOC_")})
         print(f"it{it}: N={n} P={P} eval {t_eval:.3f} ms ({n * P / t_eval / 1e6:.1f} Geval/s)  normalise {t_norm:.3f} ms  draw {t_draw:.3f} ms  n_out={n_out.value} sum={ws.value:.6g}")
 
 

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
@@ -34,7 +35,9 @@ class Params(C.Structure):
 
 
 def lib_path() -> Path:
-    return PKG / "lib" / "libtsdfloc.so"
+    # TSDFLOC_LIB: alternative build of the same library (kernel tuning experiments); never a different implementation
+    override = os.environ.get("TSDFLOC_LIB")
+    return Path(override) if override else PKG / "lib" / "libtsdfloc.so"
 
 
 _LIB = None

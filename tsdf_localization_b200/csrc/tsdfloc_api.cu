@@ -7,6 +7,7 @@
 // No CPU fallback anywhere: without a CUDA device every compute entry point fails with TSDFLOC_E_CUDA.
 #include "../../include/tsdfloc.h"
 #include "tsdfloc_kernels.cuh"
+#include "tsdfloc_eval2.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -44,6 +45,8 @@ struct tsdfloc_ctx
   float x_bound = 0.0f;     // upper bound of one point's contribution a_hit*v + term (k_eval block planning)
   uint32_t force_seq = 0;   // 1: contributions may be negative / non-finite -> always fold sequentially
   uint64_t launches = 0;
+  int eval_version = 2;     // 2: k_eval2 (TMA-streamed scan tiles); 1: k_eval (tuning/regression comparisons, TSDFLOC_EVAL=1)
+  int eval_w = 0, eval_bs = 0;  // 0: automatic; TSDFLOC_W / TSDFLOC_BS override for tuning experiments
   cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;  // bracket the last k_eval launch (tsdfloc_last_eval_ms)
   bool eval_timed = false;
 
@@ -170,12 +173,13 @@ int stage_prep_scan(tsdfloc_ctx* c, const float* d_xyz, uint64_t p, cudaStream_t
 {
   if (p > 0x7fffffffull) return fail(c, TSDFLOC_E_BAD_ARG, "scan larger than 2^31 points");
   int rc;
-  if ((rc = ensure(c, c->d_pts, sizeof(float4) * (p + 64), "cudaMalloc(scan)"))) return rc;
+  // the evaluation kernel pulls whole 256-point tiles (TMA bulk copies): pad to a tile multiple and keep the pad defined
+  const uint64_t padded = (p + kTilePoints - 1) / kTilePoints * kTilePoints + kTilePoints;
+  if ((rc = ensure(c, c->d_pts, sizeof(float4) * padded, "cudaMalloc(scan)"))) return rc;
   c->n_points = p;
   if (p == 0) return TSDFLOC_OK;
-  // the evaluation kernel reads whole 32-point steps: keep the tail of the last step defined
   {
-    cudaError_t me = cudaMemsetAsync(static_cast<float4*>(c->d_pts.p) + p, 0, sizeof(float4) * 64, s);
+    cudaError_t me = cudaMemsetAsync(static_cast<float4*>(c->d_pts.p) + p, 0, sizeof(float4) * (padded - p), s);
     if (me != cudaSuccess) return fail(c, TSDFLOC_E_CUDA, std::string("memset(scan pad): ") + cudaGetErrorString(me));
   }
   const float a_range_term = c->prm.a_range * static_cast<float>(1.0 / c->prm.max_range);
@@ -195,6 +199,39 @@ int pick_ppw(const tsdfloc_ctx* c, uint64_t count)
     if (v == 1 || v == 2) return v;
   }
   return count >= static_cast<uint64_t>(c->sm_count) * 32 ? 2 : 1;
+}
+
+template <int W, int BS>
+void launch_eval2(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s)
+{
+  const uint32_t per_cta = W * 2;
+  const uint32_t grid = (a.n_local + per_cta - 1) / per_cta;
+  if (c->map.fast_div)
+    k_eval2<W, BS, true><<<grid, W * 32, 0, s>>>(c->map, a);
+  else
+    k_eval2<W, BS, false><<<grid, W * 32, 0, s>>>(c->map, a);
+}
+
+// Warps per CTA of k_eval2: as many as share one scan tile without leaving SMs idle.
+int pick_warps(const tsdfloc_ctx* c, uint64_t count)
+{
+  if (c->eval_w) return c->eval_w;
+  const uint64_t warps = (count + 1) / 2;
+  if (warps >= static_cast<uint64_t>(c->sm_count) * 16) return 8;
+  if (warps >= static_cast<uint64_t>(c->sm_count) * 4) return 4;
+  return 1;
+}
+
+void dispatch_eval2(const tsdfloc_ctx* c, const EvalArgs& a, uint64_t count, cudaStream_t s)
+{
+  const int w = pick_warps(c, count);
+  const int bs = c->eval_bs ? c->eval_bs : 4;
+#define TSDFLOC_CASE(WW, BB) if (w == WW && bs == BB) return launch_eval2<WW, BB>(c, a, s)
+  TSDFLOC_CASE(1, 4); TSDFLOC_CASE(4, 4); TSDFLOC_CASE(8, 4); TSDFLOC_CASE(16, 4);
+  TSDFLOC_CASE(1, 8); TSDFLOC_CASE(4, 8); TSDFLOC_CASE(8, 8); TSDFLOC_CASE(16, 8);
+  TSDFLOC_CASE(4, 2); TSDFLOC_CASE(8, 2);
+#undef TSDFLOC_CASE
+  launch_eval2<8, 4>(c, a, s);
 }
 
 template <int kPPW>
@@ -241,7 +278,9 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   a.stats = c->d_eval_stats;
   a.force_seq = c->force_seq;
   CU_TRY(c, cudaEventRecord(c->ev_eval0, s), "event record");
-  if (pick_ppw(c, count) == 2)
+  if (c->eval_version == 2)
+    dispatch_eval2(c, a, count, s);
+  else if (pick_ppw(c, count) == 2)
     launch_eval<2>(c, a, s);
   else
     launch_eval<1>(c, a, s);
@@ -397,6 +436,9 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
     return bail(TSDFLOC_E_CUDA, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
                                     "; libtsdfloc is built for sm_100a (B200) only");
   c->sm_count = prop.multiProcessorCount;
+  if (const char* e = std::getenv("TSDFLOC_EVAL")) c->eval_version = (std::atoi(e) == 1) ? 1 : 2;
+  if (const char* e = std::getenv("TSDFLOC_W")) c->eval_w = std::atoi(e);
+  if (const char* e = std::getenv("TSDFLOC_BS")) c->eval_bs = std::atoi(e);
   if (params) c->prm = *params; else tsdfloc_default_params(&c->prm);
   if (!(c->prm.max_range > 0.0f)) return bail(TSDFLOC_E_BAD_ARG, "max_range must be positive");
   c->desc = *map;

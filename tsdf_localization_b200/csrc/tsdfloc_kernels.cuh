@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval(const MapDev M, const Eva
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t part0 = (blockIdx.x * kEvalWarps + warp) * kPPW;
+#ifndef TSDFLOC_LOCKSTEP
   if (part0 >= A.n_local) return;
+#endif
 
   float m[kPPW][12];
   float s[kPPW];
@@ -283,6 +285,9 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval(const MapDev M, const Eva
       }
     }
     __syncwarp();
+#ifdef TSDFLOC_LOCKSTEP
+    __syncthreads();   // experiment: keep the CTA's warps on the same point tile so its loads hit L1
+#endif
     step += nb;
   }
   if (rem)
