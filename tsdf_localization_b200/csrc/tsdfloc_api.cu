@@ -45,8 +45,8 @@ struct tsdfloc_ctx
   float x_bound = 0.0f;     // upper bound of one point's contribution a_hit*v + term (k_eval block planning)
   uint32_t force_seq = 0;   // 1: contributions may be negative / non-finite -> always fold sequentially
   uint64_t launches = 0;
-  int eval_version = 2;     // 2: k_eval2 (TMA-streamed scan tiles); 1: k_eval (tuning/regression comparisons, TSDFLOC_EVAL=1)
-  int eval_w = 0, eval_bs = 0;  // 0: automatic; TSDFLOC_W / TSDFLOC_BS override for tuning experiments
+  int eval_version = 0;     // 0: automatic; 2: k_eval2 (TMA-streamed scan tiles); 1: k_eval (one-warp CTAs)
+  int eval_w = 0, eval_bs = 0, eval_r = 0;  // 0: automatic; TSDFLOC_W / TSDFLOC_BS / TSDFLOC_R override for tuning experiments
   cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;  // bracket the last k_eval launch (tsdfloc_last_eval_ms)
   bool eval_timed = false;
 
@@ -201,37 +201,32 @@ int pick_ppw(const tsdfloc_ctx* c, uint64_t count)
   return count >= static_cast<uint64_t>(c->sm_count) * 32 ? 2 : 1;
 }
 
-template <int W, int BS>
+template <int W, int BS, int R>
 void launch_eval2(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s)
 {
   const uint32_t per_cta = W * 2;
   const uint32_t grid = (a.n_local + per_cta - 1) / per_cta;
   if (c->map.fast_div)
-    k_eval2<W, BS, true><<<grid, W * 32, 0, s>>>(c->map, a);
+    k_eval2<W, BS, R, true><<<grid, W * 32, 0, s>>>(c->map, a);
   else
-    k_eval2<W, BS, false><<<grid, W * 32, 0, s>>>(c->map, a);
+    k_eval2<W, BS, R, false><<<grid, W * 32, 0, s>>>(c->map, a);
 }
 
-// Warps per CTA of k_eval2: as many as share one scan tile without leaving SMs idle.
-int pick_warps(const tsdfloc_ctx* c, uint64_t count)
-{
-  if (c->eval_w) return c->eval_w;
-  const uint64_t warps = (count + 1) / 2;
-  if (warps >= static_cast<uint64_t>(c->sm_count) * 16) return 8;
-  if (warps >= static_cast<uint64_t>(c->sm_count) * 4) return 4;
-  return 1;
-}
-
+// k_eval2 configuration (warps per CTA sharing one scan tile ring, steps per summation block, register budget).
+// Defaults from the round-1 sweeps on B200 (profiles/r01_eval2_sweep.md); TSDFLOC_W / TSDFLOC_BS / TSDFLOC_R override.
 void dispatch_eval2(const tsdfloc_ctx* c, const EvalArgs& a, uint64_t count, cudaStream_t s)
 {
-  const int w = pick_warps(c, count);
-  const int bs = c->eval_bs ? c->eval_bs : 4;
-#define TSDFLOC_CASE(WW, BB) if (w == WW && bs == BB) return launch_eval2<WW, BB>(c, a, s)
-  TSDFLOC_CASE(1, 4); TSDFLOC_CASE(4, 4); TSDFLOC_CASE(8, 4); TSDFLOC_CASE(16, 4);
-  TSDFLOC_CASE(1, 8); TSDFLOC_CASE(4, 8); TSDFLOC_CASE(8, 8); TSDFLOC_CASE(16, 8);
-  TSDFLOC_CASE(4, 2); TSDFLOC_CASE(8, 2);
+  const uint64_t warps = (count + 1) / 2;
+  int w = 4, bs = 8, r = 24;
+  (void)warps;
+  if (c->eval_w) w = c->eval_w;
+  if (c->eval_bs) bs = c->eval_bs;
+  if (c->eval_r) r = c->eval_r;
+#define TSDFLOC_CASE(WW, BB, RR) if (w == WW && bs == BB && r == RR) return launch_eval2<WW, BB, RR>(c, a, s)
+  TSDFLOC_CASE(4, 8, 24); TSDFLOC_CASE(4, 4, 32); TSDFLOC_CASE(1, 4, 32); TSDFLOC_CASE(8, 8, 24); TSDFLOC_CASE(8, 4, 32);
+  TSDFLOC_CASE(4, 4, 24); TSDFLOC_CASE(2, 8, 24); TSDFLOC_CASE(2, 4, 32); TSDFLOC_CASE(1, 8, 24); TSDFLOC_CASE(1, 4, 24);
 #undef TSDFLOC_CASE
-  launch_eval2<8, 4>(c, a, s);
+  launch_eval2<4, 8, 24>(c, a, s);
 }
 
 template <int kPPW>
@@ -278,7 +273,20 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   a.stats = c->d_eval_stats;
   a.force_seq = c->force_seq;
   CU_TRY(c, cudaEventRecord(c->ev_eval0, s), "event record");
-  if (c->eval_version == 2)
+  // Kernel choice (B200 sweeps, profiles/r01_eval2_sweep.md): k_eval2 wins whenever its 4-warp CTAs either fit one wave
+  // (6 CTAs/SM at 80 registers) or fill many; in between (e.g. 8,192 particles = 1.15 waves) and for very few particles the
+  // one-warp-CTA kernel k_eval packs the SMs better. TSDFLOC_EVAL=1|2 forces one of them.
+  const uint64_t warps = (count + 1) / 2;
+  const uint64_t sms = static_cast<uint64_t>(c->sm_count);
+  bool use2 = true;
+  if (c->eval_version == 1) use2 = false;
+  else if (c->eval_version == 0)
+  {
+    const uint64_t ctas4 = (warps + 3) / 4;
+    if (warps < sms * 8) use2 = false;
+    else if (ctas4 > sms * 6 && warps <= sms * 32) use2 = false;
+  }
+  if (use2)
     dispatch_eval2(c, a, count, s);
   else if (pick_ppw(c, count) == 2)
     launch_eval<2>(c, a, s);
@@ -436,9 +444,10 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
     return bail(TSDFLOC_E_CUDA, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
                                     "; libtsdfloc is built for sm_100a (B200) only");
   c->sm_count = prop.multiProcessorCount;
-  if (const char* e = std::getenv("TSDFLOC_EVAL")) c->eval_version = (std::atoi(e) == 1) ? 1 : 2;
+  if (const char* e = std::getenv("TSDFLOC_EVAL")) c->eval_version = std::atoi(e);
   if (const char* e = std::getenv("TSDFLOC_W")) c->eval_w = std::atoi(e);
   if (const char* e = std::getenv("TSDFLOC_BS")) c->eval_bs = std::atoi(e);
+  if (const char* e = std::getenv("TSDFLOC_R")) c->eval_r = std::atoi(e);
   if (params) c->prm = *params; else tsdfloc_default_params(&c->prm);
   if (!(c->prm.max_range > 0.0f)) return bail(TSDFLOC_E_BAD_ARG, "max_range must be positive");
   c->desc = *map;
@@ -453,7 +462,9 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
     thr[a] = bound_threshold(map->dim[a], map->resolution);
     if (thr[a] >= (1u << 22)) return bail(TSDFLOC_E_BAD_ARG, "map extent too large");
   }
-  const uint64_t px = thr[0] + 2ull, py = thr[1] + 2ull, pz = thr[2] + 2ull;
+  // x and y strides of the padded table are rounded up to powers of two: the kernel can index with shifts (ALU pipe)
+  auto pow2_at_least = [](uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; };
+  const uint64_t px = pow2_at_least(thr[0] + 2ull), py = pow2_at_least(thr[1] + 2ull), pz = thr[2] + 2ull;
   const uint64_t table_n = px * py * pz;
   if (table_n >= (1ull << 31)) return bail(TSDFLOC_E_BAD_ARG, "padded brick table too large");
   const uint64_t sub_n = map->sub_dim * map->sub_dim * map->sub_dim;
@@ -502,6 +513,10 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
   }
   M.pad_x = static_cast<uint32_t>(px);
   M.pad_xy = static_cast<uint32_t>(px * py);
+  M.shift_x = 0;
+  while ((1ull << M.shift_x) < px) ++M.shift_x;
+  M.shift_xy = M.shift_x;
+  while ((1ull << M.shift_xy) < px * py) ++M.shift_xy;
   M.sub_dim = static_cast<uint32_t>(map->sub_dim);
   M.sub_dim_2 = static_cast<uint32_t>(map->sub_dim_2);
   M.data_size = static_cast<uint32_t>(map->data_size);

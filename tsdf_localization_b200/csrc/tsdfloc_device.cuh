@@ -32,8 +32,10 @@ struct MapDev
   float clamp_hi[3];   // (float)thr[a]: offsets are clamped into [-1, thr]
   float res;
   float inv_res;       // RN(1/res)
-  uint32_t pad_x;      // thr[0] + 2
-  uint32_t pad_xy;     // (thr[0]+2)*(thr[1]+2)
+  uint32_t pad_x;      // x stride of the padded table: pow2 >= thr[0] + 2
+  uint32_t pad_xy;     // z stride: pad_x * (pow2 >= thr[1] + 2)
+  uint32_t shift_x;    // log2(pad_x)
+  uint32_t shift_xy;   // log2(pad_xy)
   uint32_t sub_dim;
   uint32_t sub_dim_2;
   uint32_t data_size;  // reference data_size; every index >= data_size is a miss
@@ -122,6 +124,9 @@ __device__ __forceinline__ float2 clamp2(float2 o, float hi)
 template <bool kFastDiv>
 __device__ __forceinline__ float2 div_res2(float2 a, float res, float inv_res)
 {
+#ifdef TSDFLOC_EXP_NODIV   // timing experiment only (wrong at rounding boundaries): how much of the time is the FMA pipe?
+  return __fmul2_rn(a, dup2(inv_res));
+#endif
   if (kFastDiv)
   {
     const float2 ir = dup2(inv_res);
@@ -149,16 +154,45 @@ __device__ __forceinline__ void voxel_index2(const MapDev& M, float2 tx, float2 
   const float2 px = __fadd2_rn(ox, make_float2(-fx.x, -fx.y));
   const float2 py = __fadd2_rn(oy, make_float2(-fy.x, -fy.y));
   const float2 pz = __fadd2_rn(oz, make_float2(-fz.x, -fz.y));
+#ifndef TSDFLOC_MUL_INDEX
+  const uint32_t ta = __float_as_uint(bx.x) + (__float_as_uint(by.x) << M.shift_x) + (__float_as_uint(bz.x) << M.shift_xy) - M.table_bias;
+  const uint32_t tb = __float_as_uint(bx.y) + (__float_as_uint(by.y) << M.shift_x) + (__float_as_uint(bz.y) << M.shift_xy) - M.table_bias;
+#else
   const uint32_t ta = __float_as_uint(bx.x) + __float_as_uint(by.x) * M.pad_x + __float_as_uint(bz.x) * M.pad_xy - M.table_bias;
   const uint32_t tb = __float_as_uint(bx.y) + __float_as_uint(by.y) * M.pad_x + __float_as_uint(bz.y) * M.pad_xy - M.table_bias;
+#endif
+#ifdef TSDFLOC_EXP_NOTABLE  // timing experiment only: table lookups collapse onto 64 entries
+  const uint32_t brick_a = static_cast<uint32_t>(__ldg(M.table + (ta & 63u)));
+  const uint32_t brick_b = static_cast<uint32_t>(__ldg(M.table + (tb & 63u)));
+#else
   const uint32_t brick_a = static_cast<uint32_t>(__ldg(M.table + ta));
   const uint32_t brick_b = static_cast<uint32_t>(__ldg(M.table + tb));
+#endif
   const float2 km = dup2(kMagic);
   const float2 qx = __fadd2_rd(div_res2<kFastDiv>(px, M.res, M.inv_res), km);
   const float2 qy = __fadd2_rd(div_res2<kFastDiv>(py, M.res, M.inv_res), km);
   const float2 qz = __fadd2_rd(div_res2<kFastDiv>(pz, M.res, M.inv_res), km);
+#ifdef TSDFLOC_SUB20   // timing experiment: sub_dim == 20 assumed, multiplies as shift/add chains
+  {
+    const uint32_t ya = __float_as_uint(qy.x), za = __float_as_uint(qz.x), yb = __float_as_uint(qy.y), zb = __float_as_uint(qz.y);
+    const uint32_t wa = ya + 20u * za, wb = yb + 20u * zb;   // y + 20 z
+    ia = brick_a + __float_as_uint(qx.x) + ((wa + (wa << 2)) << 2) - M.sub_bias;
+    ib = brick_b + __float_as_uint(qx.y) + ((wb + (wb << 2)) << 2) - M.sub_bias;
+  }
+#else
   ia = brick_a + __float_as_uint(qx.x) + __float_as_uint(qy.x) * M.sub_dim + __float_as_uint(qz.x) * M.sub_dim_2 - M.sub_bias;
   ib = brick_b + __float_as_uint(qx.y) + __float_as_uint(qy.y) * M.sub_dim + __float_as_uint(qz.y) * M.sub_dim_2 - M.sub_bias;
+#endif
+#ifdef TSDFLOC_EXP_NOGATHER  // timing experiment only: every gather hits the same 4 KB (L1-resident)
+  ia &= 1023u;
+  ib &= 1023u;
+#endif
+#ifdef TSDFLOC_EXP_LINEGATHER  // timing experiment only: the 32 lanes of a gather share one 128 B line (1 tag, 4 sectors)
+  ia = (ia & ~31u) % M.data_size;
+  ia = __shfl_sync(0xffffffffu, ia, 0) + (threadIdx.x & 31u);
+  ib = (ib & ~31u) % M.data_size;
+  ib = __shfl_sync(0xffffffffu, ib, 0) + (threadIdx.x & 31u);
+#endif
 }
 
 }  // namespace tsdfloc

@@ -80,8 +80,16 @@ __device__ __forceinline__ float fold_block(float a, const float (&xv)[BS], int 
   return a;
 }
 
-template <int W, int BS, bool kFastDiv>
-__global__ void __launch_bounds__(W * 32) k_eval2(const MapDev M, const EvalArgs A)
+#ifdef TSDFLOC_EXP_NOFOLD   // timing experiment only (wrong sums): never take the sequential fold
+#define TSDFLOC_NOFOLD true
+#else
+#define TSDFLOC_NOFOLD false
+#endif
+
+// R = resident warps per SM the register allocation is budgeted for (65536 / (32 R) registers per thread):
+// R = 24 (80 registers) lets a BS = 8 block keep all its gathers in flight; R = 32 (64 registers) fits one more wave slot.
+template <int W, int BS, int R, bool kFastDiv>
+__global__ void __launch_bounds__(W * 32, (R / W) > 0 ? (R / W) : 1) k_eval2(const MapDev M, const EvalArgs A)
 {
   static_assert(kTileSteps % BS == 0, "a summation block must not straddle two tiles");
   __shared__ __align__(128) float4 tiles[kStages][kTilePoints];
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(W * 32) k_eval2(const MapDev M, const EvalArgs
         const uint32_t tot = __reduce_add_sync(0xffffffffu, acc0);
         const bool any_tie = __any_sync(0xffffffffu, mr0 == 0.5f);
         const float cand = __fadd_rn(s[0], __fmul_rn(static_cast<float>(tot), u[0]));
-        if (whole && fast[0] && !any_tie && tot < (1u << 24) && cand <= limit[0])
+        if (TSDFLOC_NOFOLD || (whole && fast[0] && !any_tie && tot < (1u << 24) && cand <= limit[0]))
           s[0] = cand;
         else
         {
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(W * 32) k_eval2(const MapDev M, const EvalArgs
         const uint32_t tot = __reduce_add_sync(0xffffffffu, acc1);
         const bool any_tie = __any_sync(0xffffffffu, mr1 == 0.5f);
         const float cand = __fadd_rn(s[1], __fmul_rn(static_cast<float>(tot), u[1]));
-        if (whole && fast[1] && !any_tie && tot < (1u << 24) && cand <= limit[1])
+        if (TSDFLOC_NOFOLD || (whole && fast[1] && !any_tie && tot < (1u << 24) && cand <= limit[1]))
           s[1] = cand;
         else
         {
