@@ -99,7 +99,9 @@ uint64_t oracle_get_index(const oracle_map* m, float x, float y, float z, int ne
   for (int a = 0; a < 3; ++a)
   {
     off[a] = p[a] - c->min[a];
-    if (neg_mode == ORACLE_NEG_AS_MISS && !(off[a] >= 0.0f)) return c->data_size;
+    /* product policy: every offset whose float->unsigned conversion is undefined in the reference (negative, NaN,
+     * >= 2^64) is a miss; for all other offsets the three modes are identical */
+    if (neg_mode == ORACLE_NEG_AS_MISS && (!(off[a] >= 0.0f) || off[a] >= 18446744073709551616.0f)) return c->data_size;
   }
   for (int a = 0; a < 3; ++a)
   {

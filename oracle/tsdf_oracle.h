@@ -26,7 +26,7 @@ extern "C" {
  * undefined behaviour there; three behaviours exist in the wild: */
 enum oracle_neg_mode
 {
-  ORACLE_NEG_AS_MISS = 0,      /* product policy: any axis offset not >= 0 -> miss (init_value)           */
+  ORACLE_NEG_AS_MISS = 0,      /* product policy: any axis offset not in [0, 2^64) -> miss (init_value)   */
   ORACLE_NEG_REF_HOST_X86 = 1, /* what the reference CPU build does on x86-64 (cvttss2si wrap-around)      */
   ORACLE_NEG_REF_DEVICE_SAT = 2 /* what the reference CUDA build does (cvt.rzi.u32.f32 saturates to 0)    */
 };

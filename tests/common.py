@@ -52,3 +52,39 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+@functools.lru_cache(maxsize=2)
+def grid_rooms(extent=(100.0, 100.0, 10.0), room: float = 20.0, resolution: float = 0.05):
+    """C4/C5 map (1.4 GB at the default size; exceeds the 126 MB L2): product map adopting directly-built arrays."""
+    mk = lambda mn, mx, res, init: CudaSubVoxelMap(*mn, *mx, res, init)   # noqa: E731
+    desc, occ, data = syn.grid_rooms_arrays(mk, likelihood_value, likelihood_init(syn.SIGMA), extent=extent, room=room,
+                                            resolution=resolution)
+    return CudaSubVoxelMap.from_arrays(desc, occ, data)
+
+
+ROOMS_POSE = (47.0, 52.5, 1.5, 0.01, -0.02, 0.4)
+
+
+def rooms_scan(reduce_cell=None, extent=(100.0, 100.0, 10.0), room: float = 20.0, pose=ROOMS_POSE):
+    dirs, ring = syn.lidar_directions(128, 1024, 22.5)
+    pts, ok = syn.raycast_rooms(pose, dirs, room, extent[2])
+    pts, ring = np.ascontiguousarray(pts[ok]), np.ascontiguousarray(ring[ok])
+    if reduce_cell:
+        pts, ring = syn.reduce_scan(pts, ring, reduce_cell)
+    return np.ascontiguousarray(pts), ring
+
+
+def config_c4(n_particles: int = 1 << 20):
+    """C4: global localisation — particles uniform over the 100x100 m building, OS1-128 scan after the ring-aware 0.256 m
+    reduction (launch/mcl_3d_hilti.launch:81)."""
+    pts, ring = rooms_scan(reduce_cell=0.256)
+    ps = syn.uniform_particles(n_particles, (0.5, 0.5, 0.3), (99.5, 99.5, 2.5))
+    return ps, pts, ring
+
+
+def config_c5(n_particles: int = 262144):
+    """C5: tracking cloud inside the larger-than-L2 map, full OS1-128 scan."""
+    pts, ring = rooms_scan()
+    ps = syn.tracking_particles(n_particles, ROOMS_POSE)
+    return ps, pts, ring

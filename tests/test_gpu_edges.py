@@ -1,0 +1,228 @@
+"""GPU edge cases through the C ABI: ragged / tiny / empty inputs, non-finite points, the negative-offset policy, other map
+resolutions, sensor-model variants, error statuses, several contexts per process. Checker: the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import common
+from oracle_lib import NEG_AS_MISS, NEG_REF_DEVICE_SAT, NEG_REF_HOST_X86
+from tsdf_localization_b200 import CudaEvaluator, CudaSubVoxelMap, SystematicResampler, capi, likelihood_init, likelihood_value
+from tsdf_localization_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+GT = (0.4, -0.3, 1.2, 0.01, -0.02, 0.4)
+ROOM = dict(room_lo=(-3.0, -2.5, 0.0), room_hi=(3.0, 2.5, 3.0))
+
+
+@pytest.fixture(scope="module")
+def small():
+    spec, m = common.box_room(small=True)
+    return spec, m
+
+
+@pytest.fixture(scope="module")
+def ev(small):
+    e = CudaEvaluator(small[1])
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def omap(oracle, small):
+    return common.oracle_map_of(oracle, small[1])
+
+
+def _scan(p):
+    pts, _ = syn.make_scan("vlp16", GT, n_points=p, **ROOM)
+    return pts
+
+
+@pytest.mark.parametrize("n,p", [(1, 1), (1, 31), (2, 32), (3, 33), (7, 255), (5, 256), (9, 257), (33, 1000), (64, 4097), (257, 511)])
+def test_ragged_shapes_bit_exact(oracle, omap, ev, n, p):
+    """P not a multiple of the 32-point step or the 256-point TMA tile; odd particle counts (warps pair particles)."""
+    ps = syn.tracking_particles(n, GT, sigma_xy=0.2, seed=n + p)
+    pts = _scan(p)
+    ref = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.CALIB_TF, want_idx=True)
+    idx, hits, raw = ev.debug_eval(ps, pts, syn.CALIB_TF)
+    assert np.array_equal(idx, ref["idx"]) and np.array_equal(hits, ref["hits"])
+    assert raw.tobytes() == ref["raw"].tobytes()
+    mine = ps.copy()
+    ev.evaluate(mine, pts, syn.CALIB_TF)
+    assert common.rel_err(mine[:, 6], ref["particles"][:, 6]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("force", ["1", "2"])
+def test_both_eval_kernels_agree(oracle, omap, small, monkeypatch, force):
+    """k_eval (one-warp CTAs) and k_eval2 (TMA-streamed tiles) are interchangeable: same bits as the oracle."""
+    monkeypatch.setenv("TSDFLOC_EVAL", force)
+    e = CudaEvaluator(small[1])
+    ps = syn.tracking_particles(301, GT, sigma_xy=0.2)
+    pts = _scan(3001)
+    ref = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF)
+    _, hits, raw = e.debug_eval(ps, pts, syn.IDENTITY_TF, want_idx=False)
+    assert raw.tobytes() == ref["raw"].tobytes() and np.array_equal(hits, ref["hits"])
+    e.close()
+
+
+def test_non_finite_and_far_points_are_misses(oracle, omap, ev):
+    ps = syn.tracking_particles(16, GT, sigma_xy=0.2)
+    pts = _scan(200).copy()
+    pts[3] = (np.nan, 0.0, 0.0)
+    pts[10] = (np.inf, 1.0, 1.0)
+    pts[20] = (-np.inf, 1.0, 1.0)
+    pts[30] = (1e30, -1e30, 1e30)
+    pts[40] = (4e6, 0.0, 0.0)          # beyond the 2^22 range of the magic-number floor: must be clamped, not wrapped
+    pts[50] = (-4e6, 5e6, -8e6)
+    ref = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF, want_idx=True)
+    idx, hits, raw = ev.debug_eval(ps, pts, syn.IDENTITY_TF)
+    assert np.array_equal(idx, ref["idx"])
+    data_size = ev.data_size
+    for j in (3, 10, 20, 30, 40, 50):
+        assert (idx[:, j] == data_size).all()
+    assert np.array_equal(hits, ref["hits"])
+    # NaN points poison the reference's sum (NaN range test -> a_max; value stays finite here), weights stay comparable
+    assert raw.tobytes() == ref["raw"].tobytes()
+
+
+def test_negative_offset_policy_is_miss(oracle):
+    """Map whose walls lie ON the bounding-box faces (margin 0): a quarter of all lookups land at negative axis offsets,
+    where the reference is undefined behaviour (its x86 CPU build and its CUDA build disagree). Product == NEG_AS_MISS."""
+    spec = syn.box_room_map(likelihood_value, likelihood_init(0.1), resolution=0.05, margin=0.0, **ROOM)
+    m = CudaSubVoxelMap(*spec.min, *spec.max, spec.resolution, spec.init_value)
+    m.setData(spec.cells)
+    om = common.oracle_map_of(oracle, m)
+    e = CudaEvaluator(m)
+    ps = syn.tracking_particles(64, GT, sigma_xy=0.3)
+    pts = _scan(2000)
+    pol = oracle.evaluate(om, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF, mode=NEG_AS_MISS, want_idx=True)
+    x86 = oracle.evaluate(om, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF, mode=NEG_REF_HOST_X86, want_idx=True)
+    sat = oracle.evaluate(om, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF, mode=NEG_REF_DEVICE_SAT, want_idx=True)
+    idx, hits, raw = e.debug_eval(ps, pts, syn.IDENTITY_TF)
+    assert np.array_equal(idx, pol["idx"]) and raw.tobytes() == pol["raw"].tobytes()
+    band_x86, band_sat = (pol["idx"] != x86["idx"]), (pol["idx"] != sat["idx"])
+    print(f"negative band: {band_x86.mean():.1%} of pairs differ from the reference's x86 build, {band_sat.mean():.1%} from its CUDA build")
+    assert band_x86.mean() > 0.05 and band_sat.mean() > 0.05      # the band is populated: the policy matters here
+    # outside the band all three agree with the product
+    ok = ~(band_x86 | band_sat)
+    assert np.array_equal(idx[ok], x86["idx"][ok]) and np.array_equal(idx[ok], sat["idx"][ok])
+    e.close()
+
+
+@pytest.mark.parametrize("res", [0.064, 0.1, 0.03])
+def test_other_resolutions(oracle, res):
+    """sub_dim 16 / 10 / 34; the exhaustive division self-check decides between the 3-instruction and the IEEE division."""
+    spec = syn.box_room_map(likelihood_value, likelihood_init(0.1), resolution=res, **ROOM)
+    m = CudaSubVoxelMap(*spec.min, *spec.max, spec.resolution, spec.init_value)
+    m.setData(spec.cells)
+    om = common.oracle_map_of(oracle, m)
+    e = CudaEvaluator(m)
+    ps = syn.tracking_particles(100, GT, sigma_xy=0.1, sigma_yaw=0.1)
+    pts = _scan(3000)
+    ref = oracle.evaluate(om, common.DEFAULT_PARAMS, ps, pts, syn.CALIB_TF, want_idx=True)
+    idx, hits, raw = e.debug_eval(ps, pts, syn.CALIB_TF)
+    assert np.array_equal(idx, ref["idx"]) and np.array_equal(hits, ref["hits"]) and raw.tobytes() == ref["raw"].tobytes()
+    assert hits.sum() > 0.3 * idx.size
+    e.close()
+
+
+@pytest.mark.parametrize("params", [(0.7, 0.2, 0.05, 4.0), (1.0, 0.0, 0.0, 100.0), (0.5, 0.5, 0.3, 7.5)])
+def test_sensor_model_variants(oracle, omap, small, params):
+    """max_range inside the scan's extent: both branches of the range term (a_range/max_range vs a_max) are exercised."""
+    e = CudaEvaluator(small[1], False, *params)
+    ps = syn.tracking_particles(50, GT, sigma_xy=0.1)
+    pts = _scan(2500)
+    r2 = (pts.astype(np.float64) ** 2).sum(1)
+    if params[3] < 50:
+        assert (r2 < params[3] ** 2).any() and (r2 >= params[3] ** 2).any()
+    ref = oracle.evaluate(omap, params, ps, pts, syn.IDENTITY_TF)
+    _, hits, raw = e.debug_eval(ps, pts, syn.IDENTITY_TF, want_idx=False)
+    assert raw.tobytes() == ref["raw"].tobytes()
+    mine = ps.copy()
+    e.evaluate(mine, pts, syn.IDENTITY_TF)
+    assert common.rel_err(mine[:, 6], ref["particles"][:, 6]).max() <= 1e-5
+    e.close()
+
+
+def test_negative_sensor_model_forces_sequential_sum(oracle, omap, small):
+    """a_max < 0 makes addends negative: the integer-block summation is not valid and every block folds sequentially."""
+    params = (0.9, 0.1, -0.5, 3.0)
+    e = CudaEvaluator(small[1], False, *params)
+    ps = syn.tracking_particles(20, GT, sigma_xy=0.1)
+    pts = _scan(1500)
+    ref = oracle.evaluate(omap, params, ps, pts, syn.IDENTITY_TF)
+    _, _, raw = e.debug_eval(ps, pts, syn.IDENTITY_TF, want_idx=False)
+    assert raw.tobytes() == ref["raw"].tobytes()
+    e.close()
+
+
+def test_errors_and_states(ev, small):
+    ps = syn.tracking_particles(8, GT)
+    pts = _scan(64)
+    # empty scan: default pose, weights untouched (cuda_evaluator.cu:122-125)
+    ps[:, 6] = 0.5
+    before = ps.copy()
+    pose = ev.evaluate(ps, np.zeros((0, 3), dtype=np.float32), syn.IDENTITY_TF)
+    assert np.array_equal(ps, before) and pose.position == (0.0, 0.0, 0.0)
+    # all particles far outside with a_range = 0: "No particle is valid!" (cuda_evaluator.cu:366-369)
+    e0 = CudaEvaluator(small[1], False, 0.9, 0.0, 0.0, 100.0)
+    far = ps.copy()
+    far[:, :3] += 400.0
+    with pytest.raises(RuntimeError, match="No particle is valid!"):
+        e0.evaluate(far, pts, syn.IDENTITY_TF)
+    # resample before any update -> state error; too small a capacity -> capacity error
+    lib = capi.load_library()
+    with pytest.raises(capi.TsdflocError) as ei:
+        e0.resample_systematic(0.0, capacity=16)
+    assert ei.value.status == capi.E_STATE
+    ev.evaluate(ps, pts, syn.IDENTITY_TF)
+    with pytest.raises(capi.TsdflocError) as ei:
+        ev.resample_systematic(0.01, capacity=2)
+    assert ei.value.status == capi.E_CAPACITY
+    out = ev.resample_systematic(0.01, capacity=64)
+    assert len(out) == 8
+    # bad arguments
+    assert lib.tsdfloc_sensor_update(ev.ctx, None, 4, None, 4, None, None) == capi.E_BAD_ARG
+    e0.close()
+
+
+def test_two_contexts_are_independent(oracle, omap, small):
+    """No process-wide globals (the reference keeps its map pointers in file-scope device globals, cuda_data.h:17-26)."""
+    a = CudaEvaluator(small[1])
+    spec2 = syn.box_room_map(likelihood_value, likelihood_init(0.1), resolution=0.1, **ROOM)
+    m2 = CudaSubVoxelMap(*spec2.min, *spec2.max, spec2.resolution, spec2.init_value)
+    m2.setData(spec2.cells)
+    b = CudaEvaluator(m2)
+    ps = syn.tracking_particles(40, GT, sigma_xy=0.1)
+    pts = _scan(1000)
+    ra = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF)
+    rb = oracle.evaluate(common.oracle_map_of(oracle, m2), common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF)
+    for _ in range(2):
+        _, _, raw_b = b.debug_eval(ps, pts, syn.IDENTITY_TF, want_idx=False)
+        _, _, raw_a = a.debug_eval(ps, pts, syn.IDENTITY_TF, want_idx=False)
+        assert raw_a.tobytes() == ra["raw"].tobytes() and raw_b.tobytes() == rb["raw"].tobytes()
+    a.close()
+    b.close()
+
+
+def test_resampler_edge_cases(oracle, ev):
+    rs = SystematicResampler(ev, seed=3)
+    # a single particle, all weight on one particle, zeros in between, and u0 at both ends of [0, 1/N)
+    for n, hot in [(1, 0), (5, 4), (64, 17), (1000, 999)]:
+        ps = np.zeros((n, 7), dtype=np.float32)
+        ps[:, 0] = np.arange(n)
+        ps[hot, 6] = 1.0
+        for u0 in (0.0, float(np.nextafter(np.float32(1.0 / n), np.float32(0)))):
+            out, parents = rs.resample(ps, u0=u0, want_parents=True)
+            m_ref, p_ref = oracle.systematic_resample(ps[:, 6], u0)
+            assert len(out) == m_ref and np.array_equal(parents, p_ref)
+    # all-zero weights: the reference loop never draws -> empty cloud
+    ps = np.zeros((10, 7), dtype=np.float32)
+    out = rs.resample(ps, u0=0.01)
+    assert len(out) == 0
+    # un-normalised weights (sum 3): the reference recurrence simply keeps drawing -> ~3N particles
+    ps = np.zeros((200, 7), dtype=np.float32)
+    ps[:, 6] = 3.0 / 200
+    with pytest.raises(capi.TsdflocError):
+        rs.resample(ps, u0=0.001)          # exceeds the default capacity: reported, not truncated

@@ -1,0 +1,91 @@
+"""Full-size GPU runs (BASELINE.json configs C3, C4, C5) checked through size-independent properties plus oracle spot checks:
+  * a random subset of particles re-evaluated by the CPU oracle: un-normalised weights bit-exact;
+  * evaluating the particles in a different order / different warp pairing gives the same per-particle bits;
+  * normalised weights sum to 1; systematic resampling: parents non-decreasing, copy counts within 1 of N*w_i, n_out as the
+    reference recurrence dictates (== N for powers of two, the oracle's count otherwise — the N = 10^6 short-output case).
+"""
+import numpy as np
+import pytest
+
+import common
+from tsdf_localization_b200 import CudaEvaluator, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _spot_check(oracle, omap, ev, ps, pts, tf, raw, k=48, seed=0):
+    sel = np.random.default_rng(seed).choice(len(ps), size=k, replace=False)
+    ref = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps[sel], pts, tf)
+    assert raw[sel].tobytes() == ref["raw"].tobytes(), "un-normalised weights differ from the oracle on the sampled particles"
+    return sel
+
+
+def _resample_properties(oracle, ev, mine, n, u0):
+    out, parents = ev.resample_systematic(u0, capacity=n + n // 8 + 64, want_parents=True)
+    w = mine[:, 6].astype(np.float64)
+    assert abs(w.sum() - 1.0) < 1e-5
+    assert np.all(np.diff(parents.astype(np.int64)) >= 0), "systematic resampling emits parents in order"
+    counts = np.bincount(parents, minlength=n)
+    n_out = len(out)
+    assert np.abs(counts - n_out * w).max() < 1.0 + 1e-3 * n_out * w.max(), "copy counts must track N*w_i within one"
+    assert np.array_equal(out[:, :7], mine[parents])
+    m_ref, p_ref = oracle.systematic_resample(mine[:, 6], u0, cap=n + n // 8 + 64)
+    assert n_out == m_ref and np.array_equal(parents, p_ref)
+    return n_out
+
+
+def test_c3_full_size(oracle):
+    _, m = common.box_room()
+    omap = common.oracle_map_of(oracle, m)
+    ev = CudaEvaluator(m)
+    ps, pts, _ = common.config_c3()
+    n = len(ps)
+    assert n == 65536 and len(pts) == 131072
+    mine = ps.copy()
+    ev.evaluate(mine, pts, syn.IDENTITY_TF)
+    _, hits, raw = ev.debug_eval(ps[:8192], pts, syn.IDENTITY_TF, want_idx=False)
+    _spot_check(oracle, omap, ev, ps[:8192], pts, syn.IDENTITY_TF, raw)
+    # order / pairing independence: reversed particle order, and an odd offset that changes which particles share a warp
+    _, _, raw_rev = ev.debug_eval(ps[:8192][::-1].copy(), pts, syn.IDENTITY_TF, want_idx=False)
+    assert raw_rev[::-1].tobytes() == raw.tobytes()
+    _, _, raw_off = ev.debug_eval(ps[1:8192], pts, syn.IDENTITY_TF, want_idx=False)
+    assert raw_off.tobytes() == raw[1:].tobytes()
+    # normalised weights of the full run are raw / (float)sum: check against the subset's raw values
+    full_raw_ratio = mine[:8192, 6].astype(np.float64) / raw.astype(np.float64)
+    assert np.ptp(full_raw_ratio) / full_raw_ratio.mean() < 1e-6
+    assert _resample_properties(oracle, ev, mine, n, 0.37 / n) == n
+    ev.close()
+
+
+def test_c5_larger_than_l2_map(oracle):
+    m = common.grid_rooms()
+    assert m.dataBytes() > 8 * 126e6          # well beyond the L2
+    omap = common.oracle_map_of(oracle, m)
+    ev = CudaEvaluator(m)
+    ps, pts, _ = common.config_c5(262144)
+    mine = ps.copy()
+    ev.evaluate(mine, pts, syn.IDENTITY_TF)
+    _, hits, raw = ev.debug_eval(ps[:4096], pts, syn.IDENTITY_TF, want_idx=False)
+    assert hits.sum() > 0.3 * 4096 * len(pts)
+    _spot_check(oracle, omap, ev, ps[:4096], pts, syn.IDENTITY_TF, raw, k=32)
+    assert _resample_properties(oracle, ev, mine, len(ps), 0.5 / len(ps)) == len(ps)
+    ev.close()
+
+
+@pytest.mark.parametrize("n", [1 << 20, 1_000_000])
+def test_c4_global_localisation(oracle, n):
+    m = common.grid_rooms()
+    omap = common.oracle_map_of(oracle, m)
+    ev = CudaEvaluator(m)
+    ps, pts, _ = common.config_c4(n)
+    assert 20000 < len(pts) < 80000
+    mine = ps.copy()
+    ev.evaluate(mine, pts, syn.CALIB_TF)
+    _, hits, raw = ev.debug_eval(ps[:2048], pts, syn.CALIB_TF, want_idx=False)
+    _spot_check(oracle, omap, ev, ps[:2048], pts, syn.CALIB_TF, raw, k=32)
+    n_out = _resample_properties(oracle, ev, mine, n, 0.37 / n)
+    if n == 1 << 20:
+        assert n_out == n
+    else:
+        assert n_out != n, "N = 10^6: the reference's fp32 U recurrence drifts and emits a different particle count"
+    ev.close()

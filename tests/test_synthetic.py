@@ -1,0 +1,38 @@
+"""Host-side checks of the synthetic workload generators (CPU)."""
+import numpy as np
+
+import common
+from tsdf_localization_b200 import CudaSubVoxelMap, likelihood_init, likelihood_value, synthetic as syn
+
+
+def test_direct_brick_builder_equals_set_data():
+    ext, room, res = (8.0, 6.0, 3.0), 4.0, 0.05
+    mk = lambda mn, mx, r, init: CudaSubVoxelMap(*mn, *mx, r, init)   # noqa: E731
+    desc, occ, data = syn.grid_rooms_arrays(mk, likelihood_value, likelihood_init(0.1), extent=ext, room=room, resolution=res)
+    cells = syn.grid_rooms_cells(likelihood_value, ext, room, res)
+    lo, hi = syn.chunk_aligned_bounds((0, 0, 0), ext, res)
+    m = CudaSubVoxelMap(*lo, *hi, res, likelihood_init(0.1))
+    m.setData(cells)
+    assert desc.data_size == m.coef().data_size
+    assert np.array_equal(occ, m.rawGridOcc()) and data.tobytes() == m.rawData().tobytes()
+
+
+def test_reduce_scan_keeps_first_point_per_ring_cell():
+    pts, ring = syn.make_scan("vlp16", syn.GT_POSE)
+    rp, rr = syn.reduce_scan(pts, ring, 0.256)
+    assert 0 < len(rp) < len(pts)
+    assert np.all(np.diff(rr) >= 0)                      # ring-major
+    keys = set()
+    for p, r in zip(rp, rr):
+        k = (int(r),) + tuple(np.floor(p / np.float32(0.256)).astype(int))
+        assert k not in keys
+        keys.add(k)
+    # every input (ring, cell) is represented
+    all_keys = {(int(r),) + tuple(np.floor(p / np.float32(0.256)).astype(int)) for p, r in zip(pts, ring)}
+    assert keys == all_keys
+
+
+def test_box_room_is_chunk_aligned_and_scan_hits_it():
+    spec, m = common.box_room(small=True)
+    assert spec.min == (-6.4, -3.2, -3.2) and spec.max == (6.4, 3.2, 6.4)
+    assert (m.rawGridOcc() >= 0).sum() * 8000 == m.coef().data_size

@@ -168,3 +168,145 @@ CALIB_TF = np.array([0.99939083, 0.0, 0.0348995, 0.10,
                      0.0, 1.0, 0.0, 0.0,
                      -0.0348995, 0.0, 0.99939083, 0.30,
                      0.0, 0.0, 0.0, 1.0], dtype=np.float32)
+
+
+# ---- large sparse maps (configs C4 / C5) ---------------------------------------------------------------------------------
+
+def grid_rooms_arrays(make_map, value_fn, init_value: float, extent=(100.0, 100.0, 10.0), room: float = 20.0,
+                      resolution: float = 0.05, ceiling: bool = False):
+    """Multi-room building for the global-localisation / larger-than-L2 configs: walls on every `room`-metre grid line in x
+    and y up to height extent[2], a floor at z = 0 (optionally a ceiling), stored as the +-0.6 m truncation band only.
+
+    Builds the reference's two arrays DIRECTLY (bricks in increasing upper-cell order, unset voxels = init_value; the layout
+    CudaSubVoxelMap::setData produces, cuda_sub_voxel_map.tcc:170-230) instead of going through a cell list, because the
+    full-size map has ~2e8 stored voxels. `make_map(min, max, res, init)` must return an empty product CudaSubVoxelMap (its
+    coef() supplies the geometry). Returns (desc, grid_occ int32[], data float32[]). tests/test_synthetic.py checks a small
+    instance against setData on the equivalent cell list."""
+    ex = np.asarray(extent, dtype=np.float64)
+    lo, hi = chunk_aligned_bounds((0.0, 0.0, 0.0), ex, resolution)
+    m = make_map(tuple(lo.tolist()), tuple(hi.tolist()), resolution, init_value)
+    c = m.coef()
+    sub = int(c.sub_dim)
+    up = [int(c.up_dim[a]) for a in range(3)]
+    mn = [float(np.float32(c.min[a])) for a in range(3)]
+    lut = _likelihood_lut(value_fn)
+    band = TRUNCATION_MM * 1e-3
+
+    def axis_coords(a):
+        k = np.arange(up[a] * sub, dtype=np.float64)
+        return mn[a] + (k + 0.5) * resolution            # voxel centres
+
+    X, Y, Z = axis_coords(0), axis_coords(1), axis_coords(2)
+    dx = np.abs(X - np.clip(np.rint(X / room), 0, round(ex[0] / room)) * room)
+    dy = np.abs(Y - np.clip(np.rint(Y / room), 0, round(ex[1] / room)) * room)
+    dz = np.abs(Z)
+    if ceiling:
+        dz = np.minimum(dz, np.abs(Z - ex[2]))
+    # walls exist for 0 <= z <= H and inside the footprint (+ band); beyond that only the floor/ceiling planes count
+    wall_z = (Z >= -band) & (Z <= ex[2] + band)
+    in_x = (X >= -band) & (X <= ex[0] + band)
+    in_y = (Y >= -band) & (Y <= ex[1] + band)
+    big = 1e9
+    dxw = np.where(in_x, dx, big)
+    dyw = np.where(in_y, dy, big)
+
+    def near(d1):      # per upper cell: does any voxel column of it come within the band
+        return (d1.reshape(-1, sub) < band).any(axis=1)
+
+    nx, ny, nz = near(dxw), near(dyw), near(np.where(wall_z, dz, big) if not ceiling else dz)
+    zw = wall_z.reshape(-1, sub).any(axis=1)
+    fx, fy = in_x.reshape(-1, sub).any(axis=1), in_y.reshape(-1, sub).any(axis=1)
+    cand = ((nx[:, None, None] & fy[None, :, None] & zw[None, None, :]) | (fx[:, None, None] & ny[None, :, None] & zw[None, None, :])
+            | (fx[:, None, None] & fy[None, :, None] & nz[None, None, :]))
+    uxs, uys, uzs = np.nonzero(cand)
+    order = np.argsort(uxs + uys * up[0] + uzs * up[0] * up[1], kind="stable")
+    uxs, uys, uzs = uxs[order], uys[order], uzs[order]
+    brick = sub ** 3
+    grid_occ = np.full(up[0] * up[1] * up[2], -1, dtype=np.int32)
+    data = np.full(len(uxs) * brick, np.float32(init_value), dtype=np.float32)
+    n_alloc = 0
+    for ux, uy, uz in zip(uxs.tolist(), uys.tolist(), uzs.tolist()):
+        sx, sy, sz = slice(ux * sub, (ux + 1) * sub), slice(uy * sub, (uy + 1) * sub), slice(uz * sub, (uz + 1) * sub)
+        wz = wall_z[sz][:, None, None]
+        d_wall = np.minimum(np.where(in_y[sy][None, :, None], dxw[sx][None, None, :], big),
+                            np.where(in_x[sx][None, None, :], dyw[sy][None, :, None], big))
+        d_floor = np.where(in_x[sx][None, None, :] & in_y[sy][None, :, None], dz[sz][:, None, None], big)
+        d = np.minimum(np.where(wz, d_wall, big), d_floor)          # [sz][sy][sx]
+        mm = np.rint(d * 1000.0)
+        keep = mm < TRUNCATION_MM
+        if not keep.any():
+            continue
+        vals = np.full(d.shape, np.float32(init_value), dtype=np.float32)
+        vals[keep] = lut[mm[keep].astype(np.int64) + TRUNCATION_MM - 1]
+        off = n_alloc * brick
+        data[off:off + brick] = vals.reshape(-1)
+        grid_occ[ux + uy * up[0] + uz * up[0] * up[1]] = off
+        n_alloc += 1
+    data = data[:n_alloc * brick].copy()
+    import copy
+    desc = copy.copy(c)
+    desc = type(c).from_buffer_copy(bytes(c))
+    desc.data_size = n_alloc * brick
+    return desc, grid_occ, data
+
+
+def grid_rooms_cells(value_fn, extent, room: float, resolution: float, ceiling: bool = False) -> np.ndarray:
+    """The same building as an explicit (x, y, z, value) cell list at voxel centres (small instances only: the check that
+    grid_rooms_arrays equals what setData builds)."""
+    ex = np.asarray(extent, dtype=np.float64)
+    lo, hi = chunk_aligned_bounds((0.0, 0.0, 0.0), ex, resolution)
+    band = TRUNCATION_MM * 1e-3
+    lut = _likelihood_lut(value_fn)
+    flo = np.float32(lo).astype(np.float64)
+    n = np.ceil((hi - lo) / resolution - 1e-9).astype(np.int64)
+    X = flo[0] + (np.arange(n[0]) + 0.5) * resolution
+    Y = flo[1] + (np.arange(n[1]) + 0.5) * resolution
+    Z = flo[2] + (np.arange(n[2]) + 0.5) * resolution
+    big = 1e9
+    in_x, in_y = (X >= -band) & (X <= ex[0] + band), (Y >= -band) & (Y <= ex[1] + band)
+    wall_z = (Z >= -band) & (Z <= ex[2] + band)
+    dx = np.where(in_x, np.abs(X - np.clip(np.rint(X / room), 0, round(ex[0] / room)) * room), big)
+    dy = np.where(in_y, np.abs(Y - np.clip(np.rint(Y / room), 0, round(ex[1] / room)) * room), big)
+    dz = np.abs(Z)
+    if ceiling:
+        dz = np.minimum(dz, np.abs(Z - ex[2]))
+    out = []
+    for kz in range(len(Z)):
+        d_wall = np.minimum(np.where(in_y[None, :], dx[:, None], big), np.where(in_x[:, None], dy[None, :], big))
+        d_floor = np.where(in_x[:, None] & in_y[None, :], dz[kz], big)
+        d = np.minimum(d_wall if wall_z[kz] else big, d_floor)
+        mm = np.rint(d * 1000.0)
+        keep = mm < TRUNCATION_MM
+        if not keep.any():
+            continue
+        ix, iy = np.nonzero(keep)
+        vals = lut[mm[keep].astype(np.int64) + TRUNCATION_MM - 1]
+        out.append(np.stack([X[ix], Y[iy], np.full(len(ix), Z[kz]), vals], axis=1).astype(np.float32))
+    return np.concatenate(out, axis=0)
+
+
+def raycast_rooms(pose6, dirs: np.ndarray, room: float, height: float, noise_sigma: float = 0.01, seed: int = 1) -> np.ndarray:
+    """Scan inside one room of the grid building (no ceiling: rays that leave above the walls give no return)."""
+    o = np.asarray(pose6[:3], dtype=np.float64)
+    lo = np.array([np.floor(o[0] / room) * room, np.floor(o[1] / room) * room, 0.0])
+    hi = np.array([lo[0] + room, lo[1] + room, 1e9])
+    pts = raycast_box(pose6, dirs, lo, hi, noise_sigma=noise_sigma, seed=seed)
+    R = rpy_matrix(*pose6[3:6])
+    zw = (pts.astype(np.float64) @ R.T)[:, 2] + o[2]
+    ok = np.isfinite(pts).all(axis=1) & (zw <= height) & (np.linalg.norm(pts.astype(np.float64), axis=1) < 200.0)
+    return pts, ok
+
+
+def reduce_scan(points: np.ndarray, ring: np.ndarray, cell: float) -> Tuple[np.ndarray, np.ndarray]:
+    """Ring-aware voxel reduction of TSDFEvaluator::evaluateParticles (src/evaluation/tsdf_evaluator.cpp:304-376) for clouds
+    WITHOUT points nearer than 1 m (where the reference's ring iterator desynchronises): per (ring, cell) the first point in
+    scan order is kept; output ordered by (ring, original index). Returns (points, ring)."""
+    p = np.ascontiguousarray(points, dtype=np.float32)
+    res = np.float32(cell)
+    key = np.floor(p / res).astype(np.int64)          # float32 division + floor, as the reference evaluates it
+    full = np.concatenate([ring.astype(np.int64)[:, None], key], axis=1)
+    _, first = np.unique(full, axis=0, return_index=True)
+    first = np.sort(first)
+    order = np.lexsort((first, ring[first]))
+    sel = first[order]
+    return p[sel], ring[sel]
