@@ -49,6 +49,9 @@ WORKLOADS = {
     "c3": dict(scan="os1-128", particles=65536, desc="OS1-128 scan (131,072 pts) x 65,536 particles, box room 20x20x5 m @ 5 cm"),
     "c2": dict(scan="vlp16", particles=5000, desc="VLP-16 scan (30,000 pts) x 5,000 particles, box room 20x20x5 m @ 5 cm"),
     "c1": dict(scan="vlp16", particles=500, n_points=1024, desc="1,024 pts x 500 particles, box room 20x20x5 m @ 5 cm"),
+    "c4": dict(desc="global localisation: 1,048,576 uniform particles x OS1-128 scan after 0.256 m ring-aware reduction, "
+                    "multi-room 100x100x10 m map (1.4 GB, > L2)"),
+    "c5": dict(desc="262,144 tracking particles x OS1-128 scan (131,072 pts), multi-room 100x100x10 m map (1.4 GB, > L2)"),
 }
 
 
@@ -56,6 +59,10 @@ def build_workload(name: str):
     import common
     from tsdf_localization_b200 import synthetic as syn
     w = WORKLOADS[name]
+    if name in ("c4", "c5"):
+        m = common.grid_rooms()
+        ps, pts, _ = common.config_c4() if name == "c4" else common.config_c5()
+        return None, m, ps, pts, syn.IDENTITY_TF
     spec, m = common.box_room()
     pts, _ = syn.make_scan(w["scan"], syn.GT_POSE, n_points=w.get("n_points"))
     ps = syn.tracking_particles(w["particles"], syn.GT_POSE)
@@ -131,6 +138,8 @@ def reference_runner(spec, ps, pts, tf, sample: int):
     from oracle_lib import Ref, ref_available
     if not ref_available():
         raise RuntimeError("oracle/_ref not built: run `make -C oracle` in the container that has /root/reference")
+    if spec is None:
+        raise RuntimeError("the reference CPU arm is wired for the box-room workloads (c1-c3) only")
     t = pick_ref_threads()
     ref = Ref(None if t == 8 else t)
     rm = ref.map_create(spec.min, spec.max, spec.resolution, spec.init_value)
@@ -318,7 +327,7 @@ def run_b200_arm(args):
         roofline = {"bound": "hbm", "kernel": "k_eval", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src, "kernel_ms": eval_mean_ms,
                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_EVAL * n_local * p,
-                    "note": "8 B per particle-point evaluation; the 77 MB map is L2-resident, so DRAM traffic is far below the algorithmic bytes"}
+                    "note": "8 B per particle-point evaluation (4 B brick-table entry + 4 B voxel); when the map is L2-resident DRAM traffic is far below the algorithmic bytes and the binding resources are the SM FP32 pipe / L2 (DESIGN.md)"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:

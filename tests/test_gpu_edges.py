@@ -127,7 +127,7 @@ def test_other_resolutions(oracle, res):
     e.close()
 
 
-@pytest.mark.parametrize("params", [(0.7, 0.2, 0.05, 4.0), (1.0, 0.0, 0.0, 100.0), (0.5, 0.5, 0.3, 7.5)])
+@pytest.mark.parametrize("params", [(0.7, 0.2, 0.05, 4.0), (1.0, 0.0, 0.0, 100.0), (0.5, 0.5, 0.3, 3.5)])
 def test_sensor_model_variants(oracle, omap, small, params):
     """max_range inside the scan's extent: both branches of the range term (a_range/max_range vs a_max) are exercised."""
     e = CudaEvaluator(small[1], False, *params)

@@ -27,7 +27,10 @@ def _resample_properties(oracle, ev, mine, n, u0):
     assert np.all(np.diff(parents.astype(np.int64)) >= 0), "systematic resampling emits parents in order"
     counts = np.bincount(parents, minlength=n)
     n_out = len(out)
-    assert np.abs(counts - n_out * w).max() < 1.0 + 1e-3 * n_out * w.max(), "copy counts must track N*w_i within one"
+    # the property holds for the exact recurrence U_j = U_0 + j/N; for N that is not a power of two the reference's fp32 U
+    # drifts (n_out != n), which bends it slightly — identity with the oracle's parents below is the real check there
+    slack = 1.0 if n_out == n else 2.0
+    assert np.abs(counts - n_out * w).max() < slack + 1e-3 * n_out * w.max(), "copy counts must track N*w_i"
     assert np.array_equal(out[:, :7], mine[parents])
     m_ref, p_ref = oracle.systematic_resample(mine[:, 6], u0, cap=n + n // 8 + 64)
     assert n_out == m_ref and np.array_equal(parents, p_ref)
@@ -43,6 +46,7 @@ def test_c3_full_size(oracle):
     assert n == 65536 and len(pts) == 131072
     mine = ps.copy()
     ev.evaluate(mine, pts, syn.IDENTITY_TF)
+    assert _resample_properties(oracle, ev, mine, n, 0.37 / n) == n     # on the particle set evaluate() left on the device
     _, hits, raw = ev.debug_eval(ps[:8192], pts, syn.IDENTITY_TF, want_idx=False)
     _spot_check(oracle, omap, ev, ps[:8192], pts, syn.IDENTITY_TF, raw)
     # order / pairing independence: reversed particle order, and an odd offset that changes which particles share a warp
@@ -53,7 +57,6 @@ def test_c3_full_size(oracle):
     # normalised weights of the full run are raw / (float)sum: check against the subset's raw values
     full_raw_ratio = mine[:8192, 6].astype(np.float64) / raw.astype(np.float64)
     assert np.ptp(full_raw_ratio) / full_raw_ratio.mean() < 1e-6
-    assert _resample_properties(oracle, ev, mine, n, 0.37 / n) == n
     ev.close()
 
 
@@ -65,10 +68,10 @@ def test_c5_larger_than_l2_map(oracle):
     ps, pts, _ = common.config_c5(262144)
     mine = ps.copy()
     ev.evaluate(mine, pts, syn.IDENTITY_TF)
+    assert _resample_properties(oracle, ev, mine, len(ps), 0.5 / len(ps)) == len(ps)
     _, hits, raw = ev.debug_eval(ps[:4096], pts, syn.IDENTITY_TF, want_idx=False)
     assert hits.sum() > 0.3 * 4096 * len(pts)
     _spot_check(oracle, omap, ev, ps[:4096], pts, syn.IDENTITY_TF, raw, k=32)
-    assert _resample_properties(oracle, ev, mine, len(ps), 0.5 / len(ps)) == len(ps)
     ev.close()
 
 
@@ -81,9 +84,9 @@ def test_c4_global_localisation(oracle, n):
     assert 20000 < len(pts) < 80000
     mine = ps.copy()
     ev.evaluate(mine, pts, syn.CALIB_TF)
+    n_out = _resample_properties(oracle, ev, mine, n, 0.37 / n)
     _, hits, raw = ev.debug_eval(ps[:2048], pts, syn.CALIB_TF, want_idx=False)
     _spot_check(oracle, omap, ev, ps[:2048], pts, syn.CALIB_TF, raw, k=32)
-    n_out = _resample_properties(oracle, ev, mine, n, 0.37 / n)
     if n == 1 << 20:
         assert n_out == n
     else:
