@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TSDFLOC_ABI_VERSION 1
+#define TSDFLOC_ABI_VERSION 2
 
 typedef struct tsdfloc_ctx tsdfloc_ctx;
 
@@ -177,6 +177,43 @@ int tsdfloc_draw_device(tsdfloc_ctx* ctx, const float* d_particles, uint64_t n_t
 /* Synchronises `stream` and reports what the device recorded for the last normalize/draw:
  * n_out = number of particles the reference recurrence emits; returns TSDFLOC_E_NO_VALID_PARTICLE if sum == 0. */
 int tsdfloc_check(tsdfloc_ctx* ctx, uint64_t* n_out, double* weight_sum, void* stream);
+
+/* ---- scan reduction (the step in front of the evaluation) -------------------------------------------------------
+ * Replaces the serial host reduction inside TSDFEvaluator::evaluateParticles (src/evaluation/tsdf_evaluator.cpp:304-376):
+ * points nearer than 1 m are dropped, per (ring, reduction cell of `cell_size`) the FIRST point in cloud order is kept,
+ * and the ORIGINAL points are emitted ring by ring, inside a ring in cloud order. Bit-identical to the reference for
+ * every input it defines; defined divergences: points with a non-finite coordinate (or an overflowing cell centre) are
+ * dropped, and a ring outside [0, n_rings) fails with TSDFLOC_E_BAD_ARG (the reference indexes 64 ring buckets out of
+ * bounds, :342,358). n_rings <= 1024, n_points <= 2^22. */
+#define TSDFLOC_REDUCE_RING_DESYNC_LIKE_REFERENCE 1u /* reproduce :319-322: a dropped point does not advance the ring
+                                                        iterator, so survivor #k is paired with the ring of cloud point #k.
+                                                        Default (flag clear): every point keeps its own ring. */
+#define TSDFLOC_REDUCE_EMIT_CENTRES 2u /* the cell-CENTRE variant of CudaEvaluator::evaluate(PointCloud2)
+                                          (src/cuda/cuda_evaluator.cu:78-116) and src/num_particles_eval.cpp:134-191: no 1 m
+                                          test, centres computed in double (`floor(x / cell) * cell + cell/2`), the centres are
+                                          emitted instead of the points; ring == NULL deduplicates across rings. */
+
+/* Device pointers: d_points_xyz n x 3 fp32, d_ring n int32 (NULL = one ring), d_points_out capacity n x 3 fp32,
+ * d_src_index (optional) capacity n uint32 = cloud position of every emitted point. Enqueues on `stream`. */
+int tsdfloc_reduce_scan_device(tsdfloc_ctx* ctx, const float* d_points_xyz, const int32_t* d_ring, uint64_t n_points, double cell_size,
+                               uint32_t n_rings, uint32_t flags, float* d_points_out, uint32_t* d_src_index, void* stream);
+/* Synchronises `stream`; n_out = number of points the last tsdfloc_reduce_scan_device emitted. */
+int tsdfloc_reduce_result(tsdfloc_ctx* ctx, uint64_t* n_out, void* stream);
+
+/* Host buffers, strided so that a sensor_msgs::PointCloud2 byte buffer can be passed as it is: point i has its x, y, z
+ * (3 consecutive fp32, like the reference's iter_x[0..2]) at xyz_base + i * xyz_stride and its ring (ring_bytes = 2:
+ * int16 as the reference reads it, :305; 4: int32) at ring_base + i * ring_stride; ring_base NULL = one ring.
+ * points_out: capacity cap x 3 fp32; src_index optional. */
+int tsdfloc_reduce_scan(tsdfloc_ctx* ctx, const void* xyz_base, uint64_t xyz_stride, const void* ring_base, uint64_t ring_stride,
+                        int ring_bytes, uint64_t n_points, double cell_size, uint32_t n_rings, uint32_t flags, float* points_out,
+                        uint32_t* src_index, uint64_t cap, uint64_t* n_out);
+
+/* One sensor update on a raw cloud — the drop-in for TSDFEvaluator::evaluateParticles(cloud, ..., use_cuda = true)
+ * (tsdf_evaluator.cpp:247-378): reduction as above, then exactly tsdfloc_sensor_update on the reduced scan, which never
+ * leaves the device. n_points_used (optional) receives the size of the reduced scan. */
+int tsdfloc_sensor_update_cloud(tsdfloc_ctx* ctx, float* particles, uint64_t n, const void* xyz_base, uint64_t xyz_stride,
+                                const void* ring_base, uint64_t ring_stride, int ring_bytes, uint64_t n_points, double cell_size,
+                                uint32_t n_rings, uint32_t flags, const float tf[16], float mean_pose[6], uint64_t* n_points_used);
 
 /* Host-only test hook: the reference's fp32 U recurrence U_{j+1} = (float)((double)U_j + 1/n) evaluated through the
  * same segment-table code the device uses; writes U_j for all j with U_j < limit (at most cap) and returns their count. */

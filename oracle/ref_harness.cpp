@@ -94,6 +94,19 @@ struct ExposedEvaluator : public TSDFEvaluator
   }
 };
 
+// evaluate() is virtual (tsdf_evaluator.h:114): capture the reduced, ordered scan evaluateParticles hands to it
+// (tsdf_evaluator.cpp:378) instead of evaluating it.
+struct CaptureEvaluator : public TSDFEvaluator
+{
+  using TSDFEvaluator::TSDFEvaluator;
+  std::vector<CudaPoint> captured;
+  geometry_msgs::PoseWithCovariance evaluate(std::vector<Particle>&, const std::vector<CudaPoint>& points, FLOAT_T*, bool) override
+  {
+    captured = points;
+    return geometry_msgs::PoseWithCovariance();
+  }
+};
+
 // m_generator_ptr is protected (resampler.h:28) — reseed it so U0 is reproducible.
 struct SeededSystematic : public SystematicResampler
 {
@@ -304,6 +317,50 @@ uint64_t ref_systematic_resample(const float* particles, uint64_t n, uint32_t se
   }
   return m;
 }
+
+#ifndef TSDF_REF_WITH_B200_SHIM
+// The scan reduction inside TSDFEvaluator::evaluateParticles (tsdf_evaluator.cpp:304-376), run verbatim on a packed cloud
+// (x y z float32 at byte 0/4/8, ring int16 at byte 12, point_step 16) with ignore_tf = true; returns the number of points
+// handed to evaluate() and copies at most cap of them (3 floats each). Rings must stay below the reference's 64 buckets.
+int64_t ref_reduce_scan(const float* xyz, const int16_t* ring, uint64_t n, float cell_size, float* points_out, uint64_t cap)
+{
+  try
+  {
+    const FLOAT_T lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+    auto map = std::make_shared<RefMap>(lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], 0.5f, 0.0f);
+    CaptureEvaluator ev(map, false, 0.9f, 0.1f, 0.0f, 100.0f, cell_size);
+    sensor_msgs::PointCloud2 cloud;
+    cloud.width = static_cast<uint32_t>(n);
+    cloud.height = 1;
+    cloud.point_step = 16;
+    cloud.row_step = cloud.point_step * cloud.width;
+    cloud.fields.resize(4);
+    const char* names[4] = {"x", "y", "z", "ring"};
+    for (int f = 0; f < 4; ++f)
+    {
+      cloud.fields[f].name = names[f];
+      cloud.fields[f].offset = 4u * f;
+    }
+    cloud.data.assign(static_cast<size_t>(n) * 16, 0);
+    for (uint64_t i = 0; i < n; ++i)
+    {
+      std::memcpy(&cloud.data[16 * i], xyz + 3 * i, 12);
+      std::memcpy(&cloud.data[16 * i + 12], ring + i, 2);
+    }
+    ParticleCloud pc;
+    ev.evaluateParticles(pc, cloud, "", "", false, true);
+    const uint64_t m = ev.captured.size();
+    const uint64_t c = m < cap ? m : cap;
+    if (points_out && c) std::memcpy(points_out, static_cast<void*>(ev.captured.data()), c * sizeof(CudaPoint));
+    return static_cast<int64_t>(m);
+  }
+  catch (std::exception& ex)
+  {
+    g_last_error = ex.what();
+    return -1;
+  }
+}
+#endif
 
 #ifdef TSDF_REF_WITH_B200_SHIM
 // GpuSystematicResampler (the product's Resampler subclass) through the reference's Resampler interface, same seed

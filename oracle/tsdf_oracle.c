@@ -365,3 +365,159 @@ uint64_t oracle_systematic_resample(const float* w, uint64_t n, float u0, uint32
   }
   return out;
 }
+
+/* ---- scan reduction ---------------------------------------------------------------------------------- */
+
+typedef struct red_key
+{
+  int32_t ring;
+  float c[3];
+  uint32_t src;  /* cloud position of the first point with this key */
+  uint32_t order; /* running index among surviving points (the reference's `index`) */
+} red_key;
+
+static uint64_t red_hash(int32_t ring, const float c[3])
+{
+  uint32_t b[3];
+  memcpy(b, c, sizeof(b));
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)(uint32_t)ring;
+  for (int a = 0; a < 3; ++a)
+  {
+    h ^= b[a];
+    h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33;
+  }
+  return h;
+}
+
+static int red_cmp(const void* pa, const void* pb)
+{
+  const red_key* a = (const red_key*)pa;
+  const red_key* b = (const red_key*)pb;
+  if (a->ring != b->ring) return a->ring < b->ring ? -1 : 1;
+  if (a->order != b->order) return a->order < b->order ? -1 : 1;
+  return 0;
+}
+
+/* shared tail: dedup (first wins) + (ring, order) ordering */
+static int64_t red_finish(red_key* keys, uint64_t nk, const float* emit_xyz /* NULL: emit the centres */, float* points_out,
+                          uint32_t* src_index_out)
+{
+  uint64_t cap = 16;
+  while (cap < 2 * nk + 1) cap <<= 1;
+  int64_t* table = (int64_t*)malloc(sizeof(int64_t) * cap);
+  red_key* kept = (red_key*)malloc(sizeof(red_key) * (nk ? nk : 1));
+  uint64_t n_kept = 0;
+  for (uint64_t i = 0; i < cap; ++i) table[i] = -1;
+  for (uint64_t i = 0; i < nk; ++i)
+  {
+    uint64_t slot = red_hash(keys[i].ring, keys[i].c) & (cap - 1);
+    int dup = 0;
+    while (table[slot] >= 0)
+    {
+      const red_key* o = &kept[table[slot]];
+      /* SortClass::operator== (cuda_evaluator.h:56-59): ring and the three centre floats compare equal */
+      if (o->ring == keys[i].ring && o->c[0] == keys[i].c[0] && o->c[1] == keys[i].c[1] && o->c[2] == keys[i].c[2])
+      {
+        dup = 1; /* unordered_set::insert keeps the element already present */
+        break;
+      }
+      slot = (slot + 1) & (cap - 1);
+    }
+    if (!dup)
+    {
+      table[slot] = (int64_t)n_kept;
+      kept[n_kept++] = keys[i];
+    }
+  }
+  qsort(kept, n_kept, sizeof(red_key), red_cmp);
+  for (uint64_t j = 0; j < n_kept; ++j)
+  {
+    if (points_out)
+    {
+      const float* src = emit_xyz ? emit_xyz + 3ull * kept[j].src : kept[j].c;
+      points_out[3 * j + 0] = src[0];
+      points_out[3 * j + 1] = src[1];
+      points_out[3 * j + 2] = src[2];
+    }
+    if (src_index_out) src_index_out[j] = kept[j].src;
+  }
+  free(table);
+  free(kept);
+  return (int64_t)n_kept;
+}
+
+int64_t oracle_reduce_scan(const float* P, const int32_t* ring, uint64_t n, float cell, uint32_t n_rings, int ring_desync,
+                           float* points_out, uint32_t* src_index_out)
+{
+  const float res = cell;        /* map_res_ (tsdf_evaluator.h:76) */
+  const float half = cell / 2;   /* map_res_half_ */
+  red_key* keys = (red_key*)malloc(sizeof(red_key) * (n ? n : 1));
+  uint64_t nk = 0;
+  uint32_t index = 0; /* tsdf_evaluator.cpp:309 */
+  int64_t result = 0;
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    const float x = P[3 * i], y = P[3 * i + 1], z = P[3 * i + 2];
+    if (!isfinite(x) || !isfinite(y) || !isfinite(z)) continue; /* defined divergence, see header */
+    const float dist = sqrtf(x * x + y * y + z * z); /* :317 */
+    if (dist < 1.0) continue;                        /* :319-322 (index and the ring iterator stay) */
+    const int32_t r = ring_desync ? ring[index] : ring[i];
+    if (r < 0 || (uint32_t)r >= n_rings)
+    {
+      result = -1;
+      break;
+    }
+    const float cx = floorf(x / res) * res + half; /* :324-326, fp32, every operation rounded (-ffp-contract=off) */
+    const float cy = floorf(y / res) * res + half;
+    const float cz = floorf(z / res) * res + half;
+    if (isfinite(cx) && isfinite(cy) && isfinite(cz)) /* an overflowing centre drops the point (policy, like NaN input) */
+    {
+      red_key* k = &keys[nk++];
+      k->ring = r;
+      k->c[0] = cx;
+      k->c[1] = cy;
+      k->c[2] = cz;
+      k->src = (uint32_t)i;
+      k->order = index;
+    }
+    ++index; /* :331-332 */
+  }
+  if (result == 0) result = red_finish(keys, nk, P, points_out, src_index_out);
+  free(keys);
+  return result;
+}
+
+int64_t oracle_reduce_scan_centres(const float* P, const int32_t* ring, uint64_t n, double cell, uint32_t n_rings, float* points_out,
+                                   uint32_t* src_index_out)
+{
+  const double half = cell / 2; /* 0.032 for the reference's literal 0.064 */
+  red_key* keys = (red_key*)malloc(sizeof(red_key) * (n ? n : 1));
+  uint64_t nk = 0;
+  int64_t result = 0;
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    const float x = P[3 * i], y = P[3 * i + 1], z = P[3 * i + 2];
+    if (!isfinite(x) || !isfinite(y) || !isfinite(z)) continue;
+    const int32_t r = ring ? ring[i] : 0;
+    if (r < 0 || (uint32_t)r >= n_rings)
+    {
+      result = -1;
+      break;
+    }
+    const float cx = (float)(floor((double)x / cell) * cell + half); /* cuda_evaluator.cu:100-102, num_particles_eval.cpp:140-142 */
+    const float cy = (float)(floor((double)y / cell) * cell + half);
+    const float cz = (float)(floor((double)z / cell) * cell + half);
+    if (!(isfinite(cx) && isfinite(cy) && isfinite(cz))) continue;
+    red_key* k = &keys[nk++];
+    k->ring = r;
+    k->c[0] = cx;
+    k->c[1] = cy;
+    k->c[2] = cz;
+    k->src = (uint32_t)i;
+    k->order = (uint32_t)i;
+  }
+  if (result == 0) result = red_finish(keys, nk, NULL, points_out, src_index_out);
+  free(keys);
+  return result;
+}

@@ -103,6 +103,29 @@ int oracle_evaluate(const oracle_map* m, const oracle_params* prm, float* partic
  * from N); at most cap parents are written. */
 uint64_t oracle_systematic_resample(const float* weights, uint64_t n, float u0, uint32_t* parents_out, uint64_t cap);
 
+
+/* Scan reduction of TSDFEvaluator::evaluateParticles, src/evaluation/tsdf_evaluator.cpp:304-376: drop points nearer than
+ * 1 m (:317-322), keep per (ring, reduction cell) the FIRST point in cloud order (unordered_set insert of SortClass keyed
+ * on ring + cell centre, :324-329; equality cuda_evaluator.h:56-59), emit the ORIGINAL points ordered by ring, then by the
+ * running index of the kept points (:340-376).
+ *   ring_desync != 0 reproduces the reference's iterator bug: iter_ring is not advanced for a dropped point (:319-322 `continue`
+ *   skips `++iter_ring`), so the k-th point that survives the 1 m test is paired with the ring field of the k-th cloud point.
+ *   ring_desync == 0 is the product's default: every point keeps its own ring.
+ * Defined divergences (reference is undefined there): points with a non-finite coordinate are dropped (the reference's
+ * hash casts NaN*1000 to long long); rings outside [0, n_rings) make the call fail with -1 (the reference indexes a
+ * 64-entry vector out of bounds, :342,358).
+ * src_index_out[j] = cloud position of output point j. Returns the number of output points, or -1. */
+int64_t oracle_reduce_scan(const float* points_xyz, const int32_t* ring, uint64_t n, float cell_size, uint32_t n_rings,
+                           int ring_desync, float* points_out, uint32_t* src_index_out);
+
+/* The ring-agnostic cell-CENTRE reduction the reference's PointCloud2 overload and benchmark driver use
+ * (src/cuda/cuda_evaluator.cu:78-116, src/num_particles_eval.cpp:134-191): every point is replaced by the centre of its
+ * `cell` (double arithmetic, `floor(x / 0.064) * 0.064 + 0.032` rounded to float), duplicates (per ring when ring != NULL,
+ * else globally) are dropped keeping the first, order = ring, then cloud position (the ring-agnostic reference variant
+ * emits unordered_set iteration order, which is implementation-defined; as a SET the output is identical). */
+int64_t oracle_reduce_scan_centres(const float* points_xyz, const int32_t* ring, uint64_t n, double cell_size, uint32_t n_rings,
+                                   float* points_out, uint32_t* src_index_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,35 @@ class Oracle:
                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_systematic_resample.restype = C.c_uint64
         L.oracle_systematic_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_uint64]
+        L.oracle_reduce_scan.restype = C.c_int64
+        L.oracle_reduce_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_reduce_scan_centres.restype = C.c_int64
+        L.oracle_reduce_scan_centres.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_uint32, C.c_void_p, C.c_void_p]
+
+    # -- scan reduction --
+    def reduce_scan(self, points, ring, cell, n_rings=128, ring_desync=False):
+        """(points_out [m,3], src_index [m]) or raises ValueError when a ring is outside [0, n_rings)."""
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        rg = np.ascontiguousarray(ring, dtype=np.int32)
+        n = pts.shape[0]
+        out = np.empty((max(n, 1), 3), dtype=np.float32)
+        src = np.empty(max(n, 1), dtype=np.uint32)
+        m = int(self.lib.oracle_reduce_scan(_fp(pts), _fp(rg), n, C.c_float(cell), n_rings, 1 if ring_desync else 0, _fp(out), _fp(src)))
+        if m < 0:
+            raise ValueError("ring outside [0, n_rings)")
+        return out[:m].copy(), src[:m].copy()
+
+    def reduce_scan_centres(self, points, ring, cell=0.064, n_rings=128):
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        rg = None if ring is None else np.ascontiguousarray(ring, dtype=np.int32)
+        n = pts.shape[0]
+        out = np.empty((max(n, 1), 3), dtype=np.float32)
+        src = np.empty(max(n, 1), dtype=np.uint32)
+        m = int(self.lib.oracle_reduce_scan_centres(_fp(pts), _fp(rg) if rg is not None else None, n, C.c_double(cell), n_rings,
+                                                    _fp(out), _fp(src)))
+        if m < 0:
+            raise ValueError("ring outside [0, n_rings)")
+        return out[:m].copy(), src[:m].copy()
 
     # -- map --
     def map_create(self, mn, mx, res, init):
@@ -197,8 +226,23 @@ class Ref:
         L.ref_systematic_resample.restype = C.c_uint64
         L.ref_systematic_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
 
+        if not shim:
+            L.ref_reduce_scan.restype = C.c_int64
+            L.ref_reduce_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_uint64]
+
     def omp_threads(self):
         return int(self.lib.ref_omp_threads())
+
+    def reduce_scan(self, points, ring, cell):
+        """TSDFEvaluator::evaluateParticles' own reduction (verbatim); rings must be < 64."""
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        rg = np.ascontiguousarray(ring, dtype=np.int16)
+        n = pts.shape[0]
+        out = np.empty((max(n, 1), 3), dtype=np.float32)
+        m = int(self.lib.ref_reduce_scan(_fp(pts), _fp(rg), n, C.c_float(cell), _fp(out), n))
+        if m < 0:
+            raise RuntimeError(self.last_error())
+        return out[:m].copy()
 
     def map_create(self, mn, mx, res, init):
         a = np.asarray(mn, dtype=np.float32)

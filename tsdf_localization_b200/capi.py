@@ -10,6 +10,9 @@ PKG = Path(__file__).resolve().parent
 OK, E_BAD_ARG, E_CUDA, E_NO_VALID_PARTICLE, E_EMPTY_SCAN, E_CAPACITY, E_STATE = range(7)
 
 
+REDUCE_RING_DESYNC_LIKE_REFERENCE, REDUCE_EMIT_CENTRES = 1, 2
+
+
 class LibraryNotBuilt(RuntimeError):
     pass
 
@@ -71,6 +74,12 @@ SIGNATURES = {
     "tsdfloc_normalize_device": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "tsdfloc_draw_device": (C.c_int, [_vp, _vp, _u64, C.c_float, _u64, _u64, _vp, _vp, _vp]),
     "tsdfloc_check": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double), _vp]),
+    "tsdfloc_reduce_scan_device": (C.c_int, [_vp, _vp, _vp, _u64, C.c_double, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
+    "tsdfloc_reduce_result": (C.c_int, [_vp, C.POINTER(_u64), _vp]),
+    "tsdfloc_reduce_scan": (C.c_int, [_vp, _vp, _u64, _vp, _u64, C.c_int, _u64, C.c_double, C.c_uint32, C.c_uint32, _vp, _vp, _u64,
+                                      C.POINTER(_u64)]),
+    "tsdfloc_sensor_update_cloud": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _vp, _u64, C.c_int, _u64, C.c_double, C.c_uint32, C.c_uint32,
+                                              _fp, _fp, C.POINTER(_u64)]),
     "tsdfloc_host_u_sequence": (_u64, [C.c_float, _u64, C.c_double, _vp, _u64, _u32p, _u32p]),
     "tsdfloc_eval_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "tsdfloc_last_eval_ms": (C.c_int, [_vp, _fp]),

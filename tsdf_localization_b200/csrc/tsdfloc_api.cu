@@ -8,6 +8,7 @@
 #include "../../include/tsdfloc.h"
 #include "tsdfloc_kernels.cuh"
 #include "tsdfloc_eval2.cuh"
+#include "tsdfloc_reduce.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -67,6 +68,12 @@ struct tsdfloc_ctx
   Status* d_status = nullptr;
   uint64_t n_resident = 0;  // particles left on the device by tsdfloc_sensor_update
   bool have_cdf = false;
+
+  // scan reduction scratch
+  DevBuf d_red_in_xyz, d_red_in_ring, d_red_key4, d_red_table, d_red_cta, d_red_hist, d_red_win, d_red_rank, d_red_out, d_red_src;
+  RedStatus* d_red_status = nullptr;
+  RedStatus* h_red_status = nullptr;
+  bool have_reduce = false;
 
   // pinned staging
   void* h_stage = nullptr;
@@ -341,6 +348,118 @@ int stage_draw(tsdfloc_ctx* c, const float* d_particles, uint64_t n, float u0, u
   return launch_check(c, "k_draw");
 }
 
+// Scan reduction (tsdfloc_reduce.cuh). All pointers are device pointers.
+int stage_reduce(tsdfloc_ctx* c, const float* d_xyz, const int32_t* d_ring, uint64_t n, double cell, uint32_t n_rings, uint32_t flags,
+                 float* d_out, uint32_t* d_src, cudaStream_t s)
+{
+  if (n > (1ull << 22)) return fail(c, TSDFLOC_E_BAD_ARG, "scan reduction is limited to 2^22 points");
+  if (!(cell > 0.0) || !std::isfinite(cell) || !(static_cast<float>(cell) > 0.0f)) return fail(c, TSDFLOC_E_BAD_ARG, "cell_size must be positive");
+  if (n_rings == 0 || n_rings > kRedMaxRings) return fail(c, TSDFLOC_E_BAD_ARG, "n_rings must be in [1, 1024]");
+  if (flags & ~(kRedFlagDesync | kRedFlagCentres)) return fail(c, TSDFLOC_E_BAD_ARG, "unknown reduction flag");
+  c->have_reduce = false;
+  CU_TRY(c, cudaMemsetAsync(c->d_red_status, 0, sizeof(RedStatus), s), "memset(reduce status)");
+  if (n == 0)
+  {
+    c->have_reduce = true;
+    return TSDFLOC_OK;
+  }
+  const uint32_t n32 = static_cast<uint32_t>(n);
+  const uint32_t n_ctas = (n32 + kRedThreads - 1) / kRedThreads;
+  uint32_t table_n = 1024;
+  while (table_n < 2u * n32) table_n <<= 1;
+  const size_t hist_n = static_cast<size_t>(n_rings) * n_ctas;
+  int rc;
+  if ((rc = ensure(c, c->d_red_key4, sizeof(int4) * n, "cudaMalloc(reduce keys)"))) return rc;
+  if ((rc = ensure(c, c->d_red_table, sizeof(uint32_t) * table_n, "cudaMalloc(reduce table)"))) return rc;
+  if ((rc = ensure(c, c->d_red_cta, sizeof(uint32_t) * n_ctas, "cudaMalloc(reduce cta counts)"))) return rc;
+  if ((rc = ensure(c, c->d_red_hist, sizeof(uint32_t) * hist_n, "cudaMalloc(reduce histogram)"))) return rc;
+  if ((rc = ensure(c, c->d_red_win, sizeof(int32_t) * n, "cudaMalloc(reduce winners)"))) return rc;
+  if ((rc = ensure(c, c->d_red_rank, sizeof(uint32_t) * n, "cudaMalloc(reduce ranks)"))) return rc;
+  CU_TRY(c, cudaMemsetAsync(c->d_red_table.p, 0xff, sizeof(uint32_t) * table_n, s), "memset(reduce table)");
+
+  RedArgs a{};
+  a.xyz = d_xyz;
+  a.ring = d_ring;
+  a.n = n32;
+  a.n_rings = n_rings;
+  a.flags = flags;
+  a.n_ctas = n_ctas;
+  a.res = static_cast<float>(cell);       // FLOAT_T map_res_ = reduction_cell_size (tsdf_evaluator.h:76)
+  a.half = a.res / 2;                     // map_res_half_ (:77)
+  a.res_d = cell;
+  a.half_d = cell / 2;
+  uint32_t* cta = static_cast<uint32_t*>(c->d_red_cta.p);
+  uint32_t* hist = static_cast<uint32_t*>(c->d_red_hist.p);
+  uint32_t* table = static_cast<uint32_t*>(c->d_red_table.p);
+  int4* key4 = static_cast<int4*>(c->d_red_key4.p);
+  int32_t* win = static_cast<int32_t*>(c->d_red_win.p);
+  uint32_t* rank = static_cast<uint32_t*>(c->d_red_rank.p);
+  k_red_mark<<<n_ctas, kRedThreads, 0, s>>>(a, cta);
+  if ((rc = launch_check(c, "k_red_mark"))) return rc;
+  k_red_scan<<<1, 1024, 0, s>>>(cta, n_ctas, &c->d_red_status->n_kept);
+  if ((rc = launch_check(c, "k_red_scan"))) return rc;
+  k_red_keys<<<n_ctas, kRedThreads, 0, s>>>(a, cta, key4, c->d_red_status);
+  if ((rc = launch_check(c, "k_red_keys"))) return rc;
+  k_red_insert<<<n_ctas, kRedThreads, 0, s>>>(key4, n32, table, table_n - 1);
+  if ((rc = launch_check(c, "k_red_insert"))) return rc;
+  k_red_count<<<n_ctas, kRedThreads, sizeof(uint16_t) * kRedWarps * n_rings, s>>>(key4, n32, table, table_n - 1, n_rings, n_ctas, win, rank, hist);
+  if ((rc = launch_check(c, "k_red_count"))) return rc;
+  k_red_scan<<<1, 1024, 0, s>>>(hist, static_cast<uint32_t>(hist_n), &c->d_red_status->n_out);
+  if ((rc = launch_check(c, "k_red_scan"))) return rc;
+  k_red_scatter<<<n_ctas, kRedThreads, 0, s>>>(a, key4, win, rank, hist, d_out, d_src);
+  if ((rc = launch_check(c, "k_red_scatter"))) return rc;
+  c->have_reduce = true;
+  return TSDFLOC_OK;
+}
+
+int reduce_result(tsdfloc_ctx* c, uint64_t* n_out, cudaStream_t s)
+{
+  if (!c->have_reduce) return fail(c, TSDFLOC_E_STATE, "reduce_result before reduce_scan");
+  CU_TRY(c, cudaMemcpyAsync(c->h_red_status, c->d_red_status, sizeof(RedStatus), cudaMemcpyDeviceToHost, s), "reduce status readback");
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  if (c->h_red_status->bad_ring) return fail(c, TSDFLOC_E_BAD_ARG, "scan reduction: ring outside [0, n_rings)");
+  if (n_out) *n_out = c->h_red_status->n_out;
+  return TSDFLOC_OK;
+}
+
+// Packs a strided host cloud (PointCloud2-style) into the pinned staging buffer and uploads it: xyz -> d_red_in_xyz,
+// rings (widened to int32) -> d_red_in_ring.
+int upload_cloud(tsdfloc_ctx* c, const void* xyz_base, uint64_t xyz_stride, const void* ring_base, uint64_t ring_stride, int ring_bytes,
+                 uint64_t n, cudaStream_t s)
+{
+  if (n && !xyz_base) return fail(c, TSDFLOC_E_BAD_ARG, "xyz_base is NULL");
+  if (xyz_stride < 12) return fail(c, TSDFLOC_E_BAD_ARG, "xyz_stride must be >= 12");
+  if (ring_base && ring_bytes != 2 && ring_bytes != 4) return fail(c, TSDFLOC_E_BAD_ARG, "ring_bytes must be 2 or 4");
+  if (ring_base && ring_stride < static_cast<uint64_t>(ring_bytes)) return fail(c, TSDFLOC_E_BAD_ARG, "ring_stride smaller than ring_bytes");
+  if (n > (1ull << 22)) return fail(c, TSDFLOC_E_BAD_ARG, "scan reduction is limited to 2^22 points");
+  int rc;
+  if ((rc = ensure_host(c, 16 * (n + 1)))) return rc;
+  if ((rc = ensure(c, c->d_red_in_xyz, 12 * (n + 1), "cudaMalloc(cloud xyz)"))) return rc;
+  if ((rc = ensure(c, c->d_red_in_ring, 4 * (n + 1), "cudaMalloc(cloud rings)"))) return rc;
+  if (n == 0) return TSDFLOC_OK;
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");  // the pinned buffer may still feed an earlier copy
+  float* hx = static_cast<float*>(c->h_stage);
+  int32_t* hr = reinterpret_cast<int32_t*>(static_cast<char*>(c->h_stage) + 12 * n);
+  const char* xb = static_cast<const char*>(xyz_base);
+  for (uint64_t i = 0; i < n; ++i) std::memcpy(hx + 3 * i, xb + i * xyz_stride, 12);
+  if (ring_base)
+  {
+    const char* rb = static_cast<const char*>(ring_base);
+    if (ring_bytes == 2)
+      for (uint64_t i = 0; i < n; ++i)
+      {
+        int16_t v;
+        std::memcpy(&v, rb + i * ring_stride, 2);
+        hr[i] = v;
+      }
+    else
+      for (uint64_t i = 0; i < n; ++i) std::memcpy(hr + i, rb + i * ring_stride, 4);
+  }
+  CU_TRY(c, cudaMemcpyAsync(c->d_red_in_xyz.p, hx, 12 * n, cudaMemcpyHostToDevice, s), "H2D cloud xyz");
+  if (ring_base) CU_TRY(c, cudaMemcpyAsync(c->d_red_in_ring.p, hr, 4 * n, cudaMemcpyHostToDevice, s), "H2D cloud rings");
+  return TSDFLOC_OK;
+}
+
 int read_status(tsdfloc_ctx* c, cudaStream_t s)
 {
   CU_TRY(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s), "status readback");
@@ -552,6 +671,9 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
   CU_CREATE(cudaMemset(c->d_status, 0, sizeof(Status)), "memset(status)");
   CU_CREATE(cudaMallocHost(&c->h_status, sizeof(Status)), "cudaMallocHost(status)");
   CU_CREATE(cudaMallocHost(&c->h_mean, sizeof(float) * 8), "cudaMallocHost(mean)");
+  CU_CREATE(cudaMalloc(&c->d_red_status, sizeof(RedStatus)), "cudaMalloc(reduce status)");
+  CU_CREATE(cudaMemset(c->d_red_status, 0, sizeof(RedStatus)), "memset(reduce status)");
+  CU_CREATE(cudaMallocHost(&c->h_red_status, sizeof(RedStatus)), "cudaMallocHost(reduce status)");
 
   // ---- verify the 3-instruction division for this resolution (exhaustive over [0,1)) --------------------------
   {
@@ -584,7 +706,9 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
   DeviceGuard guard(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->d_xyz_stage, &c->d_pts, &c->d_particles, &c->d_particles_out, &c->d_mats,
-                    &c->d_raw, &c->d_cdf, &c->d_tile_total, &c->d_tile_offset, &c->d_tile_moments, &c->d_parents, &c->d_idx, &c->d_hits};
+                    &c->d_raw, &c->d_cdf, &c->d_tile_total, &c->d_tile_offset, &c->d_tile_moments, &c->d_parents, &c->d_idx, &c->d_hits,
+                    &c->d_red_in_xyz, &c->d_red_in_ring, &c->d_red_key4, &c->d_red_table, &c->d_red_cta, &c->d_red_hist, &c->d_red_win,
+                    &c->d_red_rank, &c->d_red_out, &c->d_red_src};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->d_table) cudaFree(c->d_table);
@@ -596,6 +720,8 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->h_mean) cudaFreeHost(c->h_mean);
+  if (c->d_red_status) cudaFree(c->d_red_status);
+  if (c->h_red_status) cudaFreeHost(c->h_red_status);
   if (c->ev_eval0) cudaEventDestroy(c->ev_eval0);
   if (c->ev_eval1) cudaEventDestroy(c->ev_eval1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -674,29 +800,15 @@ int tsdfloc_check(tsdfloc_ctx* c, uint64_t* n_out, double* weight_sum, void* str
 
 // ---- (A) host-buffer calls ---------------------------------------------------------------------------------------
 
-int tsdfloc_sensor_update(tsdfloc_ctx* c, float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],
-                          float mean_pose[6])
+// Second half of a host-buffer sensor update: the prepared scan is resident in c->d_pts (stage_prep_scan was enqueued on s).
+static int update_with_resident_scan(tsdfloc_ctx* c, float* particles, uint64_t n, const float tf[16], float mean_pose[6], cudaStream_t s)
 {
-  if (!c) return TSDFLOC_E_BAD_ARG;
-  if (!particles || !tf || (p && !points)) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
-  if (p == 0) return fail(c, TSDFLOC_E_EMPTY_SCAN, "empty scan: weights left untouched");
-  if (n == 0) return fail(c, TSDFLOC_E_BAD_ARG, "no particles");
-  DeviceGuard guard(c->device);
-  cudaStream_t s = c->stream;
   int rc;
   const size_t pbytes = sizeof(float) * 7 * n;
   if ((rc = ensure(c, c->d_particles, pbytes, "cudaMalloc(particles)"))) return rc;
   if ((rc = ensure(c, c->d_raw, sizeof(float) * n, "cudaMalloc(raw weights)"))) return rc;
-  if ((rc = ensure_host(c, std::max(pbytes, sizeof(float) * 3 * p)))) return rc;
-  c->have_cdf = false;
-  c->n_resident = 0;
-
-  // scan: host -> pinned -> device, then prep
-  std::memcpy(c->h_stage, points, sizeof(float) * 3 * p);
-  if ((rc = ensure(c, c->d_xyz_stage, sizeof(float) * 3 * (p + 1), "cudaMalloc(scan staging)"))) return rc;
-  CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, c->h_stage, sizeof(float) * 3 * p, cudaMemcpyHostToDevice, s), "H2D scan");
-  if ((rc = stage_prep_scan(c, static_cast<const float*>(c->d_xyz_stage.p), p, s))) return rc;
-  // the pinned buffer is reused for the particles: wait for the scan copy to leave it
+  if ((rc = ensure_host(c, pbytes))) return rc;
+  // the pinned buffer is reused for the particles: wait for earlier copies to leave it
   CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
   std::memcpy(c->h_stage, particles, pbytes);
   float* d_p = static_cast<float*>(c->d_particles.p);
@@ -714,6 +826,105 @@ int tsdfloc_sensor_update(tsdfloc_ctx* c, float* particles, uint64_t n, const fl
   if (mean_pose) std::memcpy(mean_pose, c->h_mean, sizeof(float) * 6);
   c->n_resident = n;
   return TSDFLOC_OK;
+}
+
+int tsdfloc_sensor_update(tsdfloc_ctx* c, float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],
+                          float mean_pose[6])
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!particles || !tf || (p && !points)) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (p == 0) return fail(c, TSDFLOC_E_EMPTY_SCAN, "empty scan: weights left untouched");
+  if (n == 0) return fail(c, TSDFLOC_E_BAD_ARG, "no particles");
+  DeviceGuard guard(c->device);
+  cudaStream_t s = c->stream;
+  int rc;
+  if ((rc = ensure_host(c, std::max(sizeof(float) * 7 * n, sizeof(float) * 3 * p)))) return rc;
+  c->have_cdf = false;
+  c->n_resident = 0;
+
+  // scan: host -> pinned -> device, then prep
+  std::memcpy(c->h_stage, points, sizeof(float) * 3 * p);
+  if ((rc = ensure(c, c->d_xyz_stage, sizeof(float) * 3 * (p + 1), "cudaMalloc(scan staging)"))) return rc;
+  CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, c->h_stage, sizeof(float) * 3 * p, cudaMemcpyHostToDevice, s), "H2D scan");
+  if ((rc = stage_prep_scan(c, static_cast<const float*>(c->d_xyz_stage.p), p, s))) return rc;
+  return update_with_resident_scan(c, particles, n, tf, mean_pose, s);
+}
+
+// ---- scan reduction -----------------------------------------------------------------------------------------------
+
+int tsdfloc_reduce_scan_device(tsdfloc_ctx* c, const float* d_points_xyz, const int32_t* d_ring, uint64_t n_points, double cell_size,
+                               uint32_t n_rings, uint32_t flags, float* d_points_out, uint32_t* d_src_index, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (n_points && (!d_points_xyz || !d_points_out)) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  DeviceGuard guard(c->device);
+  return stage_reduce(c, d_points_xyz, d_ring, n_points, cell_size, n_rings, flags, d_points_out, d_src_index, pick(c, stream));
+}
+
+int tsdfloc_reduce_result(tsdfloc_ctx* c, uint64_t* n_out, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  DeviceGuard guard(c->device);
+  return reduce_result(c, n_out, pick(c, stream));
+}
+
+// host cloud -> device -> reduced scan left in c->d_red_out (+ c->d_red_src); *m = its size
+static int reduce_host_cloud(tsdfloc_ctx* c, const void* xyz_base, uint64_t xyz_stride, const void* ring_base, uint64_t ring_stride,
+                             int ring_bytes, uint64_t n, double cell, uint32_t n_rings, uint32_t flags, uint64_t* m, cudaStream_t s)
+{
+  int rc;
+  if ((rc = upload_cloud(c, xyz_base, xyz_stride, ring_base, ring_stride, ring_bytes, n, s))) return rc;
+  if ((rc = ensure(c, c->d_red_out, 12 * (n + 1), "cudaMalloc(reduced scan)"))) return rc;
+  if ((rc = ensure(c, c->d_red_src, 4 * (n + 1), "cudaMalloc(reduced scan sources)"))) return rc;
+  if ((rc = stage_reduce(c, static_cast<const float*>(c->d_red_in_xyz.p), ring_base ? static_cast<const int32_t*>(c->d_red_in_ring.p) : nullptr,
+                         n, cell, n_rings, flags, static_cast<float*>(c->d_red_out.p), static_cast<uint32_t*>(c->d_red_src.p), s)))
+    return rc;
+  return reduce_result(c, m, s);
+}
+
+int tsdfloc_reduce_scan(tsdfloc_ctx* c, const void* xyz_base, uint64_t xyz_stride, const void* ring_base, uint64_t ring_stride,
+                        int ring_bytes, uint64_t n_points, double cell_size, uint32_t n_rings, uint32_t flags, float* points_out,
+                        uint32_t* src_index, uint64_t cap, uint64_t* n_out)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!n_out || (cap && !points_out)) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  DeviceGuard guard(c->device);
+  cudaStream_t s = c->stream;
+  uint64_t m = 0;
+  int rc;
+  if ((rc = reduce_host_cloud(c, xyz_base, xyz_stride, ring_base, ring_stride, ring_bytes, n_points, cell_size, n_rings, flags, &m, s))) return rc;
+  *n_out = m;
+  if (m > cap) return fail(c, TSDFLOC_E_CAPACITY, "reduced scan has " + std::to_string(m) + " points, capacity is " + std::to_string(cap));
+  if (m == 0) return TSDFLOC_OK;
+  // the pinned buffer holds 16 B per input point: room for 12 + 4 B per output point
+  float* hx = static_cast<float*>(c->h_stage);
+  uint32_t* hs = reinterpret_cast<uint32_t*>(static_cast<char*>(c->h_stage) + 12 * m);
+  CU_TRY(c, cudaMemcpyAsync(hx, c->d_red_out.p, 12 * m, cudaMemcpyDeviceToHost, s), "D2H reduced scan");
+  if (src_index) CU_TRY(c, cudaMemcpyAsync(hs, c->d_red_src.p, 4 * m, cudaMemcpyDeviceToHost, s), "D2H reduced scan sources");
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  std::memcpy(points_out, hx, 12 * m);
+  if (src_index) std::memcpy(src_index, hs, 4 * m);
+  return TSDFLOC_OK;
+}
+
+int tsdfloc_sensor_update_cloud(tsdfloc_ctx* c, float* particles, uint64_t n, const void* xyz_base, uint64_t xyz_stride,
+                                const void* ring_base, uint64_t ring_stride, int ring_bytes, uint64_t n_points, double cell_size,
+                                uint32_t n_rings, uint32_t flags, const float tf[16], float mean_pose[6], uint64_t* n_points_used)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!particles || !tf) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (n == 0) return fail(c, TSDFLOC_E_BAD_ARG, "no particles");
+  DeviceGuard guard(c->device);
+  cudaStream_t s = c->stream;
+  c->have_cdf = false;
+  c->n_resident = 0;
+  uint64_t m = 0;
+  int rc;
+  if ((rc = reduce_host_cloud(c, xyz_base, xyz_stride, ring_base, ring_stride, ring_bytes, n_points, cell_size, n_rings, flags, &m, s))) return rc;
+  if (n_points_used) *n_points_used = m;
+  if (m == 0) return fail(c, TSDFLOC_E_EMPTY_SCAN, "empty scan after reduction: weights left untouched");
+  if ((rc = stage_prep_scan(c, static_cast<const float*>(c->d_red_out.p), m, s))) return rc;
+  return update_with_resident_scan(c, particles, n, tf, mean_pose, s);
 }
 
 int tsdfloc_resample_systematic(tsdfloc_ctx* c, float u0, float* particles_out, uint64_t cap, uint64_t* n_out, uint32_t* parents)

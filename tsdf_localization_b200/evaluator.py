@@ -165,6 +165,55 @@ class CudaEvaluator:
         capi.check(self._lib, self._ctx, rc)
         return PoseWithCovariance.from_mean(list(mean))
 
+    # -- scan reduction + evaluation on a raw cloud (TSDFEvaluator::evaluateParticles, tsdf_evaluator.cpp:304-378) ----------
+    @staticmethod
+    def _cloud_args(points, ring):
+        pts = _f32(np.asarray(points).reshape(-1, 3), 3, "points")
+        if ring is None:
+            return pts, None, (pts.ctypes.data_as(C.c_void_p), 12, None, 0, 4, pts.shape[0])
+        rg = np.ascontiguousarray(ring)
+        if rg.dtype not in (np.int16, np.int32):
+            rg = rg.astype(np.int32)
+        if rg.shape != (pts.shape[0],):
+            raise ValueError("ring must have one entry per point")
+        return pts, rg, (pts.ctypes.data_as(C.c_void_p), 12, rg.ctypes.data_as(C.c_void_p), rg.itemsize, rg.itemsize, pts.shape[0])
+
+    def reduce_scan(self, points, ring, cell_size: float = 0.064, n_rings: int = 128, ring_desync_like_reference: bool = False,
+                    emit_centres: bool = False, want_src: bool = False):
+        """The reference's scan reduction on the GPU: drop points nearer than 1 m, keep the first point per (ring, cell),
+        emit the original points ring-major in cloud order (tsdf_evaluator.cpp:304-376). ring=None: one ring."""
+        pts, rg, args = self._cloud_args(points, ring)
+        n = pts.shape[0]
+        flags = (capi.REDUCE_RING_DESYNC_LIKE_REFERENCE if ring_desync_like_reference else 0) | (capi.REDUCE_EMIT_CENTRES if emit_centres else 0)
+        out = np.empty((max(n, 1), 3), dtype=np.float32)
+        src = np.empty(max(n, 1), dtype=np.uint32) if want_src else None
+        n_out = C.c_uint64(0)
+        rc = self._lib.tsdfloc_reduce_scan(self._ctx, *args, C.c_double(cell_size), n_rings, flags, out.ctypes.data_as(C.c_void_p),
+                                           src.ctypes.data_as(C.c_void_p) if want_src else None, n, C.byref(n_out))
+        capi.check(self._lib, self._ctx, rc)
+        m = int(n_out.value)
+        return (out[:m], src[:m]) if want_src else out[:m]
+
+    def evaluate_cloud(self, particles: np.ndarray, points, ring, tf_matrix, cell_size: float = 0.064, n_rings: int = 128,
+                       ring_desync_like_reference: bool = False):
+        """Reduction + evaluate() in one call; the reduced scan stays on the device. Returns (pose, reduced scan size)."""
+        if not (isinstance(particles, np.ndarray) and particles.dtype == np.float32 and particles.ndim == 2
+                and particles.shape[1] == 7 and particles.flags.c_contiguous):
+            raise ValueError("particles must be a C-contiguous float32[n, 7] array (it is updated in place)")
+        pts, rg, args = self._cloud_args(points, ring)
+        tf = (C.c_float * 16)(*[float(v) for v in np.asarray(tf_matrix, dtype=np.float32).reshape(-1)[:16]])
+        mean = (C.c_float * 6)()
+        used = C.c_uint64(0)
+        flags = capi.REDUCE_RING_DESYNC_LIKE_REFERENCE if ring_desync_like_reference else 0
+        rc = self._lib.tsdfloc_sensor_update_cloud(self._ctx, particles.ctypes.data_as(C.c_void_p), particles.shape[0], *args,
+                                                   C.c_double(cell_size), n_rings, flags, tf, mean, C.byref(used))
+        if rc == capi.E_EMPTY_SCAN:
+            return PoseWithCovariance(), 0
+        if rc == capi.E_NO_VALID_PARTICLE:
+            raise RuntimeError("No particle is valid!")
+        capi.check(self._lib, self._ctx, rc)
+        return PoseWithCovariance.from_mean(list(mean)), int(used.value)
+
     # -- resampling on the particle set the last evaluate() left on the device -------------------------------------
     def resample_systematic(self, u0: float, capacity: Optional[int] = None, want_parents: bool = False):
         n = capacity if capacity is not None else 0
@@ -228,6 +277,17 @@ class TSDFEvaluator:
         if not use_cuda:
             raise RuntimeError("tsdf_localization_b200 has no CPU evaluator: call evaluate(..., use_cuda=True)")
         return self.cuda_evaluator_.evaluate(particles, points, tf_matrix)
+
+    def evaluateParticles(self, particles: np.ndarray, points, ring, tf_matrix=None, use_cuda: bool = True, n_rings: int = 128,
+                          ring_desync_like_reference: bool = False) -> PoseWithCovariance:
+        """evaluateParticles(particle_cloud, real_cloud, ..., use_cuda, ignore_tf) (tsdf_evaluator.cpp:247-378) with the cloud
+        given as points + per-point ring and the scanner->robot transform as a matrix (None = ignore_tf): GPU scan reduction
+        at reduction_cell_size, then evaluate()."""
+        if not use_cuda:
+            raise RuntimeError("tsdf_localization_b200 has no CPU evaluator: call evaluateParticles(..., use_cuda=True)")
+        tf = np.eye(4, dtype=np.float32).reshape(-1) if tf_matrix is None else tf_matrix
+        pose, _ = self.cuda_evaluator_.evaluate_cloud(particles, points, ring, tf, self.map_res_, n_rings, ring_desync_like_reference)
+        return pose
 
 
 class SystematicResampler:
