@@ -215,6 +215,12 @@ int tsdfloc_sensor_update_cloud(tsdfloc_ctx* ctx, float* particles, uint64_t n, 
                                 const void* ring_base, uint64_t ring_stride, int ring_bytes, uint64_t n_points, double cell_size,
                                 uint32_t n_rings, uint32_t flags, const float tf[16], float mean_pose[6], uint64_t* n_points_used);
 
+/* Arg-max particle of the last normalisation (tsdfloc_sensor_update*, tsdfloc_normalize_device, tsdfloc_cdf_device), the
+ * "best pose" mcl_3d picks between evaluation and resampling (src/mcl_3d.cpp:382-399: `if (value > max_value)` starting from
+ * 0, i.e. the FIRST particle carrying the largest weight > 0). Reduced inside the normalisation kernels; this call only
+ * synchronises `stream` and reads the result. index = -1 (pose zeroed) when no particle has a weight > 0. */
+int tsdfloc_best_particle(tsdfloc_ctx* ctx, int64_t* index, float pose[6], float* weight, void* stream);
+
 /* Host-only test hook: the reference's fp32 U recurrence U_{j+1} = (float)((double)U_j + 1/n) evaluated through the
  * same segment-table code the device uses; writes U_j for all j with U_j < limit (at most cap) and returns their count. */
 uint64_t tsdfloc_host_u_sequence(float u0, uint64_t n, double limit, float* out, uint64_t cap, uint32_t* n_segs, uint32_t* flags);

@@ -60,7 +60,7 @@ struct tsdfloc_ctx
   uint64_t n_points = 0;
 
   // particles / scratch
-  DevBuf d_particles, d_particles_out, d_mats, d_raw, d_cdf, d_tile_total, d_tile_offset, d_tile_moments, d_parents,
+  DevBuf d_particles, d_particles_out, d_mats, d_raw, d_cdf, d_tile_total, d_tile_offset, d_tile_moments, d_tile_best, d_parents,
       d_idx, d_hits;
   float* d_mean = nullptr;
   USeg* d_segs = nullptr;
@@ -315,16 +315,19 @@ int stage_normalize(tsdfloc_ctx* c, float* d_particles, uint64_t n, const float*
   if ((rc = ensure(c, c->d_tile_total, sizeof(double) * tiles, "cudaMalloc(tile totals)"))) return rc;
   if ((rc = ensure(c, c->d_tile_offset, sizeof(double) * tiles, "cudaMalloc(tile offsets)"))) return rc;
   if ((rc = ensure(c, c->d_tile_moments, sizeof(double) * 9 * tiles, "cudaMalloc(tile moments)"))) return rc;
+  if ((rc = ensure(c, c->d_tile_best, sizeof(unsigned long long) * tiles, "cudaMalloc(tile arg-max)"))) return rc;
   const uint32_t n32 = static_cast<uint32_t>(n);
   // d_raw == nullptr: scan the weights the particles already carry (slot 6, stride 7) without normalising them
   k_weight_sum<<<tiles, kScanThreads, 0, s>>>(d_raw ? d_raw : d_particles + 6, d_raw ? 1u : 7u, n32,
                                               static_cast<double*>(c->d_tile_total.p), c->d_status);
   if ((rc = launch_check(c, "k_weight_sum"))) return rc;
   k_normalise_scan<<<tiles, kScanThreads, 0, s>>>(d_particles, d_raw, n32, c->d_status, static_cast<double*>(c->d_cdf.p),
-                                                  static_cast<double*>(c->d_tile_total.p), static_cast<double*>(c->d_tile_moments.p));
+                                                  static_cast<double*>(c->d_tile_total.p), static_cast<double*>(c->d_tile_moments.p),
+                                                  static_cast<unsigned long long*>(c->d_tile_best.p));
   if ((rc = launch_check(c, "k_normalise_scan"))) return rc;
   k_scan_tiles<<<1, 32, 0, s>>>(static_cast<const double*>(c->d_tile_total.p), static_cast<double*>(c->d_tile_offset.p), tiles,
-                                static_cast<const double*>(c->d_tile_moments.p), d_mean, c->d_status);
+                                static_cast<const double*>(c->d_tile_moments.p), d_mean, c->d_status,
+                                static_cast<const unsigned long long*>(c->d_tile_best.p), d_particles);
   if ((rc = launch_check(c, "k_scan_tiles"))) return rc;
   k_cdf_finalize<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(static_cast<double*>(c->d_cdf.p),
                                                                        static_cast<const double*>(c->d_tile_offset.p), n32, c->d_status);
@@ -706,7 +709,7 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
   DeviceGuard guard(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->d_xyz_stage, &c->d_pts, &c->d_particles, &c->d_particles_out, &c->d_mats,
-                    &c->d_raw, &c->d_cdf, &c->d_tile_total, &c->d_tile_offset, &c->d_tile_moments, &c->d_parents, &c->d_idx, &c->d_hits,
+                    &c->d_raw, &c->d_cdf, &c->d_tile_total, &c->d_tile_offset, &c->d_tile_moments, &c->d_tile_best, &c->d_parents, &c->d_idx, &c->d_hits,
                     &c->d_red_in_xyz, &c->d_red_in_ring, &c->d_red_key4, &c->d_red_table, &c->d_red_cta, &c->d_red_hist, &c->d_red_win,
                     &c->d_red_rank, &c->d_red_out, &c->d_red_src};
   for (DevBuf* b : bufs)
@@ -795,6 +798,21 @@ int tsdfloc_check(tsdfloc_ctx* c, uint64_t* n_out, double* weight_sum, void* str
   if (weight_sum) *weight_sum = c->h_status->weight_sum;
   if (c->h_status->zero_sum) return fail(c, TSDFLOC_E_NO_VALID_PARTICLE, "No particle is valid!");
   if (c->h_status->table_overflow & 3u) return fail(c, TSDFLOC_E_CAPACITY, "U recurrence table overflow or stalled recurrence");
+  return TSDFLOC_OK;
+}
+
+int tsdfloc_best_particle(tsdfloc_ctx* c, int64_t* index, float pose[6], float* weight, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!c->have_cdf) return fail(c, TSDFLOC_E_STATE, "best_particle needs a preceding sensor update / normalisation");
+  DeviceGuard guard(c->device);
+  int rc = read_status(c, pick(c, stream));
+  if (rc) return rc;
+  const unsigned long long key = c->h_status->best_key;
+  if (index) *index = key ? static_cast<int64_t>(~static_cast<uint32_t>(key & 0xffffffffull)) : -1;
+  if (pose)
+    for (int k = 0; k < 6; ++k) pose[k] = key ? c->h_status->best_pose[k] : 0.0f;
+  if (weight) *weight = key ? c->h_status->best_weight : 0.0f;
   return TSDFLOC_OK;
 }
 

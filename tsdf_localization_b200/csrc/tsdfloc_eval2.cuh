@@ -24,7 +24,10 @@ namespace tsdfloc
 constexpr int kTileSteps = 8;                    // 32-point steps per scan tile
 constexpr int kTilePoints = kTileSteps * 32;     // 256 points = 4 KB
 constexpr int kTileBytes = kTilePoints * 16;
-constexpr int kStages = 4;
+#ifndef TSDFLOC_STAGES
+#define TSDFLOC_STAGES 4
+#endif
+constexpr int kStages = TSDFLOC_STAGES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 

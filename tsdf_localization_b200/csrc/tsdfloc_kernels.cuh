@@ -38,7 +38,19 @@ struct Status
   unsigned long long n_out;  // particles the reference recurrence emits
   uint32_t ticket;        // last-block-done counter of k_weight_sum (self-resetting)
   uint32_t table_overflow;   // build_u_table flags: 1 table full, 2 stalled recurrence, 4 max_j reached
+  unsigned long long best_key;  // arg-max of the weights: (weight bits << 32) | ~index; 0 = no particle with weight > 0
+  float best_pose[6];        // pose of that particle
+  float best_weight;
+  uint32_t pad;
 };
+
+// Arg-max key of mcl_3d.cpp:382-395 (`if (value > max_value)` from max_value = 0: the FIRST particle carrying the largest
+// weight > 0): a larger weight wins, among equal weights the smaller index; weights <= 0 and NaN never win.
+__device__ __forceinline__ unsigned long long best_key_of(float w, uint32_t i)
+{
+  if (!(w > 0.0f)) return 0ull;
+  return (static_cast<unsigned long long>(__float_as_uint(w)) << 32) | static_cast<unsigned long long>(~i);
+}
 
 // One linear run of the reference's fp32 U recurrence: U_j = u_start + (j - j0) * step, exact, for j0 <= j < next j0.
 struct USeg
@@ -411,10 +423,13 @@ __device__ __forceinline__ double add_checked(double a, double b, bool& bad)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads) k_normalise_scan(float* __restrict__ particles, const float* __restrict__ raw, uint32_t n,
                                                                  Status* __restrict__ st, double* __restrict__ cdf,
-                                                                 double* __restrict__ tile_total, double* __restrict__ tile_moments)
+                                                                 double* __restrict__ tile_total, double* __restrict__ tile_moments,
+                                                                 unsigned long long* __restrict__ tile_best)
 {
   __shared__ double s_warp[kScanThreads / 32];
   __shared__ double s_mom[kScanThreads / 32][9];
+  __shared__ unsigned long long s_best[kScanThreads / 32];
+  unsigned long long best = 0ull;
   const float inv_den = st->weight_sum_f;
   const bool dead = st->zero_sum != 0u;
   const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
@@ -442,6 +457,8 @@ __global__ void __launch_bounds__(kScanThreads) k_normalise_scan(float* __restri
       {
         w = p[6];
       }
+      const unsigned long long key = best_key_of(w, i);
+      best = key > best ? key : best;
       const float x = p[0], y = p[1], z = p[2];
       mom[0] += static_cast<double>(__fmul_rn(x, w));
       mom[1] += static_cast<double>(__fmul_rn(y, w));
@@ -478,6 +495,12 @@ __global__ void __launch_bounds__(kScanThreads) k_normalise_scan(float* __restri
     for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if (lane == 0) s_mom[warp][q] = v;
   }
+  for (int o = 16; o; o >>= 1)
+  {
+    const unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  if (lane == 0) s_best[warp] = best;
   __syncthreads();
   double warp_off = 0.0;
   for (uint32_t w = 0; w < warp; ++w) warp_off = add_checked(warp_off, s_warp[w], bad);
@@ -495,14 +518,33 @@ __global__ void __launch_bounds__(kScanThreads) k_normalise_scan(float* __restri
     for (int w = 0; w < kScanThreads / 32; ++w) v += s_mom[w][threadIdx.x];
     tile_moments[static_cast<size_t>(blockIdx.x) * 9 + threadIdx.x] = v;
   }
+  if (threadIdx.x == 9)
+  {
+    unsigned long long b = 0ull;
+    for (int w = 0; w < kScanThreads / 32; ++w) b = s_best[w] > b ? s_best[w] : b;
+    tile_best[blockIdx.x] = b;
+  }
   if (bad) atomicOr(&st->inexact, 1u);
 }
 
 // K2c: one block. Exclusive scan of the tile totals (fp64, exactness-checked), moments -> mean pose.
 __global__ void k_scan_tiles(const double* __restrict__ tile_total, double* __restrict__ tile_offset, uint32_t n_tiles,
-                             const double* __restrict__ tile_moments, float* __restrict__ mean_pose, Status* __restrict__ st)
+                             const double* __restrict__ tile_moments, float* __restrict__ mean_pose, Status* __restrict__ st,
+                             const unsigned long long* __restrict__ tile_best, const float* __restrict__ particles)
 {
   __shared__ double s_mom[9];
+  if (threadIdx.x == 9)
+  {
+    unsigned long long b = 0ull;
+    for (uint32_t t = 0; t < n_tiles; ++t) b = tile_best[t] > b ? tile_best[t] : b;
+    st->best_key = b;
+    if (b)
+    {
+      const uint32_t i = ~static_cast<uint32_t>(b & 0xffffffffull);
+      for (int k = 0; k < 6; ++k) st->best_pose[k] = particles[7ull * i + k];
+      st->best_weight = particles[7ull * i + 6];
+    }
+  }
   if (threadIdx.x == 0)
   {
     bool bad = false;

@@ -214,6 +214,15 @@ class CudaEvaluator:
         capi.check(self._lib, self._ctx, rc)
         return PoseWithCovariance.from_mean(list(mean)), int(used.value)
 
+    def best_particle(self):
+        """(index, pose6, weight) of the first particle carrying the largest weight of the last evaluate()
+        (src/mcl_3d.cpp:382-399); index -1 when no weight is > 0."""
+        idx = C.c_int64(-1)
+        pose = (C.c_float * 6)()
+        w = C.c_float(0.0)
+        capi.check(self._lib, self._ctx, self._lib.tsdfloc_best_particle(self._ctx, C.byref(idx), pose, C.byref(w), None))
+        return int(idx.value), np.array(list(pose), dtype=np.float32), float(w.value)
+
     # -- resampling on the particle set the last evaluate() left on the device -------------------------------------
     def resample_systematic(self, u0: float, capacity: Optional[int] = None, want_parents: bool = False):
         n = capacity if capacity is not None else 0
