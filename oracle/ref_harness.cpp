@@ -83,10 +83,17 @@ namespace
 
 using RefMap = CudaSubVoxelMap<FLOAT_T, FLOAT_T>;
 
+// With the B200 shim the facade is the shim's TSDFEvaluatorB200 (evaluateParticles override: GPU scan reduction).
+#ifdef TSDF_REF_WITH_B200_SHIM
+using EvaluatorBase = TSDFEvaluatorB200;
+#else
+using EvaluatorBase = TSDFEvaluator;
+#endif
+
 // evaluatePose is protected virtual (tsdf_evaluator.h:59) — expose it unchanged.
-struct ExposedEvaluator : public TSDFEvaluator
+struct ExposedEvaluator : public EvaluatorBase
 {
-  using TSDFEvaluator::TSDFEvaluator;
+  using EvaluatorBase::EvaluatorBase;
   FLOAT_T pose_weight(FLOAT_T* pose, const std::vector<CudaPoint>& cloud)
   {
     LikelihoodEvaluation eval(10000);
@@ -240,7 +247,97 @@ void* ref_eval_create(void* map_h, float a_hit, float a_range, float a_max, floa
   }
 }
 
+// Same with TSDFEvaluator's 7th constructor argument (reduction_cell_size, tsdf_evaluator.h:72).
+void* ref_eval_create_cell(void* map_h, float a_hit, float a_range, float a_max, float max_range, float reduction_cell_size)
+{
+  try
+  {
+    auto* e = new EvalHandle;
+    e->map = static_cast<MapHandle*>(map_h)->map;
+    e->eval.reset(new ExposedEvaluator(e->map, false, a_hit, a_range, a_max, max_range, reduction_cell_size));
+    return e;
+  }
+  catch (std::exception& ex)
+  {
+    g_last_error = ex.what();
+    return nullptr;
+  }
+}
+
 void ref_eval_destroy(void* e) { delete static_cast<EvalHandle*>(e); }
+
+namespace
+{
+// Packed test cloud: x y z float32 at byte 0/4/8, ring int16 at byte 12, point_step 16.
+sensor_msgs::PointCloud2 make_cloud(const float* xyz, const int16_t* ring, uint64_t n)
+{
+  sensor_msgs::PointCloud2 cloud;
+  cloud.width = static_cast<uint32_t>(n);
+  cloud.height = 1;
+  cloud.point_step = 16;
+  cloud.row_step = cloud.point_step * cloud.width;
+  cloud.fields.resize(4);
+  const char* names[4] = {"x", "y", "z", "ring"};
+  for (int f = 0; f < 4; ++f)
+  {
+    cloud.fields[f].name = names[f];
+    cloud.fields[f].offset = 4u * f;
+  }
+  cloud.data.assign(static_cast<size_t>(n) * 16, 0);
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    std::memcpy(&cloud.data[16 * i], xyz + 3 * i, 12);
+    std::memcpy(&cloud.data[16 * i + 12], ring + i, 2);
+  }
+  return cloud;
+}
+}  // namespace
+
+// TSDFEvaluator::evaluateParticles(particle_cloud, cloud, "", "", use_cuda, ignore_tf = true) (tsdf_evaluator.cpp:247-378) on a
+// packed cloud. CPU build: the reference's own reduction + CPU evaluation. Shim build: the facade is TSDFEvaluatorB200, so
+// use_cuda != 0 runs reduction + evaluation on the B200 (desync: reproduce the reference's ring-iterator bug).
+// reduced_out (shim build, use_cuda only): size of the reduced scan.
+int ref_evaluate_cloud(void* eh, float* particles, uint64_t n, const float* xyz, const int16_t* ring, uint64_t n_points, int use_cuda,
+                       int desync, uint32_t n_rings, double pose_out[7], uint64_t* reduced_out)
+{
+  auto* e = static_cast<EvalHandle*>(eh);
+  try
+  {
+    ParticleCloud pc;
+    pc.particles().resize(n);
+    std::memcpy(static_cast<void*>(pc.particles().data()), particles, n * sizeof(Particle));
+    const sensor_msgs::PointCloud2 cloud = make_cloud(xyz, ring, n_points);
+#ifdef TSDF_REF_WITH_B200_SHIM
+    e->eval->ring_desync_like_reference = desync != 0;
+    e->eval->n_rings = n_rings;
+#else
+    (void)desync;
+    (void)n_rings;
+#endif
+    auto pose = e->eval->evaluateParticles(pc, cloud, "", "", use_cuda != 0, true);
+    std::memcpy(particles, static_cast<void*>(pc.particles().data()), n * sizeof(Particle));
+    if (pose_out)
+    {
+      pose_out[0] = pose.pose.position.x; pose_out[1] = pose.pose.position.y; pose_out[2] = pose.pose.position.z;
+      pose_out[3] = pose.pose.orientation.x; pose_out[4] = pose.pose.orientation.y;
+      pose_out[5] = pose.pose.orientation.z; pose_out[6] = pose.pose.orientation.w;
+    }
+    if (reduced_out)
+    {
+#ifdef TSDF_REF_WITH_B200_SHIM
+      *reduced_out = use_cuda ? e->eval->last_reduced_size() : 0;
+#else
+      *reduced_out = 0;
+#endif
+    }
+    return 0;
+  }
+  catch (std::exception& ex)
+  {
+    g_last_error = ex.what();
+    return 1;
+  }
+}
 
 // TSDFEvaluator::evaluate(particles, points, tf, use_cuda) (tsdf_evaluator.cpp:78-245).
 // particles: N × 7 fp32 (x y z roll pitch yaw weight), weights overwritten with the NORMALISED weights.
@@ -329,24 +426,7 @@ int64_t ref_reduce_scan(const float* xyz, const int16_t* ring, uint64_t n, float
     const FLOAT_T lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
     auto map = std::make_shared<RefMap>(lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], 0.5f, 0.0f);
     CaptureEvaluator ev(map, false, 0.9f, 0.1f, 0.0f, 100.0f, cell_size);
-    sensor_msgs::PointCloud2 cloud;
-    cloud.width = static_cast<uint32_t>(n);
-    cloud.height = 1;
-    cloud.point_step = 16;
-    cloud.row_step = cloud.point_step * cloud.width;
-    cloud.fields.resize(4);
-    const char* names[4] = {"x", "y", "z", "ring"};
-    for (int f = 0; f < 4; ++f)
-    {
-      cloud.fields[f].name = names[f];
-      cloud.fields[f].offset = 4u * f;
-    }
-    cloud.data.assign(static_cast<size_t>(n) * 16, 0);
-    for (uint64_t i = 0; i < n; ++i)
-    {
-      std::memcpy(&cloud.data[16 * i], xyz + 3 * i, 12);
-      std::memcpy(&cloud.data[16 * i + 12], ring + i, 2);
-    }
+    const sensor_msgs::PointCloud2 cloud = make_cloud(xyz, ring, n);
     ParticleCloud pc;
     ev.evaluateParticles(pc, cloud, "", "", false, true);
     const uint64_t m = ev.captured.size();

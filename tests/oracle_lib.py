@@ -221,6 +221,10 @@ class Ref:
         L.ref_eval_create.restype = C.c_void_p
         L.ref_eval_create.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
         L.ref_eval_destroy.argtypes = [C.c_void_p]
+        L.ref_eval_create_cell.restype = C.c_void_p
+        L.ref_eval_create_cell.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.ref_evaluate_cloud.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int,
+                                         C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
         L.ref_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_pose_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
         L.ref_systematic_resample.restype = C.c_uint64
@@ -272,6 +276,22 @@ class Ref:
 
     def eval_create(self, m, a_hit=0.9, a_range=0.1, a_max=0.0, max_range=100.0):
         return self.lib.ref_eval_create(m, a_hit, a_range, a_max, max_range)
+
+    def eval_create_cell(self, m, cell, a_hit=0.9, a_range=0.1, a_max=0.0, max_range=100.0):
+        return self.lib.ref_eval_create_cell(m, a_hit, a_range, a_max, max_range, cell)
+
+    def evaluate_cloud(self, e, particles, points, ring, use_cuda=False, desync=False, n_rings=64):
+        """TSDFEvaluator::evaluateParticles(..., use_cuda, ignore_tf=true) on a packed cloud. Returns (rc, particles with the
+        normalised weights, pose[7], error text, reduced scan size (B200 shim build with use_cuda only))."""
+        ps = np.array(particles, dtype=np.float32, copy=True, order="C")
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        rg = np.ascontiguousarray(ring, dtype=np.int16)
+        pose = np.zeros(7, dtype=np.float64)
+        used = C.c_uint64(0)
+        rc = self.lib.ref_evaluate_cloud(e, _fp(ps), ps.shape[0], _fp(pts), _fp(rg), pts.shape[0], 1 if use_cuda else 0,
+                                         1 if desync else 0, n_rings, _fp(pose), C.byref(used))
+        err = self.lib.ref_last_error().decode() if rc else ""
+        return rc, ps, pose, err, int(used.value)
 
     def eval_destroy(self, e):
         self.lib.ref_eval_destroy(e)

@@ -104,3 +104,26 @@ def test_centre_variant_properties():
     assert len(np.unique(want.astype(np.float32), axis=0)) == len(out)
     out_r, src_r = o.reduce_scan_centres(pts, ring, 0.064, n_rings=16)
     assert len(out_r) >= len(out) and (np.diff(ring[src_r]) >= 0).all()
+
+
+@needs_ref
+def test_oracle_evaluateParticles_end_to_end_matches_reference():
+    """Reference evaluateParticles (reduction + CPU evaluation, verbatim) == oracle reduction followed by the oracle evaluation."""
+    import common
+    from oracle_lib import NEG_REF_HOST_X86
+    ref, o = Ref(), Oracle()
+    spec, m = common.box_room(small=True)
+    rm = ref.map_create(spec.min, spec.max, spec.resolution, spec.init_value)
+    assert ref.map_set_data(rm, spec.cells) == 0
+    ev = ref.eval_create_cell(rm, 0.256)
+    gt = (0.4, -0.3, 1.2, 0.01, -0.02, 0.4)
+    pts, ring = syn.make_scan("vlp16", gt, room_lo=(-3.0, -2.5, 0.0), room_hi=(3.0, 2.5, 3.0))
+    ps = syn.tracking_particles(64, gt, sigma_xy=0.05, sigma_z=0.05, sigma_yaw=0.03)
+    rc, got, pose, err, _ = ref.evaluate_cloud(ev, ps, pts, ring, use_cuda=False)
+    assert rc == 0, err
+    red, _ = o.reduce_scan(pts, ring, 0.256, n_rings=64, ring_desync=True)
+    want = o.evaluate(common.oracle_map_of(o, m), common.DEFAULT_PARAMS, ps, red, syn.IDENTITY_TF, mode=NEG_REF_HOST_X86)
+    assert want["status"] == 0
+    assert common.rel_err(got[:, 6], want["particles"][:, 6]).max() <= 2e-6   # weight_sum order differs (OpenMP reduction)
+    ref.eval_destroy(ev)
+    ref.map_destroy(rm)

@@ -97,3 +97,40 @@ def test_gpu_resampler_subclass_matches_reference_resampler(shim, small_map, n):
         assert m_gpu == m_ref
         assert np.array_equal(out_gpu, out_ref)
     shim.eval_destroy(ev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("near", [0, 400])
+def test_reference_evaluateParticles_gpu_branch_matches_its_cpu_branch(shim, small_map, near):
+    """TSDFEvaluatorB200::evaluateParticles (GPU scan reduction + evaluation, the reduced scan never leaves the device)
+    against the reference's own evaluateParticles CPU branch (tsdf_evaluator.cpp:247-378) on the same facade object.
+    near > 0: points closer than 1 m desynchronise the reference's ring iterator; RING_DESYNC mode reproduces that."""
+    from test_reduce_oracle import scan_with_rings
+    from oracle_lib import Oracle
+    ev = shim.eval_create_cell(small_map, 0.064)
+    assert ev, shim.last_error()
+    gt = (0.4, -0.3, 1.2, 0.01, -0.02, 0.4)
+    pts, ring = syn.make_scan("vlp16", gt, room_lo=(-3.0, -2.5, 0.0), room_hi=(3.0, 2.5, 3.0))
+    if near:
+        rng = np.random.default_rng(near)
+        d = rng.normal(size=(near, 3)).astype(np.float32)
+        d *= (rng.uniform(0.05, 0.99, size=(near, 1)) / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        pos = np.sort(rng.integers(0, len(pts), size=near))
+        pts = np.ascontiguousarray(np.insert(pts, pos, d, axis=0))
+        ring = np.ascontiguousarray(np.insert(ring, pos, rng.integers(0, 16, size=near), axis=0))
+    ps = syn.tracking_particles(256, gt, sigma_xy=0.05, sigma_z=0.05, sigma_yaw=0.03)
+    rc_c, cpu, pose_c, err_c, _ = shim.evaluate_cloud(ev, ps, pts, ring, use_cuda=False)
+    rc_g, gpu, pose_g, err_g, used = shim.evaluate_cloud(ev, ps, pts, ring, use_cuda=True, desync=True, n_rings=64)
+    assert rc_c == 0 and rc_g == 0, (err_c, err_g)
+    want, _ = Oracle().reduce_scan(pts, ring, 0.064, n_rings=64, ring_desync=True)
+    assert used == len(want) and 0 < used < len(pts)
+    rel = common.rel_err(gpu[:, 6], cpu[:, 6])
+    assert rel.max() <= 1e-5, f"normalised weights: max rel err {rel.max():.2e}"
+    np.testing.assert_allclose(pose_g[3:], pose_c[3:], atol=1e-5)
+    if near:
+        # product default (every point keeps its own ring) differs from the reference's desynchronised pairing
+        rc_f, fixed, _, err_f, used_f = shim.evaluate_cloud(ev, ps, pts, ring, use_cuda=True, desync=False, n_rings=64)
+        assert rc_f == 0, err_f
+        want_f, _ = Oracle().reduce_scan(pts, ring, 0.064, n_rings=64, ring_desync=False)
+        assert used_f == len(want_f)
+    shim.eval_destroy(ev)

@@ -19,14 +19,14 @@
 #include <tsdf_localization/cuda/cuda_evaluator.h>
 
 #include <sensor_msgs/point_cloud2_iterator.h>
+#include <tf2_geometry_msgs/tf2_geometry_msgs.h>
+#include <tf2_ros/transform_listener.h>
 
 #include <cmath>
 #include <cstdlib>
-#include <map>
 #include <mutex>
 #include <stdexcept>
 #include <string>
-#include <unordered_set>
 #include <vector>
 
 #include "tsdfloc.h"
@@ -108,48 +108,25 @@ CudaEvaluator::~CudaEvaluator()
   d_transform_ = nullptr;
 }
 
-// PointCloud2 overload (cuda_evaluator.cu:78-116): ring-major ordering, then the ring-agnostic 6.4 cm cell-centre
-// reduction, then the vector overload. No caller in the reference; kept for interface completeness.
-geometry_msgs::PoseWithCovariance CudaEvaluator::evaluate(std::vector<Particle>& particles, const sensor_msgs::PointCloud2& real_cloud, FLOAT_T tf_matrix[16])
+namespace
 {
-  sensor_msgs::PointCloud2ConstIterator<float> iter_x(real_cloud, "x");
-  sensor_msgs::PointCloud2ConstIterator<int> iter_ring(real_cloud, "ring");
-  std::multimap<int, CudaPoint> by_ring;
-  for (; iter_x != iter_x.end(); ++iter_x, ++iter_ring)
-  {
-    by_ring.insert(std::pair<int, CudaPoint>(iter_ring[0], CudaPoint(iter_x[0], iter_x[1], iter_x[2])));
-  }
-  std::unordered_set<CudaPoint, hash> cells;
-  for (const auto& entry : by_ring)
-  {
-    const CudaPoint& p = entry.second;
-    cells.insert(CudaPoint(static_cast<float>(std::floor(p.x / 0.064) * 0.064 + 0.032),
-                           static_cast<float>(std::floor(p.y / 0.064) * 0.064 + 0.032),
-                           static_cast<float>(std::floor(p.z / 0.064) * 0.064 + 0.032)));
-  }
-  std::vector<CudaPoint> reduced(cells.begin(), cells.end());
-  return evaluate(particles, reduced, tf_matrix);
+// Byte offset of a named PointCloud2 field; throws like sensor_msgs::PointCloud2ConstIterator does for a missing field.
+uint32_t field_offset(const sensor_msgs::PointCloud2& cloud, const std::string& name)
+{
+  for (const auto& f : cloud.fields)
+    if (f.name == name) return f.offset;
+  throw std::runtime_error("Field " + name + " does not exist");
 }
 
-geometry_msgs::PoseWithCovariance CudaEvaluator::evaluate(std::vector<Particle>& particles, const std::vector<CudaPoint>& points, FLOAT_T tf_matrix[16])
+void throw_update_error(tsdfloc_ctx* ctx, int rc)
 {
-  if (points.size() == 0)
-  {
-    return geometry_msgs::PoseWithCovariance();
-  }
-  tsdfloc_ctx* ctx = ctx_of(d_transform_);
-  float mean[6] = {0, 0, 0, 0, 0, 0};
-  const int rc = tsdfloc_sensor_update(ctx, reinterpret_cast<float*>(particles.data()), particles.size(),
-                                       reinterpret_cast<const float*>(points.data()), points.size(), tf_matrix, mean);
-  if (rc == TSDFLOC_E_NO_VALID_PARTICLE)
-  {
-    throw std::runtime_error("No particle is valid!");
-  }
-  if (rc != TSDFLOC_OK)
-  {
-    throw std::runtime_error(std::string("Error occured during the sensor update on the gpu! ") + tsdfloc_last_error(ctx));
-  }
+  if (rc == TSDFLOC_E_NO_VALID_PARTICLE) throw std::runtime_error("No particle is valid!");
+  throw std::runtime_error(std::string("Error occured during the sensor update on the gpu! ") + tsdfloc_last_error(ctx));
+}
+}  // namespace
 
+geometry_msgs::PoseWithCovariance tsdfloc_shim_pose(const float mean[6])
+{
   geometry_msgs::PoseWithCovariance average_pose;
   average_pose.pose.position.x = mean[0];
   average_pose.pose.position.y = mean[1];
@@ -163,6 +140,81 @@ geometry_msgs::PoseWithCovariance CudaEvaluator::evaluate(std::vector<Particle>&
   average_pose.pose.orientation.w = cr * cp * cy + sr * sp * sy;
   for (auto& v : average_pose.covariance) v = 0.0;  // the reference leaves all six variances at 0 (cuda_evaluator.cu:418-423)
   return average_pose;
+}
+
+// PointCloud2 overload (cuda_evaluator.cu:78-116): the ring-agnostic 6.4 cm cell-CENTRE reduction, then the evaluation.
+// The reference builds a ring-ordered multimap and an unordered_set on the host; here the raw cloud goes to the device
+// and is reduced there (TSDFLOC_REDUCE_EMIT_CENTRES, one ring): the same SET of centres, emitted in cloud order (the
+// reference's order is its unordered_set's iteration order). No caller in the reference; kept for interface completeness.
+geometry_msgs::PoseWithCovariance CudaEvaluator::evaluate(std::vector<Particle>& particles, const sensor_msgs::PointCloud2& real_cloud, FLOAT_T tf_matrix[16])
+{
+  const uint64_t n_points = static_cast<uint64_t>(real_cloud.width) * real_cloud.height;
+  if (n_points == 0) return geometry_msgs::PoseWithCovariance();
+  field_offset(real_cloud, "ring");  // the reference's iterator throws when the field is missing
+  tsdfloc_ctx* ctx = ctx_of(d_transform_);
+  float mean[6] = {0, 0, 0, 0, 0, 0};
+  const int rc = tsdfloc_sensor_update_cloud(ctx, reinterpret_cast<float*>(particles.data()), particles.size(),
+                                             real_cloud.data.data() + field_offset(real_cloud, "x"), real_cloud.point_step, nullptr, 0, 4,
+                                             n_points, 0.064, 1, TSDFLOC_REDUCE_EMIT_CENTRES, tf_matrix, mean, nullptr);
+  if (rc == TSDFLOC_E_EMPTY_SCAN) return geometry_msgs::PoseWithCovariance();
+  if (rc != TSDFLOC_OK) throw_update_error(ctx, rc);
+  return tsdfloc_shim_pose(mean);
+}
+
+// TSDFEvaluator::evaluateParticles with the reduction on the GPU (tsdf_evaluator.cpp:247-378).
+geometry_msgs::PoseWithCovariance TSDFEvaluatorB200::evaluateParticles(ParticleCloud& particle_cloud, const sensor_msgs::PointCloud2& real_cloud,
+                                                                       const std::string& robot_frame, const std::string& scan_frame,
+                                                                       bool use_cuda, bool ignore_tf)
+{
+  if (!use_cuda) return TSDFEvaluator::evaluateParticles(particle_cloud, real_cloud, robot_frame, scan_frame, use_cuda, ignore_tf);
+  if (!ctx_) throw std::runtime_error("TSDFEvaluatorB200: no CudaEvaluator context alive");
+
+  FLOAT_T tf_matrix[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  if (!ignore_tf)
+  {
+    // scanner -> robot transform, as tsdf_evaluator.cpp:251-287
+    static tf2_ros::Buffer tf_buffer;
+    static tf2_ros::TransformListener tf_listener(tf_buffer);
+    geometry_msgs::TransformStamped scan_to_base = tf_buffer.lookupTransform(robot_frame, scan_frame, real_cloud.header.stamp, ros::Duration(0.5));
+    tf2::Transform t;
+    tf2::convert(scan_to_base.transform, t);
+    for (int r = 0; r < 3; ++r)
+    {
+      for (int c = 0; c < 3; ++c) tf_matrix[4 * r + c] = t.getBasis()[r][c];
+    }
+    tf_matrix[3] = t.getOrigin().getX();
+    tf_matrix[7] = t.getOrigin().getY();
+    tf_matrix[11] = t.getOrigin().getZ();
+  }
+
+  const uint64_t n_points = static_cast<uint64_t>(real_cloud.width) * real_cloud.height;
+  const uint8_t* base = real_cloud.data.data();
+  std::vector<Particle>& particles = particle_cloud.particles();
+  float mean[6] = {0, 0, 0, 0, 0, 0};
+  last_reduced_ = 0;
+  // x y z are read as three consecutive floats at the "x" field (iter_x[0..2], :311-315), the ring as a short (:305)
+  const int rc = tsdfloc_sensor_update_cloud(ctx_, reinterpret_cast<float*>(particles.data()), particles.size(),
+                                             base + field_offset(real_cloud, "x"), real_cloud.point_step,
+                                             base + field_offset(real_cloud, "ring"), real_cloud.point_step, 2, n_points, cell_, n_rings,
+                                             ring_desync_like_reference ? TSDFLOC_REDUCE_RING_DESYNC_LIKE_REFERENCE : 0u, tf_matrix, mean,
+                                             &last_reduced_);
+  if (rc == TSDFLOC_E_EMPTY_SCAN) return geometry_msgs::PoseWithCovariance();  // evaluate() on an empty scan, cuda_evaluator.cu:122-125
+  if (rc != TSDFLOC_OK) throw_update_error(ctx_, rc);
+  return tsdfloc_shim_pose(mean);
+}
+
+geometry_msgs::PoseWithCovariance CudaEvaluator::evaluate(std::vector<Particle>& particles, const std::vector<CudaPoint>& points, FLOAT_T tf_matrix[16])
+{
+  if (points.size() == 0)
+  {
+    return geometry_msgs::PoseWithCovariance();
+  }
+  tsdfloc_ctx* ctx = ctx_of(d_transform_);
+  float mean[6] = {0, 0, 0, 0, 0, 0};
+  const int rc = tsdfloc_sensor_update(ctx, reinterpret_cast<float*>(particles.data()), particles.size(),
+                                       reinterpret_cast<const float*>(points.data()), points.size(), tf_matrix, mean);
+  if (rc != TSDFLOC_OK) throw_update_error(ctx, rc);
+  return tsdfloc_shim_pose(mean);
 }
 
 }  // namespace tsdf_localization

@@ -1,11 +1,15 @@
 // tsdfloc_shim.h — C++ glue between the reference's class interfaces and the C ABI (include/tsdfloc.h).
 //
 //   * cuda_evaluator_b200.cpp defines the reference's own `CudaEvaluator` (header unchanged) on top of libtsdfloc.so.
+//   * TSDFEvaluatorB200 overrides the reference's virtual TSDFEvaluator::evaluateParticles (evaluation/tsdf_evaluator.h:102,
+//     src/evaluation/tsdf_evaluator.cpp:247-378) so that the scan reduction (:304-376) also runs on the GPU and the reduced
+//     scan never visits the host: construct it in mcl_3d instead of TSDFEvaluator (src/mcl_3d.cpp:749).
 //   * GpuSystematicResampler plugs into the reference's `Resampler` interface (resampling/resampler.h:16-31) exactly
 //     like SystematicResampler (resampling/novel_resampling.h:38-74): select it in mcl_3d's reconfigure callback
 //     (src/mcl_3d.cpp:243-263) instead of `new SystematicResampler()`.
 #pragma once
 
+#include <tsdf_localization/evaluation/tsdf_evaluator.h>
 #include <tsdf_localization/particle_cloud.h>
 #include <tsdf_localization/resampling/resampler.h>
 
@@ -22,6 +26,41 @@ namespace tsdf_localization
 // Context of the most recently constructed CudaEvaluator (the reference keeps one per process, cuda_data.h:17-26);
 // nullptr when none is alive.
 tsdfloc_ctx* tsdfloc_shim_context();
+
+// geometry_msgs::PoseWithCovariance from (x y z roll pitch yaw): position + setRPY quaternion, covariance 0, exactly what
+// CudaEvaluator::evaluate returns (src/cuda/cuda_evaluator.cu:410-423).
+geometry_msgs::PoseWithCovariance tsdfloc_shim_pose(const float mean[6]);
+
+class TSDFEvaluatorB200 : public TSDFEvaluator
+{
+public:
+  TSDFEvaluatorB200(const std::shared_ptr<CudaSubVoxelMap<FLOAT_T, FLOAT_T>>& map_ptr, bool per_point = false, FLOAT_T a_hit = 0.9,
+                    FLOAT_T a_range = 0.1, FLOAT_T a_max = 0.0, FLOAT_T max_range = 100.0, FLOAT_T reduction_cell_size = 0.064)
+  : TSDFEvaluator(map_ptr, per_point, a_hit, a_range, a_max, max_range, reduction_cell_size), cell_(reduction_cell_size),
+    ctx_(tsdfloc_shim_context())  // the CudaEvaluator the base class just constructed (tsdf_evaluator.h:78)
+  {
+  }
+
+  // use_cuda == false falls through to the reference's own CPU implementation.
+  geometry_msgs::PoseWithCovariance evaluateParticles(ParticleCloud& particle_cloud, const sensor_msgs::PointCloud2& real_cloud,
+                                                      const std::string& robot_frame = "base_footprint",
+                                                      const std::string& scan_frame = "scanner", bool use_cuda = false,
+                                                      bool ignore_tf = false) override;
+
+  // Size of the reduced scan of the last GPU evaluateParticles call.
+  uint64_t last_reduced_size() const { return last_reduced_; }
+
+  // true: pair survivor #k of the 1 m test with the ring of cloud point #k like the reference (tsdf_evaluator.cpp:319-322
+  // skips ++iter_ring); false (default): every point keeps its own ring.
+  bool ring_desync_like_reference = false;
+  // rings must lie in [0, n_rings); the reference has 64 buckets (:342) and overruns them with an OS1-128.
+  uint32_t n_rings = 128;
+
+private:
+  FLOAT_T cell_;
+  tsdfloc_ctx* ctx_;
+  uint64_t last_reduced_ = 0;
+};
 
 class GpuSystematicResampler : public Resampler
 {
