@@ -215,6 +215,38 @@ int tsdfloc_sensor_update_cloud(tsdfloc_ctx* ctx, float* particles, uint64_t n, 
                                 const void* ring_base, uint64_t ring_stride, int ring_bytes, uint64_t n_points, double cell_size,
                                 uint32_t n_rings, uint32_t flags, const float tf[16], float mean_pose[6], uint64_t* n_points_used);
 
+/* ---- motion update -------------------------------------------------------------------------------------------------
+ * ParticleCloud::motionUpdate (src/particle_cloud.cpp:153-617) split in two: a scalar model (host) and the per-particle
+ * application (device). Variants and their inputs `in`:
+ *   TSDFLOC_MOTION_NOISE      motionUpdate(lin_scale, ang_scale)  :388-420   {lin_scale, ang_scale}
+ *   TSDFLOC_MOTION_ODOM       motionUpdate(odom)                  :153-331   {twist.linear.x, twist.angular.z}
+ *   TSDFLOC_MOTION_IMU        motionUpdate(imu_data)              :333-386   {linear_vel, angular_yaw}
+ *   TSDFLOC_MOTION_NOISE_IMU  motionUpdate(lin_scale, imu_data)   :422-462   {lin_scale, delta_roll, delta_pitch, delta_yaw} */
+#define TSDFLOC_MOTION_NOISE 0
+#define TSDFLOC_MOTION_ODOM 1
+#define TSDFLOC_MOTION_IMU 2
+#define TSDFLOC_MOTION_NOISE_IMU 3
+
+/* Mean and standard deviation of the six normal distributions (x y z roll pitch yaw) the variant samples, bit-identical to the
+ * reference's (operand types follow it variant by variant). time_diff = seconds since the previous motion update (the
+ * reference's FLOAT_T time_diff), a = a_1_..a_12_ (particle_cloud.h:57-68). ref_pose (optional, 6 fp32, in/out): the reference
+ * pose whose travelled distance / angle gate the sensor update (particle_cloud.h refDist/refAngle, src/mcl_3d.cpp:353); it is
+ * advanced by the ODOM and IMU variants (:180-182, :352-354). Pure host code. */
+int tsdfloc_motion_model(int variant, const double in[4], float time_diff, const float a[12], double mean[6], double sigma[6],
+                         float ref_pose[6]);
+
+/* apply_model (:496-617) on the device, in place: every particle is moved by its own sample of the six distributions and its
+ * Euler angles are read back from the composed rotation; the weight slot is untouched.
+ *   d_draws != NULL : n x 6 doubles, the samples themselves (parity mode: with the reference's draws the result is the
+ *                     reference's bit for bit); mean/sigma are ignored.
+ *   d_draws == NULL : samples = mean + sigma * z with z from a counter-based Philox4x32-10 + Box-Muller stream keyed by
+ *                     (seed, sequence, particle index); pass a new `sequence` every update. */
+int tsdfloc_motion_update_device(tsdfloc_ctx* ctx, float* d_particles, uint64_t n, const double mean[6], const double sigma[6],
+                                 const double* d_draws, uint64_t seed, uint64_t sequence, void* stream);
+/* Same on host buffers (particles n x 7 fp32 in place; draws optional n x 6 doubles). */
+int tsdfloc_motion_update(tsdfloc_ctx* ctx, float* particles, uint64_t n, const double mean[6], const double sigma[6],
+                          const double* draws, uint64_t seed, uint64_t sequence);
+
 /* Arg-max particle of the last normalisation (tsdfloc_sensor_update*, tsdfloc_normalize_device, tsdfloc_cdf_device), the
  * "best pose" mcl_3d picks between evaluation and resampling (src/mcl_3d.cpp:382-399: `if (value > max_value)` starting from
  * 0, i.e. the FIRST particle carrying the largest weight > 0). Reduced inside the normalisation kernels; this call only

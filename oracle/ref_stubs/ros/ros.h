@@ -17,11 +17,14 @@ struct Duration {
   explicit Duration(double s) : sec_(s) {}
   double toSec() const { return sec_; }
 };
+// Test clock: >= 0 makes ros::Time::now() return this value (the motion-update harness steps it by hand).
+inline double& tsdf_stub_clock() { static double t = -1.0; return t; }
 struct Time {
   double sec_ = 0.0;
   Time() = default;
   explicit Time(double s) : sec_(s) {}
   static Time now() {
+    if (tsdf_stub_clock() >= 0.0) return Time(tsdf_stub_clock());
     using namespace std::chrono;
     return Time(duration<double>(steady_clock::now().time_since_epoch()).count());
   }

@@ -521,3 +521,149 @@ int64_t oracle_reduce_scan_centres(const float* P, const int32_t* ring, uint64_t
   free(keys);
   return result;
 }
+
+/* ---- motion update ---------------------------------------------------------------------------------------- */
+
+int oracle_motion_model(int variant, const double in[4], float time_diff, const float a[12], double mean[6], double sigma[6],
+                        float ref_pose[6])
+{
+  for (int k = 0; k < 6; ++k) mean[k] = 0.0;
+  if (variant == 1)
+  {
+    /* particle_cloud.cpp:167-217: linear_velocity / angular_velocity are doubles -> double arithmetic throughout */
+    const double lv = in[0], av = in[1];
+    if (ref_pose)
+    {
+      /* :180-182, float = float + double expression */
+      const float r0 = (float)(ref_pose[0] + lv * time_diff * cos(ref_pose[5] + (av / 2 * time_diff)));
+      const float r1 = (float)(ref_pose[1] + lv * time_diff * sin(ref_pose[5] + (av / 2 * time_diff)));
+      const float r5 = (float)(ref_pose[5] + av * time_diff);
+      ref_pose[0] = r0;
+      ref_pose[1] = r1;
+      ref_pose[5] = r5;
+    }
+    const double d = lv * time_diff, d2 = d * d, th = av * time_diff, t2 = th * th;
+    sigma[0] = a[0] * d2 + a[1] * t2;
+    sigma[1] = a[2] * d2 + a[3] * t2;
+    sigma[2] = a[4] * d2 + a[5] * t2;
+    sigma[3] = a[6] * d2 + a[7] * t2;
+    sigma[4] = a[8] * d2 + a[9] * t2;
+    sigma[5] = a[10] * d2 + a[11] * t2;
+    mean[0] = d;
+    mean[5] = th;
+    return 0;
+  }
+  if (variant == 0 || variant == 2)
+  {
+    /* :388-414 / :337-374: FLOAT_T operands -> fp32 arithmetic, each operation rounded */
+    const float s0 = (float)in[0], s1 = (float)in[1];
+    if (variant == 2 && ref_pose)
+    {
+      /* :352-354: float operands, cos/sin evaluated in double (the object file imports sincos) and the product rounded to float */
+      const float arg = ref_pose[5] + (s1 / 2 * time_diff);
+      const float r0 = (float)(ref_pose[0] + s0 * time_diff * cos(arg));
+      const float r1 = (float)(ref_pose[1] + s0 * time_diff * sin(arg));
+      const float r5 = ref_pose[5] + s1 * time_diff;
+      ref_pose[0] = r0;
+      ref_pose[1] = r1;
+      ref_pose[5] = r5;
+    }
+    const float d = s0 * time_diff, d2 = d * d, th = s1 * time_diff, t2 = th * th;
+    sigma[0] = a[0] * d2 + a[1] * t2;
+    sigma[1] = a[2] * d2 + a[3] * t2;
+    sigma[2] = a[4] * d2 + a[5] * t2;
+    sigma[3] = a[6] * d2 + a[7] * t2;
+    sigma[4] = a[8] * d2 + a[9] * t2;
+    sigma[5] = a[10] * d2 + a[11] * t2;
+    if (variant == 2)
+    {
+      mean[0] = d;
+      mean[5] = th;
+    }
+    return 0;
+  }
+  if (variant == 3)
+  {
+    /* :436-456 */
+    const float d = (float)in[0] * time_diff, d2 = d * d;
+    const float roll = (float)in[1], pitch = (float)in[2], th = (float)in[3];
+    const float r2 = roll * roll, p2 = pitch * pitch, t2 = th * th;
+    sigma[0] = a[0] * d2 + a[1] * t2;
+    sigma[1] = a[2] * d2 + a[3] * t2;
+    sigma[2] = a[4] * d2 + a[5] * t2;
+    sigma[3] = a[7] * r2;
+    sigma[4] = a[9] * p2;
+    sigma[5] = a[11] * t2;
+    mean[3] = roll;
+    mean[4] = pitch;
+    mean[5] = th;
+    return 0;
+  }
+  return 1;
+}
+
+/* rotation part of R = Rz(c) Ry(b) Rx(a) from float sines / cosines, written like particle_cloud.cpp:525-539 */
+static void rot_rows(float sa, float ca, float sb, float cb, float sc, float cc, float m[12])
+{
+  m[0] = cb * cc;
+  m[4] = cb * sc;
+  m[8] = -sb;
+  m[1] = sa * sb * cc - ca * sc;
+  m[5] = sa * sb * sc + ca * cc;
+  m[9] = sa * cb;
+  m[2] = ca * sb * cc + sa * sc;
+  m[6] = ca * sb * sc - sa * cc;
+  m[10] = ca * cb;
+}
+
+void oracle_motion_apply(float* P, uint64_t n, const double* draws)
+{
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    float* p = P + 7 * i;
+    const double dx = draws[6 * i], dy = draws[6 * i + 1], dz = draws[6 * i + 2];
+    const double roll = draws[6 * i + 3], pitch = draws[6 * i + 4], yaw = draws[6 * i + 5];
+    float o[12], q[12], tf[12];
+    /* :508-513 FLOAT_T s = sin(double) */
+    rot_rows((float)sin(roll), (float)cos(roll), (float)sin(pitch), (float)cos(pitch), (float)sin(yaw), (float)cos(yaw), o);
+    o[3] = (float)dx;
+    o[7] = (float)dy;
+    o[11] = (float)dz;
+    /* :543-553 the particle's own angles are floats; sin/cos still evaluate in double */
+    rot_rows((float)sin((double)p[3]), (float)cos((double)p[3]), (float)sin((double)p[4]), (float)cos((double)p[4]),
+             (float)sin((double)p[5]), (float)cos((double)p[5]), q);
+    q[3] = 0;
+    q[7] = 0;
+    q[11] = 0;
+    /* :575-588 */
+    for (int r = 0; r < 3; ++r)
+    {
+      tf[4 * r + 0] = q[4 * r] * o[0] + q[4 * r + 1] * o[4] + q[4 * r + 2] * o[8];
+      tf[4 * r + 1] = q[4 * r] * o[1] + q[4 * r + 1] * o[5] + q[4 * r + 2] * o[9];
+      tf[4 * r + 2] = q[4 * r] * o[2] + q[4 * r + 1] * o[6] + q[4 * r + 2] * o[10];
+      tf[4 * r + 3] = q[4 * r] * o[3] + q[4 * r + 1] * o[7] + q[4 * r + 2] * o[11] + q[4 * r + 3];
+    }
+    /* getAngleFromMat, src/util/util.cpp:86-111 */
+    float t_roll, t_pitch, t_yaw;
+    if (fabs((double)tf[8]) >= 1)
+    {
+      t_yaw = 0;
+      const double delta = atan2((double)tf[9], (double)tf[10]);
+      t_pitch = (float)(tf[8] < 0 ? M_PI / 2.0 : -M_PI / 2.0);
+      t_roll = (float)delta;
+    }
+    else
+    {
+      t_pitch = (float)(-asin((double)tf[8]));
+      t_roll = (float)atan2(tf[9] / cos((double)t_pitch), tf[10] / cos((double)t_pitch));
+      t_yaw = (float)atan2(tf[4] / cos((double)t_pitch), tf[0] / cos((double)t_pitch));
+    }
+    /* :600-616 */
+    p[0] = p[0] + tf[3];
+    p[1] = p[1] + tf[7];
+    p[2] = p[2] + tf[11];
+    p[3] = t_roll;
+    p[4] = t_pitch;
+    p[5] = t_yaw;
+  }
+}

@@ -126,6 +126,20 @@ int64_t oracle_reduce_scan(const float* points_xyz, const int32_t* ring, uint64_
 int64_t oracle_reduce_scan_centres(const float* points_xyz, const int32_t* ring, uint64_t n, double cell_size, uint32_t n_rings,
                                    float* points_out, uint32_t* src_index_out);
 
+/* ---- motion update ------------------------------------------------------------------------------
+ * The four ParticleCloud::motionUpdate variants (src/particle_cloud.cpp:153-462) differ only in the mean / standard
+ * deviation of six normal distributions (x y z roll pitch yaw); the per-particle work is apply_model (:496-617).
+ *   variant 0  motionUpdate(lin_scale, ang_scale)  :388-420   in = {lin_scale, ang_scale}            (fp32 arithmetic)
+ *   variant 1  motionUpdate(odom)                  :153-331   in = {linear.x, angular.z}             (fp64 arithmetic)
+ *   variant 2  motionUpdate(imu_data)              :333-386   in = {linear_vel, angular_yaw}         (fp32)
+ *   variant 3  motionUpdate(lin_scale, imu_data)   :422-462   in = {lin_scale, d_roll, d_pitch, d_yaw} (fp32)
+ * time_diff is the reference's FLOAT_T time_diff; a = a_1_..a_12_ (particle_cloud.h:57-68). Also advances the reference
+ * pose (ref_pose, :180-182 / :352-354) when ref_pose != NULL (variants 1 and 2 only). Returns 0, or 1 for a bad variant. */
+int oracle_motion_model(int variant, const double in[4], float time_diff, const float a[12], double mean[6], double sigma[6],
+                        float ref_pose[6]);
+/* apply_model: particles n x 7 in place (weights untouched), draws n x 6 doubles (the values the six distributions returned). */
+void oracle_motion_apply(float* particles7, uint64_t n, const double* draws6);
+
 #ifdef __cplusplus
 }
 #endif

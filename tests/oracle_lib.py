@@ -72,10 +72,33 @@ class Oracle:
                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_systematic_resample.restype = C.c_uint64
         L.oracle_systematic_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_uint64]
+        L.oracle_motion_model.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_motion_apply.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.oracle_reduce_scan.restype = C.c_int64
         L.oracle_reduce_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_reduce_scan_centres.restype = C.c_int64
         L.oracle_reduce_scan_centres.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_uint32, C.c_void_p, C.c_void_p]
+
+    # -- motion update --
+    def motion_model(self, variant, inputs, time_diff, a, ref_pose=None):
+        """(mean[6], sigma[6], ref_pose') of the six normal distributions of ParticleCloud::motionUpdate variant `variant`."""
+        inp = np.zeros(4, dtype=np.float64)
+        inp[:len(inputs)] = inputs
+        av = np.ascontiguousarray(a, dtype=np.float32)
+        mean, sigma = np.zeros(6), np.zeros(6)
+        rp = None if ref_pose is None else np.array(ref_pose, dtype=np.float32)
+        rc = self.lib.oracle_motion_model(int(variant), _fp(inp), C.c_float(time_diff), _fp(av), _fp(mean), _fp(sigma),
+                                          _fp(rp) if rp is not None else None)
+        if rc:
+            raise ValueError("bad motion variant")
+        return mean, sigma, rp
+
+    def motion_apply(self, particles, draws):
+        ps = np.array(particles, dtype=np.float32, copy=True, order="C")
+        dr = np.ascontiguousarray(draws, dtype=np.float64)
+        assert dr.shape == (ps.shape[0], 6)
+        self.lib.oracle_motion_apply(_fp(ps), ps.shape[0], _fp(dr))
+        return ps
 
     # -- scan reduction --
     def reduce_scan(self, points, ring, cell, n_rings=128, ring_desync=False):
@@ -333,3 +356,33 @@ class Ref:
         u0 = C.c_float(0)
         m = int(self.lib.ref_systematic_resample(_fp(ps), n, seed, _fp(out), cap, C.byref(u0)))
         return m, out[:min(m, cap)], u0.value
+
+
+def ref_pc_path() -> Path:
+    return ORACLE_DIR / "_ref" / "libtsdf_ref_pc.so"
+
+
+class RefPC:
+    """The verbatim reference ParticleCloud motion update (oracle/pc_harness.cpp)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(str(ref_pc_path()))
+        self.lib.ref_pc_motion_update.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+        self.lib.ref_pc_draws.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+
+    def motion_update(self, variant, inputs, dt, a, seed, particles, ref_pose=None):
+        inp = np.zeros(4, dtype=np.float64)
+        inp[:len(inputs)] = inputs
+        av = np.ascontiguousarray(a, dtype=np.float32)
+        ps = np.array(particles, dtype=np.float32, copy=True, order="C")
+        rp = np.zeros(6, dtype=np.float32) if ref_pose is None else np.array(ref_pose, dtype=np.float32)
+        rc = self.lib.ref_pc_motion_update(int(variant), _fp(inp), C.c_double(dt), _fp(av), seed, _fp(ps), ps.shape[0], _fp(rp))
+        assert rc == 0
+        return ps, rp
+
+    def draws(self, seed, mean, sigma, n):
+        m = np.ascontiguousarray(mean, dtype=np.float64)
+        s = np.ascontiguousarray(sigma, dtype=np.float64)
+        out = np.empty((n, 6), dtype=np.float64)
+        self.lib.ref_pc_draws(seed, _fp(m), _fp(s), n, _fp(out))
+        return out

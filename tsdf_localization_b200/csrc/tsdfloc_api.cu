@@ -9,6 +9,7 @@
 #include "tsdfloc_kernels.cuh"
 #include "tsdfloc_eval2.cuh"
 #include "tsdfloc_reduce.cuh"
+#include "tsdfloc_motion.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -74,6 +75,9 @@ struct tsdfloc_ctx
   RedStatus* d_red_status = nullptr;
   RedStatus* h_red_status = nullptr;
   bool have_reduce = false;
+
+  // motion update
+  DevBuf d_draws;
 
   // pinned staging
   void* h_stage = nullptr;
@@ -711,7 +715,7 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
   DevBuf* bufs[] = {&c->d_xyz_stage, &c->d_pts, &c->d_particles, &c->d_particles_out, &c->d_mats,
                     &c->d_raw, &c->d_cdf, &c->d_tile_total, &c->d_tile_offset, &c->d_tile_moments, &c->d_tile_best, &c->d_parents, &c->d_idx, &c->d_hits,
                     &c->d_red_in_xyz, &c->d_red_in_ring, &c->d_red_key4, &c->d_red_table, &c->d_red_cta, &c->d_red_hist, &c->d_red_win,
-                    &c->d_red_rank, &c->d_red_out, &c->d_red_src};
+                    &c->d_red_rank, &c->d_red_out, &c->d_red_src, &c->d_draws};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->d_table) cudaFree(c->d_table);
@@ -798,6 +802,69 @@ int tsdfloc_check(tsdfloc_ctx* c, uint64_t* n_out, double* weight_sum, void* str
   if (weight_sum) *weight_sum = c->h_status->weight_sum;
   if (c->h_status->zero_sum) return fail(c, TSDFLOC_E_NO_VALID_PARTICLE, "No particle is valid!");
   if (c->h_status->table_overflow & 3u) return fail(c, TSDFLOC_E_CAPACITY, "U recurrence table overflow or stalled recurrence");
+  return TSDFLOC_OK;
+}
+
+// ---- motion update ------------------------------------------------------------------------------------------------
+
+static int stage_motion(tsdfloc_ctx* c, float* d_particles, uint64_t n, const double mean[6], const double sigma[6], const double* d_draws,
+                        uint64_t seed, uint64_t sequence, cudaStream_t s)
+{
+  if (n > (1ull << 31)) return fail(c, TSDFLOC_E_BAD_ARG, "too many particles");
+  if (n == 0) return TSDFLOC_OK;
+  MotionArgs a{};
+  for (int k = 0; k < 6; ++k)
+  {
+    a.mean[k] = mean ? mean[k] : 0.0;
+    a.sigma[k] = sigma ? sigma[k] : 0.0;
+  }
+  a.seed = seed;
+  a.sequence = sequence;
+  k_motion_apply<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(d_particles, static_cast<uint32_t>(n), d_draws, a);
+  return launch_check(c, "k_motion_apply");
+}
+
+int tsdfloc_motion_update_device(tsdfloc_ctx* c, float* d_particles, uint64_t n, const double mean[6], const double sigma[6],
+                                 const double* d_draws, uint64_t seed, uint64_t sequence, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (n && !d_particles) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (!d_draws && (!mean || !sigma)) return fail(c, TSDFLOC_E_BAD_ARG, "mean and sigma are required without injected draws");
+  DeviceGuard guard(c->device);
+  return stage_motion(c, d_particles, n, mean, sigma, d_draws, seed, sequence, pick(c, stream));
+}
+
+int tsdfloc_motion_update(tsdfloc_ctx* c, float* particles, uint64_t n, const double mean[6], const double sigma[6], const double* draws,
+                          uint64_t seed, uint64_t sequence)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (n && !particles) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (!draws && (!mean || !sigma)) return fail(c, TSDFLOC_E_BAD_ARG, "mean and sigma are required without injected draws");
+  if (n == 0) return TSDFLOC_OK;
+  DeviceGuard guard(c->device);
+  cudaStream_t s = c->stream;
+  int rc;
+  const size_t pbytes = sizeof(float) * 7 * n, dbytes = draws ? sizeof(double) * 6 * n : 0;
+  if ((rc = ensure(c, c->d_particles, pbytes, "cudaMalloc(particles)"))) return rc;
+  if (draws && (rc = ensure(c, c->d_draws, dbytes, "cudaMalloc(motion draws)"))) return rc;
+  if ((rc = ensure_host(c, pbytes + dbytes + 64))) return rc;
+  c->have_cdf = false;
+  c->n_resident = 0;
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  char* h = static_cast<char*>(c->h_stage);
+  const size_t doff = (pbytes + 63) / 64 * 64;
+  std::memcpy(h, particles, pbytes);
+  float* d_p = static_cast<float*>(c->d_particles.p);
+  CU_TRY(c, cudaMemcpyAsync(d_p, h, pbytes, cudaMemcpyHostToDevice, s), "H2D particles");
+  if (draws)
+  {
+    std::memcpy(h + doff, draws, dbytes);
+    CU_TRY(c, cudaMemcpyAsync(c->d_draws.p, h + doff, dbytes, cudaMemcpyHostToDevice, s), "H2D motion draws");
+  }
+  if ((rc = stage_motion(c, d_p, n, mean, sigma, draws ? static_cast<const double*>(c->d_draws.p) : nullptr, seed, sequence, s))) return rc;
+  CU_TRY(c, cudaMemcpyAsync(h, d_p, pbytes, cudaMemcpyDeviceToHost, s), "D2H particles");
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  std::memcpy(particles, h, pbytes);
   return TSDFLOC_OK;
 }
 

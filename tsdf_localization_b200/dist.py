@@ -71,6 +71,15 @@ class GpuStages:
                                                                    first_out, count_out, C.c_void_p(d_out.data_ptr()), None,
                                                                    self._stream()))
 
+    def motion(self, d_particles, n, mean, sigma, seed: int, sequence: int, d_draws=None) -> None:
+        """In-place motion update of the (replicated) particle set: every rank applies the same Philox stream, keyed by the
+        particle index, so the replicas stay bit-identical without any exchange."""
+        m = (C.c_double * 6)(*[float(v) for v in mean])
+        s = (C.c_double * 6)(*[float(v) for v in sigma])
+        capi.check(self.lib, self.ctx, self.lib.tsdfloc_motion_update_device(
+            self.ctx, C.c_void_p(d_particles.data_ptr()), n, m, s, C.c_void_p(d_draws.data_ptr()) if d_draws is not None else None,
+            int(seed), int(sequence), self._stream()))
+
     def check(self) -> Tuple[int, float]:
         n_out, wsum = C.c_uint64(0), C.c_double(0.0)
         rc = self.lib.tsdfloc_check(self.ctx, C.byref(n_out), C.byref(wsum), self._stream())

@@ -269,6 +269,87 @@ class CudaEvaluator:
         self.close()
 
 
+class ParticleCloud:
+    """Motion-update half of the reference's ParticleCloud (include/tsdf_localization/particle_cloud.h:44-258,
+    src/particle_cloud.cpp:153-617) on the GPU: the four ``motionUpdate`` variants, the reference pose that gates the sensor
+    update (``refDist`` / ``refAngle`` / ``resetRef``) and the motion parameters a_1..a_12. ``particles`` is a float32[n, 7]
+    array updated in place. The reference measures ``time_diff`` with ros::Time::now(); here the caller passes it.
+
+    Samples come from a counter-based Philox stream on the device (``seed``; one sequence number per update), or — parity
+    mode — from ``draws`` (float64[n, 6]), the values the reference's six std::normal_distribution<> objects returned.
+    """
+
+    def __init__(self, evaluator, particles: Optional[np.ndarray] = None, seed: int = 0):
+        self._ev = evaluator.cuda_evaluator_ if isinstance(evaluator, TSDFEvaluator) else evaluator
+        self._lib = capi.load_library()
+        self.m_particles = particles
+        self.ref_pose = np.zeros(6, dtype=np.float32)
+        self.a = np.full(12, 0.1, dtype=np.float32)           # particle_cloud.h:57-68
+        self.seed = int(seed)
+        self.sequence = 0
+
+    def particles(self) -> np.ndarray:
+        return self.m_particles
+
+    def size(self) -> int:
+        return 0 if self.m_particles is None else len(self.m_particles)
+
+    def setAParams(self, *a) -> None:
+        if len(a) != 12:
+            raise ValueError("a_1 .. a_12 expected")
+        self.a = np.asarray(a, dtype=np.float32)
+
+    def refDist(self) -> float:
+        r = self.ref_pose
+        return float(np.sqrt(np.float32(r[0] * r[0] + r[1] * r[1] + r[2] * r[2])))
+
+    def refAngle(self) -> float:
+        return float(abs(self.ref_pose[5]))
+
+    def resetRef(self) -> None:
+        self.ref_pose[:] = 0
+
+    def model(self, variant: int, inputs, time_diff: float):
+        """(mean[6], sigma[6]) of the variant's six normal distributions; advances ref_pose like the reference."""
+        inp = (C.c_double * 4)(*([float(v) for v in inputs] + [0.0] * (4 - len(inputs))))
+        mean, sigma = (C.c_double * 6)(), (C.c_double * 6)()
+        rc = self._lib.tsdfloc_motion_model(int(variant), inp, C.c_float(time_diff), self.a.ctypes.data_as(C.POINTER(C.c_float)), mean,
+                                            sigma, self.ref_pose.ctypes.data_as(C.POINTER(C.c_float)))
+        if rc != capi.OK:
+            raise ValueError("unknown motion variant")
+        return np.array(list(mean)), np.array(list(sigma))
+
+    def _apply(self, mean, sigma, draws):
+        ps = self.m_particles
+        if not (isinstance(ps, np.ndarray) and ps.dtype == np.float32 and ps.ndim == 2 and ps.shape[1] == 7 and ps.flags.c_contiguous):
+            raise ValueError("particles must be a C-contiguous float32[n, 7] array (it is updated in place)")
+        m = (C.c_double * 6)(*mean)
+        s = (C.c_double * 6)(*sigma)
+        dptr = None
+        if draws is not None:
+            draws = np.ascontiguousarray(draws, dtype=np.float64)
+            if draws.shape != (len(ps), 6):
+                raise ValueError("draws must have shape [n, 6]")
+            dptr = draws.ctypes.data_as(C.c_void_p)
+        self.sequence += 1
+        capi.check(self._lib, self._ev.ctx, self._lib.tsdfloc_motion_update(self._ev.ctx, ps.ctypes.data_as(C.c_void_p), len(ps), m, s, dptr,
+                                                                           self.seed, self.sequence))
+
+    # the reference's four motionUpdate overloads (particle_cloud.cpp:153, 333, 388, 422), one method each
+    def motionUpdateNoise(self, lin_scale: float, ang_scale: float, time_diff: float, draws=None) -> None:
+        self._apply(*self.model(capi.MOTION_NOISE, [lin_scale, ang_scale], time_diff), draws)
+
+    def motionUpdateOdom(self, linear_x: float, angular_z: float, time_diff: float, draws=None) -> None:
+        self._apply(*self.model(capi.MOTION_ODOM, [linear_x, angular_z], time_diff), draws)
+
+    def motionUpdateImu(self, linear_vel: float, angular_yaw: float, time_diff: float, draws=None) -> None:
+        self._apply(*self.model(capi.MOTION_IMU, [linear_vel, angular_yaw], time_diff), draws)
+
+    def motionUpdateNoiseImu(self, lin_scale: float, delta_roll: float, delta_pitch: float, delta_yaw: float, time_diff: float,
+                             draws=None) -> None:
+        self._apply(*self.model(capi.MOTION_NOISE_IMU, [lin_scale, delta_roll, delta_pitch, delta_yaw], time_diff), draws)
+
+
 class TSDFEvaluator:
     """Sensor-update facade with the reference's constructor and evaluate() signature (tsdf_evaluator.h:72-114).
 
