@@ -247,6 +247,24 @@ int tsdfloc_motion_update_device(tsdfloc_ctx* ctx, float* d_particles, uint64_t 
 int tsdfloc_motion_update(tsdfloc_ctx* ctx, float* particles, uint64_t n, const double mean[6], const double sigma[6],
                           const double* draws, uint64_t seed, uint64_t sequence);
 
+/* Particle initialisation on the device — ParticleCloud::initialize x 3 (src/particle_cloud.cpp:32-148). Every particle gets
+ * weight 1/n; the six pose components come from the same Philox stream family as the motion update.
+ *   TSDFLOC_INIT_NORMAL    ~ N(mean[k], spread[k])                                  initialize(center, n, sigma_x ...)   :32-62
+ *   TSDFLOC_INIT_UNIFORM   ~ U(mean[k] - spread[k], mean[k] + spread[k])            initialize(n, center, dx ...)        :64-103
+ *   TSDFLOC_INIT_FREE_MAP  xyz = a uniformly drawn free-space voxel with z - 0.5, angles ~ U(mean +- spread)
+ *                          initialize(n, free_map, center, droll ...)  :105-148 (global localisation); d_free_map: n_free x 3
+ *                          fp32 device array. The reference's index distribution includes size() (:109, out of bounds);
+ *                          here it is uniform over [0, n_free).
+ * mean = x y z roll pitch yaw of the centre pose (the reference extracts roll/pitch/yaw from the pose's quaternion). */
+#define TSDFLOC_INIT_NORMAL 0
+#define TSDFLOC_INIT_UNIFORM 1
+#define TSDFLOC_INIT_FREE_MAP 2
+int tsdfloc_init_particles_device(tsdfloc_ctx* ctx, float* d_particles, uint64_t n, int mode, const double mean[6], const double spread[6],
+                                  const float* d_free_map, uint64_t n_free, uint64_t seed, uint64_t sequence, void* stream);
+/* Same into a host buffer (particles: n x 7 fp32; free_map: n_free x 3 fp32 host array, uploaded for the call). */
+int tsdfloc_init_particles(tsdfloc_ctx* ctx, float* particles, uint64_t n, int mode, const double mean[6], const double spread[6],
+                           const float* free_map, uint64_t n_free, uint64_t seed, uint64_t sequence);
+
 /* Arg-max particle of the last normalisation (tsdfloc_sensor_update*, tsdfloc_normalize_device, tsdfloc_cdf_device), the
  * "best pose" mcl_3d picks between evaluation and resampling (src/mcl_3d.cpp:382-399: `if (value > max_value)` starting from
  * 0, i.e. the FIRST particle carrying the largest weight > 0). Reduced inside the normalisation kernels; this call only

@@ -123,3 +123,35 @@ def test_philox_statistics_and_determinism(evaluator):
     b.m_particles = base[:1000].copy()
     b.motionUpdateOdom(1.3, -0.4, time_diff=0.5)           # second update: next sequence number -> fresh samples
     assert b.particles().tobytes() != out[:1000].tobytes()
+
+
+def test_initialize_three_modes(evaluator):
+    """ParticleCloud::initialize x 3 (particle_cloud.cpp:32-148): weights 1/n, sample statistics, determinism."""
+    n = 100000
+    centre = (1.0, -2.0, 0.5, 0.01, -0.02, 0.7)
+    pc = ParticleCloud(evaluator, seed=9)
+    sig = (0.5, 0.25, 0.1, 0.02, 0.03, 0.4)
+    ps = pc.initialize(n, centre, sig, capi.INIT_NORMAL)
+    assert ps.shape == (n, 7) and (ps[:, 6] == np.float32(1.0 / n)).all() and not pc.ref_pose.any()
+    for k in range(6):
+        assert abs(ps[:, k].mean() - centre[k]) < 5 * sig[k] / np.sqrt(n)
+        assert abs(ps[:, k].std() - sig[k]) < 0.02 * sig[k]
+    half = (2.0, 3.0, 0.5, 0.1, 0.2, np.pi)
+    ps = pc.initialize(n, centre, half, capi.INIT_UNIFORM)
+    for k in range(6):
+        assert ps[:, k].min() >= centre[k] - half[k] - 1e-5 and ps[:, k].max() <= centre[k] + half[k] + 1e-5
+        assert abs(ps[:, k].std() - half[k] / np.sqrt(3)) < 0.02 * half[k]
+    rng = np.random.default_rng(0)
+    free = rng.uniform(-5, 5, size=(777, 3)).astype(np.float32)
+    ps = pc.initialize(n, centre, half, capi.INIT_FREE_MAP, free_map=free)
+    want = free.copy()
+    want[:, 2] = (free[:, 2].astype(np.float64) - 0.5).astype(np.float32)
+    rows = {r.tobytes() for r in want}
+    assert all(p.tobytes() in rows for p in ps[:2000, :3])
+    counts = np.unique(ps[:, 0], return_counts=True)[1]
+    assert len(counts) == len(np.unique(free[:, 0])) and counts.min() > 0.5 * n / len(free)      # every voxel drawn, roughly evenly
+    again = ParticleCloud(evaluator, seed=9)
+    again.sequence = pc.sequence - 1
+    assert again.initialize(n, centre, half, capi.INIT_FREE_MAP, free_map=free).tobytes() == ps.tobytes()
+    with pytest.raises(capi.TsdflocError):
+        pc.initialize(10, centre, half, capi.INIT_FREE_MAP)

@@ -12,6 +12,7 @@ OK, E_BAD_ARG, E_CUDA, E_NO_VALID_PARTICLE, E_EMPTY_SCAN, E_CAPACITY, E_STATE = 
 
 REDUCE_RING_DESYNC_LIKE_REFERENCE, REDUCE_EMIT_CENTRES = 1, 2
 MOTION_NOISE, MOTION_ODOM, MOTION_IMU, MOTION_NOISE_IMU = range(4)
+INIT_NORMAL, INIT_UNIFORM, INIT_FREE_MAP = range(3)
 
 
 class LibraryNotBuilt(RuntimeError):
@@ -84,6 +85,8 @@ SIGNATURES = {
     "tsdfloc_motion_model": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_float, _fp, C.POINTER(C.c_double), C.POINTER(C.c_double), _fp]),
     "tsdfloc_motion_update_device": (C.c_int, [_vp, _vp, _u64, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _u64, _u64, _vp]),
     "tsdfloc_motion_update": (C.c_int, [_vp, _vp, _u64, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _u64, _u64]),
+    "tsdfloc_init_particles_device": (C.c_int, [_vp, _vp, _u64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _u64, _u64, _u64, _vp]),
+    "tsdfloc_init_particles": (C.c_int, [_vp, _vp, _u64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _u64, _u64, _u64]),
     "tsdfloc_best_particle": (C.c_int, [_vp, C.POINTER(C.c_int64), _fp, _fp, _vp]),
     "tsdfloc_host_u_sequence": (_u64, [C.c_float, _u64, C.c_double, _vp, _u64, _u32p, _u32p]),
     "tsdfloc_eval_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),

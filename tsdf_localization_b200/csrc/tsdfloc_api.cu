@@ -868,6 +868,66 @@ int tsdfloc_motion_update(tsdfloc_ctx* c, float* particles, uint64_t n, const do
   return TSDFLOC_OK;
 }
 
+static int stage_init(tsdfloc_ctx* c, float* d_particles, uint64_t n, int mode, const double mean[6], const double spread[6],
+                      const float* d_free_map, uint64_t n_free, uint64_t seed, uint64_t sequence, cudaStream_t s)
+{
+  if (mode < kInitNormal || mode > kInitFreeMap) return fail(c, TSDFLOC_E_BAD_ARG, "unknown initialisation mode");
+  if (n == 0 || n > (1ull << 24)) return fail(c, TSDFLOC_E_BAD_ARG, "particle count must be in [1, 2^24]");
+  if (mode == kInitFreeMap && (!d_free_map || n_free == 0 || n_free > 0xffffffffull)) return fail(c, TSDFLOC_E_BAD_ARG, "free map required");
+  InitArgs a{};
+  for (int k = 0; k < 6; ++k)
+  {
+    a.mean[k] = mean[k];
+    a.spread[k] = spread[k];
+  }
+  a.seed = seed;
+  a.sequence = sequence;
+  a.free_map = d_free_map;
+  a.n_free = static_cast<uint32_t>(n_free);
+  a.mode = mode;
+  k_init_particles<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(d_particles, static_cast<uint32_t>(n), a);
+  return launch_check(c, "k_init_particles");
+}
+
+int tsdfloc_init_particles_device(tsdfloc_ctx* c, float* d_particles, uint64_t n, int mode, const double mean[6], const double spread[6],
+                                  const float* d_free_map, uint64_t n_free, uint64_t seed, uint64_t sequence, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!d_particles || !mean || !spread) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  DeviceGuard guard(c->device);
+  return stage_init(c, d_particles, n, mode, mean, spread, d_free_map, n_free, seed, sequence, pick(c, stream));
+}
+
+int tsdfloc_init_particles(tsdfloc_ctx* c, float* particles, uint64_t n, int mode, const double mean[6], const double spread[6],
+                           const float* free_map, uint64_t n_free, uint64_t seed, uint64_t sequence)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!particles || !mean || !spread) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (n == 0 || n > (1ull << 24)) return fail(c, TSDFLOC_E_BAD_ARG, "particle count must be in [1, 2^24]");
+  DeviceGuard guard(c->device);
+  cudaStream_t s = c->stream;
+  int rc;
+  const size_t pbytes = sizeof(float) * 7 * n;
+  if ((rc = ensure(c, c->d_particles, pbytes, "cudaMalloc(particles)"))) return rc;
+  if ((rc = ensure_host(c, pbytes))) return rc;
+  c->have_cdf = false;
+  c->n_resident = 0;
+  const float* d_free = nullptr;
+  if (mode == kInitFreeMap)
+  {
+    if (!free_map || n_free == 0) return fail(c, TSDFLOC_E_BAD_ARG, "free map required");
+    if ((rc = ensure(c, c->d_draws, sizeof(float) * 3 * n_free, "cudaMalloc(free map)"))) return rc;
+    CU_TRY(c, cudaMemcpyAsync(c->d_draws.p, free_map, sizeof(float) * 3 * n_free, cudaMemcpyHostToDevice, s), "H2D free map");
+    d_free = static_cast<const float*>(c->d_draws.p);
+  }
+  float* d_p = static_cast<float*>(c->d_particles.p);
+  if ((rc = stage_init(c, d_p, n, mode, mean, spread, d_free, n_free, seed, sequence, s))) return rc;
+  CU_TRY(c, cudaMemcpyAsync(c->h_stage, d_p, pbytes, cudaMemcpyDeviceToHost, s), "D2H particles");
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  std::memcpy(particles, c->h_stage, pbytes);
+  return TSDFLOC_OK;
+}
+
 int tsdfloc_best_particle(tsdfloc_ctx* c, int64_t* index, float pose[6], float* weight, void* stream)
 {
   if (!c) return TSDFLOC_E_BAD_ARG;

@@ -160,4 +160,83 @@ __global__ void __launch_bounds__(128) k_motion_apply(float* __restrict__ partic
   p[5] = yaw;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Particle initialisation (ParticleCloud::initialize x 3, src/particle_cloud.cpp:32-148): every particle gets weight 1/n and
+//   kInitNormal   x y z roll pitch yaw ~ N(mean[k], spread[k])                                   (:32-62)
+//   kInitUniform  x y z roll pitch yaw ~ U(mean[k] - spread[k], mean[k] + spread[k])             (:64-103)
+//   kInitFreeMap  xyz = a uniformly drawn free-space voxel (z - 0.5), angles ~ U(mean +- spread)  (:105-148)
+// The double samples are rounded to fp32 when stored, like the reference's `first[k] = distribution(gen)`.
+// Divergence: the reference draws the free-map index from [0, size] INCLUSIVE (:109) and reads one element past the end
+// with probability 1/(size+1); here the index is uniform over [0, size).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kInitNormal = 0, kInitUniform = 1, kInitFreeMap = 2;
+
+struct InitArgs
+{
+  double mean[6];
+  double spread[6];
+  unsigned long long seed;
+  unsigned long long sequence;
+  const float* __restrict__ free_map;  // [n_free][3] or nullptr
+  uint32_t n_free;
+  int mode;
+};
+
+__device__ __forceinline__ double uniform53(uint32_t hi, uint32_t lo)
+{
+  const unsigned long long a = (static_cast<unsigned long long>(hi) << 32) | lo;
+  return static_cast<double>(a >> 11) * (1.0 / 9007199254740992.0);  // [0, 1), like std::generate_canonical<double, 53>
+}
+
+__global__ void __launch_bounds__(128) k_init_particles(float* __restrict__ particles, uint32_t n, const InitArgs A)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v[6];
+#pragma unroll
+  for (int pair = 0; pair < 3; ++pair)
+  {
+    uint32_t c[4] = {i, 16u + static_cast<uint32_t>(pair), static_cast<uint32_t>(A.sequence), static_cast<uint32_t>(A.sequence >> 32)};
+    philox4x32_10(c, static_cast<uint32_t>(A.seed), static_cast<uint32_t>(A.seed >> 32));
+    if (A.mode == kInitNormal)
+    {
+      double z0, z1;
+      normal_pair(c, z0, z1);
+      v[2 * pair] = __dadd_rn(__dmul_rn(z0, A.spread[2 * pair]), A.mean[2 * pair]);
+      v[2 * pair + 1] = __dadd_rn(__dmul_rn(z1, A.spread[2 * pair + 1]), A.mean[2 * pair + 1]);
+    }
+    else
+    {
+      // std::uniform_real_distribution: (b - a) * u + a
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+      {
+        const int k = 2 * pair + h;
+        const double lo = A.mean[k] - A.spread[k], hi = A.mean[k] + A.spread[k];
+        v[k] = __dadd_rn(__dmul_rn(hi - lo, uniform53(c[2 * h], c[2 * h + 1])), lo);
+      }
+    }
+  }
+  float* p = particles + 7ull * i;
+  if (A.mode == kInitFreeMap && A.n_free)
+  {
+    uint32_t c[4] = {i, 32u, static_cast<uint32_t>(A.sequence), static_cast<uint32_t>(A.sequence >> 32)};
+    philox4x32_10(c, static_cast<uint32_t>(A.seed), static_cast<uint32_t>(A.seed >> 32));
+    const uint32_t idx = static_cast<uint32_t>((static_cast<unsigned long long>(c[0]) * A.n_free) >> 32);  // uniform over [0, n_free)
+    p[0] = A.free_map[3ull * idx];
+    p[1] = A.free_map[3ull * idx + 1];
+    p[2] = static_cast<float>(static_cast<double>(A.free_map[3ull * idx + 2]) - 0.5);  // :139, float - double literal
+  }
+  else
+  {
+    p[0] = static_cast<float>(v[0]);
+    p[1] = static_cast<float>(v[1]);
+    p[2] = static_cast<float>(v[2]);
+  }
+  p[3] = static_cast<float>(v[3]);
+  p[4] = static_cast<float>(v[4]);
+  p[5] = static_cast<float>(v[5]);
+  p[6] = static_cast<float>(1.0 / static_cast<double>(n));  // :44,56
+}
+
 }  // namespace tsdfloc

@@ -309,6 +309,25 @@ class ParticleCloud:
     def resetRef(self) -> None:
         self.ref_pose[:] = 0
 
+    def initialize(self, number_particles: int, center_pose, spread, mode: int = capi.INIT_NORMAL, free_map=None) -> np.ndarray:
+        """The reference's three initialize() overloads (particle_cloud.cpp:32-148): center_pose = x y z roll pitch yaw,
+        spread = sigmas (INIT_NORMAL) or half-widths (INIT_UNIFORM / INIT_FREE_MAP; the free-map mode ignores the xyz entries).
+        Resets the reference pose, returns (and keeps) the new float32[n, 7] particle array."""
+        self.ref_pose[:] = 0
+        ps = np.empty((int(number_particles), 7), dtype=np.float32)
+        mean = (C.c_double * 6)(*[float(v) for v in center_pose])
+        spr = (C.c_double * 6)(*[float(v) for v in spread])
+        fm, n_free = None, 0
+        if free_map is not None:
+            fm = _f32(free_map, 3, "free_map")
+            n_free = fm.shape[0]
+        self.sequence += 1
+        capi.check(self._lib, self._ev.ctx, self._lib.tsdfloc_init_particles(
+            self._ev.ctx, ps.ctypes.data_as(C.c_void_p), len(ps), int(mode), mean, spr, fm.ctypes.data_as(C.c_void_p) if fm is not None else None,
+            n_free, self.seed, self.sequence))
+        self.m_particles = ps
+        return ps
+
     def model(self, variant: int, inputs, time_diff: float):
         """(mean[6], sigma[6]) of the variant's six normal distributions; advances ref_pose like the reference."""
         inp = (C.c_double * 4)(*([float(v) for v in inputs] + [0.0] * (4 - len(inputs))))
