@@ -94,6 +94,15 @@ const tsdfloc_map_desc* tsdfloc_map_get_desc(const tsdfloc_host_map* m);
 const int32_t* tsdfloc_map_grid_occ(const tsdfloc_host_map* m);
 const float* tsdfloc_map_data(const tsdfloc_host_map* m);
 void tsdfloc_map_destroy(tsdfloc_host_map* m);
+/* Map ingest — createTSDFMap without its HDF5 layer (include/tsdf_localization/map/map_util.h:17-154). chunk_pos: n_chunks x
+ * (cx, cy, cz), the integers of the dataset names "/map/<cx>_<cy>_<cz>"; chunk_data: n_chunks x 64^3 raw TSDFValue words
+ * ({int16 value_mm, int16 weight}, util/tsdf.h:11-87) indexed 64*64*i + 64*j + k (:106). Bounding box, voxel corner
+ * positions, the +-600 mm truncation, the likelihood^3 transform (sigma; the node uses 0.1) and setData are the reference's,
+ * bit for bit; voxels with weight != 0 outside the truncation band become the free-space points global localisation
+ * samples from (:131-145; particle_cloud.cpp:105-148), in the reference's order (datasets in increasing name order). */
+int tsdfloc_map_from_chunks(const int32_t* chunk_pos, const uint32_t* chunk_data, uint64_t n_chunks, float sigma, tsdfloc_host_map** out);
+/* The free-space points of a map built by tsdfloc_map_from_chunks: *n points x 3 fp32 (NULL / 0 for other maps). */
+const float* tsdfloc_map_free_points(const tsdfloc_host_map* m, uint64_t* n);
 /* TSDF (mm) -> likelihood^3 LUT value and the value for unmapped space, createTSDFMap's transform
  * (include/tsdf_localization/map/map_util.h:68-71, 124-126). */
 float tsdfloc_likelihood_value(float tsdf_mm, float sigma);

@@ -13,6 +13,8 @@
 // What is verbatim and what is glue:
 //   * map build (setData), host getEntry, evaluate(), evaluatePose(), SystematicResampler::resample()
 //     run the reference's own code, bit for bit.
+//   * createTSDFMap (map/map_util.h:17-154) runs verbatim on an in-memory stand-in for the HDF5 file
+//     (ref_stubs/highfive/H5File.hpp; libhdf5 is not in this image).
 //   * ParticleCloud's three trivial accessors (default ctor, operator[], size) are defined here because
 //     src/particle_cloud.cpp drags in tf2/ROS-time code unrelated to this path
 //     (reference: src/particle_cloud.cpp:11-15, 619-632).
@@ -30,6 +32,7 @@
 #include <tsdf_localization/cuda/cuda_sub_voxel_map.h>
 #include <tsdf_localization/evaluation/tsdf_evaluator.h>
 #include <tsdf_localization/evaluation/model/likelihood_evaluation.h>
+#include <tsdf_localization/map/map_util.h>
 #include <tsdf_localization/resampling/novel_resampling.h>
 #include <tsdf_localization/util/constant.h>
 #ifdef TSDF_REF_WITH_B200_SHIM
@@ -180,6 +183,41 @@ void* ref_map_create(const float mn[3], const float mx[3], float resolution, flo
 // map_util.h:73 does (the class is move-only, cuda_sub_voxel_map.h:121-137).
 
 void ref_map_destroy(void* h) { delete static_cast<MapHandle*>(h); }
+
+// createTSDFMap<CudaSubVoxelMap<float,float>, float, float>(file, free_map, sigma) (map_util.h:17-154) on n_chunks chunks of
+// 64^3 raw TSDFValue words, chunk_pos = n_chunks x (cx, cy, cz). Returns a map handle; free_out (optional, capacity
+// free_cap points x 3 floats) receives the free-space voxels, *n_free their number.
+void* ref_create_tsdf_map(const int32_t* chunk_pos, const uint32_t* chunk_data, uint64_t n_chunks, float sigma, float* free_out,
+                          uint64_t free_cap, uint64_t* n_free)
+{
+  try
+  {
+    const size_t words = static_cast<size_t>(CHUNK_SIZE) * CHUNK_SIZE * CHUNK_SIZE;
+    auto& group = HighFive::stub_files()["mem.h5"]["/map"];
+    group.clear();
+    for (uint64_t c = 0; c < n_chunks; ++c)
+    {
+      const std::string tag = std::to_string(chunk_pos[3 * c]) + "_" + std::to_string(chunk_pos[3 * c + 1]) + "_" + std::to_string(chunk_pos[3 * c + 2]);
+      group[tag].assign(chunk_data + c * words, chunk_data + (c + 1) * words);
+    }
+    std::vector<CudaPoint> free_map;
+    auto* h = new MapHandle;
+    h->map = createTSDFMap<RefMap, FLOAT_T, FLOAT_T>("mem.h5", free_map, sigma);
+    group.clear();
+    if (n_free) *n_free = free_map.size();
+    if (free_out)
+    {
+      const uint64_t c = free_map.size() < free_cap ? free_map.size() : free_cap;
+      if (c) std::memcpy(free_out, static_cast<void*>(free_map.data()), c * sizeof(CudaPoint));
+    }
+    return h;
+  }
+  catch (std::exception& ex)
+  {
+    g_last_error = ex.what();
+    return nullptr;
+  }
+}
 
 // cells: n × (x, y, z, value) fp32 — the tuple list createTSDFMap hands to setData (map_util.h:129,152).
 int ref_map_set_data(void* h, const float* cells, uint64_t n)

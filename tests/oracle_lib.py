@@ -241,6 +241,8 @@ class Ref:
         L.ref_map_data.restype = C.POINTER(C.c_float)
         L.ref_map_data.argtypes = [C.c_void_p]
         L.ref_map_get_entries.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.ref_create_tsdf_map.restype = C.c_void_p
+        L.ref_create_tsdf_map.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.ref_eval_create.restype = C.c_void_p
         L.ref_eval_create.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
         L.ref_eval_destroy.argtypes = [C.c_void_p]
@@ -290,6 +292,18 @@ class Ref:
 
     def map_destroy(self, m):
         self.lib.ref_map_destroy(m)
+
+    def create_tsdf_map(self, chunk_pos, chunk_data, sigma=0.1):
+        """createTSDFMap (map_util.h:17-154), verbatim, on in-memory chunks. Returns (map handle, free_map [n, 3])."""
+        pos = np.ascontiguousarray(chunk_pos, dtype=np.int32).reshape(-1, 3)
+        dat = np.ascontiguousarray(chunk_data, dtype=np.uint32).reshape(len(pos), -1)
+        cap = dat.size
+        free = np.empty((max(cap, 1), 3), dtype=np.float32)
+        n_free = C.c_uint64(0)
+        h = self.lib.ref_create_tsdf_map(_fp(pos), _fp(dat), len(pos), C.c_float(sigma), _fp(free), cap, C.byref(n_free))
+        if not h:
+            raise RuntimeError(self.last_error())
+        return h, free[:int(n_free.value)].copy()
 
     def get_entries(self, m, xyz):
         xyz = np.ascontiguousarray(xyz, dtype=np.float32)

@@ -8,9 +8,11 @@
 // bounding box instead of invoking undefined float->unsigned conversions.
 #include "../../include/tsdfloc.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -19,6 +21,7 @@ struct tsdfloc_host_map
   tsdfloc_map_desc desc{};
   std::vector<int32_t> grid_occ;
   std::vector<float> data;
+  std::vector<float> free_points;  // x y z of the free-space voxels createTSDFMap collects (map_util.h:131-145)
 };
 
 namespace
@@ -118,6 +121,114 @@ const tsdfloc_map_desc* tsdfloc_map_get_desc(const tsdfloc_host_map* m) { return
 const int32_t* tsdfloc_map_grid_occ(const tsdfloc_host_map* m) { return m ? m->grid_occ.data() : nullptr; }
 const float* tsdfloc_map_data(const tsdfloc_host_map* m) { return m ? m->data.data() : nullptr; }
 void tsdfloc_map_destroy(tsdfloc_host_map* m) { delete m; }
+
+// Map ingest: createTSDFMap without the HDF5 layer (include/tsdf_localization/map/map_util.h:17-154). The mapping
+// pipeline stores the TSDF as 64^3-voxel chunks of packed {int16 value_mm, int16 weight} words (util/tsdf.h:11-87,
+// map/grid_map.h:18-24) in datasets named "<cx>_<cy>_<cz>"; the caller reads them with whatever HDF5 binding it has and
+// hands over the raw words.
+int tsdfloc_map_from_chunks(const int32_t* chunk_pos, const uint32_t* chunk_data, uint64_t n_chunks, float sigma, tsdfloc_host_map** out)
+{
+  if (!out) return TSDFLOC_E_BAD_ARG;
+  *out = nullptr;
+  if (n_chunks && (!chunk_pos || !chunk_data)) return TSDFLOC_E_BAD_ARG;
+  if (!(sigma > 0.0f)) return TSDFLOC_E_BAD_ARG;
+  constexpr int kChunk = 64;          // CHUNK_SIZE (grid_map.h:18-19)
+  constexpr int kResMm = 64;          // MAP_RESOLUTION in millimetres (grid_map.h:21-22)
+  constexpr float kTruncation = 600;  // grid_map.h:24
+
+  // bounding box over the chunk coordinates, starting from 0 like the reference's min(3, 0) / max(3, 0) (:23-59)
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  for (uint64_t c = 0; c < n_chunks; ++c)
+    for (int a = 0; a < 3; ++a)
+    {
+      const float v = static_cast<float>(chunk_pos[3 * c + a]);
+      if (v < lo[a]) lo[a] = v;
+      if (v > hi[a]) hi[a] = v;
+    }
+  float mn[3], mx[3];
+  for (int a = 0; a < 3; ++a)
+  {
+    // float * int * int stays fp32, the final * 0.001 is a double product stored back into the float (:61-65)
+    volatile float t0 = lo[a] * kChunk;
+    volatile float t1 = t0 * kResMm;
+    mn[a] = static_cast<float>(t1 * 0.001);
+    volatile float u0 = hi[a] * kChunk;
+    volatile float u1 = u0 + kChunk;
+    volatile float u2 = u1 * kResMm;
+    mx[a] = static_cast<float>(u2 * 0.001);
+  }
+  const float res = static_cast<float>(kResMm * 0.001);
+  tsdfloc_host_map* m = nullptr;
+  int rc = tsdfloc_map_create(mn, mx, res, tsdfloc_likelihood_init(sigma), &m);
+  if (rc != TSDFLOC_OK) return rc;
+
+  // datasets are visited in increasing name order (HDF5's default name index), which fixes the order of the free points
+  std::vector<std::string> tags(n_chunks);
+  for (uint64_t c = 0; c < n_chunks; ++c)
+    tags[c] = std::to_string(chunk_pos[3 * c]) + "_" + std::to_string(chunk_pos[3 * c + 1]) + "_" + std::to_string(chunk_pos[3 * c + 2]);
+  std::vector<uint64_t> order(n_chunks);
+  std::iota(order.begin(), order.end(), 0ull);
+  std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) { return tags[x] < tags[y]; });
+  for (uint64_t k = 1; k < n_chunks; ++k)
+    if (tags[order[k]] == tags[order[k - 1]])
+    {
+      delete m;
+      return TSDFLOC_E_BAD_ARG;  // the same chunk twice
+    }
+
+  // likelihood of every representable in-band TSDF value, indexed by value_mm + 599
+  std::vector<float> lut(1199);
+  for (int mm = -599; mm <= 599; ++mm) lut[mm + 599] = tsdfloc_likelihood_value(static_cast<float>(mm), sigma);
+
+  std::vector<float> cells;
+  const size_t words = static_cast<size_t>(kChunk) * kChunk * kChunk;
+  for (uint64_t k = 0; k < n_chunks; ++k)
+  {
+    const uint64_t c = order[k];
+    const uint32_t* w = chunk_data + c * words;
+    const int bx = kChunk * chunk_pos[3 * c], by = kChunk * chunk_pos[3 * c + 1], bz = kChunk * chunk_pos[3 * c + 2];
+    for (int i = 0; i < kChunk; ++i)
+      for (int j = 0; j < kChunk; ++j)
+        for (int q = 0; q < kChunk; ++q)
+        {
+          const uint32_t raw = w[(static_cast<size_t>(i) * kChunk + j) * kChunk + q];  // :106
+          const int16_t value_mm = static_cast<int16_t>(raw & 0xffffu);                // TSDFValueHW::value (tsdf.h:16)
+          const int16_t weight = static_cast<int16_t>(raw >> 16);                      // TSDFValueHW::weight
+          if (weight == 0) continue;
+          const float tsdf = static_cast<float>(value_mm);
+          // voxel CORNER position: float(index) * 64 in fp32, * 0.001 in double, stored as fp32 (:118-120, :129)
+          volatile float fx = static_cast<float>(bx + i) * kResMm, fy = static_cast<float>(by + j) * kResMm, fz = static_cast<float>(bz + q) * kResMm;
+          const float px = static_cast<float>(fx * 0.001), py = static_cast<float>(fy * 0.001), pz = static_cast<float>(fz * 0.001);
+          if (std::fabs(tsdf) < kTruncation)
+          {
+            cells.push_back(px);
+            cells.push_back(py);
+            cells.push_back(pz);
+            cells.push_back(lut[value_mm + 599]);
+          }
+          else
+          {
+            m->free_points.push_back(px);
+            m->free_points.push_back(py);
+            m->free_points.push_back(pz);
+          }
+        }
+  }
+  rc = tsdfloc_map_set_data(m, cells.data(), cells.size() / 4);
+  if (rc != TSDFLOC_OK)
+  {
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return TSDFLOC_OK;
+}
+
+const float* tsdfloc_map_free_points(const tsdfloc_host_map* m, uint64_t* n)
+{
+  if (n) *n = m ? m->free_points.size() / 3 : 0;
+  return m && !m->free_points.empty() ? m->free_points.data() : nullptr;
+}
 
 float tsdfloc_likelihood_init(float sigma)
 {

@@ -81,6 +81,34 @@ class CudaSubVoxelMap:
         self._adopted = (d, np.ascontiguousarray(grid_occ, dtype=np.int32), np.ascontiguousarray(data, dtype=np.float32))
         return self
 
+    @classmethod
+    def from_chunks(cls, chunk_pos, chunk_data, sigma: float = 0.1) -> "CudaSubVoxelMap":
+        """createTSDFMap (map_util.h:17-154) on chunks already read from the map file: chunk_pos int32[n, 3] (the integers of
+        the dataset names "<cx>_<cy>_<cz>"), chunk_data uint32[n, 64, 64, 64] raw TSDFValue words. The free-space points are
+        available as ``free_map()``."""
+        pos = np.ascontiguousarray(chunk_pos, dtype=np.int32).reshape(-1, 3)
+        dat = np.ascontiguousarray(chunk_data, dtype=np.uint32).reshape(len(pos), -1)
+        if dat.shape[1] != 64 ** 3:
+            raise ValueError("every chunk must hold 64^3 words")
+        self = cls.__new__(cls)
+        self._lib = capi.load_library()
+        self._adopted = None
+        self._h = C.c_void_p()
+        rc = self._lib.tsdfloc_map_from_chunks(pos.ctypes.data_as(C.c_void_p), dat.ctypes.data_as(C.c_void_p), len(pos), C.c_float(sigma),
+                                               C.byref(self._h))
+        if rc != capi.OK:
+            raise ValueError("invalid chunk set")
+        return self
+
+    def free_map(self) -> np.ndarray:
+        if self._h is None:
+            return np.zeros((0, 3), dtype=np.float32)
+        n = C.c_uint64(0)
+        p = self._lib.tsdfloc_map_free_points(self._h, C.byref(n))
+        if not p or n.value == 0:
+            return np.zeros((0, 3), dtype=np.float32)
+        return np.ctypeslib.as_array(p, shape=(int(n.value), 3)).copy()
+
     def setData(self, cells) -> None:
         """cells: [n, 4] (x, y, z, value) — the tuple list createTSDFMap hands to setData (map_util.h:129,152)."""
         if self._h is None:
