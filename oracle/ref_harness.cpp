@@ -35,6 +35,7 @@
 #include <tsdf_localization/map/map_util.h>
 #include <tsdf_localization/resampling/novel_resampling.h>
 #include <tsdf_localization/util/constant.h>
+#include <tsdf_localization/util/mcl_file.h>
 #ifdef TSDF_REF_WITH_B200_SHIM
 #include "tsdfloc_shim.h"
 #endif
@@ -451,6 +452,60 @@ uint64_t ref_systematic_resample(const float* particles, uint64_t n, uint32_t se
     std::memcpy(particles_out, static_cast<void*>(cloud.particles().data()), c * sizeof(Particle));
   }
   return m;
+}
+
+// MCLFile::write / MCLFile::read (src/util/mcl_file.cpp:14-113), verbatim. pose7 = x y z q1 q2 q3 q4.
+int ref_mcl_write(const char* name, const float* points, const int32_t* rings, uint64_t p, const float* particles, uint64_t n,
+                  const float tf[16], const float pose7[7])
+{
+  try
+  {
+    std::vector<CudaPoint> pts(p);
+    if (p) std::memcpy(static_cast<void*>(pts.data()), points, p * sizeof(CudaPoint));
+    std::vector<int> rg(rings, rings + p);
+    std::vector<Particle> ps(n);
+    if (n) std::memcpy(static_cast<void*>(ps.data()), particles, n * sizeof(Particle));
+    std::array<FLOAT_T, 16> t;
+    std::memcpy(t.data(), tf, sizeof(float) * 16);
+    MCLFile(name).write(pts, rg, ps, t, pose7[0], pose7[1], pose7[2], pose7[3], pose7[4], pose7[5], pose7[6]);
+    return 0;
+  }
+  catch (std::exception& ex)
+  {
+    g_last_error = ex.what();
+    return 1;
+  }
+}
+
+// Two-step read: sizes first (points_out == NULL), then the payload into caller buffers of those sizes.
+int ref_mcl_read(const char* name, uint64_t* p, uint64_t* n, float* points_out, int32_t* rings_out, float* particles_out, float tf_out[16],
+                 float pose7_out[7])
+{
+  try
+  {
+    std::vector<CudaPoint> pts;
+    std::vector<int> rg;
+    std::vector<Particle> ps;
+    std::array<FLOAT_T, 16> t;
+    FLOAT_T v[7];
+    MCLFile(name).read(pts, rg, ps, t, v[0], v[1], v[2], v[3], v[4], v[5], v[6]);
+    *p = pts.size();
+    *n = ps.size();
+    if (points_out)
+    {
+      if (!pts.empty()) std::memcpy(points_out, static_cast<void*>(pts.data()), pts.size() * sizeof(CudaPoint));
+      for (size_t i = 0; i < rg.size(); ++i) rings_out[i] = rg[i];
+      if (!ps.empty()) std::memcpy(particles_out, static_cast<void*>(ps.data()), ps.size() * sizeof(Particle));
+      std::memcpy(tf_out, t.data(), sizeof(float) * 16);
+      for (int k = 0; k < 7; ++k) pose7_out[k] = v[k];
+    }
+    return 0;
+  }
+  catch (std::exception& ex)
+  {
+    g_last_error = ex.what();
+    return 1;
+  }
 }
 
 #ifndef TSDF_REF_WITH_B200_SHIM

@@ -293,6 +293,31 @@ class Ref:
     def map_destroy(self, m):
         self.lib.ref_map_destroy(m)
 
+    def mcl_write(self, name, points, rings, particles, tf, pose7):
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        rg = np.ascontiguousarray(rings, dtype=np.int32)
+        ps = np.ascontiguousarray(particles, dtype=np.float32).reshape(-1, 7)
+        t = np.ascontiguousarray(tf, dtype=np.float32)
+        po = np.ascontiguousarray(pose7, dtype=np.float32)
+        self.lib.ref_mcl_write.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        if self.lib.ref_mcl_write(str(name).encode(), _fp(pts), _fp(rg), len(pts), _fp(ps), len(ps), _fp(t), _fp(po)):
+            raise RuntimeError(self.last_error())
+
+    def mcl_read(self, name):
+        self.lib.ref_mcl_read.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]
+        p, n = C.c_uint64(0), C.c_uint64(0)
+        if self.lib.ref_mcl_read(str(name).encode(), C.byref(p), C.byref(n), None, None, None, None, None):
+            raise RuntimeError(self.last_error())
+        pts = np.empty((p.value, 3), dtype=np.float32)
+        rg = np.empty(p.value, dtype=np.int32)
+        ps = np.empty((n.value, 7), dtype=np.float32)
+        t = np.empty(16, dtype=np.float32)
+        po = np.empty(7, dtype=np.float32)
+        if self.lib.ref_mcl_read(str(name).encode(), C.byref(p), C.byref(n), _fp(pts), _fp(rg), _fp(ps), _fp(t), _fp(po)):
+            raise RuntimeError(self.last_error())
+        return pts, rg, ps, t, po
+
     def create_tsdf_map(self, chunk_pos, chunk_data, sigma=0.1):
         """createTSDFMap (map_util.h:17-154), verbatim, on in-memory chunks. Returns (map handle, free_map [n, 3])."""
         pos = np.ascontiguousarray(chunk_pos, dtype=np.int32).reshape(-1, 3)
