@@ -223,7 +223,8 @@ def run_b200_arm(args):
     ev = CudaEvaluator(m, device=local)
     lib = capi.load_library()
     stages = GpuStages(ev)
-    upd = ShardedSensorUpdate(stages, world=world, rank=rank, device=dev, max_particles=n)
+    fused = {"auto": None, "nccl": False, "fused": True}[args.transport]
+    upd = ShardedSensorUpdate(stages, world=world, rank=rank, device=dev, max_particles=n, fused=fused)
     stream = torch.cuda.Stream(device=dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     d_ps = torch.from_numpy(ps).to(dev)
@@ -345,7 +346,10 @@ def run_b200_arm(args):
             "data": "synthetic",
             "config": {"workload": args.workload + ": " + WORKLOADS[args.workload]["desc"], "particles": n, "points": p,
                        "particles_per_gpu": n_local, "map_mb": m.dataBytes() / 1e6, "sharding": f"particles/{world}, map replicated",
-                       "step": "scan prep + eval + normalise/mean/CDF + systematic resample" + (" + 2 NCCL all-gathers" if world > 1 else ""),
+                       "step": "scan prep + eval + normalise/mean/CDF + systematic resample" + (
+                           "" if world == 1 else " + 2 NCCL all-gathers" if upd.transport == "all_gather"
+                           else "; eval and draw kernels store into all peers' symmetric-memory buffers over NVLink (no collective), 3 signal barriers"),
+                       "transport": upd.transport,
                        "l2": "flushed (256 MiB memset) between timed steps, outside the CUDA-event pairs",
                        "n_out": int(n_out), "weight_sum": wsum},
             "roofline": roofline, "cpu_baseline": cpu,
@@ -369,6 +373,8 @@ def main():
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--workload", choices=tuple(WORKLOADS), default="c3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", choices=("auto", "nccl", "fused"), default="auto",
+                    help="multi-GPU exchange: fused = kernels store straight into the peers' buffers (default when available); nccl = all-gathers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

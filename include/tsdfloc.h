@@ -183,6 +183,19 @@ int tsdfloc_cdf_device(tsdfloc_ctx* ctx, float* d_particles, uint64_t n_total, f
 int tsdfloc_draw_device(tsdfloc_ctx* ctx, const float* d_particles, uint64_t n_total, float u0, uint64_t first_out,
                         uint64_t count_out, float* d_particles_out, uint32_t* d_parents, void* stream);
 
+/* Multi-GPU, fused compute + all-gather (no reference counterpart; the reference is single-GPU). Same kernels as
+ * tsdfloc_eval_device / tsdfloc_draw_device, but every result is stored not only into this rank's buffer but straight into
+ * the same position of every peer's buffer — plain stores through peer-mapped pointers (CUDA IPC / symmetric memory) over
+ * NVLink — so no collective follows the kernel; the caller only orders the ranks with a signal barrier.
+ *   d_raw_peers / d_out_peers: host array of n_peers (<= 8) device pointers, entry r = rank r's buffer BASE (same layout as
+ *   d_raw_weights / the buffer d_particles_out is a slice of: d_out_peers[r] must point at the slot of output `first_out`);
+ *   entries that are NULL or equal to the local pointer are skipped. */
+int tsdfloc_eval_device_peers(tsdfloc_ctx* ctx, const float* d_particles, uint64_t n_total, uint64_t first, uint64_t count,
+                              const float tf[16], float* d_raw_weights, float* const* d_raw_peers, uint32_t n_peers, void* stream);
+int tsdfloc_draw_device_peers(tsdfloc_ctx* ctx, const float* d_particles, uint64_t n_total, float u0, uint64_t first_out,
+                              uint64_t count_out, float* d_particles_out, float* const* d_out_peers, uint32_t n_peers,
+                              uint32_t* d_parents, void* stream);
+
 /* Synchronises `stream` and reports what the device recorded for the last normalize/draw:
  * n_out = number of particles the reference recurrence emits; returns TSDFLOC_E_NO_VALID_PARTICLE if sum == 0. */
 int tsdfloc_check(tsdfloc_ctx* ctx, uint64_t* n_out, double* weight_sum, void* stream);

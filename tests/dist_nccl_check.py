@@ -30,23 +30,28 @@ def main():
     for n in (4096, 5001):
         ps = syn.tracking_particles(n, syn.GT_POSE)
         tf, u0 = syn.CALIB_TF, 0.37 / n
-        ev1, evw = CudaEvaluator(m, device=local), CudaEvaluator(m, device=local)
-        one = ShardedSensorUpdate(GpuStages(ev1), device=dev)
-        many = ShardedSensorUpdate(GpuStages(evw), world=world, rank=rank, device=dev)
-        d_pts = torch.from_numpy(pts).to(dev)
-        one.set_scan(d_pts)
-        many.set_scan(d_pts)
-        a, b = torch.from_numpy(ps).to(dev), torch.from_numpy(ps).to(dev)
-        for it in range(2):
-            o1, m1, n1, w1 = one.step(a, len(a), tf, u0)
-            o2, m2, n2, w2 = many.step(b, len(b), tf, u0)
-            assert n1 == n2 and w1 == w2, (n1, n2, w1, w2)
-            assert torch.equal(a, b), "normalised weights differ"
-            assert torch.equal(o1, o2), "resampled particles differ"
-            assert torch.equal(m1, m2), "mean pose differs"
-            a, b = o1.clone(), o2.clone()
-        ev1.close()
-        evw.close()
+        # both transports: NCCL all-gathers, and the fused kernels storing straight into the peers' symmetric-memory buffers
+        for fused in (False, True):
+            ev1, evw = CudaEvaluator(m, device=local), CudaEvaluator(m, device=local)
+            one = ShardedSensorUpdate(GpuStages(ev1), device=dev)
+            many = ShardedSensorUpdate(GpuStages(evw), world=world, rank=rank, device=dev, max_particles=n, fused=fused)
+            assert many.transport == ("fused_p2p" if fused else "all_gather"), many.transport
+            d_pts = torch.from_numpy(pts).to(dev)
+            one.set_scan(d_pts)
+            many.set_scan(d_pts)
+            a, b = torch.from_numpy(ps).to(dev), torch.from_numpy(ps).to(dev)
+            for it in range(3):
+                o1, m1, n1, w1 = one.step(a, len(a), tf, u0)
+                o2, m2, n2, w2 = many.step(b, len(b), tf, u0)
+                assert n1 == n2 and w1 == w2, (fused, n1, n2, w1, w2)
+                assert torch.equal(a, b), f"normalised weights differ (fused={fused})"
+                assert torch.equal(o1, o2), f"resampled particles differ (fused={fused})"
+                assert torch.equal(m1, m2), f"mean pose differs (fused={fused})"
+                a, b = o1.clone(), o2.clone()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            ev1.close()
+            evw.close()
     dist.barrier()
     if rank == 0:
         print("NCCL_CHECK_OK")

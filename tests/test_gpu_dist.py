@@ -95,6 +95,51 @@ def test_thread_emulated_ranks_equal_single_rank(world, n):
         assert mean.tobytes() == single[2].tobytes()
 
 
+def test_peer_store_kernels_on_one_gpu():
+    """tsdfloc_eval_device_peers / tsdfloc_draw_device_peers with the "peers" being two buffers on the same GPU: every rank's
+    kernel stores its slice into both weight vectors / particle buffers, so after both ranks ran, both copies hold the full
+    result — no all-gather anywhere."""
+    import torch
+    from tsdf_localization_b200 import CudaEvaluator
+    from tsdf_localization_b200.dist import GpuStages, output_capacity, shard
+
+    _, m = common.box_room()
+    n, world = 5001, 2
+    pts, _ = syn.make_scan("vlp16", syn.GT_POSE, n_points=4000)
+    ps = syn.tracking_particles(n, syn.GT_POSE)
+    tf, u0 = syn.CALIB_TF, 0.37 / n
+    single = _single(m, ps, pts, tf, u0)
+    dev = torch.device("cuda", 0)
+    evs = [CudaEvaluator(m) for _ in range(world)]
+    st = [GpuStages(e) for e in evs]
+    chunk = shard(n, world, 0)[0]
+    ocap = output_capacity(n, world)
+    ochunk = ocap // world
+    raws = [torch.zeros(world * chunk, device=dev) for _ in range(world)]
+    outs = [torch.zeros((ocap, 7), device=dev) for _ in range(world)]
+    parts = [torch.from_numpy(ps).to(dev) for _ in range(world)]
+    means = [torch.zeros(8, device=dev) for _ in range(world)]
+    d_pts = torch.from_numpy(pts).to(dev)
+    for r in range(world):
+        st[r].set_scan(d_pts)
+        _, first, count = shard(n, world, r)
+        st[r].eval_peers(parts[r], n, first, count, tf, raws[r], [t.data_ptr() for t in raws])
+    torch.cuda.synchronize()
+    assert torch.equal(raws[0], raws[1])
+    for r in range(world):
+        st[r].normalize(parts[r], n, raws[r], means[r])
+        slot = r * ochunk * 28
+        st[r].draw_peers(parts[r], n, u0, r * ochunk, ochunk, outs[r][r * ochunk:(r + 1) * ochunk], [t.data_ptr() + slot for t in outs])
+    torch.cuda.synchronize()
+    for r in range(world):
+        n_out, wsum = st[r].check()
+        assert n_out == single[3] and wsum == single[4]
+        assert parts[r].cpu().numpy().tobytes() == single[1].tobytes()
+        assert outs[r][:n_out].cpu().numpy().tobytes() == single[0].tobytes()
+    for e in evs:
+        e.close()
+
+
 def test_nccl_two_ranks_equal_single_rank():
     import torch
     if torch.cuda.device_count() < 2:

@@ -75,6 +75,8 @@ SIGNATURES = {
     "tsdfloc_set_scan_device": (C.c_int, [_vp, _vp, _u64, _vp]),
     "tsdfloc_set_scan_host": (C.c_int, [_vp, _vp, _u64, _vp]),
     "tsdfloc_eval_device": (C.c_int, [_vp, _vp, _u64, _u64, _u64, _fp, _vp, _vp]),
+    "tsdfloc_eval_device_peers": (C.c_int, [_vp, _vp, _u64, _u64, _u64, _fp, _vp, C.POINTER(_vp), C.c_uint32, _vp]),
+    "tsdfloc_draw_device_peers": (C.c_int, [_vp, _vp, _u64, C.c_float, _u64, _u64, _vp, C.POINTER(_vp), C.c_uint32, _vp, _vp]),
     "tsdfloc_normalize_device": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "tsdfloc_draw_device": (C.c_int, [_vp, _vp, _u64, C.c_float, _u64, _u64, _vp, _vp, _vp]),
     "tsdfloc_check": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double), _vp]),

@@ -264,8 +264,9 @@ int stage_matrices(tsdfloc_ctx* c, const float* d_particles, uint64_t first, uin
 }
 
 int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint64_t first, uint64_t count, const float tf[16],
-               float* d_raw, cudaStream_t s)
+               float* d_raw, cudaStream_t s, float* const* d_raw_peers = nullptr, uint32_t n_peers = 0)
 {
+  if (n_peers > static_cast<uint32_t>(kMaxPeers)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 8 peer buffers");
   if (first + count > n_total) return fail(c, TSDFLOC_E_BAD_ARG, "particle slice exceeds n_total");
   if (n_total > (1ull << 24)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 2^24 particles: the reference's fp32 U recurrence stalls");
   if (c->n_points == 0) return fail(c, TSDFLOC_E_EMPTY_SCAN, "empty scan");
@@ -276,6 +277,9 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   a.pts = static_cast<const float4*>(c->d_pts.p);
   a.mats = static_cast<const float*>(c->d_mats.p);
   a.raw_out = d_raw + first;
+  a.n_peer_out = 0;
+  for (uint32_t r = 0; r < n_peers; ++r)
+    if (d_raw_peers[r] && d_raw_peers[r] != d_raw) a.peer_out[a.n_peer_out++] = d_raw_peers[r] + first;
   a.n_points = static_cast<uint32_t>(c->n_points);
   a.n_local = static_cast<uint32_t>(count);
   a.a_hit = c->prm.a_hit;
@@ -341,8 +345,12 @@ int stage_normalize(tsdfloc_ctx* c, float* d_particles, uint64_t n, const float*
 }
 
 int stage_draw(tsdfloc_ctx* c, const float* d_particles, uint64_t n, float u0, uint64_t first_out, uint64_t count_out, float* d_out,
-               uint32_t* d_parents, cudaStream_t s)
+               uint32_t* d_parents, cudaStream_t s, float* const* d_out_peers = nullptr, uint32_t n_peers = 0)
 {
+  if (n_peers > static_cast<uint32_t>(kMaxPeers)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 8 peer buffers");
+  DrawPeers peers{};
+  for (uint32_t r = 0; r < n_peers; ++r)
+    if (d_out_peers[r] && d_out_peers[r] != d_out) peers.out[peers.n++] = d_out_peers[r];
   if (!c->have_cdf) return fail(c, TSDFLOC_E_STATE, "draw before normalize");
   if (!(u0 >= 0.0f)) return fail(c, TSDFLOC_E_BAD_ARG, "u0 must be >= 0");
   k_finish_cdf_utable<<<1, 32, 0, s>>>(d_particles, static_cast<double*>(c->d_cdf.p), static_cast<uint32_t>(n), u0, c->d_segs, c->d_status);
@@ -351,7 +359,7 @@ int stage_draw(tsdfloc_ctx* c, const float* d_particles, uint64_t n, float u0, u
   if (count_out == 0) return TSDFLOC_OK;
   k_draw<<<static_cast<unsigned>((count_out + 255) / 256), 256, 0, s>>>(d_particles, static_cast<const double*>(c->d_cdf.p),
                                                                        static_cast<uint32_t>(n), c->d_segs, c->d_status, first_out,
-                                                                       static_cast<uint32_t>(count_out), d_out, d_parents);
+                                                                       static_cast<uint32_t>(count_out), d_out, d_parents, peers);
   return launch_check(c, "k_draw");
 }
 
@@ -764,6 +772,24 @@ int tsdfloc_eval_device(tsdfloc_ctx* c, const float* d_particles, uint64_t n_tot
   if (!d_particles || !tf || !d_raw_weights) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
   DeviceGuard guard(c->device);
   return stage_eval(c, d_particles, n_total, first, count, tf, d_raw_weights, pick(c, stream));
+}
+
+int tsdfloc_eval_device_peers(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint64_t first, uint64_t count, const float tf[16],
+                              float* d_raw_weights, float* const* d_raw_peers, uint32_t n_peers, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!d_particles || !tf || !d_raw_weights || (n_peers && !d_raw_peers)) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  DeviceGuard guard(c->device);
+  return stage_eval(c, d_particles, n_total, first, count, tf, d_raw_weights, pick(c, stream), d_raw_peers, n_peers);
+}
+
+int tsdfloc_draw_device_peers(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, float u0, uint64_t first_out, uint64_t count_out,
+                              float* d_particles_out, float* const* d_out_peers, uint32_t n_peers, uint32_t* d_parents, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!d_particles || (count_out && !d_particles_out) || (n_peers && !d_out_peers)) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  DeviceGuard guard(c->device);
+  return stage_draw(c, d_particles, n_total, u0, first_out, count_out, d_particles_out, d_parents, pick(c, stream), d_out_peers, n_peers);
 }
 
 int tsdfloc_normalize_device(tsdfloc_ctx* c, float* d_particles, uint64_t n_total, const float* d_raw_weights, float* d_mean_pose,

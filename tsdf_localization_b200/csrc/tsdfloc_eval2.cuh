@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(W * 32, (R / W) > 0 ? (R / W) : 1) k_eval2(con
 
   if (lane == 0)
   {
-    if (part0 < A.n_local) A.raw_out[part0] = s[0];
-    if (part0 + 1 < A.n_local) A.raw_out[part0 + 1] = s[1];
+    if (part0 < A.n_local) store_weight(A, part0, s[0]);
+    if (part0 + 1 < A.n_local) store_weight(A, part0 + 1, s[1]);
     if (A.stats && part0 < A.n_local)
     {
       atomicAdd(A.stats + 0, static_cast<unsigned long long>(n_blocks) * 2ull);

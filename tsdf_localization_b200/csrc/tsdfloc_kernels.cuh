@@ -143,11 +143,20 @@ __global__ void k_pose_matrices(const float* __restrict__ particles, uint32_t fi
 constexpr float kRoundMagic = 12582912.0f;       // 1.5 * 2^23: x + magic rounds x to an integer (RN-even) for 0 <= x < 2^22
 constexpr uint32_t kRoundMagicBits = 0x4B400000u;
 
+constexpr int kMaxPeers = 8;         // ranks of one NVSwitch domain
+
+// Final store of a particle's weight: into this rank's vector and — fused all-gather — straight into every peer's
+// (P2P stores over NVLink; the kernel boundary + the driver's signal barrier order them before the peers' reads).
+struct EvalArgs;
+__device__ __forceinline__ void store_weight(const EvalArgs& A, uint32_t part, float w);
+
 struct EvalArgs
 {
   const float4* __restrict__ pts;   // x y z term, padded to a multiple of 32 points
   const float* __restrict__ mats;   // [n_local][12]
-  float* __restrict__ raw_out;      // [n_local] un-normalised weights
+  float* raw_out;                   // [n_local] un-normalised weights (this rank's slice of its own weight vector)
+  float* peer_out[kMaxPeers];       // multi-GPU: the same slice inside every OTHER rank's weight vector (peer-mapped, NVLink)
+  uint32_t n_peer_out;              // 0 on one GPU
   unsigned long long* __restrict__ stats;  // [4]: blocks, blocks folded sequentially (binade crossing / early phase), tie folds, -
   uint32_t n_points;
   uint32_t n_local;
@@ -156,6 +165,14 @@ struct EvalArgs
   float s_min;                      // integer-block summation is used once s >= s_min (= 32 * bound of one addend)
   uint32_t force_seq;               // 1: negative/non-finite addends possible -> always fold sequentially
 };
+
+__device__ __forceinline__ void store_weight(const EvalArgs& A, uint32_t part, float w)
+{
+  A.raw_out[part] = w;
+#pragma unroll   // constant indices: the pointers stay in the constant bank (a dynamic index would copy them to local memory)
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (static_cast<uint32_t>(r) < A.n_peer_out) A.peer_out[r][part] = w;
+}
 
 // One point against one particle: transform, voxel gather, x = a_hit * v + term (two roundings, like the CPU build).
 template <bool kFastDiv>
@@ -318,7 +335,7 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval(const MapDev M, const Eva
   }
 #pragma unroll
   for (int k = 0; k < kPPW; ++k)
-    if (lane == 0 && part0 + k < A.n_local) A.raw_out[part0 + k] = s[k];
+    if (lane == 0 && part0 + k < A.n_local) store_weight(A, part0 + k, s[k]);
   if (lane == 0 && A.stats)
   {
     atomicAdd(A.stats + 0, static_cast<unsigned long long>(n_blocks) * kPPW);
@@ -725,10 +742,17 @@ __global__ void k_finish_cdf_utable(const float* __restrict__ particles, double*
   st->table_overflow = flags;
 }
 
+// Multi-GPU: the same output slice inside every other rank's particle buffer (peer-mapped); n == 0 on one GPU.
+struct DrawPeers
+{
+  float* out[kMaxPeers];
+  uint32_t n;
+};
+
 // K4: draw. Output slot j copies the first particle m with s_m > U_j (strict, novel_resampling.h:59).
 __global__ void k_draw(const float* __restrict__ particles, const double* __restrict__ cdf, uint32_t n, const USeg* __restrict__ segs,
                        const Status* __restrict__ st, unsigned long long first_out, uint32_t count_out, float* __restrict__ out,
-                       uint32_t* __restrict__ parents)
+                       uint32_t* __restrict__ parents, const DrawPeers peers)
 {
   __shared__ USeg s_segs[kMaxUSegs];
   const uint32_t ns = st->n_segs;
@@ -753,8 +777,19 @@ __global__ void k_draw(const float* __restrict__ particles, const double* __rest
   }
   const float* src = particles + 7ull * parent;
   float* dst = out + 7ull * t;
+  float v[7];
 #pragma unroll
-  for (int k = 0; k < 7; ++k) dst[k] = src[k];
+  for (int k = 0; k < 7; ++k) v[k] = src[k];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) dst[k] = v[k];
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (static_cast<uint32_t>(r) < peers.n)
+    {
+      float* pd = peers.out[r] + 7ull * t;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) pd[k] = v[k];
+    }
   if (parents) parents[t] = parent;
 }
 

@@ -61,6 +61,21 @@ class GpuStages:
         capi.check(self.lib, self.ctx, self.lib.tsdfloc_eval_device(self.ctx, C.c_void_p(d_particles.data_ptr()), n, first, count, tfc,
                                                                    C.c_void_p(d_raw.data_ptr()), self._stream()))
 
+    def eval_peers(self, d_particles, n, first, count, tf, d_raw, peer_raw_ptrs) -> None:
+        """eval() whose final stores also go into every peer's weight vector (fused all-gather over NVLink)."""
+        tfc = (C.c_float * 16)(*[float(v) for v in tf])
+        arr = (C.c_void_p * len(peer_raw_ptrs))(*[int(p) for p in peer_raw_ptrs])
+        capi.check(self.lib, self.ctx, self.lib.tsdfloc_eval_device_peers(self.ctx, C.c_void_p(d_particles.data_ptr()), n, first, count, tfc,
+                                                                         C.c_void_p(d_raw.data_ptr()), arr, len(peer_raw_ptrs), self._stream()))
+
+    def draw_peers(self, d_particles, n, u0, first_out, count_out, d_out, peer_out_ptrs) -> None:
+        """draw() whose output slice is also stored into every peer's particle buffer (peer_out_ptrs[r] = address of slot
+        first_out in rank r's buffer)."""
+        arr = (C.c_void_p * len(peer_out_ptrs))(*[int(p) for p in peer_out_ptrs])
+        capi.check(self.lib, self.ctx, self.lib.tsdfloc_draw_device_peers(self.ctx, C.c_void_p(d_particles.data_ptr()), n, C.c_float(u0),
+                                                                         first_out, count_out, C.c_void_p(d_out.data_ptr()), arr,
+                                                                         len(peer_out_ptrs), None, self._stream()))
+
     def normalize(self, d_particles, n, d_raw, d_mean) -> None:
         capi.check(self.lib, self.ctx, self.lib.tsdfloc_normalize_device(self.ctx, C.c_void_p(d_particles.data_ptr()), n,
                                                                         C.c_void_p(d_raw.data_ptr()), C.c_void_p(d_mean.data_ptr()),
@@ -105,9 +120,15 @@ class ShardedSensorUpdate:
     """
 
     def __init__(self, stages, world: int = 1, rank: int = 0, group=None, device: Optional[torch.device] = None,
-                 max_particles: int = 0, all_gather=None):
+                 max_particles: int = 0, all_gather=None, fused: Optional[bool] = None):
+        """fused: True = the evaluation and draw kernels store their results straight into every peer's buffers (symmetric
+        memory over NVLink; three signal barriers per update instead of two NCCL all-gathers); False = NCCL all-gathers;
+        None = fused when the stages support it and symmetric memory can be set up on this device, else NCCL."""
         self.stages = stages
         self.world, self.rank, self.group = int(world), int(rank), group
+        self.transport = "none" if self.world == 1 else "all_gather"
+        self._want_fused = fused
+        self._symm = None
         # all_gather(out_flat, in_flat): torch.distributed (NCCL on GPUs, gloo in the CPU tests) unless injected
         self._all_gather = all_gather if all_gather is not None else self._dist_all_gather
         self.device = device if device is not None else torch.device("cpu")
@@ -125,10 +146,45 @@ class ShardedSensorUpdate:
         chunk = (n + W - 1) // W
         ocap = output_capacity(n, W)
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.raw = torch.zeros(W * chunk, **f32)              # un-normalised weights, slice r at [r*chunk, (r+1)*chunk)
-        self.out = torch.zeros((ocap, 7), **f32)              # resampled particles, slice r at [r*ochunk, (r+1)*ochunk)
         self.mean = torch.zeros(8, **f32)
         self._cap = n
+        self._symm = None
+        want = self._want_fused
+        can = (W > 1 and self._all_gather == self._dist_all_gather and self.device.type == "cuda" and hasattr(self.stages, "eval_peers"))
+        if want is not False and can:
+            try:
+                self._setup_symmetric(W * chunk, ocap)
+                self.transport = "fused_p2p"
+                return
+            except Exception as e:  # noqa: BLE001
+                if want:
+                    raise
+                import warnings
+                warnings.warn(f"symmetric memory unavailable ({e}); using NCCL all-gathers")
+        elif want and W > 1:
+            raise RuntimeError("fused=True needs CUDA devices, torch.distributed collectives and peer-capable stages")
+        self.raw = torch.zeros(W * chunk, **f32)              # un-normalised weights, slice r at [r*chunk, (r+1)*chunk)
+        self.out = torch.zeros((ocap, 7), **f32)              # resampled particles, slice r at [r*ochunk, (r+1)*ochunk)
+
+    def _setup_symmetric(self, n_raw: int, ocap: int) -> None:
+        """Weight vector and output particle buffer in symmetric memory: every rank maps every peer's copy."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group if self.group is not None else dist.group.WORLD
+        # two copies of each buffer, used alternately: a rank may start storing update k+1 into its peers while they still
+        # read update k (the barrier inside update k+1 orders it against update k-1, the last user of the same copy)
+        raw = symm_mem.empty((2, n_raw), dtype=torch.float32, device=self.device)
+        out = symm_mem.empty((2, ocap, 7), dtype=torch.float32, device=self.device)
+        raw.zero_()
+        out.zero_()
+        h_raw = symm_mem.rendezvous(raw, group)
+        h_out = symm_mem.rendezvous(out, group)
+        self._raw2, self._out2 = raw, out
+        self.raw, self.out = raw[0], out[0]
+        self._symm = (h_raw, h_out, [int(p) for p in h_raw.buffer_ptrs], [int(p) for p in h_out.buffer_ptrs])
+        self._tick = 0
+        torch.cuda.synchronize(self.device)
+        h_raw.barrier(channel=0)
 
     def set_scan(self, d_points: torch.Tensor) -> None:
         self.stages.set_scan(d_points)
@@ -140,20 +196,41 @@ class ShardedSensorUpdate:
         W, r = self.world, self.rank
         self._reserve(n)
         chunk, first, count = shard(n, W, r)
-        self.stages.eval(particles, n, first, count, tf, self.raw)
-        if W > 1:
-            self._all_gather(self.raw[:W * chunk], self.raw[r * chunk:(r + 1) * chunk])
-        self.stages.normalize(particles, n, self.raw, self.mean)
         ocap = output_capacity(n, W)
         ochunk = ocap // W
-        out = self.out[:ocap]
-        self.stages.draw(particles, n, u0, r * ochunk, ochunk, out[r * ochunk:(r + 1) * ochunk])
-        if W > 1:
-            self._all_gather(out.view(-1), out[r * ochunk:(r + 1) * ochunk].reshape(-1))
+        if self._symm is not None:
+            h_raw, h_out, raw_ptrs, out_ptrs = self._symm
+            which = self._select_copy()
+            out = self.out[:ocap]
+            raw_off = which * self._raw2.shape[1] * 4
+            out_off = which * self._out2.shape[1] * 28 + r * ochunk * 28
+            # The kernels themselves do the "all-gather" (P2P stores into every peer's copy); the two barriers only say
+            # "all weights have landed everywhere" and "all resampled slices have landed everywhere".
+            self.stages.eval_peers(particles, n, first, count, tf, self.raw, [p + raw_off for p in raw_ptrs])
+            h_raw.barrier(channel=0)
+            self.stages.normalize(particles, n, self.raw, self.mean)
+            self.stages.draw_peers(particles, n, u0, r * ochunk, ochunk, out[r * ochunk:(r + 1) * ochunk], [p + out_off for p in out_ptrs])
+            h_out.barrier(channel=0)
+        else:
+            out = self.out[:ocap]
+            self.stages.eval(particles, n, first, count, tf, self.raw)
+            if W > 1:
+                self._all_gather(self.raw[:W * chunk], self.raw[r * chunk:(r + 1) * chunk])
+            self.stages.normalize(particles, n, self.raw, self.mean)
+            self.stages.draw(particles, n, u0, r * ochunk, ochunk, out[r * ochunk:(r + 1) * ochunk])
+            if W > 1:
+                self._all_gather(out.view(-1), out[r * ochunk:(r + 1) * ochunk].reshape(-1))
         n_out, wsum = self.stages.check()
         if n_out > ocap:
             raise RuntimeError(f"resampling emits {n_out} particles, capacity is {ocap}")
         return out[:n_out], self.mean[:6], n_out, wsum
+
+    def _select_copy(self) -> int:
+        """Alternate between the two symmetric-memory copies of the weight vector / output buffer."""
+        which = self._tick & 1
+        self._tick += 1
+        self.raw, self.out = self._raw2[which], self._out2[which]
+        return which
 
     def evaluate_only(self, particles: torch.Tensor, n: int, tf):
         """Evaluation + normalisation without resampling (what the reference's evaluate() covers). Returns
@@ -161,9 +238,15 @@ class ShardedSensorUpdate:
         W, r = self.world, self.rank
         self._reserve(n)
         chunk, first, count = shard(n, W, r)
-        self.stages.eval(particles, n, first, count, tf, self.raw)
-        if W > 1:
-            self._all_gather(self.raw[:W * chunk], self.raw[r * chunk:(r + 1) * chunk])
+        if self._symm is not None:
+            h_raw, _, raw_ptrs, _ = self._symm
+            raw_off = self._select_copy() * self._raw2.shape[1] * 4
+            self.stages.eval_peers(particles, n, first, count, tf, self.raw, [p + raw_off for p in raw_ptrs])
+            h_raw.barrier(channel=0)
+        else:
+            self.stages.eval(particles, n, first, count, tf, self.raw)
+            if W > 1:
+                self._all_gather(self.raw[:W * chunk], self.raw[r * chunk:(r + 1) * chunk])
         self.stages.normalize(particles, n, self.raw, self.mean)
         _, wsum = self.stages.check()
         return self.mean[:6], wsum
