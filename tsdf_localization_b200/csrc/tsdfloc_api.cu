@@ -76,6 +76,16 @@ struct tsdfloc_ctx
   RedStatus* h_red_status = nullptr;
   bool have_reduce = false;
 
+  // multi-GPU: device copies of the peer-pointer tables handed to tsdfloc_eval_device_peers (a few distinct sets, cached)
+  struct PeerTable
+  {
+    float* host[8] = {};
+    uint32_t n = 0;
+    float** dev = nullptr;
+  };
+  PeerTable peer_tables[8];
+  uint32_t peer_tables_used = 0, peer_tables_next = 0;
+
   // motion update
   DevBuf d_draws;
 
@@ -212,6 +222,36 @@ int pick_ppw(const tsdfloc_ctx* c, uint64_t count)
   return count >= static_cast<uint64_t>(c->sm_count) * 32 ? 2 : 1;
 }
 
+// Device copy of a set of peer pointers. The sets repeat from update to update (two per buffer with double buffering), so
+// they are cached; a new set is uploaded once (pageable source: staged by the driver before the call returns).
+int peer_table(tsdfloc_ctx* c, float* const* want, uint32_t n, cudaStream_t s, float*** out)
+{
+  for (uint32_t k = 0; k < c->peer_tables_used; ++k)
+  {
+    tsdfloc_ctx::PeerTable& t = c->peer_tables[k];
+    if (t.n == n && std::memcmp(t.host, want, sizeof(float*) * n) == 0)
+    {
+      *out = t.dev;
+      return TSDFLOC_OK;
+    }
+  }
+  uint32_t slot;
+  if (c->peer_tables_used < 8) slot = c->peer_tables_used++;
+  else
+  {
+    slot = c->peer_tables_next++ % 8;
+    CU_TRY(c, cudaDeviceSynchronize(), "sync before peer-table reuse");  // a launch in flight may still read the old entry
+  }
+  tsdfloc_ctx::PeerTable& t = c->peer_tables[slot];
+  if (!t.dev) CU_TRY(c, cudaMalloc(&t.dev, sizeof(float*) * 8), "cudaMalloc(peer table)");
+  std::memset(t.host, 0, sizeof(t.host));
+  std::memcpy(t.host, want, sizeof(float*) * n);
+  t.n = n;
+  CU_TRY(c, cudaMemcpyAsync(t.dev, t.host, sizeof(float*) * 8, cudaMemcpyHostToDevice, s), "H2D peer table");
+  *out = t.dev;
+  return TSDFLOC_OK;
+}
+
 template <int W, int BS, int R>
 void launch_eval2(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s)
 {
@@ -278,8 +318,21 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   a.mats = static_cast<const float*>(c->d_mats.p);
   a.raw_out = d_raw + first;
   a.n_peer_out = 0;
-  for (uint32_t r = 0; r < n_peers; ++r)
-    if (d_raw_peers[r] && d_raw_peers[r] != d_raw) a.peer_out[a.n_peer_out++] = d_raw_peers[r] + first;
+  a.peer_out = nullptr;
+  if (n_peers)
+  {
+    float* want[8] = {};
+    uint32_t nw = 0;
+    for (uint32_t r = 0; r < n_peers; ++r)
+      if (d_raw_peers[r] && d_raw_peers[r] != d_raw) want[nw++] = d_raw_peers[r] + first;
+    if (nw)
+    {
+      float** table = nullptr;
+      if ((rc = peer_table(c, want, nw, s, &table))) return rc;
+      a.peer_out = table;
+      a.n_peer_out = nw;
+    }
+  }
   a.n_points = static_cast<uint32_t>(c->n_points);
   a.n_local = static_cast<uint32_t>(count);
   a.a_hit = c->prm.a_hit;
@@ -735,6 +788,8 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_status) cudaFreeHost(c->h_status);
   if (c->h_mean) cudaFreeHost(c->h_mean);
+  for (auto& t : c->peer_tables)
+    if (t.dev) cudaFree(t.dev);
   if (c->d_red_status) cudaFree(c->d_red_status);
   if (c->h_red_status) cudaFreeHost(c->h_red_status);
   if (c->ev_eval0) cudaEventDestroy(c->ev_eval0);

@@ -155,8 +155,8 @@ struct EvalArgs
   const float4* __restrict__ pts;   // x y z term, padded to a multiple of 32 points
   const float* __restrict__ mats;   // [n_local][12]
   float* raw_out;                   // [n_local] un-normalised weights (this rank's slice of its own weight vector)
-  float* peer_out[kMaxPeers];       // multi-GPU: the same slice inside every OTHER rank's weight vector (peer-mapped, NVLink)
-  uint32_t n_peer_out;              // 0 on one GPU
+  float* const* peer_out;           // multi-GPU: device table of n_peer_out pointers = the same slice inside every OTHER
+  uint32_t n_peer_out;              //            rank's weight vector (peer-mapped, NVLink); 0 / nullptr on one GPU
   unsigned long long* __restrict__ stats;  // [4]: blocks, blocks folded sequentially (binade crossing / early phase), tie folds, -
   uint32_t n_points;
   uint32_t n_local;
@@ -169,9 +169,9 @@ struct EvalArgs
 __device__ __forceinline__ void store_weight(const EvalArgs& A, uint32_t part, float w)
 {
   A.raw_out[part] = w;
-#pragma unroll   // constant indices: the pointers stay in the constant bank (a dynamic index would copy them to local memory)
-  for (int r = 0; r < kMaxPeers; ++r)
-    if (static_cast<uint32_t>(r) < A.n_peer_out) A.peer_out[r][part] = w;
+#ifndef TSDFLOC_EXP_NO_PEERS   // (timing experiment: single-GPU kernel without the peer stores)
+  for (uint32_t r = 0; r < A.n_peer_out; ++r) A.peer_out[r][part] = w;   // pointer table in global memory: no register cost in the loop
+#endif
 }
 
 // One point against one particle: transform, voxel gather, x = a_hit * v + term (two roundings, like the CPU build).
