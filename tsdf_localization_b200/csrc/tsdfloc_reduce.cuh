@@ -76,15 +76,24 @@ __global__ void __launch_bounds__(kRedThreads) k_red_mark(const RedArgs A, uint3
   if (threadIdx.x == 0) cta_count[blockIdx.x] = static_cast<uint32_t>(c);
 }
 
-// In-place exclusive scan of v[0..m) by ONE CTA of 1024 threads (contiguous chunks per thread); *total = sum.
+// In-place exclusive scan of v[0..m) by ONE CTA of 1024 threads; *total = sum. Every thread owns a contiguous chunk of
+// `per` elements (a multiple of 4, so chunks are 16 B aligned: v comes from cudaMalloc) and moves it with unrolled uint4
+// accesses — all loads of a pass are in flight together instead of `per` dependent round trips to L2.
 __global__ void __launch_bounds__(1024) k_red_scan(uint32_t* __restrict__ v, uint32_t m, uint32_t* __restrict__ total)
 {
   __shared__ uint32_t warp_sum[32];
   const uint32_t t = threadIdx.x;
-  const uint32_t per = (m + 1023u) / 1024u;
+  const uint32_t per = ((m + 1023u) / 1024u + 3u) & ~3u;
   const uint32_t lo = min(t * per, m), hi = min(lo + per, m);
+  const uint32_t full = lo + ((hi - lo) & ~3u);   // whole uint4 groups
   uint32_t s = 0;
-  for (uint32_t i = lo; i < hi; ++i) s += v[i];
+#pragma unroll 8
+  for (uint32_t i = lo; i < full; i += 4)
+  {
+    const uint4 q = *reinterpret_cast<const uint4*>(v + i);
+    s += q.x + q.y + q.z + q.w;
+  }
+  for (uint32_t i = full; i < hi; ++i) s += v[i];
   // block-wide exclusive scan of s
   uint32_t incl = s;
 #pragma unroll
@@ -109,7 +118,19 @@ __global__ void __launch_bounds__(1024) k_red_scan(uint32_t* __restrict__ v, uin
   __syncthreads();
   const uint32_t warp_off = (t >> 5) ? warp_sum[(t >> 5) - 1u] : 0u;
   uint32_t run = warp_off + incl - s;
-  for (uint32_t i = lo; i < hi; ++i)
+#pragma unroll 8
+  for (uint32_t i = lo; i < full; i += 4)
+  {
+    const uint4 q = *reinterpret_cast<const uint4*>(v + i);
+    uint4 o;
+    o.x = run;
+    o.y = o.x + q.x;
+    o.z = o.y + q.y;
+    o.w = o.z + q.z;
+    run = o.w + q.w;
+    *reinterpret_cast<uint4*>(v + i) = o;
+  }
+  for (uint32_t i = full; i < hi; ++i)
   {
     const uint32_t x = v[i];
     v[i] = run;
