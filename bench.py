@@ -325,7 +325,20 @@ def run_b200_arm(args):
                 traffic = json.loads(tpath.read_text()).get(args.workload, {}).get("dram_bytes_per_launch")
             except Exception:  # noqa: BLE001
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "k_eval", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        # complementary view: the measured ceiling for independent random 4 B gathers out of an L2-resident array
+        # (scripts/probe_gather.py -> profiles/r01c_probe_gather.jsonl); the kernel issues 2 gathers per evaluation
+        gather_view = None
+        ppath = ROOT / "profiles" / "r01c_probe_gather.jsonl"
+        if ppath.exists():
+            try:
+                rows = [json.loads(l) for l in ppath.read_text().splitlines() if l.strip()]
+                rnd = max(r["gathers_per_s"] for r in rows if isinstance(r["lanes_share_sectors"], str))
+                mine = 2.0 * n_local * p / (eval_mean_ms * 1e-3)
+                gather_view = {"achieved_gathers_per_s": mine, "random_gather_ceiling_per_s": rnd, "ratio": mine / rnd,
+                               "source": "profiles/r01c_probe_gather.jsonl (k_probe_gather, every lane its own random word)"}
+            except Exception:  # noqa: BLE001
+                gather_view = None
+        roofline = {"bound": "hbm", "kernel": "k_eval", "l2_gather_view": gather_view, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src, "kernel_ms": eval_mean_ms,
                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_EVAL * n_local * p,
                     "note": "8 B per particle-point evaluation (4 B brick-table entry + 4 B voxel); when the map is L2-resident DRAM traffic is far below the algorithmic bytes and the binding resources are the SM FP32 pipe / L2 (DESIGN.md)"}

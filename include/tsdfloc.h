@@ -297,6 +297,13 @@ int tsdfloc_best_particle(tsdfloc_ctx* ctx, int64_t* index, float pose[6], float
  * same segment-table code the device uses; writes U_j for all j with U_j < limit (at most cap) and returns their count. */
 uint64_t tsdfloc_host_u_sequence(float u0, uint64_t n, double limit, float* out, uint64_t cap, uint32_t* n_segs, uint32_t* flags);
 
+/* Measurement probe (not part of the product path): the chip's ceiling for independent 4 B gathers out of the
+ * first `bytes` of the uploaded voxel array (0 = all of it; L2-resident up to ~100 MB). spread_sectors = 0: every lane its own
+ * random word (32 sectors per warp request, the reference kernel's access shape); 1..32: the 32 lanes of a request fall into
+ * that many consecutive 32 B sectors (the evaluation kernel measures 12.5). Average time of `reps` launches after a warm-up. */
+int tsdfloc_probe_gather(tsdfloc_ctx* ctx, uint64_t bytes, uint32_t spread_sectors, uint32_t reps, float* ms_per_launch,
+                         uint64_t* gathers_per_launch);
+
 /* Cumulative statistics of the evaluation kernel's summation blocks (synchronises the device):
  * out[0] = (particle, block) pairs processed, out[1] = of those folded sequentially (binade crossing, early phase or tie),
  * out[2] = of those caused by an exact rounding tie, out[3] reserved. */

@@ -93,6 +93,7 @@ SIGNATURES = {
     "tsdfloc_init_particles": (C.c_int, [_vp, _vp, _u64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _u64, _u64, _u64]),
     "tsdfloc_best_particle": (C.c_int, [_vp, C.POINTER(C.c_int64), _fp, _fp, _vp]),
     "tsdfloc_host_u_sequence": (_u64, [C.c_float, _u64, C.c_double, _vp, _u64, _u32p, _u32p]),
+    "tsdfloc_probe_gather": (C.c_int, [_vp, _u64, C.c_uint32, C.c_uint32, _fp, C.POINTER(_u64)]),
     "tsdfloc_eval_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "tsdfloc_last_eval_ms": (C.c_int, [_vp, _fp]),
     "tsdfloc_kernel_launches": (_u64, [_vp]),

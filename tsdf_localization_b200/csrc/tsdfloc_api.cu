@@ -1244,6 +1244,45 @@ int tsdfloc_debug_eval(tsdfloc_ctx* c, const float* particles, uint64_t n, const
   return TSDFLOC_OK;
 }
 
+// Measurement probe: random 4 B gathers over the first `bytes` of the voxel array (L2-resident when bytes <= ~100 MB).
+// spread_sectors == 0: every lane its own random word; otherwise the lanes of a request share `spread_sectors` consecutive
+// 32 B sectors. Reports the average kernel time over `reps` launches after one warm-up and the gathers per launch.
+int tsdfloc_probe_gather(tsdfloc_ctx* c, uint64_t bytes, uint32_t spread_sectors, uint32_t reps, float* ms_per_launch, uint64_t* gathers_per_launch)
+{
+  if (!c || !ms_per_launch || !gathers_per_launch || reps == 0) return TSDFLOC_E_BAD_ARG;
+  DeviceGuard guard(c->device);
+  const uint64_t have = static_cast<uint64_t>(c->map.data_size) * 4ull;
+  if (bytes == 0 || bytes > have) bytes = have;
+  const uint32_t n_words = static_cast<uint32_t>(bytes / 4);
+  if (n_words < 4096u || spread_sectors > 32u) return fail(c, TSDFLOC_E_BAD_ARG, "probe needs >= 16 KB of map data and spread <= 32");
+  const uint32_t rounds = 64, grid = static_cast<uint32_t>(c->sm_count) * 8u * 16u;
+  cudaStream_t s = c->stream;
+  cudaEvent_t e0, e1;
+  CU_TRY(c, cudaEventCreate(&e0), "event create");
+  CU_TRY(c, cudaEventCreate(&e1), "event create");
+  k_probe_gather<<<grid, 256, 0, s>>>(c->d_voxels, n_words, rounds, spread_sectors, c->d_mean);
+  int rc = launch_check(c, "k_probe_gather");
+  if (rc == TSDFLOC_OK)
+  {
+    cudaEventRecord(e0, s);
+    for (uint32_t r = 0; r < reps; ++r)
+    {
+      k_probe_gather<<<grid, 256, 0, s>>>(c->d_voxels, n_words, rounds, spread_sectors, c->d_mean);
+      ++c->launches;
+    }
+    cudaEventRecord(e1, s);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e != cudaSuccess) rc = fail(c, TSDFLOC_E_CUDA, std::string("probe: ") + cudaGetErrorString(e));
+    *ms_per_launch = ms / static_cast<float>(reps);
+    *gathers_per_launch = static_cast<uint64_t>(grid) * 256ull * rounds * 8ull;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
+
 int tsdfloc_eval_stats(tsdfloc_ctx* c, uint64_t out[4])
 {
   if (!c || !out) return TSDFLOC_E_BAD_ARG;

@@ -61,6 +61,43 @@ struct USeg
 };
 
 // ------------------------------------------------------------------------------------------------------------
+// Measurement probe: the chip's ceiling for dependent-free 4 B gathers out of an L2-resident array, in the
+// two access shapes that bracket the evaluation kernel — every lane its own random sector (32 sectors per request, what the
+// reference's one-particle-per-thread kernel does) and the 32 lanes of a request spread over `spread` consecutive sectors
+// around a random base (12.5 sectors per request is what k_eval2 measures). 8 independent gathers per thread per round,
+// ld.global.nc like the kernel's table/voxel loads. Not part of the product path.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_probe_gather(const float* __restrict__ data, uint32_t n_words, uint32_t rounds, uint32_t spread_sectors,
+                                                      float* __restrict__ sink)
+{
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u, warp_id = tid >> 5;
+  uint32_t state = (spread_sectors ? warp_id : tid) * 747796405u + 2891336453u;
+  float acc = 0.0f;
+  for (uint32_t r = 0; r < rounds; ++r)
+  {
+    uint32_t idx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+      state = state * 1664525u + 1013904223u;   // LCG; warp-uniform when the lanes share a neighbourhood
+      const uint32_t h = (state >> 8) ^ (state << 7);
+      if (spread_sectors)
+      {
+        // lanes land in `spread` consecutive sectors (8 words each) behind a random base
+        const uint32_t base = (h % (n_words - spread_sectors * 8u)) & ~7u;
+        idx[k] = base + ((lane * spread_sectors) >> 5) * 8u + (lane & 7u);
+      }
+      else
+        idx[k] = h % n_words;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += __ldg(data + idx[k]);
+  }
+  if (acc == 123456.789f) sink[0] = acc;   // keep the loads alive
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Scan preparation: xyz -> float4 with w = the point's range term
 //   |p|^2 < max_range^2 ? a_range * (1/max_range) : a_max     (tsdf_evaluator.cpp:56-65, cuda_eval_particles.h:200-209)
 // ------------------------------------------------------------------------------------------------------------
