@@ -226,3 +226,28 @@ def test_resampler_edge_cases(oracle, ev):
     ps[:, 6] = 3.0 / 200
     with pytest.raises(capi.TsdflocError):
         rs.resample(ps, u0=0.001)          # exceeds the default capacity: reported, not truncated
+
+
+def test_spatial_evaluation_order_changes_nothing(monkeypatch):
+    """TSDFLOC_SORT=1 (counting sort of the particles by map cell in front of the evaluation, tsdfloc_sort.cuh) against
+    TSDFLOC_SORT=0: raw weights, normalised weights, mean pose and resampled particles must be byte-identical — including
+    particles outside the map and NaN poses, whose cell key is clamped."""
+    import common
+    from tsdf_localization_b200 import CudaEvaluator, SystematicResampler, synthetic as syn
+    _, m = common.box_room()
+    pts, _ = syn.make_scan("vlp16", syn.GT_POSE, n_points=3000)
+    ps = syn.uniform_particles(20011, (-14.0, -14.0, -1.0), (14.0, 14.0, 7.0))      # partly outside the 25.6 m box
+    ps[17, 0] = np.nan
+    ps[18, 1] = 1e30
+    results = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("TSDFLOC_SORT", mode)
+        ev = CudaEvaluator(m)
+        mine = ps.copy()
+        _, _, raw = ev.debug_eval(mine, pts, syn.CALIB_TF, want_idx=False)
+        pose = ev.evaluate(mine, pts, syn.CALIB_TF)
+        out = SystematicResampler(ev).resample_resident(len(ps), u0=0.37 / len(ps))
+        results.append((raw.tobytes(), mine.tobytes(), np.asarray(pose.position, dtype=np.float64).tobytes(), out.tobytes(), ev.kernel_launches()))
+        ev.close()
+    assert results[0][:4] == results[1][:4]
+    assert results[1][4] > results[0][4]            # the sort kernels really ran

@@ -10,6 +10,7 @@
 #include "tsdfloc_eval2.cuh"
 #include "tsdfloc_reduce.cuh"
 #include "tsdfloc_motion.cuh"
+#include "tsdfloc_sort.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -85,6 +86,12 @@ struct tsdfloc_ctx
   };
   PeerTable peer_tables[8];
   uint32_t peer_tables_used = 0, peer_tables_next = 0;
+
+  // spatial evaluation order (tsdfloc_sort.cuh)
+  DevBuf d_sort_keys, d_sort_hist, d_perm;
+  int sort_mode = -1;       // -1: automatic (map larger than L2 and enough particles); 0 / 1: TSDFLOC_SORT override
+  size_t l2_bytes = 0;
+  SortArgs sort_args{};
 
   // motion update
   DevBuf d_draws;
@@ -291,7 +298,36 @@ void launch_eval(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s)
     k_eval<kPPW, false><<<grid, kEvalThreads, 0, s>>>(c->map, a);
 }
 
-int stage_matrices(tsdfloc_ctx* c, const float* d_particles, uint64_t first, uint64_t count, const float tf[16], cudaStream_t s)
+// Spatial evaluation order of particles [first, first + count): *perm = device permutation, or nullptr when ordering is off
+// (map fits in L2, few particles, or TSDFLOC_SORT=0).
+int stage_sort(tsdfloc_ctx* c, const float* d_particles, uint64_t first, uint64_t count, cudaStream_t s, const uint32_t** perm)
+{
+  *perm = nullptr;
+  bool on = c->sort_mode == 1;
+  if (c->sort_mode < 0) on = static_cast<size_t>(c->map.data_size) * 4u > c->l2_bytes && count >= 16384;
+  if (!on || count < 2) return TSDFLOC_OK;
+  int rc;
+  const SortArgs& a = c->sort_args;
+  if ((rc = ensure(c, c->d_sort_keys, sizeof(uint32_t) * count, "cudaMalloc(sort keys)"))) return rc;
+  if ((rc = ensure(c, c->d_perm, sizeof(uint32_t) * count, "cudaMalloc(permutation)"))) return rc;
+  if ((rc = ensure(c, c->d_sort_hist, sizeof(uint32_t) * (a.n_keys + 4), "cudaMalloc(sort histogram)"))) return rc;
+  uint32_t* hist = static_cast<uint32_t*>(c->d_sort_hist.p);
+  CU_TRY(c, cudaMemsetAsync(hist, 0, sizeof(uint32_t) * a.n_keys, s), "memset(sort histogram)");
+  const unsigned blocks = static_cast<unsigned>((count + 255) / 256);
+  k_sort_keys<<<blocks, 256, 0, s>>>(d_particles, static_cast<uint32_t>(first), static_cast<uint32_t>(count), a,
+                                    static_cast<uint32_t*>(c->d_sort_keys.p), hist);
+  if ((rc = launch_check(c, "k_sort_keys"))) return rc;
+  k_red_scan<<<1, 1024, 0, s>>>(hist, a.n_keys, nullptr);
+  if ((rc = launch_check(c, "k_red_scan"))) return rc;
+  k_sort_scatter<<<blocks, 256, 0, s>>>(static_cast<const uint32_t*>(c->d_sort_keys.p), static_cast<uint32_t>(count), hist,
+                                       static_cast<uint32_t*>(c->d_perm.p));
+  if ((rc = launch_check(c, "k_sort_scatter"))) return rc;
+  *perm = static_cast<const uint32_t*>(c->d_perm.p);
+  return TSDFLOC_OK;
+}
+
+int stage_matrices(tsdfloc_ctx* c, const float* d_particles, uint64_t first, uint64_t count, const float tf[16], cudaStream_t s,
+                   const uint32_t* perm)
 {
   int rc;
   if ((rc = ensure(c, c->d_mats, sizeof(float) * 12 * count, "cudaMalloc(matrices)"))) return rc;
@@ -299,7 +335,7 @@ int stage_matrices(tsdfloc_ctx* c, const float* d_particles, uint64_t first, uin
   std::memcpy(t.m, tf, sizeof(t.m));
   k_pose_matrices<<<static_cast<unsigned>((count + 127) / 128), 128, 0, s>>>(d_particles, static_cast<uint32_t>(first),
                                                                             static_cast<uint32_t>(count), t,
-                                                                            static_cast<float*>(c->d_mats.p));
+                                                                            static_cast<float*>(c->d_mats.p), perm);
   return launch_check(c, "k_pose_matrices");
 }
 
@@ -312,8 +348,11 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   if (c->n_points == 0) return fail(c, TSDFLOC_E_EMPTY_SCAN, "empty scan");
   if (count == 0) return TSDFLOC_OK;
   int rc;
-  if ((rc = stage_matrices(c, d_particles, first, count, tf, s))) return rc;
+  const uint32_t* perm = nullptr;
+  if ((rc = stage_sort(c, d_particles, first, count, s, &perm))) return rc;
+  if ((rc = stage_matrices(c, d_particles, first, count, tf, s, perm))) return rc;
   EvalArgs a{};
+  a.perm = perm;
   a.pts = static_cast<const float4*>(c->d_pts.p);
   a.mats = static_cast<const float*>(c->d_mats.p);
   a.raw_out = d_raw + first;
@@ -631,6 +670,8 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
     return bail(TSDFLOC_E_CUDA, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
                                     "; libtsdfloc is built for sm_100a (B200) only");
   c->sm_count = prop.multiProcessorCount;
+  c->l2_bytes = static_cast<size_t>(prop.l2CacheSize);
+  if (const char* e = std::getenv("TSDFLOC_SORT")) c->sort_mode = std::atoi(e) ? 1 : 0;
   if (const char* e = std::getenv("TSDFLOC_EVAL")) c->eval_version = std::atoi(e);
   if (const char* e = std::getenv("TSDFLOC_W")) c->eval_w = std::atoi(e);
   if (const char* e = std::getenv("TSDFLOC_BS")) c->eval_bs = std::atoi(e);
@@ -710,6 +751,34 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
   M.table_bias = kMagicBits * (1u + M.pad_x + M.pad_xy);
   M.sub_bias = kMagicBits * (1u + M.sub_dim + M.sub_dim_2);
 
+  // ---- cell keys of the spatial evaluation order: cells of 2^k metres so that the key space stays <= 2^20 ------------------
+  {
+    SortArgs& sa = c->sort_args;
+    float cell = 1.0f;
+    for (;;)
+    {
+      uint32_t d[3];
+      for (int a = 0; a < 3; ++a) d[a] = std::max<uint32_t>(1u, static_cast<uint32_t>(std::ceil((map->max[a] - map->min[a]) / cell)));
+      uint32_t xy_bits = 0;
+      while ((1u << xy_bits) < std::max(d[0], d[1])) ++xy_bits;
+      uint32_t z_bits = 0;
+      while ((1u << z_bits) < d[2]) ++z_bits;
+      if (2 * xy_bits + z_bits <= 20)
+      {
+        for (int a = 0; a < 3; ++a)
+        {
+          sa.min[a] = map->min[a];
+          sa.dim[a] = d[a];
+        }
+        sa.inv_cell = 1.0f / cell;
+        sa.z_bits = z_bits;
+        sa.n_keys = 1u << (2 * xy_bits + z_bits);
+        break;
+      }
+      cell *= 2.0f;
+    }
+  }
+
   // ---- bound of one point's contribution, for the evaluation kernel's binade planning ---------------------------
   {
     float vmax = map->init_value, vmin = map->init_value;
@@ -776,7 +845,7 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
   DevBuf* bufs[] = {&c->d_xyz_stage, &c->d_pts, &c->d_particles, &c->d_particles_out, &c->d_mats,
                     &c->d_raw, &c->d_cdf, &c->d_tile_total, &c->d_tile_offset, &c->d_tile_moments, &c->d_tile_best, &c->d_parents, &c->d_idx, &c->d_hits,
                     &c->d_red_in_xyz, &c->d_red_in_ring, &c->d_red_key4, &c->d_red_table, &c->d_red_cta, &c->d_red_hist, &c->d_red_win,
-                    &c->d_red_rank, &c->d_red_out, &c->d_red_src, &c->d_draws};
+                    &c->d_red_rank, &c->d_red_out, &c->d_red_src, &c->d_draws, &c->d_sort_keys, &c->d_sort_hist, &c->d_perm};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->d_table) cudaFree(c->d_table);
@@ -1224,7 +1293,14 @@ int tsdfloc_debug_eval(tsdfloc_ctx* c, const float* particles, uint64_t n, const
   if ((rc = stage_prep_scan(c, static_cast<const float*>(c->d_xyz_stage.p), p, s))) return rc;
   float* d_p = static_cast<float*>(c->d_particles.p);
   CU_TRY(c, cudaMemcpyAsync(d_p, particles, sizeof(float) * 7 * n, cudaMemcpyHostToDevice, s), "H2D particles");
-  if ((rc = stage_eval(c, d_p, n, 0, n, tf, static_cast<float*>(c->d_raw.p), s))) return rc;
+  {
+    // the index dump below reads the matrices particle-major: evaluate in identity order
+    const int saved = c->sort_mode;
+    c->sort_mode = 0;
+    rc = stage_eval(c, d_p, n, 0, n, tf, static_cast<float*>(c->d_raw.p), s);
+    c->sort_mode = saved;
+    if (rc) return rc;
+  }
   CU_TRY(c, cudaMemsetAsync(c->d_hits.p, 0, sizeof(uint32_t) * n, s), "memset hits");
   const unsigned long long total = n * p;
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);

@@ -121,11 +121,13 @@ struct Tf12
   float m[12];
 };
 
-__global__ void k_pose_matrices(const float* __restrict__ particles, uint32_t first, uint32_t count, Tf12 tf, float* __restrict__ mats)
+// perm (optional): matrix i belongs to particle first + perm[i] (spatial evaluation order, tsdfloc_sort.cuh).
+__global__ void k_pose_matrices(const float* __restrict__ particles, uint32_t first, uint32_t count, Tf12 tf, float* __restrict__ mats,
+                                const uint32_t* __restrict__ perm)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  const float* p = particles + 7ull * (first + i);
+  const float* p = particles + 7ull * (first + (perm ? perm[i] : i));
   double sd, cd;
   sincos(static_cast<double>(p[3]), &sd, &cd);
   const float sa = static_cast<float>(sd), ca = static_cast<float>(cd);
@@ -192,6 +194,7 @@ struct EvalArgs
   const float4* __restrict__ pts;   // x y z term, padded to a multiple of 32 points
   const float* __restrict__ mats;   // [n_local][12]
   float* raw_out;                   // [n_local] un-normalised weights (this rank's slice of its own weight vector)
+  const uint32_t* perm;             // evaluation order: slot j is particle perm[j] (nullptr = identity), tsdfloc_sort.cuh
   float* const* peer_out;           // multi-GPU: device table of n_peer_out pointers = the same slice inside every OTHER
   uint32_t n_peer_out;              //            rank's weight vector (peer-mapped, NVLink); 0 / nullptr on one GPU
   unsigned long long* __restrict__ stats;  // [4]: blocks, blocks folded sequentially (binade crossing / early phase), tie folds, -
@@ -203,8 +206,9 @@ struct EvalArgs
   uint32_t force_seq;               // 1: negative/non-finite addends possible -> always fold sequentially
 };
 
-__device__ __forceinline__ void store_weight(const EvalArgs& A, uint32_t part, float w)
+__device__ __forceinline__ void store_weight(const EvalArgs& A, uint32_t slot, float w)
 {
+  const uint32_t part = A.perm ? A.perm[slot] : slot;
   A.raw_out[part] = w;
 #ifndef TSDFLOC_EXP_NO_PEERS   // (timing experiment: single-GPU kernel without the peer stores)
   for (uint32_t r = 0; r < A.n_peer_out; ++r) A.peer_out[r][part] = w;   // pointer table in global memory: no register cost in the loop
