@@ -13,11 +13,15 @@ from tsdf_localization_b200 import CudaEvaluator, capi, synthetic as syn  # noqa
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 kind = sys.argv[2] if len(sys.argv) > 2 else "os1-128"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-spec, m = common.box_room()
+if kind in ("c4", "c5"):          # the 1.4 GB multi-room map (beyond L2): global localisation / tracking cloud
+    m = common.grid_rooms()
+    ps, pts, _ = common.config_c4(n) if kind == "c4" else common.config_c5(n)
+else:
+    spec, m = common.box_room()
+    pts, _ = syn.make_scan(kind, syn.GT_POSE)
+    ps = syn.tracking_particles(n, syn.GT_POSE)
 ev = CudaEvaluator(m)
 lib = capi.load_library()
-pts, _ = syn.make_scan(kind, syn.GT_POSE)
-ps = syn.tracking_particles(n, syn.GT_POSE)
 dev = torch.device("cuda:0")
 d_ps = torch.from_numpy(ps).to(dev)
 d_pts = torch.from_numpy(pts).to(dev)
