@@ -45,6 +45,8 @@ UNIT = "evals/s"
 ALG_BYTES_PER_EVAL = 8          # 4 B brick-table entry + 4 B voxel
 L2_FLUSH_BYTES = 256 << 20
 
+PARTICLES_OVERRIDE = 0      # --particles: development runs of the box-room workloads at another particle count
+
 WORKLOADS = {
     "c3": dict(scan="os1-128", particles=65536, desc="OS1-128 scan (131,072 pts) x 65,536 particles, box room 20x20x5 m @ 5 cm"),
     "c2": dict(scan="vlp16", particles=5000, desc="VLP-16 scan (30,000 pts) x 5,000 particles, box room 20x20x5 m @ 5 cm"),
@@ -65,7 +67,7 @@ def build_workload(name: str):
         return None, m, ps, pts, syn.IDENTITY_TF
     spec, m = common.box_room()
     pts, _ = syn.make_scan(w["scan"], syn.GT_POSE, n_points=w.get("n_points"))
-    ps = syn.tracking_particles(w["particles"], syn.GT_POSE)
+    ps = syn.tracking_particles(PARTICLES_OVERRIDE or w["particles"], syn.GT_POSE)
     return spec, m, ps, pts, syn.IDENTITY_TF
 
 
@@ -357,8 +359,8 @@ def run_b200_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": args.workload + ": " + WORKLOADS[args.workload]["desc"], "particles": n, "points": p,
-                       "particles_per_gpu": n_local, "map_mb": m.dataBytes() / 1e6, "sharding": f"particles/{world}, map replicated",
+            "config": {"workload": args.workload + ": " + WORKLOADS[args.workload]["desc"] + (" [--particles override]" if PARTICLES_OVERRIDE else ""),
+                       "particles": n, "points": p, "particles_per_gpu": n_local, "map_mb": m.dataBytes() / 1e6, "sharding": f"particles/{world}, map replicated",
                        "step": "scan prep + eval + normalise/mean/CDF + systematic resample" + (
                            "" if world == 1 else " + 2 NCCL all-gathers" if upd.transport == "all_gather"
                            else "; eval and draw kernels store into all peers' symmetric-memory buffers over NVLink (no collective), 3 signal barriers"),
@@ -388,7 +390,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--transport", choices=("auto", "nccl", "fused"), default="auto",
                     help="multi-GPU exchange: fused = kernels store straight into the peers' buffers (default when available); nccl = all-gathers")
+    ap.add_argument("--particles", type=int, default=0, help="development: override the particle count of c1-c3 (not a BASELINE config)")
     args = ap.parse_args()
+    global PARTICLES_OVERRIDE
+    PARTICLES_OVERRIDE = args.particles
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
