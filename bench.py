@@ -161,9 +161,10 @@ def reference_runner(spec, ps, pts, tf, sample: int):
     return run_once, ref.omp_threads(), f"first {sample} of {len(ps)} particles x full {len(pts)}-point scan"
 
 
-def cpu_sample_size(n_particles: int, n_points: int) -> int:
-    """~3e8 evaluations per run (about a second on 16 cores), capped by the workload."""
-    return int(max(16, min(n_particles, 3.0e8 // max(n_points, 1))))
+def cpu_sample_size(n_particles: int, n_points: int, evals: float = 3.0e8) -> int:
+    """Particles of the bounded CPU sample: ~`evals` particle-point evaluations per run (3e8 = about 0.3 s on 16 cores),
+    capped by the workload."""
+    return int(max(16, min(n_particles, evals // max(n_points, 1))))
 
 
 def run_reference_arm(args):
@@ -347,7 +348,7 @@ def run_b200_arm(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                sample = cpu_sample_size(n, p)
+                sample = cpu_sample_size(n, p, 2.0e9)      # ~2 s per run on 16 cores; 1 warm-up + best of 5 = ~12 s of CPU work
                 run_once, cores, what = reference_runner(spec, ps, pts, tf, sample)
                 run_once()
                 best = min(run_once() for _ in range(5))

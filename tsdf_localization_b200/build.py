@@ -72,7 +72,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
 
 def build_oracle(verbose: bool = False) -> None:
     """Build oracle/_build/libtsdf_oracle.so and, when /root/reference is present, oracle/_ref/*.so."""
-    res = subprocess.run(["make", "-C", str(ROOT / "oracle"), "all"], capture_output=True, text=True)
+    res = subprocess.run(["make", "-j8", "-C", str(ROOT / "oracle"), "all"], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
     if verbose:
