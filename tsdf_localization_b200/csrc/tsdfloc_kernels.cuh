@@ -585,50 +585,73 @@ __global__ void __launch_bounds__(kScanThreads) k_normalise_scan(float* __restri
   if (bad) atomicOr(&st->inexact, 1u);
 }
 
-// K2c: one block. Exclusive scan of the tile totals (fp64, exactness-checked), moments -> mean pose.
-__global__ void k_scan_tiles(const double* __restrict__ tile_total, double* __restrict__ tile_offset, uint32_t n_tiles,
-                             const double* __restrict__ tile_moments, float* __restrict__ mean_pose, Status* __restrict__ st,
-                             const unsigned long long* __restrict__ tile_best, const float* __restrict__ particles)
+// K2c: one warp. Exclusive scan of the tile totals (fp64, exactness-checked: when every addition is exact the result does
+// not depend on the order, so the warp scans 32 tiles at a time instead of one thread walking them; an inexact addition
+// raises st->inexact and K3 redoes the CDF sequentially), moments -> mean pose, per-tile arg-max -> best particle.
+__global__ void __launch_bounds__(32) k_scan_tiles(const double* __restrict__ tile_total, double* __restrict__ tile_offset, uint32_t n_tiles,
+                                                   const double* __restrict__ tile_moments, float* __restrict__ mean_pose,
+                                                   Status* __restrict__ st, const unsigned long long* __restrict__ tile_best,
+                                                   const float* __restrict__ particles)
 {
-  __shared__ double s_mom[9];
-  if (threadIdx.x == 9)
+  const uint32_t lane = threadIdx.x;
+  bool bad = false;
+  double carry = 0.0;
+  double mom[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) mom[q] = 0.0;
+  unsigned long long best = 0ull;
+  for (uint32_t base = 0; base < n_tiles; base += 32u)
   {
-    unsigned long long b = 0ull;
-    for (uint32_t t = 0; t < n_tiles; ++t) b = tile_best[t] > b ? tile_best[t] : b;
-    st->best_key = b;
-    if (b)
+    const uint32_t t = base + lane;
+    const bool live = t < n_tiles;
+    const double v = live ? tile_total[t] : 0.0;
+    double incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
     {
-      const uint32_t i = ~static_cast<uint32_t>(b & 0xffffffffull);
+      const double up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= static_cast<uint32_t>(o)) incl = add_checked(incl, up, bad);
+    }
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 0.0;
+    if (live) tile_offset[t] = add_checked(carry, excl, bad);
+    carry = add_checked(carry, __shfl_sync(0xffffffffu, incl, 31), bad);
+    if (live)
+    {
+      // per-lane partial sums in a fixed (tile-index) order; combined below in a fixed tree order -> deterministic
+#pragma unroll
+      for (int q = 0; q < 9; ++q) mom[q] += tile_moments[static_cast<size_t>(t) * 9 + q];
+      const unsigned long long b = tile_best[t];
+      best = b > best ? b : best;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q)
+    for (int o = 16; o; o >>= 1) mom[q] += __shfl_down_sync(0xffffffffu, mom[q], o);
+  for (int o = 16; o; o >>= 1)
+  {
+    const unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&st->inexact, 1u);
+  if (lane == 0)
+  {
+    if (mean_pose)
+    {
+      mean_pose[0] = static_cast<float>(mom[0]);
+      mean_pose[1] = static_cast<float>(mom[1]);
+      mean_pose[2] = static_cast<float>(mom[2]);
+      mean_pose[3] = static_cast<float>(atan2(mom[3], mom[4]));
+      mean_pose[4] = static_cast<float>(atan2(mom[5], mom[6]));
+      mean_pose[5] = static_cast<float>(atan2(mom[7], mom[8]));
+    }
+    st->best_key = best;
+    if (best)
+    {
+      const uint32_t i = ~static_cast<uint32_t>(best & 0xffffffffull);
       for (int k = 0; k < 6; ++k) st->best_pose[k] = particles[7ull * i + k];
       st->best_weight = particles[7ull * i + 6];
     }
-  }
-  if (threadIdx.x == 0)
-  {
-    bool bad = false;
-    double run = 0.0;
-    for (uint32_t t = 0; t < n_tiles; ++t)
-    {
-      tile_offset[t] = run;
-      run = add_checked(run, tile_total[t], bad);
-    }
-    if (bad) atomicOr(&st->inexact, 1u);
-  }
-  if (threadIdx.x < 9)
-  {
-    double v = 0.0;
-    for (uint32_t t = 0; t < n_tiles; ++t) v += tile_moments[static_cast<size_t>(t) * 9 + threadIdx.x];
-    s_mom[threadIdx.x] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0 && mean_pose)
-  {
-    mean_pose[0] = static_cast<float>(s_mom[0]);
-    mean_pose[1] = static_cast<float>(s_mom[1]);
-    mean_pose[2] = static_cast<float>(s_mom[2]);
-    mean_pose[3] = static_cast<float>(atan2(s_mom[3], s_mom[4]));
-    mean_pose[4] = static_cast<float>(atan2(s_mom[5], s_mom[6]));
-    mean_pose[5] = static_cast<float>(atan2(s_mom[7], s_mom[8]));
   }
 }
 
