@@ -196,6 +196,26 @@ int tsdfloc_draw_device_peers(tsdfloc_ctx* ctx, const float* d_particles, uint64
                               uint64_t count_out, float* d_particles_out, float* const* d_out_peers, uint32_t n_peers,
                               uint32_t* d_parents, void* stream);
 
+/* ---- one process, several GPUs ---------------------------------------------------------------------------------
+ * The same two host-buffer calls as layer (A), sharded over up to 8 peer-capable devices of one box (no reference
+ * counterpart: the reference is single-GPU; its caller, the mcl_3d node, is ONE process — this is how it can use the whole
+ * box). Map and scan are replicated, the particles sharded contiguously; the evaluation / draw kernels store their results
+ * straight into every device's buffers over NVLink (the *_peers variants above) and CUDA events order the devices — no NCCL,
+ * no helper threads. Results are bit-identical to the single-GPU calls. `devices` may name the same device more than once
+ * (testing on a one-GPU machine). */
+typedef struct tsdfloc_multi tsdfloc_multi;
+int tsdfloc_multi_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const float* data, const tsdfloc_params* params,
+                         const int* devices, int n_devices, tsdfloc_multi** out);
+void tsdfloc_multi_destroy(tsdfloc_multi* m);
+int tsdfloc_multi_device_count(const tsdfloc_multi* m);
+const char* tsdfloc_multi_last_error(const tsdfloc_multi* m);
+/* The single-device context of rank `rank` (owned by m), e.g. for tsdfloc_resample_particles / tsdfloc_reduce_scan. */
+tsdfloc_ctx* tsdfloc_multi_ctx(tsdfloc_multi* m, int rank);
+/* tsdfloc_sensor_update / tsdfloc_resample_systematic over all devices (same arguments and status codes). */
+int tsdfloc_multi_sensor_update(tsdfloc_multi* m, float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],
+                                float mean_pose[6]);
+int tsdfloc_multi_resample_systematic(tsdfloc_multi* m, float u0, float* particles_out, uint64_t cap, uint64_t* n_out);
+
 /* Synchronises `stream` and reports what the device recorded for the last normalize/draw:
  * n_out = number of particles the reference recurrence emits; returns TSDFLOC_E_NO_VALID_PARTICLE if sum == 0. */
 int tsdfloc_check(tsdfloc_ctx* ctx, uint64_t* n_out, double* weight_sum, void* stream);

@@ -150,3 +150,40 @@ def test_nccl_two_ranks_equal_single_rank():
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "NCCL_CHECK_OK" in res.stdout
+
+
+@pytest.mark.parametrize("n", [4096, 5001])
+def test_single_process_multi_gpu_equals_single_gpu(n):
+    """tsdfloc_multi_* (one process, one ctx per device, peer stores + CUDA events): bit-identical to the single-GPU calls.
+    Runs over the real devices when there are >= 2, and always over the same device used three times (three ranks)."""
+    import torch
+    from tsdf_localization_b200 import CudaEvaluator, MultiGpuEvaluator
+    _, m = common.box_room()
+    pts, _ = syn.make_scan("vlp16", syn.GT_POSE, n_points=5000)
+    ps = syn.tracking_particles(n, syn.GT_POSE)
+    tf, u0 = syn.CALIB_TF, 0.37 / n
+    ev = CudaEvaluator(m)
+    want = ps.copy()
+    pose1 = ev.evaluate(want, pts, tf)
+    out1 = ev.resample_systematic(u0, capacity=n + n // 8 + 64)
+    ev.close()
+    layouts = [[0, 0, 0]]
+    if torch.cuda.device_count() >= 2:
+        layouts.append(list(range(min(torch.cuda.device_count(), 8))))
+    for devices in layouts:
+        mev = MultiGpuEvaluator(m, devices)
+        for _ in range(2):                      # twice: buffers and peer tables are reused
+            got = ps.copy()
+            pose = mev.evaluate(got, pts, tf)
+            out = mev.resample_systematic(u0, capacity=n + n // 8 + 64)
+            assert got.tobytes() == want.tobytes(), f"normalised weights differ on devices {devices}"
+            assert out.tobytes() == out1.tobytes(), f"resampled particles differ on devices {devices}"
+            assert pose.position == pose1.position and pose.rpy == pose1.rpy
+        mev.close()
+    # the "No particle is valid!" condition (all weights 0) is detected on every device and reported like the 1-GPU call
+    mev = MultiGpuEvaluator(m, [0, 0], a_range=0.0)
+    far = ps.copy()
+    far[:, :3] += 500.0
+    with pytest.raises(RuntimeError, match="No particle is valid!"):
+        mev.evaluate(far, pts, tf)
+    mev.close()

@@ -134,3 +134,25 @@ def test_reference_evaluateParticles_gpu_branch_matches_its_cpu_branch(shim, sma
         want_f, _ = Oracle().reduce_scan(pts, ring, 0.064, n_rings=64, ring_desync=False)
         assert used_f == len(want_f)
     shim.eval_destroy(ev)
+
+
+@pytest.mark.gpu
+def test_reference_facade_over_several_devices(shim, small_map, monkeypatch):
+    """TSDFLOC_DEVICES="a,b,..": the reference's TSDFEvaluator::evaluate(use_cuda=true) runs sharded over those GPUs from the one
+    process (here: the same device twice, or two devices when present) and returns what the single-device run returns."""
+    import torch
+    ps, pts = _workload()
+    ev = shim.eval_create(small_map)
+    rc, one, pose_one, err = shim.evaluate(ev, ps, pts, syn.CALIB_TF, use_cuda=True)
+    assert rc == 0, err
+    shim.eval_destroy(ev)
+    monkeypatch.setenv("TSDFLOC_DEVICES", "0,1" if torch.cuda.device_count() >= 2 else "0,0")
+    ev = shim.eval_create(small_map)
+    assert ev, shim.last_error()
+    rc, many, pose_many, err = shim.evaluate(ev, ps, pts, syn.CALIB_TF, use_cuda=True)
+    assert rc == 0, err
+    assert many.tobytes() == one.tobytes() and pose_many.tobytes() == pose_one.tobytes()
+    m_ref, out_ref, _ = shim.systematic_resample(many, 3)
+    m_gpu, out_gpu = shim.gpu_systematic_resample(many, 3)      # the resampler borrows rank 0's context
+    assert m_gpu == m_ref and np.array_equal(out_gpu, out_ref)
+    shim.eval_destroy(ev)

@@ -77,6 +77,13 @@ SIGNATURES = {
     "tsdfloc_eval_device": (C.c_int, [_vp, _vp, _u64, _u64, _u64, _fp, _vp, _vp]),
     "tsdfloc_eval_device_peers": (C.c_int, [_vp, _vp, _u64, _u64, _u64, _fp, _vp, C.POINTER(_vp), C.c_uint32, _vp]),
     "tsdfloc_draw_device_peers": (C.c_int, [_vp, _vp, _u64, C.c_float, _u64, _u64, _vp, C.POINTER(_vp), C.c_uint32, _vp, _vp]),
+    "tsdfloc_multi_create": (C.c_int, [C.POINTER(MapDesc), _vp, _vp, C.POINTER(Params), C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
+    "tsdfloc_multi_destroy": (None, [_vp]),
+    "tsdfloc_multi_device_count": (C.c_int, [_vp]),
+    "tsdfloc_multi_last_error": (C.c_char_p, [_vp]),
+    "tsdfloc_multi_ctx": (_vp, [_vp, C.c_int]),
+    "tsdfloc_multi_sensor_update": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _fp, _fp]),
+    "tsdfloc_multi_resample_systematic": (C.c_int, [_vp, C.c_float, _vp, _u64, C.POINTER(_u64)]),
     "tsdfloc_normalize_device": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "tsdfloc_draw_device": (C.c_int, [_vp, _vp, _u64, C.c_float, _u64, _u64, _vp, _vp, _vp]),
     "tsdfloc_check": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double), _vp]),

@@ -1395,3 +1395,5 @@ uint64_t tsdfloc_host_u_sequence(float u0, uint64_t n, double limit, float* out,
 }
 
 }  // extern "C"
+
+#include "tsdfloc_multi.inc"

@@ -297,6 +297,61 @@ class CudaEvaluator:
         self.close()
 
 
+class MultiGpuEvaluator:
+    """CudaEvaluator over several GPUs of one box from ONE process (tsdfloc_multi_*): same evaluate() / resample_systematic()
+    contract and bit-identical results; particles are sharded, map and scan replicated, and the kernels store their results
+    straight into every device's buffers over NVLink. ``devices`` may repeat a device (tests on a one-GPU machine)."""
+
+    def __init__(self, map: CudaSubVoxelMap, devices: Sequence[int], per_point: bool = False, a_hit: float = 0.9, a_range: float = 0.1,
+                 a_max: float = 0.0, max_range: float = 100.0):
+        self._lib = capi.load_library()
+        self._m = C.c_void_p()
+        prm = capi.Params(a_hit, a_range, a_max, max_range, int(per_point), 0)
+        desc = map.coef()
+        occ = np.ascontiguousarray(map.rawGridOcc(), dtype=np.int32)
+        data = np.ascontiguousarray(map.rawData(), dtype=np.float32)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = self._lib.tsdfloc_multi_create(C.byref(desc), occ.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), C.byref(prm),
+                                            devs, len(devices), C.byref(self._m))
+        if rc != capi.OK:
+            raise RuntimeError("Error while creating the CUDA context for the map! " + self._lib.tsdfloc_multi_last_error(None).decode())
+        self.devices = list(devices)
+
+    def _check(self, rc: int) -> None:
+        if rc == capi.OK:
+            return
+        if rc == capi.E_NO_VALID_PARTICLE:
+            raise RuntimeError("No particle is valid!")
+        raise capi.TsdflocError(rc, self._lib.tsdfloc_multi_last_error(self._m).decode())
+
+    def evaluate(self, particles: np.ndarray, points, tf_matrix) -> PoseWithCovariance:
+        if not (isinstance(particles, np.ndarray) and particles.dtype == np.float32 and particles.ndim == 2
+                and particles.shape[1] == 7 and particles.flags.c_contiguous):
+            raise ValueError("particles must be a C-contiguous float32[n, 7] array (it is updated in place)")
+        pts = _f32(np.asarray(points).reshape(-1, 3), 3, "points")
+        if pts.shape[0] == 0:
+            return PoseWithCovariance()
+        tf = (C.c_float * 16)(*[float(v) for v in np.asarray(tf_matrix, dtype=np.float32).reshape(-1)[:16]])
+        mean = (C.c_float * 6)()
+        self._check(self._lib.tsdfloc_multi_sensor_update(self._m, particles.ctypes.data_as(C.c_void_p), particles.shape[0],
+                                                          pts.ctypes.data_as(C.c_void_p), pts.shape[0], tf, mean))
+        return PoseWithCovariance.from_mean(list(mean))
+
+    def resample_systematic(self, u0: float, capacity: int):
+        out = np.empty((capacity, 7), dtype=np.float32)
+        n_out = C.c_uint64(0)
+        self._check(self._lib.tsdfloc_multi_resample_systematic(self._m, C.c_float(u0), out.ctypes.data_as(C.c_void_p), capacity, C.byref(n_out)))
+        return out[:int(n_out.value)]
+
+    def close(self) -> None:
+        if getattr(self, "_m", None):
+            self._lib.tsdfloc_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        self.close()
+
+
 class ParticleCloud:
     """Motion-update half of the reference's ParticleCloud (include/tsdf_localization/particle_cloud.h:44-258,
     src/particle_cloud.cpp:153-617) on the GPU: the four ``motionUpdate`` variants, the reference pose that gates the sensor

@@ -15,7 +15,9 @@
 //   any CUDA failure -> std::runtime_error                                      TSDFLOC_E_CUDA -> std::runtime_error(last_error)
 //
 // The header's private data members stay as they are (binary layout unchanged); the tsdfloc context handle is kept
-// in the otherwise unused `d_transform_` pointer.
+// in the otherwise unused `d_transform_` pointer. With TSDFLOC_DEVICES="0,1,2,..." (more than one device) the evaluator
+// shards every update over those GPUs from this one process (tsdfloc_multi_*; handle in the unused `d_new_weights_` slot);
+// results are bit-identical to the single-GPU path.
 #include <tsdf_localization/cuda/cuda_evaluator.h>
 
 #include <sensor_msgs/point_cloud2_iterator.h>
@@ -44,6 +46,25 @@ std::mutex g_ctx_mutex;
 tsdfloc_ctx* g_last_ctx = nullptr;
 
 inline tsdfloc_ctx* ctx_of(FLOAT_T* slot) { return reinterpret_cast<tsdfloc_ctx*>(slot); }
+inline tsdfloc_multi* multi_of(FLOAT_T* slot) { return reinterpret_cast<tsdfloc_multi*>(slot); }
+
+// "0,1,2" -> {0, 1, 2}
+std::vector<int> device_list(const char* text)
+{
+  std::vector<int> out;
+  std::string cur;
+  for (const char* p = text; ; ++p)
+  {
+    if (*p == ',' || *p == '\0')
+    {
+      if (!cur.empty()) out.push_back(std::atoi(cur.c_str()));
+      cur.clear();
+      if (*p == '\0') break;
+    }
+    else cur.push_back(*p);
+  }
+  return out;
+}
 }  // namespace
 
 tsdfloc_ctx* tsdfloc_shim_context()
@@ -83,13 +104,29 @@ CudaEvaluator::CudaEvaluator(CudaSubVoxelMap<FLOAT_T, FLOAT_T>& map, bool per_po
 
   int device = 0;
   if (const char* e = std::getenv("TSDFLOC_DEVICE")) device = std::atoi(e);
+  std::vector<int> devices;
+  if (const char* e = std::getenv("TSDFLOC_DEVICES")) devices = device_list(e);
   tsdfloc_ctx* ctx = nullptr;
   static_assert(sizeof(OCC_T) == sizeof(int32_t), "OCC_T must be a 32-bit int (cuda_sub_voxel_map.h:13)");
-  const int rc = tsdfloc_create(&d, reinterpret_cast<const int32_t*>(map.rawGridOcc()), map.rawData(), &prm, device, &ctx);
-  if (rc != TSDFLOC_OK)
+  if (devices.size() > 1)
   {
-    // same wrapper text as cuda_evaluator.cu:52-55, with the cause appended
-    throw std::runtime_error(std::string("Error while creating the CUDA context for the map! ") + tsdfloc_last_error(nullptr));
+    tsdfloc_multi* multi = nullptr;
+    const int rc = tsdfloc_multi_create(&d, reinterpret_cast<const int32_t*>(map.rawGridOcc()), map.rawData(), &prm, devices.data(),
+                                        static_cast<int>(devices.size()), &multi);
+    if (rc != TSDFLOC_OK)
+      throw std::runtime_error(std::string("Error while creating the CUDA context for the map! ") + tsdfloc_multi_last_error(nullptr));
+    d_new_weights_ = reinterpret_cast<FLOAT_T*>(multi);
+    ctx = tsdfloc_multi_ctx(multi, 0);   // resampler / reduction entry points keep using one device's context
+  }
+  else
+  {
+    if (devices.size() == 1) device = devices[0];
+    const int rc = tsdfloc_create(&d, reinterpret_cast<const int32_t*>(map.rawGridOcc()), map.rawData(), &prm, device, &ctx);
+    if (rc != TSDFLOC_OK)
+    {
+      // same wrapper text as cuda_evaluator.cu:52-55, with the cause appended
+      throw std::runtime_error(std::string("Error while creating the CUDA context for the map! ") + tsdfloc_last_error(nullptr));
+    }
   }
   d_map_ = &map;
   d_transform_ = reinterpret_cast<FLOAT_T*>(ctx);
@@ -104,7 +141,15 @@ CudaEvaluator::~CudaEvaluator()
     std::lock_guard<std::mutex> lock(g_ctx_mutex);
     if (g_last_ctx == ctx) g_last_ctx = nullptr;
   }
-  tsdfloc_destroy(ctx);
+  if (d_new_weights_)
+  {
+    tsdfloc_multi_destroy(multi_of(d_new_weights_));   // owns the per-device contexts, incl. ctx
+    d_new_weights_ = nullptr;
+  }
+  else
+  {
+    tsdfloc_destroy(ctx);
+  }
   d_transform_ = nullptr;
 }
 
@@ -211,6 +256,16 @@ geometry_msgs::PoseWithCovariance CudaEvaluator::evaluate(std::vector<Particle>&
   }
   tsdfloc_ctx* ctx = ctx_of(d_transform_);
   float mean[6] = {0, 0, 0, 0, 0, 0};
+  if (d_new_weights_)
+  {
+    tsdfloc_multi* multi = multi_of(d_new_weights_);
+    const int rc = tsdfloc_multi_sensor_update(multi, reinterpret_cast<float*>(particles.data()), particles.size(),
+                                               reinterpret_cast<const float*>(points.data()), points.size(), tf_matrix, mean);
+    if (rc == TSDFLOC_E_NO_VALID_PARTICLE) throw std::runtime_error("No particle is valid!");
+    if (rc != TSDFLOC_OK)
+      throw std::runtime_error(std::string("Error occured during the sensor update on the gpu! ") + tsdfloc_multi_last_error(multi));
+    return tsdfloc_shim_pose(mean);
+  }
   const int rc = tsdfloc_sensor_update(ctx, reinterpret_cast<float*>(particles.data()), particles.size(),
                                        reinterpret_cast<const float*>(points.data()), points.size(), tf_matrix, mean);
   if (rc != TSDFLOC_OK) throw_update_error(ctx, rc);
