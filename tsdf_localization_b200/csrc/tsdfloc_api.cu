@@ -259,6 +259,17 @@ int peer_table(tsdfloc_ctx* c, float* const* want, uint32_t n, cudaStream_t s, f
   return TSDFLOC_OK;
 }
 
+// One-warp CTAs without shared memory (k_eval2<1, BS, R, ., kDirect = true>).
+template <int BS, int R>
+void launch_eval_direct(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s)
+{
+  const uint32_t grid = (a.n_local + 1) / 2;
+  if (c->map.fast_div)
+    k_eval2<1, BS, R, true, true><<<grid, 32, 0, s>>>(c->map, a);
+  else
+    k_eval2<1, BS, R, false, true><<<grid, 32, 0, s>>>(c->map, a);
+}
+
 template <int W, int BS, int R>
 void launch_eval2(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s)
 {
@@ -380,20 +391,22 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   a.stats = c->d_eval_stats;
   a.force_seq = c->force_seq;
   CU_TRY(c, cudaEventRecord(c->ev_eval0, s), "event record");
-  // Kernel choice (B200 sweeps, profiles/r01_eval2_sweep.md): k_eval2 wins whenever its 4-warp CTAs either fit one wave
-  // (6 CTAs/SM at 80 registers) or fill many; in between (e.g. 8,192 particles = 1.15 waves) and for very few particles the
-  // one-warp-CTA kernel k_eval packs the SMs better. TSDFLOC_EVAL=1|2 forces one of them.
-  const uint64_t warps = (count + 1) / 2;
-  const uint64_t sms = static_cast<uint64_t>(c->sm_count);
-  bool use2 = true;
-  if (c->eval_version == 1) use2 = false;
-  else if (c->eval_version == 0)
+  // Kernel choice (B200 sweeps, profiles/r01_eval2_sweep.md). Default since round 1c: the shared-memory-free one-warp-CTA
+  // shape k_eval2<1, 8, 32, ., kDirect> (64 registers, 32 CTAs per SM, points by LDG through L1) — it beats both older
+  // kernels at every particle count measured (500 ... 65,536). TSDFLOC_EVAL=1 forces k_eval (x staged in shared memory),
+  // TSDFLOC_EVAL=2 the TMA-ring kernel k_eval2<W, BS, R>, TSDFLOC_EVAL=3 the direct shape with TSDFLOC_BS / TSDFLOC_R.
+  if (c->eval_version == 0)
+    launch_eval_direct<8, 32>(c, a, s);
+  else if (c->eval_version == 3)
   {
-    const uint64_t ctas4 = (warps + 3) / 4;
-    if (warps < sms * 8) use2 = false;
-    else if (ctas4 > sms * 6 && warps <= sms * 32) use2 = false;
+    const int bs = c->eval_bs ? c->eval_bs : 8, r = c->eval_r ? c->eval_r : 32;
+    if (bs == 8 && r == 24) launch_eval_direct<8, 24>(c, a, s);
+    else if (bs == 4 && r == 32) launch_eval_direct<4, 32>(c, a, s);
+    else if (bs == 4 && r == 24) launch_eval_direct<4, 24>(c, a, s);
+    else if (bs == 4 && r == 28) launch_eval_direct<4, 28>(c, a, s);
+    else launch_eval_direct<8, 32>(c, a, s);
   }
-  if (use2)
+  else if (c->eval_version == 2)
     dispatch_eval2(c, a, count, s);
   else if (pick_ppw(c, count) == 2)
     launch_eval<2>(c, a, s);

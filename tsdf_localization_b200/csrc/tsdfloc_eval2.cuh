@@ -91,11 +91,15 @@ __device__ __forceinline__ float fold_block(float a, const float (&xv)[BS], int 
 
 // R = resident warps per SM the register allocation is budgeted for (65536 / (32 R) registers per thread):
 // R = 24 (80 registers) lets a BS = 8 block keep all its gathers in flight; R = 32 (64 registers) fits one more wave slot.
-template <int W, int BS, int R, bool kFastDiv>
+// kDirect = true (W must be 1): no shared memory at all — the points are read straight from global memory (LDG.128, L1
+// keeps the tile for the other one-warp CTAs of the SM) and the whole 228 KB stay L1. This is the shape for a partial wave
+// of warps (e.g. the 8,192-particle slice of an 8-GPU run), where independent one-warp CTAs pack the SMs best.
+template <int W, int BS, int R, bool kFastDiv, bool kDirect = false>
 __global__ void __launch_bounds__(W * 32, (R / W) > 0 ? (R / W) : 1) k_eval2(const MapDev M, const EvalArgs A)
 {
   static_assert(kTileSteps % BS == 0, "a summation block must not straddle two tiles");
-  __shared__ __align__(128) float4 tiles[kStages][kTilePoints];
+  static_assert(!kDirect || W == 1, "the direct variant is for one-warp CTAs");
+  __shared__ __align__(128) float4 tiles[kDirect ? 1 : kStages][kDirect ? 1 : kTilePoints];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
 
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(W * 32, (R / W) > 0 ? (R / W) : 1) k_eval2(con
   const uint32_t n_tiles = (n_steps + kTileSteps - 1) / kTileSteps;
   const char* __restrict__ gsrc = reinterpret_cast<const char*>(A.pts);
 
-  if (threadIdx.x == 0)
+  if (!kDirect && threadIdx.x == 0)
   {
 #pragma unroll
     for (int s = 0; s < kStages; ++s)
@@ -119,8 +123,8 @@ __global__ void __launch_bounds__(W * 32, (R / W) > 0 ? (R / W) : 1) k_eval2(con
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  __syncthreads();
-  if (threadIdx.x == 0)
+  if (!kDirect) __syncthreads();
+  if (!kDirect && threadIdx.x == 0)
   {
     const uint32_t pre = n_tiles < static_cast<uint32_t>(kStages) ? n_tiles : static_cast<uint32_t>(kStages);
     for (uint32_t t = 0; t < pre; ++t)
@@ -146,8 +150,8 @@ __global__ void __launch_bounds__(W * 32, (R / W) > 0 ? (R / W) : 1) k_eval2(con
   {
     const uint32_t stage = t % kStages;
     const uint32_t par = (t / kStages) & 1u;
-    mbar_wait(&full_bar[stage], par);
-    const float4* __restrict__ tp = tiles[stage];
+    if (!kDirect) mbar_wait(&full_bar[stage], par);
+    const float4* __restrict__ tp = kDirect ? A.pts + static_cast<size_t>(t) * kTilePoints : tiles[stage];
     const uint32_t step0 = t * kTileSteps;
 
 #pragma unroll 1
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(W * 32, (R / W) > 0 ? (R / W) : 1) k_eval2(con
 #pragma unroll
       for (int b = 0; b < BS; ++b)
       {
-        const float4 p = tp[((b0 + b) << 5) + lane];
+        const float4 p = kDirect ? __ldg(tp + (((b0 + b) << 5) + lane)) : tp[((b0 + b) << 5) + lane];
         const float2 xx = dup2(p.x), yy = dup2(p.y), zz = dup2(p.z);
         const float2 tx = row_apply2(mm[0], mm[1], mm[2], mm[3], xx, yy, zz, one);
         const float2 ty = row_apply2(mm[4], mm[5], mm[6], mm[7], xx, yy, zz, one);
@@ -227,6 +231,7 @@ __global__ void __launch_bounds__(W * 32, (R / W) > 0 ? (R / W) : 1) k_eval2(con
     }
 
     // hand the stage back; one thread refills the stage released ONE tile ago (every warp has had a whole tile to leave it)
+    if (kDirect) continue;
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[stage]);
     if (threadIdx.x == 0 && t >= 1u && (t - 1u) + kStages < n_tiles)
