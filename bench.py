@@ -16,7 +16,7 @@ BASELINE.json configs built by tsdf_localization_b200/synthetic.py (seeds fixed)
 `e2e`    : the same update through the reference-facing host-buffer calls (tsdfloc_sensor_update +
            tsdfloc_resample_systematic at N = 1; pinned-host -> device copies + the sharded update + device -> pinned-host
            copies at N > 1), host<->device copies inside the timed region.
-`roofline`: the evaluation kernel k_eval alone (tsdfloc_last_eval_ms: CUDA events on its stream), algorithmic bytes =
+`roofline`: the evaluation kernel (k_eval2<1,8,32,kDirect> by default) alone (tsdfloc_last_eval_ms: CUDA events on its stream), algorithmic bytes =
            8 B per particle-point evaluation (4 B brick-table entry + 4 B voxel) over the measured HBM copy peak.
 `cpu_baseline` / --impl reference: the UNMODIFIED reference CPU/OpenMP evaluator + SystematicResampler (oracle/_ref,
            compiled from /root/reference in the build container) on this box's host cores, on a bounded particle sample.
