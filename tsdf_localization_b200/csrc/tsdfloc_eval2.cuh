@@ -1,19 +1,22 @@
-// tsdfloc_eval2.cuh — K1 v2: the evaluation kernel with the scan streamed through shared memory by TMA.
+// tsdfloc_eval2.cuh — K1: the evaluation kernel (register-held summation blocks), in two shapes.
 //
 // Same arithmetic as k_eval (tsdfloc_kernels.cuh) — the reference's per-point term and its SEQUENTIAL fp32 sum, bit for
 // bit — with a different execution plan, driven by the round-1 ncu profile of k_eval (profiles/r01_*): 15 % of all warp
-// stalls sat on the float4 point load (a load with no dependencies), another 17 % on the brick-table load, and the
-// point stream was 24 % of the L2 sectors.
-//   * A CTA of W warps (2 particles per warp, packed fp32x2 math) shares ONE copy of the scan: 4 KB tiles
+// stalls sat on the float4 point load, another 17 % on the brick-table load, and 4 KB of shared memory per warp (the x
+// staging) came out of L1.
+//   * The summation block is BS steps whose x values stay in REGISTERS; the rare sequential fold (binade crossing, tie,
+//     early phase) walks them with warp shuffles. No shared-memory staging of x, and all 2*BS table loads / voxel gathers
+//     of a block are independent and can be in flight together.
+//   * Tie detection is a running max of |residue| (2 FMNMX per step) instead of predicate bookkeeping.
+//   * kDirect = true (the DEFAULT since round 1c, W = 1): one-warp CTAs without any shared memory; points by LDG.128 from the
+//     prepared scan (the L1 serves the other CTAs of the SM), so the whole 228 KB of the SM are L1 for voxel sectors and 32
+//     independent CTAs fill every SM. Measured 5-10 % faster than the TMA shape at every particle count
+//     (profiles/r01_eval2_sweep.md): on this gather, L1 capacity is worth more than taking the point stream out of L2.
+//   * kDirect = false: a CTA of W warps (2 particles per warp, packed fp32x2 math) shares ONE copy of the scan: 4 KB tiles
 //     (8 steps x 32 points x float4) are pulled into a 4-stage shared-memory ring by cp.async.bulk (TMA, one elected
 //     thread) and handed over with mbarriers (full: complete_tx; empty: one arrive per warp). Warps are only loosely
-//     coupled — any warp may run up to 3 tiles ahead of the slowest — so there is no per-tile __syncthreads.
-//   * Points come from LDS.128 instead of LDG: the L2 point traffic drops by W and the load leaves the dependent chain.
-//   * The summation block is BS steps whose x values stay in REGISTERS; the rare sequential fold (binade crossing, tie,
-//     early phase) walks them with warp shuffles. No shared-memory staging of x (k_eval spent 4 KB per warp on it), so
-//     the L1 keeps ~100 KB more for voxel sectors, and all 2*BS table loads / voxel gathers of a block are independent
-//     and can be in flight together.
-//   * Tie detection is a running max of |residue| (2 FMNMX per step) instead of predicate bookkeeping.
+//     coupled — any warp may run up to 3 tiles ahead of the slowest — so there is no per-tile __syncthreads. Points come
+//     from LDS.128: the L2 point traffic drops by W. Kept selectable (TSDFLOC_EVAL=2) and as the record of the experiment.
 // Reference functions replaced: cudaEvaluatePose / getIndex / getEntry, include/tsdf_localization/cuda/cuda_eval_particles.h:84-215.
 #pragma once
 #include "tsdfloc_kernels.cuh"
