@@ -1116,8 +1116,8 @@ static int update_with_resident_scan(tsdfloc_ctx* c, float* particles, uint64_t 
   if ((rc = ensure(c, c->d_particles, pbytes, "cudaMalloc(particles)"))) return rc;
   if ((rc = ensure(c, c->d_raw, sizeof(float) * n, "cudaMalloc(raw weights)"))) return rc;
   if ((rc = ensure_host(c, pbytes))) return rc;
-  // the pinned buffer is reused for the particles: wait for earlier copies to leave it
-  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  // the first pbytes of the pinned buffer are free here: tsdfloc_sensor_update stages the scan BEHIND them, and
+  // tsdfloc_sensor_update_cloud has synchronised the stream when it read the reduced scan's size
   std::memcpy(c->h_stage, particles, pbytes);
   float* d_p = static_cast<float*>(c->d_particles.p);
   CU_TRY(c, cudaMemcpyAsync(d_p, c->h_stage, pbytes, cudaMemcpyHostToDevice, s), "H2D particles");
@@ -1146,14 +1146,17 @@ int tsdfloc_sensor_update(tsdfloc_ctx* c, float* particles, uint64_t n, const fl
   DeviceGuard guard(c->device);
   cudaStream_t s = c->stream;
   int rc;
-  if ((rc = ensure_host(c, std::max(sizeof(float) * 7 * n, sizeof(float) * 3 * p)))) return rc;
+  // one pinned buffer, two regions: [particles | scan] — no host sync between the two uploads
+  const size_t scan_off = (sizeof(float) * 7 * n + 255) / 256 * 256;
+  if ((rc = ensure_host(c, scan_off + sizeof(float) * 3 * p))) return rc;
   c->have_cdf = false;
   c->n_resident = 0;
 
   // scan: host -> pinned -> device, then prep
-  std::memcpy(c->h_stage, points, sizeof(float) * 3 * p);
+  char* h_scan = static_cast<char*>(c->h_stage) + scan_off;
+  std::memcpy(h_scan, points, sizeof(float) * 3 * p);
   if ((rc = ensure(c, c->d_xyz_stage, sizeof(float) * 3 * (p + 1), "cudaMalloc(scan staging)"))) return rc;
-  CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, c->h_stage, sizeof(float) * 3 * p, cudaMemcpyHostToDevice, s), "H2D scan");
+  CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, h_scan, sizeof(float) * 3 * p, cudaMemcpyHostToDevice, s), "H2D scan");
   if ((rc = stage_prep_scan(c, static_cast<const float*>(c->d_xyz_stage.p), p, s))) return rc;
   return update_with_resident_scan(c, particles, n, tf, mean_pose, s);
 }
