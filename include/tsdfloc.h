@@ -101,7 +101,14 @@ void tsdfloc_map_destroy(tsdfloc_host_map* m);
  * bit for bit; voxels with weight != 0 outside the truncation band become the free-space points global localisation
  * samples from (:131-145; particle_cloud.cpp:105-148), in the reference's order (datasets in increasing name order). */
 int tsdfloc_map_from_chunks(const int32_t* chunk_pos, const uint32_t* chunk_data, uint64_t n_chunks, float sigma, tsdfloc_host_map** out);
-/* The free-space points of a map built by tsdfloc_map_from_chunks: *n points x 3 fp32 (NULL / 0 for other maps). */
+/* The same ingest on the GPU (`device`): the raw chunk words go to the device once, one thread per voxel marks the touched
+ * 1 m cells, a scan allocates the bricks in the reference's order and a second pass scatters the LUT values and compacts the
+ * free-space points in the reference's order. The result — host arrays, like the reference's map object — is bit-identical to
+ * tsdfloc_map_from_chunks (incl. the reference's last-writer-wins resolution of voxels whose fp32 cell selection collides);
+ * message of a failure via tsdfloc_last_error(NULL). Fewer than 16,384 chunks (16 GB of words). */
+int tsdfloc_map_from_chunks_gpu(const int32_t* chunk_pos, const uint32_t* chunk_data, uint64_t n_chunks, float sigma, int device,
+                                tsdfloc_host_map** out);
+/* The free-space points of a map built by tsdfloc_map_from_chunks[_gpu]: *n points x 3 fp32 (NULL / 0 for other maps). */
 const float* tsdfloc_map_free_points(const tsdfloc_host_map* m, uint64_t* n);
 /* TSDF (mm) -> likelihood^3 LUT value and the value for unmapped space, createTSDFMap's transform
  * (include/tsdf_localization/map/map_util.h:68-71, 124-126). */

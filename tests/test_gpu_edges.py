@@ -251,3 +251,23 @@ def test_spatial_evaluation_order_changes_nothing(monkeypatch):
         ev.close()
     assert results[0][:4] == results[1][:4]
     assert results[1][4] > results[0][4]            # the sort kernels really ran
+
+
+def test_gpu_map_ingest_equals_host_ingest():
+    """tsdfloc_map_from_chunks_gpu against tsdfloc_map_from_chunks (which tests/test_map_ingest.py pins against the reference's
+    createTSDFMap): geometry, brick table, voxels and free-space points byte-identical, incl. negative chunk coordinates and a
+    chunk order that differs from the name order."""
+    from test_map_ingest import synthetic_chunks
+    for chunk_pos, centre in (([(0, 0, 0)], (1000.0, 2000.0, 500.0)),
+                              ([(-1, 0, 0), (0, 0, -1), (0, 0, 0), (-1, -1, -1), (1, 0, 0)], (1000.0, 2000.0, 500.0)),
+                              ([(2, 1, 0), (10, 1, 0), (3, 1, 0)], (9000.0, 6000.0, 2000.0))):
+        data = synthetic_chunks(chunk_pos, seed=len(chunk_pos), centre_mm=centre)
+        host = CudaSubVoxelMap.from_chunks(chunk_pos, data, 0.1)
+        gpu = CudaSubVoxelMap.from_chunks(chunk_pos, data, 0.1, device=0)
+        a, b = host.coef(), gpu.coef()
+        assert bytes(a) == bytes(b)
+        assert np.array_equal(host.rawGridOcc(), gpu.rawGridOcc())
+        assert host.rawData().tobytes() == gpu.rawData().tobytes() and host.rawData().size > 0
+        assert host.free_map().tobytes() == gpu.free_map().tobytes() and len(host.free_map()) > 0
+    with pytest.raises(ValueError):
+        CudaSubVoxelMap.from_chunks([(0, 0, 0), (0, 0, 0)], np.zeros((2, 64 ** 3), dtype=np.uint32), device=0)

@@ -62,6 +62,7 @@ SIGNATURES = {
     "tsdfloc_map_data": (_fp, [_vp]),
     "tsdfloc_map_destroy": (None, [_vp]),
     "tsdfloc_map_from_chunks": (C.c_int, [_vp, _vp, _u64, C.c_float, C.POINTER(_vp)]),
+    "tsdfloc_map_from_chunks_gpu": (C.c_int, [_vp, _vp, _u64, C.c_float, C.c_int, C.POINTER(_vp)]),
     "tsdfloc_map_free_points": (_fp, [_vp, C.POINTER(_u64)]),
     "tsdfloc_likelihood_value": (C.c_float, [C.c_float, C.c_float]),
     "tsdfloc_likelihood_init": (C.c_float, [C.c_float]),

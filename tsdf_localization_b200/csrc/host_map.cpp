@@ -16,13 +16,7 @@
 #include <string>
 #include <vector>
 
-struct tsdfloc_host_map
-{
-  tsdfloc_map_desc desc{};
-  std::vector<int32_t> grid_occ;
-  std::vector<float> data;
-  std::vector<float> free_points;  // x y z of the free-space voxels createTSDFMap collects (map_util.h:131-145)
-};
+#include "tsdfloc_host_map.h"
 
 namespace
 {
@@ -43,6 +37,69 @@ inline void split_axis(float off, float res, uint64_t& up, uint64_t& sub)
 }
 
 }  // namespace
+
+namespace tsdfloc_host
+{
+
+// Empty host map with createTSDFMap's bounding box for these chunks (map_util.h:23-78) and the order in which the reference
+// visits the datasets (increasing name = HDF5's default name index). Returns TSDFLOC_OK or an error (e.g. a chunk twice).
+int begin_chunk_map(const int32_t* chunk_pos, uint64_t n_chunks, float sigma, tsdfloc_host_map** out, std::vector<uint64_t>& order)
+{
+  constexpr int kChunk = 64;          // CHUNK_SIZE (grid_map.h:18-19)
+  constexpr int kResMm = 64;          // MAP_RESOLUTION in millimetres (grid_map.h:21-22)
+  // bounding box over the chunk coordinates, starting from 0 like the reference's min(3, 0) / max(3, 0) (:23-59)
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  for (uint64_t c = 0; c < n_chunks; ++c)
+    for (int a = 0; a < 3; ++a)
+    {
+      const float v = static_cast<float>(chunk_pos[3 * c + a]);
+      if (v < lo[a]) lo[a] = v;
+      if (v > hi[a]) hi[a] = v;
+    }
+  float mn[3], mx[3];
+  for (int a = 0; a < 3; ++a)
+  {
+    // float * int * int stays fp32, the final * 0.001 is a double product stored back into the float (:61-65)
+    volatile float t0 = lo[a] * kChunk;
+    volatile float t1 = t0 * kResMm;
+    mn[a] = static_cast<float>(t1 * 0.001);
+    volatile float u0 = hi[a] * kChunk;
+    volatile float u1 = u0 + kChunk;
+    volatile float u2 = u1 * kResMm;
+    mx[a] = static_cast<float>(u2 * 0.001);
+  }
+  const float res = static_cast<float>(kResMm * 0.001);
+  tsdfloc_host_map* m = nullptr;
+  int rc = tsdfloc_map_create(mn, mx, res, tsdfloc_likelihood_init(sigma), &m);
+  if (rc != TSDFLOC_OK) return rc;
+
+  // datasets are visited in increasing name order (HDF5's default name index), which fixes the order of the free points
+  std::vector<std::string> tags(n_chunks);
+  for (uint64_t c = 0; c < n_chunks; ++c)
+    tags[c] = std::to_string(chunk_pos[3 * c]) + "_" + std::to_string(chunk_pos[3 * c + 1]) + "_" + std::to_string(chunk_pos[3 * c + 2]);
+  order.resize(n_chunks);
+  std::iota(order.begin(), order.end(), 0ull);
+  std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) { return tags[x] < tags[y]; });
+  for (uint64_t k = 1; k < n_chunks; ++k)
+    if (tags[order[k]] == tags[order[k - 1]])
+    {
+      delete m;
+      return TSDFLOC_E_BAD_ARG;  // the same chunk twice
+    }
+
+  *out = m;
+  return TSDFLOC_OK;
+}
+
+// likelihood^3 of every representable in-band TSDF value, indexed by value_mm + 599
+std::vector<float> likelihood_lut(float sigma)
+{
+  std::vector<float> lut(1199);
+  for (int mm = -599; mm <= 599; ++mm) lut[mm + 599] = tsdfloc_likelihood_value(static_cast<float>(mm), sigma);
+  return lut;
+}
+
+}  // namespace tsdfloc_host
 
 extern "C"
 {
@@ -136,49 +193,11 @@ int tsdfloc_map_from_chunks(const int32_t* chunk_pos, const uint32_t* chunk_data
   constexpr int kResMm = 64;          // MAP_RESOLUTION in millimetres (grid_map.h:21-22)
   constexpr float kTruncation = 600;  // grid_map.h:24
 
-  // bounding box over the chunk coordinates, starting from 0 like the reference's min(3, 0) / max(3, 0) (:23-59)
-  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
-  for (uint64_t c = 0; c < n_chunks; ++c)
-    for (int a = 0; a < 3; ++a)
-    {
-      const float v = static_cast<float>(chunk_pos[3 * c + a]);
-      if (v < lo[a]) lo[a] = v;
-      if (v > hi[a]) hi[a] = v;
-    }
-  float mn[3], mx[3];
-  for (int a = 0; a < 3; ++a)
-  {
-    // float * int * int stays fp32, the final * 0.001 is a double product stored back into the float (:61-65)
-    volatile float t0 = lo[a] * kChunk;
-    volatile float t1 = t0 * kResMm;
-    mn[a] = static_cast<float>(t1 * 0.001);
-    volatile float u0 = hi[a] * kChunk;
-    volatile float u1 = u0 + kChunk;
-    volatile float u2 = u1 * kResMm;
-    mx[a] = static_cast<float>(u2 * 0.001);
-  }
-  const float res = static_cast<float>(kResMm * 0.001);
   tsdfloc_host_map* m = nullptr;
-  int rc = tsdfloc_map_create(mn, mx, res, tsdfloc_likelihood_init(sigma), &m);
+  std::vector<uint64_t> order;
+  int rc = tsdfloc_host::begin_chunk_map(chunk_pos, n_chunks, sigma, &m, order);
   if (rc != TSDFLOC_OK) return rc;
-
-  // datasets are visited in increasing name order (HDF5's default name index), which fixes the order of the free points
-  std::vector<std::string> tags(n_chunks);
-  for (uint64_t c = 0; c < n_chunks; ++c)
-    tags[c] = std::to_string(chunk_pos[3 * c]) + "_" + std::to_string(chunk_pos[3 * c + 1]) + "_" + std::to_string(chunk_pos[3 * c + 2]);
-  std::vector<uint64_t> order(n_chunks);
-  std::iota(order.begin(), order.end(), 0ull);
-  std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) { return tags[x] < tags[y]; });
-  for (uint64_t k = 1; k < n_chunks; ++k)
-    if (tags[order[k]] == tags[order[k - 1]])
-    {
-      delete m;
-      return TSDFLOC_E_BAD_ARG;  // the same chunk twice
-    }
-
-  // likelihood of every representable in-band TSDF value, indexed by value_mm + 599
-  std::vector<float> lut(1199);
-  for (int mm = -599; mm <= 599; ++mm) lut[mm + 599] = tsdfloc_likelihood_value(static_cast<float>(mm), sigma);
+  const std::vector<float> lut = tsdfloc_host::likelihood_lut(sigma);
 
   std::vector<float> cells;
   const size_t words = static_cast<size_t>(kChunk) * kChunk * kChunk;

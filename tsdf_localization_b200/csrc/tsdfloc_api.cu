@@ -1413,3 +1413,5 @@ uint64_t tsdfloc_host_u_sequence(float u0, uint64_t n, double limit, float* out,
 }  // extern "C"
 
 #include "tsdfloc_multi.inc"
+#include "tsdfloc_host_map.h"
+#include "tsdfloc_ingest.inc"

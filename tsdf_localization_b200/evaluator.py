@@ -82,10 +82,10 @@ class CudaSubVoxelMap:
         return self
 
     @classmethod
-    def from_chunks(cls, chunk_pos, chunk_data, sigma: float = 0.1) -> "CudaSubVoxelMap":
+    def from_chunks(cls, chunk_pos, chunk_data, sigma: float = 0.1, device: Optional[int] = None) -> "CudaSubVoxelMap":
         """createTSDFMap (map_util.h:17-154) on chunks already read from the map file: chunk_pos int32[n, 3] (the integers of
         the dataset names "<cx>_<cy>_<cz>"), chunk_data uint32[n, 64, 64, 64] raw TSDFValue words. The free-space points are
-        available as ``free_map()``."""
+        available as ``free_map()``. device=None: host ingest; device=k: the same ingest on GPU k (bit-identical arrays)."""
         pos = np.ascontiguousarray(chunk_pos, dtype=np.int32).reshape(-1, 3)
         dat = np.ascontiguousarray(chunk_data, dtype=np.uint32).reshape(len(pos), -1)
         if dat.shape[1] != 64 ** 3:
@@ -94,8 +94,14 @@ class CudaSubVoxelMap:
         self._lib = capi.load_library()
         self._adopted = None
         self._h = C.c_void_p()
-        rc = self._lib.tsdfloc_map_from_chunks(pos.ctypes.data_as(C.c_void_p), dat.ctypes.data_as(C.c_void_p), len(pos), C.c_float(sigma),
-                                               C.byref(self._h))
+        if device is None:
+            rc = self._lib.tsdfloc_map_from_chunks(pos.ctypes.data_as(C.c_void_p), dat.ctypes.data_as(C.c_void_p), len(pos), C.c_float(sigma),
+                                                   C.byref(self._h))
+        else:
+            rc = self._lib.tsdfloc_map_from_chunks_gpu(pos.ctypes.data_as(C.c_void_p), dat.ctypes.data_as(C.c_void_p), len(pos),
+                                                       C.c_float(sigma), int(device), C.byref(self._h))
+        if rc == capi.E_CUDA:
+            raise RuntimeError(self._lib.tsdfloc_last_error(None).decode())
         if rc != capi.OK:
             raise ValueError("invalid chunk set")
         return self
