@@ -16,7 +16,9 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
     kind = sys.argv[2] if len(sys.argv) > 2 else "os1-128"
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-    spec, m = common.box_room()
+    import os
+    res = float(os.environ.get("QUICK_RES", "0.05"))       # QUICK_RES=0.064: the mapping pipeline's own resolution (sub_dim 16)
+    spec, m = common.box_room(resolution=res)
     ev = CudaEvaluator(m)
     lib = capi.load_library()
     pts, _ = syn.make_scan(kind, syn.GT_POSE)
