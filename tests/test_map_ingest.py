@@ -83,3 +83,12 @@ def test_rejects_bad_input():
         CudaSubVoxelMap.from_chunks([(0, 0, 0), (0, 0, 0)], np.zeros((2, 64 ** 3), dtype=np.uint32))      # duplicate chunk
     with pytest.raises(ValueError):
         CudaSubVoxelMap.from_chunks([(0, 0, 0)], np.zeros((1, 64 ** 3), dtype=np.uint32), sigma=0.0)
+
+
+def test_gpu_ingest_fails_loudly_without_gpu():
+    """No silent fallback: asking for the GPU ingest on a machine without a CUDA device is an error, not a host computation."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        CudaSubVoxelMap.from_chunks([(0, 0, 0)], np.zeros((1, 64 ** 3), dtype=np.uint32), 0.1, device=0)
