@@ -50,6 +50,17 @@ def test_no_cpu_fallback_without_gpu():
     assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
 
 
+def test_multi_gpu_evaluator_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from tsdf_localization_b200 import MultiGpuEvaluator
+    _, m = common.box_room(small=True)
+    with pytest.raises(RuntimeError) as ei:
+        MultiGpuEvaluator(m, [0, 1])
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
 def test_structs_match_header_layout():
     assert C.sizeof(capi.MapDesc) == 120     # MapCoef is 120 bytes
     assert C.sizeof(capi.Params) == 24
