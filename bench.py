@@ -198,7 +198,34 @@ def run_reference_arm(args):
 
 # ---- B200 arm ----------------------------------------------------------------------------------------------------------
 
+class StdoutGuard:
+    """Keeps stdout to the ONE JSON line: file descriptor 1 is pointed at stderr while the run is in progress (NCCL and other
+    native libraries print banners straight to fd 1), and the line is written to the saved descriptor at the end."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text: str) -> None:
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def close(self) -> None:
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def run_b200_arm(args):
+    guard = StdoutGuard()
+    try:
+        _run_b200_arm(args, guard)
+    finally:
+        guard.close()
+
+
+def _run_b200_arm(args, guard):
     import torch
     import torch.distributed as dist
 
@@ -375,7 +402,7 @@ def run_b200_arm(args):
                            else "pinned H2D + ShardedSensorUpdate.step + pinned D2H, per rank"},
             "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step_incl_flush": wall_ms / K,
         }
-        print(json.dumps(line))
+        guard.emit(json.dumps(line))
     ev.close()
     if world > 1:
         dist.destroy_process_group()
