@@ -61,6 +61,25 @@ def test_multi_gpu_evaluator_no_cpu_fallback_without_gpu():
     assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/tsdfloc.h must be usable from C (the drop-in boundary is a C ABI): compile a C99 translation unit against it with
+    -pedantic, link it against libtsdfloc.so and run it (no GPU call)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "tsdfloc.h"\n'
+                   "int main(void) { tsdfloc_params p; tsdfloc_map_desc d; (void)d; tsdfloc_default_params(&p);\n"
+                   "  return (tsdfloc_abi_version() == TSDFLOC_ABI_VERSION && p.max_range == 100.0f) ? 0 : 1; }\n")
+    exe = tmp_path / "abi"
+    lib_dir = capi.lib_path().parent
+    subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(lib_dir.parent.parent / "include"),
+                    str(src), "-L", str(lib_dir), "-ltsdfloc", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
 def test_structs_match_header_layout():
     assert C.sizeof(capi.MapDesc) == 120     # SURVEY §2.5(1): MapCoef is 120 bytes
     assert C.sizeof(capi.Params) == 24
