@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TSDFLOC_ABI_VERSION 2
+#define TSDFLOC_ABI_VERSION 3
 
 typedef struct tsdfloc_ctx tsdfloc_ctx;
 
@@ -71,8 +71,20 @@ typedef struct tsdfloc_params
   float a_max;     /* default 0.0  (util.h:18) */
   float max_range; /* default 100  (util.h:13); the range term uses 1/max_range like the CPU evaluator (tsdf_evaluator.cpp:60) */
   int32_t per_point; /* accepted for signature parity; both reference variants compute the same weights, one kernel serves both */
-  int32_t reserved;
+  int32_t neg_policy; /* enum tsdfloc_neg_policy: lookups below map.min on an axis */
 } tsdfloc_params;
+
+/* Lookups whose offset x - map.min is negative on some axis. The reference converts the negative float to unsigned, which
+ * is undefined behaviour: its CUDA build (cuda_eval_particles.h:14-16,34-36,62-64; cvt.rzi.u32.f32 saturates) clamps them
+ * onto the min face, its x86 CPU build (cuda_sub_voxel_map.tcc:50-137) wraps the flat index into a neighbouring brick.
+ *   TSDFLOC_NEG_MISS                   such a lookup is a miss (init_value), like every other lookup outside the map (default)
+ *   TSDFLOC_NEG_SATURATE_LIKE_REF_GPU  bit-for-bit what the reference's CUDA evaluator does (a drop-in for that evaluator
+ *                                      reproduces it, indices and weights included)                                        */
+enum tsdfloc_neg_policy
+{
+  TSDFLOC_NEG_MISS = 0,
+  TSDFLOC_NEG_SATURATE_LIKE_REF_GPU = 1
+};
 
 void tsdfloc_default_params(tsdfloc_params* p);
 int tsdfloc_abi_version(void);
@@ -333,8 +345,27 @@ int tsdfloc_probe_gather(tsdfloc_ctx* ctx, uint64_t bytes, uint32_t spread_secto
 
 /* Cumulative statistics of the evaluation kernel's summation blocks (synchronises the device):
  * out[0] = (particle, block) pairs processed, out[1] = of those folded sequentially (binade crossing, early phase or tie),
- * out[2] = of those caused by an exact rounding tie, out[3] reserved. */
+ * out[2] = of those caused by an exact rounding tie, out[3] = blocks evaluated a second time with the exact division
+ * because a bracketed sub-voxel quotient was open. */
 int tsdfloc_eval_stats(tsdfloc_ctx* ctx, uint64_t out[4]);
+
+/* Test / tuning hook (never needed for correct results: every setting produces the same bits). No environment variables
+ * are read anywhere in the library.
+ *   TSDFLOC_TUNE_SPATIAL_ORDER  -1 automatic (map larger than L2 and >= 16,384 particles), 0 off, 1 on (tsdfloc_sort.cuh)
+ *   TSDFLOC_TUNE_EVAL_PAIRING    0 automatic, 1 two particles per warp, 2 two points per lane (tsdfloc_eval.cuh)
+ *   TSDFLOC_TUNE_DIVISION       -1 what tsdfloc_create proved for the resolution, 0 IEEE division, 1 three-instruction
+ *                                quotient, 2 bracketed quotient (an unproven mode is never run)                            */
+enum tsdfloc_tune_knob
+{
+  TSDFLOC_TUNE_SPATIAL_ORDER = 0,
+  TSDFLOC_TUNE_EVAL_PAIRING = 1,
+  TSDFLOC_TUNE_DIVISION = 2
+};
+int tsdfloc_tune(tsdfloc_ctx* ctx, int knob, int value);
+
+/* Quotient mode tsdfloc_create proved for the map's resolution (0 IEEE, 1 three-instruction, 2 bracket); *open_brackets =
+ * how many of the 2^30 floats in [0, 1) leave the bracket open (those blocks are evaluated twice). */
+int tsdfloc_division_mode(tsdfloc_ctx* ctx, uint64_t* open_brackets);
 
 /* Device time of the most recent evaluation-kernel launch (k_eval alone, CUDA events recorded on the stream it was
  * launched on); waits for that launch to finish. This is the figure bench.py's roofline is computed from. */

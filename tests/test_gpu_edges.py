@@ -39,30 +39,73 @@ def _scan(p):
     return pts
 
 
-@pytest.mark.parametrize("n,p", [(1, 1), (1, 31), (2, 32), (3, 33), (7, 255), (5, 256), (9, 257), (33, 1000), (64, 4097), (257, 511)])
+@pytest.mark.parametrize("n,p", [(1, 1), (1, 31), (2, 32), (3, 33), (1, 63), (2, 64), (3, 65), (7, 255), (5, 256), (9, 257), (2, 511),
+                                 (2, 512), (5, 513), (33, 1000), (4, 1025), (64, 4097), (257, 511)])
 def test_ragged_shapes_bit_exact(oracle, omap, ev, n, p):
-    """P not a multiple of the 32-point step or the 256-point TMA tile; odd particle counts (warps pair particles)."""
+    """P not a multiple of the 32- / 64-point step or of the 256- / 512-point summation block; odd particle counts (the
+    particle-pair shape pairs particles); both pairings of the evaluation kernel."""
     ps = syn.tracking_particles(n, GT, sigma_xy=0.2, seed=n + p)
     pts = _scan(p)
     ref = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.CALIB_TF, want_idx=True)
-    idx, hits, raw = ev.debug_eval(ps, pts, syn.CALIB_TF)
-    assert np.array_equal(idx, ref["idx"]) and np.array_equal(hits, ref["hits"])
-    assert raw.tobytes() == ref["raw"].tobytes()
-    mine = ps.copy()
-    ev.evaluate(mine, pts, syn.CALIB_TF)
-    assert common.rel_err(mine[:, 6], ref["particles"][:, 6]).max() <= 1e-5
+    try:
+        for pairing in (1, 2):
+            ev.tune(capi.TUNE_EVAL_PAIRING, pairing)
+            idx, hits, raw = ev.debug_eval(ps, pts, syn.CALIB_TF)
+            assert np.array_equal(idx, ref["idx"]) and np.array_equal(hits, ref["hits"])
+            assert raw.tobytes() == ref["raw"].tobytes()
+            mine = ps.copy()
+            ev.evaluate(mine, pts, syn.CALIB_TF)
+            assert common.rel_err(mine[:, 6], ref["particles"][:, 6]).max() <= 1e-5
+    finally:
+        ev.tune(capi.TUNE_EVAL_PAIRING, 0)
 
 
-@pytest.mark.parametrize("force", ["1", "2"])
-def test_both_eval_kernels_agree(oracle, omap, small, monkeypatch, force):
-    """k_eval (one-warp CTAs) and k_eval2 (TMA-streamed tiles) are interchangeable: same bits as the oracle."""
-    monkeypatch.setenv("TSDFLOC_EVAL", force)
+@pytest.mark.parametrize("pairing", [1, 2], ids=["particle_pairs", "point_pairs"])
+@pytest.mark.parametrize("division", [capi.DIV_IEEE, capi.DIV_THREE, capi.DIV_BRACKET], ids=["ieee", "three", "bracket"])
+def test_every_pairing_and_quotient_mode_agrees(oracle, omap, small, pairing, division):
+    """The evaluation kernel's two pairings (two particles per warp / two points per lane) and three quotient modes are
+    interchangeable: flat indices (dumped by the production kernel itself), hit counts and raw weights equal the oracle's."""
     e = CudaEvaluator(small[1])
-    ps = syn.tracking_particles(301, GT, sigma_xy=0.2)
-    pts = _scan(3001)
-    ref = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF)
-    _, hits, raw = e.debug_eval(ps, pts, syn.IDENTITY_TF, want_idx=False)
-    assert raw.tobytes() == ref["raw"].tobytes() and np.array_equal(hits, ref["hits"])
+    mode, open_brackets = e.division_mode()
+    assert mode == capi.DIV_BRACKET and 0 < open_brackets < 2 ** 30 // 1000, "5 cm voxels: the bracket must be proven, and tight"
+    e.tune(capi.TUNE_EVAL_PAIRING, pairing)
+    e.tune(capi.TUNE_DIVISION, division)
+    for n, p in ((301, 3001), (7, 513), (64, 64), (2, 4096)):
+        ps = syn.tracking_particles(n, GT, sigma_xy=0.2, seed=n)
+        pts = _scan(p)
+        ref = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.CALIB_TF, want_idx=True)
+        idx, hits, raw = e.debug_eval(ps, pts, syn.CALIB_TF)
+        assert np.array_equal(idx, ref["idx"]) and np.array_equal(hits, ref["hits"])
+        assert raw.tobytes() == ref["raw"].tobytes()
+        mine = ps.copy()
+        e.evaluate(mine, pts, syn.CALIB_TF)      # the non-dumping instantiation
+        assert common.rel_err(mine[:, 6], ref["particles"][:, 6]).max() <= 1e-5
+    e.close()
+
+
+def test_open_brackets_are_redone_exactly(oracle):
+    """Points placed ON voxel faces (coordinates k * resolution as the map computes them) put sub-voxel quotients within an
+    ulp of an integer: the bracketed quotient is open there, the kernel must take the exact division for those blocks
+    (statistics say it did) and still match the oracle bit for bit."""
+    spec, m = common.box_room(small=True)
+    om = common.oracle_map_of(oracle, m)
+    e = CudaEvaluator(m)
+    rng = np.random.default_rng(5)
+    res = np.float32(spec.resolution)
+    k = rng.integers(-40, 40, size=(4096, 3)).astype(np.float32)
+    pts = (k * res).astype(np.float32)
+    pts[:, 2] = np.abs(pts[:, 2])
+    pts += np.float32(1.0)                       # keep |p| >= 1 m like a real scan
+    ps = np.zeros((64, 7), dtype=np.float32)     # grid-aligned poses: whole-voxel translations, no rotation
+    ps[:, :3] = (rng.integers(-10, 10, size=(64, 3)).astype(np.float32) * res)
+    ps[:, 2] = np.abs(ps[:, 2])
+    for pairing in (1, 2):
+        e.tune(capi.TUNE_EVAL_PAIRING, pairing)
+        before = e.eval_stats()["redone"]
+        ref = oracle.evaluate(om, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF, want_idx=True)
+        idx, hits, raw = e.debug_eval(ps, pts, syn.IDENTITY_TF)
+        assert np.array_equal(idx, ref["idx"]) and np.array_equal(hits, ref["hits"]) and raw.tobytes() == ref["raw"].tobytes()
+        assert e.eval_stats()["redone"] > before, "no block took the exact path: the test does not exercise open brackets"
     e.close()
 
 
@@ -107,6 +150,33 @@ def test_negative_offset_policy_is_miss(oracle):
     # outside the band all three agree with the product
     ok = ~(band_x86 | band_sat)
     assert np.array_equal(idx[ok], x86["idx"][ok]) and np.array_equal(idx[ok], sat["idx"][ok])
+    e.close()
+
+
+def test_negative_offset_saturate_like_reference_gpu(oracle):
+    """neg_policy = TSDFLOC_NEG_SATURATE_LIKE_REF_GPU reproduces the reference CUDA evaluator's saturating conversions
+    (cuda_eval_particles.h:12-67) on the same margin-0 map, where a quarter of the lookups are in the negative band: flat
+    indices, hit counts and raw weights bit-exact against the oracle's restatement of the device semantics — with every
+    pairing, incl. NaN / infinite / far points."""
+    spec = syn.box_room_map(likelihood_value, likelihood_init(0.1), resolution=0.05, margin=0.0, **ROOM)
+    m = CudaSubVoxelMap(*spec.min, *spec.max, spec.resolution, spec.init_value)
+    m.setData(spec.cells)
+    om = common.oracle_map_of(oracle, m)
+    e = CudaEvaluator(m, neg_policy=capi.NEG_SATURATE_LIKE_REF_GPU)
+    ps = syn.tracking_particles(65, GT, sigma_xy=0.3)
+    pts = _scan(2000).copy()
+    pts[3] = (np.nan, 0.0, 0.0)
+    pts[10] = (-np.inf, 1.0, 1.0)
+    pts[20] = (-4e6, 5e6, -8e6)
+    pts[30] = (np.inf, -1.0, 1.0)
+    sat = oracle.evaluate(om, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF, mode=NEG_REF_DEVICE_SAT, want_idx=True)
+    miss = oracle.evaluate(om, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF, mode=NEG_AS_MISS, want_idx=True)
+    assert (sat["idx"] != miss["idx"]).mean() > 0.05
+    for pairing in (1, 2):
+        e.tune(capi.TUNE_EVAL_PAIRING, pairing)
+        idx, hits, raw = e.debug_eval(ps, pts, syn.IDENTITY_TF)
+        assert np.array_equal(idx, sat["idx"]) and np.array_equal(hits, sat["hits"])
+        assert raw.tobytes() == sat["raw"].tobytes()
     e.close()
 
 
@@ -228,9 +298,9 @@ def test_resampler_edge_cases(oracle, ev):
         rs.resample(ps, u0=0.001)          # exceeds the default capacity: reported, not truncated
 
 
-def test_spatial_evaluation_order_changes_nothing(monkeypatch):
-    """TSDFLOC_SORT=1 (counting sort of the particles by map cell in front of the evaluation, tsdfloc_sort.cuh) against
-    TSDFLOC_SORT=0: raw weights, normalised weights, mean pose and resampled particles must be byte-identical — including
+def test_spatial_evaluation_order_changes_nothing():
+    """Spatial order on (counting sort of the particles by map cell in front of the evaluation, tsdfloc_sort.cuh) against
+    off: raw weights, normalised weights, mean pose and resampled particles must be byte-identical — including
     particles outside the map and NaN poses, whose cell key is clamped."""
     import common
     from tsdf_localization_b200 import CudaEvaluator, SystematicResampler, synthetic as syn
@@ -240,9 +310,9 @@ def test_spatial_evaluation_order_changes_nothing(monkeypatch):
     ps[17, 0] = np.nan
     ps[18, 1] = 1e30
     results = []
-    for mode in ("0", "1"):
-        monkeypatch.setenv("TSDFLOC_SORT", mode)
+    for mode in (0, 1):
         ev = CudaEvaluator(m)
+        ev.tune(capi.TUNE_SPATIAL_ORDER, mode)
         mine = ps.copy()
         _, _, raw = ev.debug_eval(mine, pts, syn.CALIB_TF, want_idx=False)
         pose = ev.evaluate(mine, pts, syn.CALIB_TF)

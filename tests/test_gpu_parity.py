@@ -9,8 +9,8 @@ import numpy as np
 import pytest
 
 import common
-from oracle_lib import NEG_AS_MISS
-from tsdf_localization_b200 import CudaEvaluator, synthetic as syn
+from oracle_lib import NEG_AS_MISS, NEG_REF_DEVICE_SAT
+from tsdf_localization_b200 import CudaEvaluator, capi, synthetic as syn
 
 pytestmark = pytest.mark.gpu
 
@@ -66,6 +66,25 @@ def test_c1_indices_hits_weights(oracle, omap, evaluator, tf):
     assert abs(float(mine[:, 6].astype(np.float64).sum()) - 1.0) < 1e-5
     assert np.allclose(pose.position, ref["mean"][:3], atol=1e-4)
     assert np.allclose(pose.rpy, ref["mean"][3:], atol=1e-4)
+
+
+def test_c1_reference_gpu_semantics_all_particles(oracle, omap, room):
+    """C1 with neg_policy = SATURATE_LIKE_REF_GPU: all 500 particles — the 10 with a lookup below map.min included — match
+    the reference CUDA evaluator's device semantics (oracle mode NEG_REF_DEVICE_SAT, cuda_eval_particles.h:12-67) bit for
+    bit: 512,000 flat indices, hit counts, raw weights; normalised weights within the north star's 1e-5."""
+    ps, pts, _ = common.config_c1()
+    ref = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF, mode=NEG_REF_DEVICE_SAT, want_idx=True)
+    miss = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF, mode=NEG_AS_MISS, want_idx=True)
+    band = (ref["idx"] != miss["idx"]).any(axis=1)
+    assert band.sum() > 0, "C1 no longer has a negative band: the test would be vacuous"
+    ev = CudaEvaluator(room[1], neg_policy=capi.NEG_SATURATE_LIKE_REF_GPU)
+    idx, hits, raw = ev.debug_eval(ps, pts, syn.IDENTITY_TF)
+    assert np.array_equal(idx, ref["idx"]) and np.array_equal(hits, ref["hits"])
+    assert raw.tobytes() == ref["raw"].tobytes()
+    mine = ps.copy()
+    ev.evaluate(mine, pts, syn.IDENTITY_TF)
+    assert common.rel_err(mine[:, 6], ref["particles"][:, 6]).max() <= WEIGHT_RTOL
+    ev.close()
 
 
 def test_c1_resample_parents_identical(oracle, evaluator):

@@ -7,7 +7,6 @@
 // No CPU fallback anywhere: without a CUDA device every compute entry point fails with TSDFLOC_E_CUDA.
 #include "../../include/tsdfloc.h"
 #include "tsdfloc_kernels.cuh"
-#include "tsdfloc_eval2.cuh"
 #include "tsdfloc_reduce.cuh"
 #include "tsdfloc_motion.cuh"
 #include "tsdfloc_sort.cuh"
@@ -48,8 +47,10 @@ struct tsdfloc_ctx
   float x_bound = 0.0f;     // upper bound of one point's contribution a_hit*v + term (k_eval block planning)
   uint32_t force_seq = 0;   // 1: contributions may be negative / non-finite -> always fold sequentially
   uint64_t launches = 0;
-  int eval_version = 0;     // 0: automatic; 2: k_eval2 (TMA-streamed scan tiles); 1: k_eval (one-warp CTAs)
-  int eval_w = 0, eval_bs = 0, eval_r = 0;  // 0: automatic; TSDFLOC_W / TSDFLOC_BS / TSDFLOC_R override for tuning experiments
+  int tune_shape = 0;       // tsdfloc_tune(TSDFLOC_TUNE_EVAL_PAIRING): 0 automatic, 1 particle pairs, 2 point pairs
+  int tune_div = -1;        // tsdfloc_tune(TSDFLOC_TUNE_DIVISION): -1 what k_check_div proved, else kDivIeee / kDivThree / kDivBracket
+  bool three_ok = false, bracket_ok = false;   // what k_check_div proved for this resolution
+  unsigned long long bracket_open = 0;         // floats in [0, 1) whose bracket is open (statistics)
   cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;  // bracket the last k_eval launch (tsdfloc_last_eval_ms)
   bool eval_timed = false;
 
@@ -89,7 +90,7 @@ struct tsdfloc_ctx
 
   // spatial evaluation order (tsdfloc_sort.cuh)
   DevBuf d_sort_keys, d_sort_hist, d_perm;
-  int sort_mode = -1;       // -1: automatic (map larger than L2 and enough particles); 0 / 1: TSDFLOC_SORT override
+  int sort_mode = -1;       // -1: automatic (map larger than L2 and enough particles); 0 / 1: tsdfloc_tune(TSDFLOC_TUNE_SPATIAL_ORDER)
   size_t l2_bytes = 0;
   SortArgs sort_args{};
 
@@ -201,8 +202,8 @@ int stage_prep_scan(tsdfloc_ctx* c, const float* d_xyz, uint64_t p, cudaStream_t
 {
   if (p > 0x7fffffffull) return fail(c, TSDFLOC_E_BAD_ARG, "scan larger than 2^31 points");
   int rc;
-  // the evaluation kernel pulls whole 256-point tiles (TMA bulk copies): pad to a tile multiple and keep the pad defined
-  const uint64_t padded = (p + kTilePoints - 1) / kTilePoints * kTilePoints + kTilePoints;
+  // the evaluation kernel reads whole summation blocks: pad to a block multiple (+ one block) and keep the pad defined
+  const uint64_t padded = (p + kEvalPadPoints - 1) / kEvalPadPoints * kEvalPadPoints + kEvalPadPoints;
   if ((rc = ensure(c, c->d_pts, sizeof(float4) * padded, "cudaMalloc(scan)"))) return rc;
   c->n_points = p;
   if (p == 0) return TSDFLOC_OK;
@@ -215,18 +216,6 @@ int stage_prep_scan(tsdfloc_ctx* c, const float* d_xyz, uint64_t p, cudaStream_t
   k_prep_scan<<<nb, 256, 0, s>>>(d_xyz, static_cast<uint32_t>(p), static_cast<float4*>(c->d_pts.p), a_range_term, c->prm.a_max,
                                  c->prm.max_range * c->prm.max_range);
   return launch_check(c, "k_prep_scan");
-}
-
-// Particles per warp: two once there are enough particles to keep every SM busy with 2-particle warps
-// (the point load, loop and planning overhead is shared); overridable for experiments with TSDFLOC_PPW=1|2.
-int pick_ppw(const tsdfloc_ctx* c, uint64_t count)
-{
-  if (const char* e = std::getenv("TSDFLOC_PPW"))
-  {
-    const int v = std::atoi(e);
-    if (v == 1 || v == 2) return v;
-  }
-  return count >= static_cast<uint64_t>(c->sm_count) * 32 ? 2 : 1;
 }
 
 // Device copy of a set of peer pointers. The sets repeat from update to update (two per buffer with double buffering), so
@@ -259,54 +248,41 @@ int peer_table(tsdfloc_ctx* c, float* const* want, uint32_t n, cudaStream_t s, f
   return TSDFLOC_OK;
 }
 
-// One-warp CTAs without shared memory (k_eval2<1, BS, R, ., kDirect = true>).
-template <int BS, int R>
-void launch_eval_direct(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s)
+// Launches the evaluation kernel: pairing (two particles per warp, or two points per lane), quotient mode and — parity
+// dumps only — the index-recording instantiation of the very same code.
+template <bool kPP, bool kDump>
+void launch_eval_mode(const tsdfloc_ctx* c, int div, const EvalArgs& a, cudaStream_t s)
 {
-  const uint32_t grid = (a.n_local + 1) / 2;
-  if (c->map.fast_div)
-    k_eval2<1, BS, R, true, true><<<grid, 32, 0, s>>>(c->map, a);
+  const uint32_t grid = kPP ? a.n_local : (a.n_local + 1u) / 2u;
+  constexpr int BS = kEvalBlockSteps;
+  if (div == kDivBracket)
+    k_eval<BS, kDivThree, true, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
+  else if (div == kDivThree)
+    k_eval<BS, kDivThree, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
   else
-    k_eval2<1, BS, R, false, true><<<grid, 32, 0, s>>>(c->map, a);
+    k_eval<BS, kDivIeee, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
 }
 
-template <int W, int BS, int R>
-void launch_eval2(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s)
-{
-  const uint32_t per_cta = W * 2;
-  const uint32_t grid = (a.n_local + per_cta - 1) / per_cta;
-  if (c->map.fast_div)
-    k_eval2<W, BS, R, true><<<grid, W * 32, 0, s>>>(c->map, a);
-  else
-    k_eval2<W, BS, R, false><<<grid, W * 32, 0, s>>>(c->map, a);
-}
+// Point pairs double the number of warps: taken while particle pairs would leave the machine short of kPairWaves full waves
+// of one-warp CTAs (32 per SM). Measured on B200, profiles/r02_eval_pairing.md.
+constexpr uint32_t kPairWaves = 2;
 
-// k_eval2 configuration (warps per CTA sharing one scan tile ring, steps per summation block, register budget).
-// Defaults from the round-1 sweeps on B200 (profiles/r01_eval2_sweep.md); TSDFLOC_W / TSDFLOC_BS / TSDFLOC_R override.
-void dispatch_eval2(const tsdfloc_ctx* c, const EvalArgs& a, uint64_t count, cudaStream_t s)
+void launch_eval(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s, bool dump)
 {
-  const uint64_t warps = (count + 1) / 2;
-  int w = 4, bs = 8, r = 24;
-  (void)warps;
-  if (c->eval_w) w = c->eval_w;
-  if (c->eval_bs) bs = c->eval_bs;
-  if (c->eval_r) r = c->eval_r;
-#define TSDFLOC_CASE(WW, BB, RR) if (w == WW && bs == BB && r == RR) return launch_eval2<WW, BB, RR>(c, a, s)
-  TSDFLOC_CASE(4, 8, 24); TSDFLOC_CASE(4, 4, 32); TSDFLOC_CASE(1, 4, 32); TSDFLOC_CASE(8, 8, 24); TSDFLOC_CASE(8, 4, 32);
-  TSDFLOC_CASE(4, 4, 24); TSDFLOC_CASE(2, 8, 24); TSDFLOC_CASE(2, 4, 32); TSDFLOC_CASE(1, 8, 24); TSDFLOC_CASE(1, 4, 24);
-#undef TSDFLOC_CASE
-  launch_eval2<4, 8, 24>(c, a, s);
-}
-
-template <int kPPW>
-void launch_eval(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s)
-{
-  const uint32_t per_cta = kEvalWarps * kPPW;
-  const uint32_t grid = (a.n_local + per_cta - 1) / per_cta;
-  if (c->map.fast_div)
-    k_eval<kPPW, true><<<grid, kEvalThreads, 0, s>>>(c->map, a);
+  int div = c->map.div_mode;
+  if (c->tune_div >= 0)
+  {
+    div = c->tune_div;
+    if (div == kDivBracket && !c->bracket_ok) div = c->map.div_mode;   // never run an unproven mode
+    if (div != kDivIeee && !c->three_ok) div = kDivIeee;
+  }
+  bool pp = static_cast<uint64_t>((a.n_local + 1u) / 2u) < static_cast<uint64_t>(c->sm_count) * 32u * kPairWaves;
+  if (c->tune_shape == 1) pp = false;
+  if (c->tune_shape == 2) pp = true;
+  if (pp)
+    dump ? launch_eval_mode<true, true>(c, div, a, s) : launch_eval_mode<true, false>(c, div, a, s);
   else
-    k_eval<kPPW, false><<<grid, kEvalThreads, 0, s>>>(c->map, a);
+    dump ? launch_eval_mode<false, true>(c, div, a, s) : launch_eval_mode<false, false>(c, div, a, s);
 }
 
 // Spatial evaluation order of particles [first, first + count): *perm = device permutation, or nullptr when ordering is off
@@ -351,7 +327,8 @@ int stage_matrices(tsdfloc_ctx* c, const float* d_particles, uint64_t first, uin
 }
 
 int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint64_t first, uint64_t count, const float tf[16],
-               float* d_raw, cudaStream_t s, float* const* d_raw_peers = nullptr, uint32_t n_peers = 0)
+               float* d_raw, cudaStream_t s, float* const* d_raw_peers = nullptr, uint32_t n_peers = 0, bool dump = false,
+               uint32_t* d_idx = nullptr, uint32_t* d_hits = nullptr)
 {
   if (n_peers > static_cast<uint32_t>(kMaxPeers)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 8 peer buffers");
   if (first + count > n_total) return fail(c, TSDFLOC_E_BAD_ARG, "particle slice exceeds n_total");
@@ -391,27 +368,9 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   a.stats = c->d_eval_stats;
   a.force_seq = c->force_seq;
   CU_TRY(c, cudaEventRecord(c->ev_eval0, s), "event record");
-  // Kernel choice (B200 sweeps, profiles/r01_eval2_sweep.md). Default since round 1c: the shared-memory-free one-warp-CTA
-  // shape k_eval2<1, 8, 32, ., kDirect> (64 registers, 32 CTAs per SM, points by LDG through L1) — it beats both older
-  // kernels at every particle count measured (500 ... 65,536). TSDFLOC_EVAL=1 forces k_eval (x staged in shared memory),
-  // TSDFLOC_EVAL=2 the TMA-ring kernel k_eval2<W, BS, R>, TSDFLOC_EVAL=3 the direct shape with TSDFLOC_BS / TSDFLOC_R.
-  if (c->eval_version == 0)
-    launch_eval_direct<8, 32>(c, a, s);
-  else if (c->eval_version == 3)
-  {
-    const int bs = c->eval_bs ? c->eval_bs : 8, r = c->eval_r ? c->eval_r : 32;
-    if (bs == 8 && r == 24) launch_eval_direct<8, 24>(c, a, s);
-    else if (bs == 4 && r == 32) launch_eval_direct<4, 32>(c, a, s);
-    else if (bs == 4 && r == 24) launch_eval_direct<4, 24>(c, a, s);
-    else if (bs == 4 && r == 28) launch_eval_direct<4, 28>(c, a, s);
-    else launch_eval_direct<8, 32>(c, a, s);
-  }
-  else if (c->eval_version == 2)
-    dispatch_eval2(c, a, count, s);
-  else if (pick_ppw(c, count) == 2)
-    launch_eval<2>(c, a, s);
-  else
-    launch_eval<1>(c, a, s);
+  a.idx_out = d_idx;
+  a.hits_out = d_hits;
+  launch_eval(c, a, s, dump);
   if ((rc = launch_check(c, "k_eval"))) return rc;
   CU_TRY(c, cudaEventRecord(c->ev_eval1, s), "event record");
   c->eval_timed = true;
@@ -580,6 +539,12 @@ int upload_cloud(tsdfloc_ctx* c, const void* xyz_base, uint64_t xyz_stride, cons
   return TSDFLOC_OK;
 }
 
+const char* overflow_text(uint32_t flags)
+{
+  if (flags & 4u) return "the weights sum to more than 2: the resampling recurrence would emit more than 2N + 64 particles (normalise them first)";
+  return "U recurrence table overflow or stalled recurrence";
+}
+
 int read_status(tsdfloc_ctx* c, cudaStream_t s)
 {
   CU_TRY(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s), "status readback");
@@ -619,7 +584,7 @@ void tsdfloc_default_params(tsdfloc_params* p)
   p->a_max = 0.0f;
   p->max_range = 100.0f;
   p->per_point = 0;
-  p->reserved = 0;
+  p->neg_policy = TSDFLOC_NEG_MISS;
 }
 
 int tsdfloc_abi_version(void) { return TSDFLOC_ABI_VERSION; }
@@ -684,13 +649,10 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
                                     "; libtsdfloc is built for sm_100a (B200) only");
   c->sm_count = prop.multiProcessorCount;
   c->l2_bytes = static_cast<size_t>(prop.l2CacheSize);
-  if (const char* e = std::getenv("TSDFLOC_SORT")) c->sort_mode = std::atoi(e) ? 1 : 0;
-  if (const char* e = std::getenv("TSDFLOC_EVAL")) c->eval_version = std::atoi(e);
-  if (const char* e = std::getenv("TSDFLOC_W")) c->eval_w = std::atoi(e);
-  if (const char* e = std::getenv("TSDFLOC_BS")) c->eval_bs = std::atoi(e);
-  if (const char* e = std::getenv("TSDFLOC_R")) c->eval_r = std::atoi(e);
   if (params) c->prm = *params; else tsdfloc_default_params(&c->prm);
   if (!(c->prm.max_range > 0.0f)) return bail(TSDFLOC_E_BAD_ARG, "max_range must be positive");
+  if (c->prm.neg_policy != TSDFLOC_NEG_MISS && c->prm.neg_policy != TSDFLOC_NEG_SATURATE_LIKE_REF_GPU)
+    return bail(TSDFLOC_E_BAD_ARG, "unknown neg_policy");
   c->desc = *map;
   CU_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
   CU_CREATE(cudaEventCreate(&c->ev_eval0), "cudaEventCreate");
@@ -747,10 +709,12 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
     M.min[a] = map->min[a];
     M.clamp_hi[a] = static_cast<float>(thr[a]);
   }
+  M.clamp_lo = c->prm.neg_policy == TSDFLOC_NEG_SATURATE_LIKE_REF_GPU ? 0.0f : -1.0f;
   M.res = map->resolution;
   {
     const volatile float inv = 1.0f / map->resolution;
     M.inv_res = inv;
+    M.inv_lo = M.inv_hi = inv;
   }
   M.pad_x = static_cast<uint32_t>(px);
   M.pad_xy = static_cast<uint32_t>(px * py);
@@ -825,25 +789,32 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
   CU_CREATE(cudaMemset(c->d_red_status, 0, sizeof(RedStatus)), "memset(reduce status)");
   CU_CREATE(cudaMallocHost(&c->h_red_status, sizeof(RedStatus)), "cudaMallocHost(reduce status)");
 
-  // ---- verify the 3-instruction division for this resolution (exhaustive over [0,1)) --------------------------
+  // ---- prove the quotient shortcuts for this resolution (exhaustive over every float in [0, 1)) ------------------
   {
-    unsigned long long* d_bad = nullptr;
-    CU_CREATE(cudaMalloc(&d_bad, sizeof(unsigned long long)), "cudaMalloc(div check)");
-    CU_CREATE(cudaMemset(d_bad, 0, sizeof(unsigned long long)), "memset(div check)");
-    k_check_div<<<c->sm_count * 8, 256, 0, c->stream>>>(M.res, M.inv_res, d_bad);
+    unsigned long long* d_out = nullptr;
+    CU_CREATE(cudaMalloc(&d_out, sizeof(unsigned long long) * 5), "cudaMalloc(div check)");
+    CU_CREATE(cudaMemset(d_out, 0, sizeof(unsigned long long) * 5), "memset(div check)");
+    const float inv = M.inv_res;
+    const float lo1 = std::nextafterf(inv, 0.0f), hi1 = std::nextafterf(inv, INFINITY);
+    const float lo2 = std::nextafterf(lo1, 0.0f), hi2 = std::nextafterf(hi1, INFINITY);
+    k_check_div<<<c->sm_count * 8, 256, 0, c->stream>>>(M, lo1, hi1, lo2, hi2, d_out);
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess)
     {
-      cudaFree(d_bad);
+      cudaFree(d_out);
       return bail(TSDFLOC_E_CUDA, std::string("kernel image not loadable on this device (built for sm_100a): ") + cudaGetErrorString(le));
     }
     ++c->launches;
-    unsigned long long bad = 0;
-    cudaError_t ce = cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, c->stream);
+    unsigned long long h[5] = {};
+    cudaError_t ce = cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
-    cudaFree(d_bad);
+    cudaFree(d_out);
     if (ce != cudaSuccess) return bail(TSDFLOC_E_CUDA, std::string("division self-check failed to run: ") + cudaGetErrorString(ce));
-    M.fast_div = (bad == 0) ? 1 : 0;
+    c->three_ok = (h[0] == 0);
+    // the bracket needs an exact mode for the blocks it leaves open; the redo uses the 3-instruction quotient
+    if (c->three_ok && h[1] == 0) { c->bracket_ok = true; M.inv_lo = lo1; M.inv_hi = hi1; c->bracket_open = h[2]; }
+    else if (c->three_ok && h[3] == 0) { c->bracket_ok = true; M.inv_lo = lo2; M.inv_hi = hi2; c->bracket_open = h[4]; }
+    M.div_mode = c->bracket_ok ? kDivBracket : c->three_ok ? kDivThree : kDivIeee;
   }
 #undef CU_CREATE
   *out = c;
@@ -964,7 +935,7 @@ int tsdfloc_check(tsdfloc_ctx* c, uint64_t* n_out, double* weight_sum, void* str
   if (n_out) *n_out = c->h_status->n_out;
   if (weight_sum) *weight_sum = c->h_status->weight_sum;
   if (c->h_status->zero_sum) return fail(c, TSDFLOC_E_NO_VALID_PARTICLE, "No particle is valid!");
-  if (c->h_status->table_overflow & 3u) return fail(c, TSDFLOC_E_CAPACITY, "U recurrence table overflow or stalled recurrence");
+  if (c->h_status->table_overflow & 7u) return fail(c, TSDFLOC_E_CAPACITY, overflow_text(c->h_status->table_overflow));
   return TSDFLOC_OK;
 }
 
@@ -1257,7 +1228,7 @@ int tsdfloc_resample_systematic(tsdfloc_ctx* c, float u0, float* particles_out, 
   uint32_t* h_par = reinterpret_cast<uint32_t*>(static_cast<char*>(c->h_stage) + sizeof(float) * 7 * cap);
   if (parents) CU_TRY(c, cudaMemcpyAsync(h_par, c->d_parents.p, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, s), "D2H parents");
   if ((rc = read_status(c, s))) return rc;
-  if (c->h_status->table_overflow & 3u) return fail(c, TSDFLOC_E_CAPACITY, "U recurrence table overflow or stalled recurrence");
+  if (c->h_status->table_overflow & 7u) return fail(c, TSDFLOC_E_CAPACITY, overflow_text(c->h_status->table_overflow));
   const uint64_t m = c->h_status->n_out;
   *n_out = m;
   if (m > cap) return fail(c, TSDFLOC_E_CAPACITY, "resampling emits " + std::to_string(m) + " particles, capacity is " + std::to_string(cap));
@@ -1309,26 +1280,16 @@ int tsdfloc_debug_eval(tsdfloc_ctx* c, const float* particles, uint64_t n, const
   if ((rc = stage_prep_scan(c, static_cast<const float*>(c->d_xyz_stage.p), p, s))) return rc;
   float* d_p = static_cast<float*>(c->d_particles.p);
   CU_TRY(c, cudaMemcpyAsync(d_p, particles, sizeof(float) * 7 * n, cudaMemcpyHostToDevice, s), "H2D particles");
+  CU_TRY(c, cudaMemsetAsync(c->d_hits.p, 0, sizeof(uint32_t) * n, s), "memset hits");
   {
-    // the index dump below reads the matrices particle-major: evaluate in identity order
+    // the index-recording instantiation of the production kernel itself (same pairing, same quotient mode), identity order
     const int saved = c->sort_mode;
     c->sort_mode = 0;
-    rc = stage_eval(c, d_p, n, 0, n, tf, static_cast<float*>(c->d_raw.p), s);
+    rc = stage_eval(c, d_p, n, 0, n, tf, static_cast<float*>(c->d_raw.p), s, nullptr, 0, true,
+                    idx ? static_cast<uint32_t*>(c->d_idx.p) : nullptr, static_cast<uint32_t*>(c->d_hits.p));
     c->sort_mode = saved;
     if (rc) return rc;
   }
-  CU_TRY(c, cudaMemsetAsync(c->d_hits.p, 0, sizeof(uint32_t) * n, s), "memset hits");
-  const unsigned long long total = n * p;
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  if (c->map.fast_div)
-    k_debug_pairs<true><<<blocks, 256, 0, s>>>(c->map, static_cast<const float4*>(c->d_pts.p), static_cast<uint32_t>(p),
-                                               static_cast<const float*>(c->d_mats.p), static_cast<uint32_t>(n),
-                                               idx ? static_cast<uint32_t*>(c->d_idx.p) : nullptr, static_cast<uint32_t*>(c->d_hits.p));
-  else
-    k_debug_pairs<false><<<blocks, 256, 0, s>>>(c->map, static_cast<const float4*>(c->d_pts.p), static_cast<uint32_t>(p),
-                                                static_cast<const float*>(c->d_mats.p), static_cast<uint32_t>(n),
-                                                idx ? static_cast<uint32_t*>(c->d_idx.p) : nullptr, static_cast<uint32_t*>(c->d_hits.p));
-  if ((rc = launch_check(c, "k_debug_pairs"))) return rc;
   if (idx) CU_TRY(c, cudaMemcpyAsync(idx, c->d_idx.p, sizeof(uint32_t) * n * p, cudaMemcpyDeviceToHost, s), "D2H index dump");
   if (hits) CU_TRY(c, cudaMemcpyAsync(hits, c->d_hits.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s), "D2H hits");
   if (raw_weights) CU_TRY(c, cudaMemcpyAsync(raw_weights, c->d_raw.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s), "D2H raw weights");
@@ -1373,6 +1334,34 @@ int tsdfloc_probe_gather(tsdfloc_ctx* c, uint64_t bytes, uint32_t spread_sectors
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return rc;
+}
+
+int tsdfloc_tune(tsdfloc_ctx* c, int knob, int value)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  switch (knob)
+  {
+    case TSDFLOC_TUNE_SPATIAL_ORDER:
+      if (value < -1 || value > 1) return fail(c, TSDFLOC_E_BAD_ARG, "spatial order: -1 automatic, 0 off, 1 on");
+      c->sort_mode = value;
+      return TSDFLOC_OK;
+    case TSDFLOC_TUNE_EVAL_PAIRING:
+      if (value < 0 || value > 2) return fail(c, TSDFLOC_E_BAD_ARG, "pairing: 0 automatic, 1 particle pairs, 2 point pairs");
+      c->tune_shape = value;
+      return TSDFLOC_OK;
+    case TSDFLOC_TUNE_DIVISION:
+      if (value < -1 || value > kDivBracket) return fail(c, TSDFLOC_E_BAD_ARG, "division: -1 automatic, 0 IEEE, 1 three-instruction, 2 bracket");
+      c->tune_div = value;
+      return TSDFLOC_OK;
+    default: return fail(c, TSDFLOC_E_BAD_ARG, "unknown tuning knob");
+  }
+}
+
+int tsdfloc_division_mode(tsdfloc_ctx* c, uint64_t* open_brackets)
+{
+  if (!c) return -1;
+  if (open_brackets) *open_brackets = c->bracket_open;
+  return c->map.div_mode;
 }
 
 int tsdfloc_eval_stats(tsdfloc_ctx* c, uint64_t out[4])

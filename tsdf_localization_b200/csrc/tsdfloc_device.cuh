@@ -9,8 +9,14 @@
 //   * misses (border, unallocated upper cells, negative/NaN offsets — policy NEG_AS_MISS) point at a
 //     MISS BRICK filled with init_value appended behind the real bricks: the gather is branch-free;
 //   * floor() is a round-down add of 2^23 (FADD.RM) instead of F2I/I2F;
-//   * x / resolution uses a verified 3-instruction correctly-rounded sequence (FMUL, FFMA, FFMA); tsdfloc_create
-//     checks it exhaustively against IEEE division for the map's resolution and falls back to __fdiv_rn.
+//   * floor(fl(x / resolution)) — the reference divides in fp32 and truncates — is BRACKETED instead of computed: two
+//     round-down FMAs  floor(x * inv_lo) <= floor(fl(x / res)) <= floor(x * inv_hi)  with inv_lo < 1/res < inv_hi one or two
+//     ulps apart. Where both floors agree (all but ~4e-6 of the quotients) that IS the reference's value; where they differ
+//     the evaluation kernel redoes the summation block with the exact division. tsdfloc_create proves the bracket for the
+//     map's resolution EXHAUSTIVELY (every float in [0, 1), k_check_div) and otherwise falls back to a verified
+//     3-instruction correctly-rounded sequence (FMUL, FFMA, FFMA) or to __fdiv_rn.
+//   * negative offsets: policy MISS (default; clamp into the padded border) or SATURATE (clamp to 0: the reference CUDA
+//     build's saturating f32->u32 conversions, cuda_eval_particles.h:14-16,34-36,62-64) — one kernel parameter, no branch.
 // All fp32 arithmetic that feeds an index uses explicit _rn/_rd intrinsics: nvcc never contracts those into FMAs.
 #pragma once
 #include <cstdint>
@@ -29,9 +35,11 @@ struct MapDev
   const int32_t* __restrict__ table;  // padded brick table [pz][py][px]: element offset of the brick in voxels
   const float* __restrict__ voxels;   // bricks in reference order + one miss brick at miss_offset
   float min[3];
-  float clamp_hi[3];   // (float)thr[a]: offsets are clamped into [-1, thr]
+  float clamp_hi[3];   // (float)thr[a]: offsets are clamped into [clamp_lo, thr]
+  float clamp_lo;      // -1: negative offsets land in the padded border (miss); 0: they saturate onto the min face (reference CUDA build)
   float res;
   float inv_res;       // RN(1/res)
+  float inv_lo, inv_hi;  // bracket of 1/res for the round-down quotient floors (div_mode == kDivBracket)
   uint32_t pad_x;      // x stride of the padded table: pow2 >= thr[0] + 2
   uint32_t pad_xy;     // z stride: pad_x * (pow2 >= thr[1] + 2)
   uint32_t shift_x;    // log2(pad_x)
@@ -41,31 +49,37 @@ struct MapDev
   uint32_t data_size;  // reference data_size; every index >= data_size is a miss
   uint32_t table_bias; // kMagicBits * (1 + pad_x + pad_xy)   (mod 2^32)
   uint32_t sub_bias;   // kMagicBits * (1 + sub_dim + sub_dim_2) (mod 2^32)
-  int32_t fast_div;    // 1: the 3-instruction division is exact for this resolution
+  int32_t div_mode;    // kDivIeee / kDivThree / kDivBracket: what k_check_div proved for this resolution
 };
 
-// q = trunc-able quotient a / res for a in [0, 1). Bit-identical to IEEE a / res when fast_div was verified.
-template <bool kFastDiv>
-__device__ __forceinline__ float div_res(float a, float res, float inv_res)
+constexpr int kDivIeee = 0;      // __fdiv_rn
+constexpr int kDivThree = 1;     // verified 3-instruction correctly-rounded quotient
+constexpr int kDivBracket = 2;   // two round-down FMAs; disagreement -> the caller redoes the block with an exact mode
+
+// 2^23 + floor(fl(a / res)) for a in [0, 1), as a float whose low mantissa bits are the sub-voxel coordinate.
+// kDiv = kDivThree is bit-identical to IEEE a / res when k_check_div verified it for this resolution.
+template <int kDiv>
+__device__ __forceinline__ float sub_coord(const MapDev& M, float a)
 {
-  if (kFastDiv)
+  static_assert(kDiv == kDivIeee || kDiv == kDivThree, "the scalar path has no bracket mode");
+  if (kDiv == kDivThree)
   {
-    const float q0 = __fmul_rn(a, inv_res);
-    const float e = __fmaf_rn(-res, q0, a);
-    return __fmaf_rn(e, inv_res, q0);
+    const float q0 = __fmul_rn(a, M.inv_res);
+    const float e = __fmaf_rn(-M.res, q0, a);
+    return __fadd_rd(__fmaf_rn(e, M.inv_res, q0), kMagic);
   }
-  return __fdiv_rn(a, res);
+  return __fadd_rd(__fdiv_rn(a, M.res), kMagic);
 }
 
 // Flat voxel offset (reference numbering: brick offset + sx + sy*sub_dim + sz*sub_dim^2) of world point t.
 // Returns a value >= M.data_size (inside the miss brick) for every miss.
-template <bool kFastDiv>
+template <int kDiv>
 __device__ __forceinline__ uint32_t voxel_index(const MapDev& M, float tx, float ty, float tz)
 {
   // offsets x - min (cuda_eval_particles.h:27-29), clamped into the padded table's range
-  const float ox = fminf(fmaxf(__fsub_rn(tx, M.min[0]), -1.0f), M.clamp_hi[0]);
-  const float oy = fminf(fmaxf(__fsub_rn(ty, M.min[1]), -1.0f), M.clamp_hi[1]);
-  const float oz = fminf(fmaxf(__fsub_rn(tz, M.min[2]), -1.0f), M.clamp_hi[2]);
+  const float ox = fminf(fmaxf(__fsub_rn(tx, M.min[0]), M.clamp_lo), M.clamp_hi[0]);
+  const float oy = fminf(fmaxf(__fsub_rn(ty, M.min[1]), M.clamp_lo), M.clamp_hi[1]);
+  const float oz = fminf(fmaxf(__fsub_rn(tz, M.min[2]), M.clamp_lo), M.clamp_hi[2]);
   // 2^23 + 1 + floor(o): the low mantissa bits are the padded upper-cell coordinate (:34-36)
   const float bx = __fadd_rd(ox, kMagicP1);
   const float by = __fadd_rd(oy, kMagicP1);
@@ -78,9 +92,7 @@ __device__ __forceinline__ uint32_t voxel_index(const MapDev& M, float tx, float
   const uint32_t ti = __float_as_uint(bx) + __float_as_uint(by) * M.pad_x + __float_as_uint(bz) * M.pad_xy - M.table_bias;
   const uint32_t brick = static_cast<uint32_t>(__ldg(M.table + ti));
   // sub-voxel coordinates (:62-64)
-  const float qx = __fadd_rd(div_res<kFastDiv>(px, M.res, M.inv_res), kMagic);
-  const float qy = __fadd_rd(div_res<kFastDiv>(py, M.res, M.inv_res), kMagic);
-  const float qz = __fadd_rd(div_res<kFastDiv>(pz, M.res, M.inv_res), kMagic);
+  const float qx = sub_coord<kDiv>(M, px), qy = sub_coord<kDiv>(M, py), qz = sub_coord<kDiv>(M, pz);
   return brick + __float_as_uint(qx) + __float_as_uint(qy) * M.sub_dim + __float_as_uint(qz) * M.sub_dim_2 - M.sub_bias;
 }
 
@@ -91,21 +103,17 @@ __device__ __forceinline__ float row_apply(float a, float b, float c, float d, f
   return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, x), __fmul_rn(b, y)), __fmul_rn(c, z)), d);
 }
 
-// ---- packed fp32x2 path (Blackwell FMUL2 / FADD2 / FFMA2): two particles per instruction ----------------------------
+// ---- packed fp32x2 path (Blackwell FMUL2 / FADD2 / FFMA2): two evaluations per instruction --------------------------
 //
 // ptxas (12.9) contracts mul.rn.f32x2 feeding add.rn.f32x2 into one FFMA2 even though both carry .rn and even with
 // --fmad=false, which would break bit-parity with the reference's separately rounded products and sums. Every
 // "sum of a product" is therefore written as fma(product, one, addend) with `one` = 1.0f read from a kernel
 // parameter the compiler cannot see through: the product feeds the MULTIPLICAND slot, where no contraction exists,
 // and fma(p, 1, q) rounds p + q exactly once — the same value as an unfused add.
-struct Pair
-{
-  float2 v;
-};
-
 __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
 
-// {A, B} rows applied to one point: ((a*x + b*y) + c*z) + d per half, each product and sum rounded separately.
+// Rows {a, b, c, d} applied to the point pair {xx, yy, zz}: ((a*x + b*y) + c*z) + d per half, each product and sum rounded
+// separately. The halves are two particles against one point, or one particle against two points.
 __device__ __forceinline__ float2 row_apply2(float2 a, float2 b, float2 c, float2 d, float2 xx, float2 yy, float2 zz, float2 one)
 {
   const float2 p1 = __fmul2_rn(a, xx);
@@ -116,34 +124,41 @@ __device__ __forceinline__ float2 row_apply2(float2 a, float2 b, float2 c, float
   return __fadd2_rn(s2, d);
 }
 
-__device__ __forceinline__ float2 clamp2(float2 o, float hi)
+__device__ __forceinline__ float2 clamp2(float2 o, float lo, float hi)
 {
-  return make_float2(fminf(fmaxf(o.x, -1.0f), hi), fminf(fmaxf(o.y, -1.0f), hi));
+  return make_float2(fminf(fmaxf(o.x, lo), hi), fminf(fmaxf(o.y, lo), hi));
 }
 
-template <bool kFastDiv>
-__device__ __forceinline__ float2 div_res2(float2 a, float res, float inv_res)
+// 2^23 + floor(fl(a / res)) per half. kDivBracket: the floor under inv_lo; `mism` collects the bits in which the floor
+// under inv_hi differs (non-zero = this quotient sits within ~4 ulps of an integer: the caller must redo it exactly).
+template <int kDiv>
+__device__ __forceinline__ float2 sub_coord2(const MapDev& M, float2 a, uint32_t& mism)
 {
-#ifdef TSDFLOC_EXP_NODIV   // timing experiment only (wrong at rounding boundaries): how much of the time is the FMA pipe?
-  return __fmul2_rn(a, dup2(inv_res));
-#endif
-  if (kFastDiv)
+  const float2 km = dup2(kMagic);
+  if (kDiv == kDivBracket)
   {
-    const float2 ir = dup2(inv_res);
-    const float2 q0 = __fmul2_rn(a, ir);
-    const float2 e = __ffma2_rn(dup2(-res), q0, a);
-    return __ffma2_rn(e, ir, q0);
+    const float2 lo = __ffma2_rd(a, dup2(M.inv_lo), km);
+    const float2 hi = __ffma2_rd(a, dup2(M.inv_hi), km);
+    mism |= (__float_as_uint(lo.x) ^ __float_as_uint(hi.x)) | (__float_as_uint(lo.y) ^ __float_as_uint(hi.y));
+    return lo;
   }
-  return make_float2(__fdiv_rn(a.x, res), __fdiv_rn(a.y, res));
+  if (kDiv == kDivThree)
+  {
+    const float2 ir = dup2(M.inv_res);
+    const float2 q0 = __fmul2_rn(a, ir);
+    const float2 e = __ffma2_rn(dup2(-M.res), q0, a);
+    return __fadd2_rd(__ffma2_rn(e, ir, q0), km);
+  }
+  return __fadd2_rd(make_float2(__fdiv_rn(a.x, M.res), __fdiv_rn(a.y, M.res)), km);
 }
 
-// voxel_index for two particles at once; same arithmetic per half as voxel_index<>.
-template <bool kFastDiv>
-__device__ __forceinline__ void voxel_index2(const MapDev& M, float2 tx, float2 ty, float2 tz, uint32_t& ia, uint32_t& ib)
+// voxel_index for two evaluations at once; same arithmetic per half as voxel_index<>.
+template <int kDiv>
+__device__ __forceinline__ void voxel_index2(const MapDev& M, float2 tx, float2 ty, float2 tz, uint32_t& ia, uint32_t& ib, uint32_t& mism)
 {
-  const float2 ox = clamp2(__fadd2_rn(tx, dup2(-M.min[0])), M.clamp_hi[0]);
-  const float2 oy = clamp2(__fadd2_rn(ty, dup2(-M.min[1])), M.clamp_hi[1]);
-  const float2 oz = clamp2(__fadd2_rn(tz, dup2(-M.min[2])), M.clamp_hi[2]);
+  const float2 ox = clamp2(__fadd2_rn(tx, dup2(-M.min[0])), M.clamp_lo, M.clamp_hi[0]);
+  const float2 oy = clamp2(__fadd2_rn(ty, dup2(-M.min[1])), M.clamp_lo, M.clamp_hi[1]);
+  const float2 oz = clamp2(__fadd2_rn(tz, dup2(-M.min[2])), M.clamp_lo, M.clamp_hi[2]);
   const float2 kp = dup2(kMagicP1), kn = dup2(-kMagicP1);
   const float2 bx = __fadd2_rd(ox, kp);
   const float2 by = __fadd2_rd(oy, kp);
@@ -154,45 +169,16 @@ __device__ __forceinline__ void voxel_index2(const MapDev& M, float2 tx, float2 
   const float2 px = __fadd2_rn(ox, make_float2(-fx.x, -fx.y));
   const float2 py = __fadd2_rn(oy, make_float2(-fy.x, -fy.y));
   const float2 pz = __fadd2_rn(oz, make_float2(-fz.x, -fz.y));
-#ifndef TSDFLOC_MUL_INDEX
+  // padded strides are powers of two: shifts on the ALU pipe instead of IMADs on the FMA pipe
   const uint32_t ta = __float_as_uint(bx.x) + (__float_as_uint(by.x) << M.shift_x) + (__float_as_uint(bz.x) << M.shift_xy) - M.table_bias;
   const uint32_t tb = __float_as_uint(bx.y) + (__float_as_uint(by.y) << M.shift_x) + (__float_as_uint(bz.y) << M.shift_xy) - M.table_bias;
-#else
-  const uint32_t ta = __float_as_uint(bx.x) + __float_as_uint(by.x) * M.pad_x + __float_as_uint(bz.x) * M.pad_xy - M.table_bias;
-  const uint32_t tb = __float_as_uint(bx.y) + __float_as_uint(by.y) * M.pad_x + __float_as_uint(bz.y) * M.pad_xy - M.table_bias;
-#endif
-#ifdef TSDFLOC_EXP_NOTABLE  // timing experiment only: table lookups collapse onto 64 entries
-  const uint32_t brick_a = static_cast<uint32_t>(__ldg(M.table + (ta & 63u)));
-  const uint32_t brick_b = static_cast<uint32_t>(__ldg(M.table + (tb & 63u)));
-#else
   const uint32_t brick_a = static_cast<uint32_t>(__ldg(M.table + ta));
   const uint32_t brick_b = static_cast<uint32_t>(__ldg(M.table + tb));
-#endif
-  const float2 km = dup2(kMagic);
-  const float2 qx = __fadd2_rd(div_res2<kFastDiv>(px, M.res, M.inv_res), km);
-  const float2 qy = __fadd2_rd(div_res2<kFastDiv>(py, M.res, M.inv_res), km);
-  const float2 qz = __fadd2_rd(div_res2<kFastDiv>(pz, M.res, M.inv_res), km);
-#ifdef TSDFLOC_SUB20   // timing experiment: sub_dim == 20 assumed, multiplies as shift/add chains
-  {
-    const uint32_t ya = __float_as_uint(qy.x), za = __float_as_uint(qz.x), yb = __float_as_uint(qy.y), zb = __float_as_uint(qz.y);
-    const uint32_t wa = ya + 20u * za, wb = yb + 20u * zb;   // y + 20 z
-    ia = brick_a + __float_as_uint(qx.x) + ((wa + (wa << 2)) << 2) - M.sub_bias;
-    ib = brick_b + __float_as_uint(qx.y) + ((wb + (wb << 2)) << 2) - M.sub_bias;
-  }
-#else
+  const float2 qx = sub_coord2<kDiv>(M, px, mism);
+  const float2 qy = sub_coord2<kDiv>(M, py, mism);
+  const float2 qz = sub_coord2<kDiv>(M, pz, mism);
   ia = brick_a + __float_as_uint(qx.x) + __float_as_uint(qy.x) * M.sub_dim + __float_as_uint(qz.x) * M.sub_dim_2 - M.sub_bias;
   ib = brick_b + __float_as_uint(qx.y) + __float_as_uint(qy.y) * M.sub_dim + __float_as_uint(qz.y) * M.sub_dim_2 - M.sub_bias;
-#endif
-#ifdef TSDFLOC_EXP_NOGATHER  // timing experiment only: every gather hits the same 4 KB (L1-resident)
-  ia &= 1023u;
-  ib &= 1023u;
-#endif
-#ifdef TSDFLOC_EXP_LINEGATHER  // timing experiment only: the 32 lanes of a gather share one 128 B line (1 tag, 4 sectors)
-  ia = (ia & ~31u) % M.data_size;
-  ia = __shfl_sync(0xffffffffu, ia, 0) + (threadIdx.x & 31u);
-  ib = (ib & ~31u) % M.data_size;
-  ib = __shfl_sync(0xffffffffu, ib, 0) + (threadIdx.x & 31u);
-#endif
 }
 
 }  // namespace tsdfloc

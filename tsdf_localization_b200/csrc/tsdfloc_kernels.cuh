@@ -1,5 +1,5 @@
-// tsdfloc_kernels.cuh — kernels of the B200 sensor update (K0 pose->matrix, K1 evaluation, K2 normalise +
-// moments + CDF, K3 U-table, K4 draw). Included once by tsdfloc_api.cu. sm_100a only.
+// tsdfloc_kernels.cuh — kernels of the B200 sensor update around the evaluation kernel (K1, tsdfloc_eval.cuh): scan
+// preparation, K0 pose->matrix, K2 normalise + moments + CDF, K3 U-table, K4 draw. Included once by tsdfloc_api.cu. sm_100a only.
 //
 // Reference functions these replace (paths relative to the reference repo):
 //   K0/K1  cudaEvaluateParticlesOrdered + cudaEvaluatePose   include/tsdf_localization/cuda/cuda_eval_particles.h:167-215, 273-333
@@ -7,20 +7,12 @@
 //   K3/K4  SystematicResampler::resample (CPU, serial)        include/tsdf_localization/resampling/novel_resampling.h:41-72
 #pragma once
 #include "tsdfloc_device.cuh"
+#include "tsdfloc_eval.cuh"
 #include <cstring>
 
 namespace tsdfloc
 {
 
-#ifndef TSDFLOC_EVAL_WARPS
-#define TSDFLOC_EVAL_WARPS 1
-#endif
-#ifndef TSDFLOC_BLOCK_STEPS
-#define TSDFLOC_BLOCK_STEPS 16
-#endif
-constexpr int kEvalWarps = TSDFLOC_EVAL_WARPS;    // independent warps per CTA (1: finest granularity for the block scheduler)
-constexpr int kEvalThreads = kEvalWarps * 32;
-constexpr int kBlockSteps = TSDFLOC_BLOCK_STEPS;  // 32-point steps summed as integers between two warp reductions
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 4;
 constexpr int kScanTile = kScanThreads * kScanItems;  // particles per scan tile
@@ -162,262 +154,31 @@ __global__ void k_pose_matrices(const float* __restrict__ particles, uint32_t fi
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// K1: evaluation. A warp owns kPPW particles (their 3x4 matrices live in registers) and its 32 lanes walk
-// CONSECUTIVE scan points, so the 32 voxel gathers of one warp instruction land on neighbouring voxels of the same
-// surface (few 128 B lines) instead of 32 unrelated particles' voxels as in the reference's one-thread-per-particle
-// kernel.
-//
-// The weight is the reference's fp32 SEQUENTIAL sum over the points in scan order, bit for bit
-// (eval_sum += a_hit*v + term, cuda_eval_particles.h:200-211 / tsdf_evaluator.cpp:56-67, unfused like the CPU
-// build). A tree reduction would be more accurate but differs from the reference by up to 1e-3 relative at
-// P = 131k, because a sequential fp32 sum absorbs addends below half an ulp of the running sum. The sequential sum
-// is reproduced in parallel with this identity: while the running sum s stays inside one binade (ulp u) and the
-// addends are >= 0,  RN(s + x) = s + RN_u(x)  unless x lies exactly between two multiples of u. So a block of
-// steps whose total provably cannot leave the binade is summed as exact integers q = RN(x/u) (magic-number
-// rounding, per-lane int32 accumulators, one warp reduction per block) and accepted only if, checked afterwards, no
-// lane saw an exact tie and the sum stayed below the top of the binade; otherwise (binade crossing, tie, or the first
-// few steps while s is still small) the block is folded truly sequentially from a shared-memory copy of its x values.
-// ------------------------------------------------------------------------------------------------------------
-constexpr float kRoundMagic = 12582912.0f;       // 1.5 * 2^23: x + magic rounds x to an integer (RN-even) for 0 <= x < 2^22
-constexpr uint32_t kRoundMagicBits = 0x4B400000u;
-
-constexpr int kMaxPeers = 8;         // ranks of one NVSwitch domain
-
-// Final store of a particle's weight: into this rank's vector and — fused all-gather — straight into every peer's
-// (P2P stores over NVLink; the kernel boundary + the driver's signal barrier order them before the peers' reads).
-struct EvalArgs;
-__device__ __forceinline__ void store_weight(const EvalArgs& A, uint32_t part, float w);
-
-struct EvalArgs
+// Exhaustive proof obligations of the sub-voxel quotient for ONE resolution, over every float a in [0, 1):
+//   out[0]  a where the 3-instruction quotient's floor differs from floor(fl(a / res))            (0 = kDivThree is exact)
+//   out[1]  a where floor(a * lo1) <= floor(fl(a / res)) <= floor(a * hi1) is VIOLATED             (0 = the bracket holds)
+//   out[2]  a where that bracket is open (the two floors differ: the kernel redoes such a block exactly)
+//   out[3], out[4]  the same for the wider pair (lo2, hi2)
+__global__ void k_check_div(MapDev M, float lo1, float hi1, float lo2, float hi2, unsigned long long* __restrict__ out)
 {
-  const float4* __restrict__ pts;   // x y z term, padded to a multiple of 32 points
-  const float* __restrict__ mats;   // [n_local][12]
-  float* raw_out;                   // [n_local] un-normalised weights (this rank's slice of its own weight vector)
-  const uint32_t* perm;             // evaluation order: slot j is particle perm[j] (nullptr = identity), tsdfloc_sort.cuh
-  float* const* peer_out;           // multi-GPU: device table of n_peer_out pointers = the same slice inside every OTHER
-  uint32_t n_peer_out;              //            rank's weight vector (peer-mapped, NVLink); 0 / nullptr on one GPU
-  unsigned long long* __restrict__ stats;  // [4]: blocks, blocks folded sequentially (binade crossing / early phase), tie folds, -
-  uint32_t n_points;
-  uint32_t n_local;
-  float a_hit;
-  float one;                        // 1.0f, opaque to the compiler (see tsdfloc_device.cuh, packed path)
-  float s_min;                      // integer-block summation is used once s >= s_min (= 32 * bound of one addend)
-  uint32_t force_seq;               // 1: negative/non-finite addends possible -> always fold sequentially
-};
-
-__device__ __forceinline__ void store_weight(const EvalArgs& A, uint32_t slot, float w)
-{
-  const uint32_t part = A.perm ? A.perm[slot] : slot;
-  A.raw_out[part] = w;
-#ifndef TSDFLOC_EXP_NO_PEERS   // (timing experiment: single-GPU kernel without the peer stores)
-  for (uint32_t r = 0; r < A.n_peer_out; ++r) A.peer_out[r][part] = w;   // pointer table in global memory: no register cost in the loop
-#endif
-}
-
-// One point against one particle: transform, voxel gather, x = a_hit * v + term (two roundings, like the CPU build).
-template <bool kFastDiv>
-__device__ __forceinline__ float eval_point(const MapDev& M, const float (&m)[12], const float4& p, float a_hit)
-{
-  const float tx = row_apply(m[0], m[1], m[2], m[3], p.x, p.y, p.z);
-  const float ty = row_apply(m[4], m[5], m[6], m[7], p.x, p.y, p.z);
-  const float tz = row_apply(m[8], m[9], m[10], m[11], p.x, p.y, p.z);
-  const float v = __ldg(M.voxels + voxel_index<kFastDiv>(M, tx, ty, tz));
-  return __fadd_rn(__fmul_rn(a_hit, v), p.w);
-}
-
-template <int kPPW, bool kFastDiv>
-__global__ void __launch_bounds__(kEvalThreads) k_eval(const MapDev M, const EvalArgs A)
-{
-  __shared__ __align__(16) float xs[kEvalWarps][kPPW][kBlockSteps * 32];
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warp = threadIdx.x >> 5;
-  const uint32_t part0 = (blockIdx.x * kEvalWarps + warp) * kPPW;
-#ifndef TSDFLOC_LOCKSTEP
-  if (part0 >= A.n_local) return;
-#endif
-
-  float m[kPPW][12];
-  float s[kPPW];
-#pragma unroll
-  for (int k = 0; k < kPPW; ++k)
-  {
-    const uint32_t pi = min(part0 + k, A.n_local - 1);
-#pragma unroll
-    for (int e = 0; e < 12; ++e) m[k][e] = __ldg(A.mats + 12ull * pi + e);
-    s[k] = 0.0f;
-  }
-
-  float2 mm[12];  // {A, B} matrix entries for the packed path
-#pragma unroll
-  for (int e = 0; e < 12; ++e) mm[e] = make_float2(m[0][e], m[kPPW - 1][e]);
-
-  uint32_t n_blocks = 0, n_fold = 0, n_tie = 0;
-  const uint32_t n_full = A.n_points >> 5;
-  const uint32_t rem = A.n_points & 31u;
-  uint32_t step = 0;
-  while (step < n_full)
-  {
-    const uint32_t nb = min(static_cast<uint32_t>(kBlockSteps), n_full - step);
-    // plan: binade of the running sum -> ulp u, 1/u, and the largest sum that still lies safely inside the binade
-    float u[kPPW], inv_u[kPPW], limit[kPPW];
-    bool fast[kPPW];
-    uint32_t acc[kPPW];
-    bool tie[kPPW];
-#pragma unroll
-    for (int k = 0; k < kPPW; ++k)
-    {
-      const uint32_t e = __float_as_uint(s[k]) >> 23;  // s >= 0
-      fast[k] = !A.force_seq && s[k] >= A.s_min && e > 24u && e < 253u;
-      const uint32_t ec = min(max(e, 25u), 252u);
-      u[k] = __uint_as_float((ec - 23u) << 23);
-      inv_u[k] = __uint_as_float((277u - ec) << 23);
-      limit[k] = __fsub_rn(__uint_as_float((ec + 1u) << 23), u[k]);  // top of the binade minus one ulp (exact)
-      acc[k] = 0u;
-      tie[k] = false;
-    }
-    const float4* __restrict__ pp = A.pts + (static_cast<size_t>(step) << 5) + lane;
-    if (kPPW == 2)
-    {
-      // two particles per instruction: matrices, offsets, quotients and rounding all as fp32x2 pairs {A, B}
-      const float2 one = dup2(A.one);
-      const float2 iu = make_float2(inv_u[0], inv_u[kPPW - 1]);
-      const float2 ah = dup2(A.a_hit);
-#pragma unroll 2
-      for (uint32_t b = 0; b < nb; ++b)
-      {
-        const float4 p = __ldg(pp + (b << 5));
-        const float2 xx = dup2(p.x), yy = dup2(p.y), zz = dup2(p.z);
-        const float2 tx = row_apply2(mm[0], mm[1], mm[2], mm[3], xx, yy, zz, one);
-        const float2 ty = row_apply2(mm[4], mm[5], mm[6], mm[7], xx, yy, zz, one);
-        const float2 tz = row_apply2(mm[8], mm[9], mm[10], mm[11], xx, yy, zz, one);
-        uint32_t ia, ib;
-        voxel_index2<kFastDiv>(M, tx, ty, tz, ia, ib);
-        const float2 v = make_float2(__ldg(M.voxels + ia), __ldg(M.voxels + ib));
-        const float2 x = __ffma2_rn(__fmul2_rn(ah, v), one, dup2(p.w));         // fl(fl(a_hit*v) + term)
-        xs[warp][0][(b << 5) + lane] = x.x;
-        xs[warp][kPPW - 1][(b << 5) + lane] = x.y;
-        const float2 t = __ffma2_rn(x, iu, dup2(kRoundMagic));
-        acc[0] += __float_as_uint(t.x) - kRoundMagicBits;
-        acc[kPPW - 1] += __float_as_uint(t.y) - kRoundMagicBits;
-        const float2 tm = __fadd2_rn(t, dup2(-kRoundMagic));
-        const float2 r = __ffma2_rn(x, iu, make_float2(-tm.x, -tm.y));
-        tie[0] |= (fabsf(r.x) == 0.5f);
-        tie[kPPW - 1] |= (fabsf(r.y) == 0.5f);
-      }
-    }
-    else
-    {
-#pragma unroll 2
-      for (uint32_t b = 0; b < nb; ++b)
-      {
-        const float4 p = __ldg(pp + (b << 5));
-#pragma unroll
-        for (int k = 0; k < kPPW; ++k)
-        {
-          const float x = eval_point<kFastDiv>(M, m[k], p, A.a_hit);
-          xs[warp][k][(b << 5) + lane] = x;
-          const float t = __fmaf_rn(x, inv_u[k], kRoundMagic);                 // RN-even(x/u) in the low mantissa bits
-          acc[k] += __float_as_uint(t) - kRoundMagicBits;
-          const float r = __fmaf_rn(x, inv_u[k], -__fsub_rn(t, kRoundMagic));   // exact rounding residue
-          tie[k] |= (fabsf(r) == 0.5f);
-        }
-      }
-    }
-    __syncwarp();
-    ++n_blocks;
-#pragma unroll
-    for (int k = 0; k < kPPW; ++k)
-    {
-      // s + sum(q) * u is the sequential fp32 sum iff no addend was an exact tie and the result stays below the top
-      // of the binade (then every partial sum did, the addends being >= 0).
-      const uint32_t tot = __reduce_add_sync(0xffffffffu, acc[k]);
-      const bool any_tie = __any_sync(0xffffffffu, tie[k]);
-      const float cand = __fadd_rn(s[k], __fmul_rn(static_cast<float>(tot), u[k]));
-      if (fast[k] && !any_tie && tot < (1u << 24) && cand <= limit[k])
-      {
-        s[k] = cand;
-      }
-      else
-      {
-        const float4* __restrict__ q = reinterpret_cast<const float4*>(xs[warp][k]);
-        float a = s[k];
-        const uint32_t cnt = nb << 3;
-#pragma unroll 2
-        for (uint32_t j = 0; j < cnt; ++j)
-        {
-          const float4 w = q[j];
-          a = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(a, w.x), w.y), w.z), w.w);
-        }
-        s[k] = a;
-        ++n_fold;
-        n_tie += (fast[k] && any_tie) ? 1u : 0u;
-      }
-    }
-    __syncwarp();
-#ifdef TSDFLOC_LOCKSTEP
-    __syncthreads();   // experiment: keep the CTA's warps on the same point tile so its loads hit L1
-#endif
-    step += nb;
-  }
-  if (rem)
-  {
-    const float4 p = __ldg(A.pts + (static_cast<size_t>(n_full) << 5) + lane);  // padded: reading past n_points is safe
-#pragma unroll
-    for (int k = 0; k < kPPW; ++k) xs[warp][k][lane] = eval_point<kFastDiv>(M, m[k], p, A.a_hit);
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < kPPW; ++k)
-    {
-      float a = s[k];
-      for (uint32_t j = 0; j < rem; ++j) a = __fadd_rn(a, xs[warp][k][j]);
-      s[k] = a;
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < kPPW; ++k)
-    if (lane == 0 && part0 + k < A.n_local) store_weight(A, part0 + k, s[k]);
-  if (lane == 0 && A.stats)
-  {
-    atomicAdd(A.stats + 0, static_cast<unsigned long long>(n_blocks) * kPPW);
-    atomicAdd(A.stats + 1, static_cast<unsigned long long>(n_fold));
-    atomicAdd(A.stats + 2, static_cast<unsigned long long>(n_tie));
-  }
-}
-
-// Parity/debug kernel: one thread per (particle, point) pair, same index function as k_eval.
-template <bool kFastDiv>
-__global__ void k_debug_pairs(const MapDev M, const float4* __restrict__ pts, uint32_t n_points, const float* __restrict__ mats, uint32_t n,
-                              uint32_t* __restrict__ idx_out, uint32_t* __restrict__ hits)
-{
-  const unsigned long long t = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const unsigned long long total = static_cast<unsigned long long>(n) * n_points;
-  if (t >= total) return;
-  const uint32_t pi = static_cast<uint32_t>(t / n_points);
-  const uint32_t qi = static_cast<uint32_t>(t % n_points);
-  const float* m = mats + 12ull * pi;
-  const float4 p = pts[qi];
-  const float tx = row_apply(m[0], m[1], m[2], m[3], p.x, p.y, p.z);
-  const float ty = row_apply(m[4], m[5], m[6], m[7], p.x, p.y, p.z);
-  const float tz = row_apply(m[8], m[9], m[10], m[11], p.x, p.y, p.z);
-  uint32_t idx = voxel_index<kFastDiv>(M, tx, ty, tz);
-  if (idx >= M.data_size) idx = M.data_size;
-  if (idx_out) idx_out[t] = idx;
-  if (hits && idx < M.data_size) atomicAdd(hits + pi, 1u);
-}
-
-// Exhaustive check of the 3-instruction division against IEEE division for every float in [0, 1).
-__global__ void k_check_div(float res, float inv_res, unsigned long long* __restrict__ mismatches)
-{
-  unsigned long long bad = 0;
+  unsigned long long bad3 = 0, bad1 = 0, open1 = 0, bad2 = 0, open2 = 0;
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < 0x3F800000u; b += gridDim.x * blockDim.x)
   {
     const float a = __uint_as_float(b);
-    const uint32_t fast = __float_as_uint(__fadd_rd(div_res<true>(a, res, inv_res), kMagic));
-    const uint32_t ieee = __float_as_uint(__fadd_rd(__fdiv_rn(a, res), kMagic));
-    bad += (fast != ieee);
+    const uint32_t ieee = __float_as_uint(sub_coord<kDivIeee>(M, a));
+    bad3 += (__float_as_uint(sub_coord<kDivThree>(M, a)) != ieee);
+    const uint32_t l1 = __float_as_uint(__fmaf_rd(a, lo1, kMagic)), h1 = __float_as_uint(__fmaf_rd(a, hi1, kMagic));
+    const uint32_t l2 = __float_as_uint(__fmaf_rd(a, lo2, kMagic)), h2 = __float_as_uint(__fmaf_rd(a, hi2, kMagic));
+    bad1 += !(l1 <= ieee && ieee <= h1);
+    open1 += (l1 != h1);
+    bad2 += !(l2 <= ieee && ieee <= h2);
+    open2 += (l2 != h2);
   }
-  if (bad) atomicAdd(mismatches, bad);
+  if (bad3) atomicAdd(out + 0, bad3);
+  if (bad1) atomicAdd(out + 1, bad1);
+  if (open1) atomicAdd(out + 2, open1);
+  if (bad2) atomicAdd(out + 3, bad2);
+  if (open2) atomicAdd(out + 4, open2);
 }
 
 // ------------------------------------------------------------------------------------------------------------

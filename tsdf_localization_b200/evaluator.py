@@ -160,10 +160,12 @@ class CudaEvaluator:
     """GPU sensor update. Constructor uploads the map once (cuda_evaluator.cu:21-59)."""
 
     def __init__(self, map: CudaSubVoxelMap, per_point: bool = False, a_hit: float = 0.9, a_range: float = 0.1,
-                 a_max: float = 0.0, max_range: float = 100.0, device: int = 0):
+                 a_max: float = 0.0, max_range: float = 100.0, device: int = 0, neg_policy: int = capi.NEG_MISS):
+        """neg_policy (not a reference argument): capi.NEG_MISS (default) or capi.NEG_SATURATE_LIKE_REF_GPU, which
+        reproduces the reference CUDA build's handling of lookups below map.min bit for bit (tsdfloc.h)."""
         self._lib = capi.load_library()
         self._ctx = C.c_void_p()
-        prm = capi.Params(a_hit, a_range, a_max, max_range, int(per_point), 0)
+        prm = capi.Params(a_hit, a_range, a_max, max_range, int(per_point), int(neg_policy))
         desc = map.coef()
         occ = np.ascontiguousarray(map.rawGridOcc(), dtype=np.int32)
         data = np.ascontiguousarray(map.rawData(), dtype=np.float32)
@@ -293,6 +295,20 @@ class CudaEvaluator:
 
     def kernel_launches(self) -> int:
         return int(self._lib.tsdfloc_kernel_launches(self._ctx))
+
+    def tune(self, knob: int, value: int) -> None:
+        """Test / tuning hook (tsdfloc_tune): every setting produces the same bits."""
+        capi.check(self._lib, self._ctx, self._lib.tsdfloc_tune(self._ctx, int(knob), int(value)))
+
+    def division_mode(self):
+        """(mode, open brackets): what tsdfloc_create proved for the map's resolution (capi.DIV_*)."""
+        n = C.c_uint64(0)
+        return int(self._lib.tsdfloc_division_mode(self._ctx, C.byref(n))), int(n.value)
+
+    def eval_stats(self):
+        st = (C.c_uint64 * 4)()
+        capi.check(self._lib, self._ctx, self._lib.tsdfloc_eval_stats(self._ctx, st))
+        return dict(blocks=int(st[0]), folded=int(st[1]), tie_folds=int(st[2]), redone=int(st[3]))
 
     def close(self) -> None:
         if getattr(self, "_ctx", None):
