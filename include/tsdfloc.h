@@ -120,6 +120,17 @@ int tsdfloc_map_from_chunks(const int32_t* chunk_pos, const uint32_t* chunk_data
  * message of a failure via tsdfloc_last_error(NULL). Fewer than 16,384 chunks (16 GB of words). */
 int tsdfloc_map_from_chunks_gpu(const int32_t* chunk_pos, const uint32_t* chunk_data, uint64_t n_chunks, float sigma, int device,
                                 tsdfloc_host_map** out);
+/* createTSDFMap + the CudaEvaluator constructor in one step, on the device: the chunk words go to `device`, the bricks are
+ * built there and become the evaluation context's voxel array WITHOUT visiting the host (only the brick table, 4 B per 1 m
+ * cell, is read back to be laid out as the padded table). The free-space points stay on the device too: tsdfloc_init_particles
+ * with TSDFLOC_INIT_FREE_MAP and free_map == NULL samples from them. Same voxels, bit for bit, as tsdfloc_map_from_chunks ->
+ * tsdfloc_create. Replaces map_util.h:17-154 followed by src/cuda/cuda_evaluator.cu:21-59. */
+int tsdfloc_create_from_chunks(const int32_t* chunk_pos, const uint32_t* chunk_data, uint64_t n_chunks, float sigma,
+                               const tsdfloc_params* params, int device, tsdfloc_ctx** out);
+/* Geometry of the map a ctx evaluates against (coef() of the reference's map object). */
+int tsdfloc_map_desc_of(const tsdfloc_ctx* ctx, tsdfloc_map_desc* desc);
+/* Device pointer to / number of the free-space points a ctx created by tsdfloc_create_from_chunks keeps (NULL / 0 otherwise). */
+int tsdfloc_free_map_device(const tsdfloc_ctx* ctx, const float** d_points, uint64_t* n_points);
 /* The free-space points of a map built by tsdfloc_map_from_chunks[_gpu]: *n points x 3 fp32 (NULL / 0 for other maps). */
 const float* tsdfloc_map_free_points(const tsdfloc_host_map* m, uint64_t* n);
 /* TSDF (mm) -> likelihood^3 LUT value and the value for unmapped space, createTSDFMap's transform
@@ -168,6 +179,65 @@ int tsdfloc_resample_particles(tsdfloc_ctx* ctx, const float* particles, uint64_
  * idx (optional): n*p uint32, particle-major. hits (optional): n uint32. raw_weights (optional): n un-normalised. */
 int tsdfloc_debug_eval(tsdfloc_ctx* ctx, const float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],
                        uint32_t* idx, uint32_t* hits, float* raw_weights);
+
+/* ---- .mcl snapshot files ---------------------------------------------------------------------------------------
+ * MCLFile::read / MCLFile::write (include/tsdf_localization/util/mcl_file.h:21-32, src/util/mcl_file.cpp:14-113): the text
+ * fixture format of one scan (points + rings), a particle set, the scanner->robot transform and a reference pose
+ * (x y z q1 q2 q3 q4). Written files are byte-identical to the reference's. Failures: TSDFLOC_E_STATE when the file cannot
+ * be opened / written, TSDFLOC_E_BAD_ARG when its content does not parse; text via tsdfloc_last_error(NULL) (the reference's
+ * exception messages). Pure host code. */
+typedef struct tsdfloc_mcl tsdfloc_mcl;
+int tsdfloc_mcl_read(const char* path, tsdfloc_mcl** out);
+void tsdfloc_mcl_free(tsdfloc_mcl* m);
+uint64_t tsdfloc_mcl_n_points(const tsdfloc_mcl* m);
+uint64_t tsdfloc_mcl_n_particles(const tsdfloc_mcl* m);
+const float* tsdfloc_mcl_points(const tsdfloc_mcl* m);      /* n_points x 3 */
+const int32_t* tsdfloc_mcl_rings(const tsdfloc_mcl* m);     /* n_points */
+const float* tsdfloc_mcl_particles(const tsdfloc_mcl* m);   /* n_particles x 7 */
+const float* tsdfloc_mcl_tf(const tsdfloc_mcl* m);          /* 16 */
+const float* tsdfloc_mcl_pose(const tsdfloc_mcl* m);        /* 7 */
+int tsdfloc_mcl_write(const char* path, const float* points, const int32_t* rings, uint64_t n_points, const float* particles,
+                      uint64_t n_particles, const float tf[16], const float pose7[7]);
+
+/* ---- the reference's other resamplers --------------------------------------------------------------------------
+ * mcl_3d selects its resampler at run time (src/mcl_3d.cpp:243-263); the compiled-in default is ResidualSystematic (:765),
+ * the dynamic-reconfigure default Residual (cfg/MCL.cfg:54). Both are SEQUENTIAL recurrences over the weights with no exact
+ * parallel form, so they are split: the recurrence runs on the host over 4 B per particle and yields RUNS (how many copies
+ * of which particle follow each other in the output); the device expands the runs, so the 28 B particles stay where the
+ * sensor update left them. Parents are identical to the reference's given the same weights and the same random draws. */
+enum tsdfloc_resample_method
+{
+  TSDFLOC_RESAMPLE_SYSTEMATIC = 0,          /* SystematicResampler          novel_resampling.h:38-74   */
+  TSDFLOC_RESAMPLE_RESIDUAL = 1,            /* ResidualResampler            novel_resampling.h:9-36    */
+  TSDFLOC_RESAMPLE_RESIDUAL_SYSTEMATIC = 2  /* ResidualSystematicResampler  novel_resampling.h:76-104  */
+};
+/* One draw of the reference's std::uniform_int_distribution<size_t>(0, n - 1)(*m_generator_ptr) (novel_resampling.h:14,21). */
+typedef uint64_t (*tsdfloc_index_draw_fn)(void* user);
+
+/* Host half of ResidualSystematicResampler::resample (:86-99): counts[m] = copies of particle m, from the fp32 remainder
+ * recurrence started at u0 (the reference's uniform_real_distribution<float>(0, 1) draw). weights[m * stride]; *total = sum
+ * of the counts (about n). Pure host code. TSDFLOC_E_BAD_ARG for a negative / NaN weight (undefined in the reference). */
+int tsdfloc_residual_systematic_counts(const float* weights, uint64_t stride, uint64_t n, float u0, uint32_t* counts, uint64_t* total);
+/* Host half of ResidualResampler::resample (:14-31): calls draw() until n output slots are filled; run k copies particle
+ * run_parent[k] run_count[k] times (ceil(w * n), cut to the slots left). run_cap >= n always suffices. max_draws bounds the
+ * loop (the reference spins forever on all-zero weights): TSDFLOC_E_CAPACITY when it is hit. Pure host code. */
+int tsdfloc_residual_runs(const float* weights, uint64_t stride, uint64_t n, tsdfloc_index_draw_fn draw, void* user, uint64_t max_draws,
+                          uint32_t* run_parent, uint32_t* run_count, uint64_t run_cap, uint64_t* n_runs, uint64_t* n_draws);
+/* Device half: expands runs over the particle set left on the device by tsdfloc_sensor_update / tsdfloc_resample*.
+ * run_parent == NULL: run r copies particle r (ResidualSystematic). Outputs as tsdfloc_resample_systematic. */
+int tsdfloc_resample_expand(tsdfloc_ctx* ctx, const uint32_t* run_parent, const uint32_t* run_count, uint64_t n_runs, float* particles_out,
+                            uint64_t cap, uint64_t* n_out, uint32_t* parents);
+/* The same kernel on caller-owned device memory (multi-GPU drivers): d_run_off = n_runs + 1 exclusive prefix sums of the run
+ * counts; output slots [first_out, first_out + count_out) go to d_particles_out (and the same slice of every peer buffer). */
+int tsdfloc_resample_expand_device(tsdfloc_ctx* ctx, const float* d_particles, const uint32_t* d_run_off, const uint32_t* d_run_parent,
+                                   uint64_t n_runs, uint64_t first_out, uint64_t count_out, float* d_particles_out,
+                                   float* const* d_out_peers, uint32_t n_peers, uint32_t* d_parents, void* stream);
+/* Resampler::resample(ParticleCloud&) for any of the three methods (resampling/resampler.h:26). particles != NULL: a weighted
+ * cloud in host memory (n x 7 fp32); particles == NULL: the set the last sensor update left on the device (n ignored).
+ * u: the method's uniform_real draw (Systematic: in [0, 1/n); ResidualSystematic: in [0, 1); unused by Residual);
+ * draw/user: the index draws of Residual (NULL otherwise). */
+int tsdfloc_resample(tsdfloc_ctx* ctx, int method, const float* particles, uint64_t n, float u, tsdfloc_index_draw_fn draw, void* user,
+                     float* particles_out, uint64_t cap, uint64_t* n_out, uint32_t* parents);
 
 /* ---- (B) device-pointer stage calls ---------------------------------------------------------------------
  * All pointers are device pointers on ctx's device; `stream` is a cudaStream_t passed as void* (NULL = the

@@ -123,6 +123,14 @@ struct SeededSystematic : public SystematicResampler
 {
   void seed(uint32_t s) { m_generator_ptr.reset(new std::mt19937(s)); }
 };
+struct SeededResidual : public ResidualResampler
+{
+  void seed(uint32_t s) { m_generator_ptr.reset(new std::mt19937(s)); }
+};
+struct SeededResidualSystematic : public ResidualSystematicResampler
+{
+  void seed(uint32_t s) { m_generator_ptr.reset(new std::mt19937(s)); }
+};
 
 struct MapHandle
 {
@@ -142,6 +150,24 @@ thread_local std::string g_last_error;
 }  // namespace tsdf_localization
 
 using namespace tsdf_localization;
+
+// ResidualSystematicResampler::resample (novel_resampling.h:79-103) / ResidualResampler::resample (:12-34), verbatim, with a
+// seeded generator. method: 1 = Residual, 2 = ResidualSystematic. u_out: the uniform(0,1) draw of ResidualSystematic.
+template <typename R>
+static uint64_t run_seeded_resampler(const float* particles, uint64_t n, uint32_t seed, float* particles_out, uint64_t cap)
+{
+  ParticleCloud cloud;
+  cloud.particles().resize(n);
+  std::memcpy(static_cast<void*>(cloud.particles().data()), particles, n * sizeof(Particle));
+  R rs;
+  rs.seed(seed);
+  Resampler& base = rs;
+  base.resample(cloud);
+  const uint64_t m = cloud.size();
+  const uint64_t c = m < cap ? m : cap;
+  if (particles_out && c) std::memcpy(particles_out, static_cast<void*>(cloud.particles().data()), c * sizeof(Particle));
+  return m;
+}
 
 extern "C"
 {
@@ -454,6 +480,28 @@ uint64_t ref_systematic_resample(const float* particles, uint64_t n, uint32_t se
   return m;
 }
 
+uint64_t ref_resample_method(int method, const float* particles, uint64_t n, uint32_t seed, float* particles_out, uint64_t cap, float* u_out)
+{
+  if (u_out)
+  {
+    std::mt19937 gen(seed);
+    std::uniform_real_distribution<FLOAT_T> uniform_distribution(0.0, 1.0);
+    *u_out = uniform_distribution(gen);
+  }
+  if (method == 1) return run_seeded_resampler<SeededResidual>(particles, n, seed, particles_out, cap);
+  if (method == 2) return run_seeded_resampler<SeededResidualSystematic>(particles, n, seed, particles_out, cap);
+  return ~0ull;
+}
+
+// The first `count` draws of std::uniform_int_distribution<size_t>(0, n - 1) on std::mt19937(seed): the index stream
+// ResidualResampler::resample consumes (novel_resampling.h:14,21), for feeding restatements the same draws.
+void ref_uniform_index_draws(uint32_t seed, uint64_t n, uint64_t count, uint64_t* out)
+{
+  std::mt19937 gen(seed);
+  std::uniform_int_distribution<size_t> uniform_distribution(0, n - 1);
+  for (uint64_t i = 0; i < count; ++i) out[i] = uniform_distribution(gen);
+}
+
 // MCLFile::write / MCLFile::read (src/util/mcl_file.cpp:14-113), verbatim. pose7 = x y z q1 q2 q3 q4.
 int ref_mcl_write(const char* name, const float* points, const int32_t* rings, uint64_t p, const float* particles, uint64_t n,
                   const float tf[16], const float pose7[7])
@@ -553,6 +601,22 @@ uint64_t ref_gpu_systematic_resample(const float* particles, uint64_t n, uint32_
     const uint64_t c = m < cap ? m : cap;
     if (particles_out && c) std::memcpy(particles_out, static_cast<void*>(cloud.particles().data()), c * sizeof(Particle));
     return m;
+  }
+  catch (std::exception& ex)
+  {
+    g_last_error = ex.what();
+    return ~0ull;
+  }
+}
+// GpuResidualResampler / GpuResidualSystematicResampler (product) through the reference's Resampler interface.
+uint64_t ref_gpu_resample_method(int method, const float* particles, uint64_t n, uint32_t seed, float* particles_out, uint64_t cap)
+{
+  try
+  {
+    if (method == 1) return run_seeded_resampler<GpuResidualResampler>(particles, n, seed, particles_out, cap);
+    if (method == 2) return run_seeded_resampler<GpuResidualSystematicResampler>(particles, n, seed, particles_out, cap);
+    g_last_error = "unknown method";
+    return ~0ull;
   }
   catch (std::exception& ex)
   {

@@ -366,6 +366,52 @@ uint64_t oracle_systematic_resample(const float* w, uint64_t n, float u0, uint32
   return out;
 }
 
+/* ---- residual-systematic and residual resampling -------------------------------------------------------- */
+
+uint64_t oracle_residual_systematic_resample(const float* w, uint64_t n, float u0, uint32_t* parents_out, uint64_t cap)
+{
+  /* novel_resampling.h:86-99. `auto u` and `auto temp` are float (size_t * float - float), `temp + 1.0` is double,
+   * `u = o - temp` converts the size_t to float. */
+  float u = u0;
+  uint64_t out = 0;
+  for (uint64_t mi = 0; mi < n; ++mi)
+  {
+    float prod = (float)n * w[mi];
+    float temp = prod - u;
+    uint64_t o = (uint64_t)((double)temp + 1.0);
+    u = (float)o - temp;
+    for (uint64_t k = 0; k < o; ++k)
+    {
+      if (parents_out && out < cap) parents_out[out] = (uint32_t)mi;
+      ++out;
+    }
+  }
+  return out;
+}
+
+uint64_t oracle_residual_resample(const float* w, uint64_t n, const uint64_t* draws, uint64_t n_draws, uint32_t* parents_out,
+                                  uint64_t* draws_used)
+{
+  /* novel_resampling.h:14-31 with the index draws handed in (the reference takes them from
+   * std::uniform_int_distribution<size_t>(0, n-1)). expected_insertions and insertions are float; the copy loop compares the
+   * size_t counter with that float. Returns the output length (n, or less if the draws ran out). */
+  uint64_t out = 0, d = 0;
+  while (out < n && d < n_draws)
+  {
+    uint64_t idx = draws[d++];
+    float expected = w[idx] * (float)n;
+    uint64_t left_i = n - out;
+    float insertions = expected <= (float)left_i ? expected : (float)left_i;
+    for (uint64_t k = 0; (float)k < insertions; ++k)
+    {
+      if (parents_out) parents_out[out] = (uint32_t)idx;
+      ++out;
+    }
+  }
+  if (draws_used) *draws_used = d;
+  return out;
+}
+
 /* ---- scan reduction ---------------------------------------------------------------------------------- */
 
 typedef struct red_key

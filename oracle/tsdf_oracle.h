@@ -103,6 +103,15 @@ int oracle_evaluate(const oracle_map* m, const oracle_params* prm, float* partic
  * from N); at most cap parents are written. */
 uint64_t oracle_systematic_resample(const float* weights, uint64_t n, float u0, uint32_t* parents_out, uint64_t cap);
 
+/* ResidualSystematicResampler::resample, novel_resampling.h:76-104, with the uniform(0,1) draw u0 handed in. Returns the
+ * output length; parents_out receives min(length, cap) source indices. */
+uint64_t oracle_residual_systematic_resample(const float* weights, uint64_t n, float u0, uint32_t* parents_out, uint64_t cap);
+
+/* ResidualResampler::resample, novel_resampling.h:9-36, with the uniform index draws handed in. parents_out: n entries.
+ * Returns the output length (n unless the draws ran out); *draws_used = draws consumed. */
+uint64_t oracle_residual_resample(const float* weights, uint64_t n, const uint64_t* draws, uint64_t n_draws, uint32_t* parents_out,
+                                  uint64_t* draws_used);
+
 
 /* Scan reduction of TSDFEvaluator::evaluateParticles, src/evaluation/tsdf_evaluator.cpp:304-376: drop points nearer than
  * 1 m (:317-322), keep per (ring, reduction cell) the FIRST point in cloud order (unordered_set insert of SortClass keyed

@@ -72,6 +72,10 @@ class Oracle:
                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_systematic_resample.restype = C.c_uint64
         L.oracle_systematic_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_uint64]
+        L.oracle_residual_systematic_resample.restype = C.c_uint64
+        L.oracle_residual_systematic_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_uint64]
+        L.oracle_residual_resample.restype = C.c_uint64
+        L.oracle_residual_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
         L.oracle_motion_model.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_motion_apply.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.oracle_reduce_scan.restype = C.c_int64
@@ -205,6 +209,25 @@ class Oracle:
         return m, parents[:min(m, cap)]
 
 
+    def residual_systematic_resample(self, weights, u0, cap=None):
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        n = w.shape[0]
+        cap = cap or (2 * n + 64)
+        parents = np.empty(cap, dtype=np.uint32)
+        m = int(self.lib.oracle_residual_systematic_resample(_fp(w), n, C.c_float(u0), _fp(parents), cap))
+        return m, parents[:min(m, cap)]
+
+    def residual_resample(self, weights, draws):
+        """(output length, parents, draws consumed) of the Residual resampler fed the given index draws."""
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        d = np.ascontiguousarray(draws, dtype=np.uint64)
+        n = w.shape[0]
+        parents = np.empty(n, dtype=np.uint32)
+        used = C.c_uint64(0)
+        m = int(self.lib.oracle_residual_resample(_fp(w), n, _fp(d), d.shape[0], _fp(parents), C.byref(used)))
+        return m, parents[:m], int(used.value)
+
+
 def ref_lib_path(threads: int | None = None) -> Path:
     name = "libtsdf_ref.so" if threads is None else f"libtsdf_ref_t{threads}.so"
     return ORACLE_DIR / "_ref" / name
@@ -229,6 +252,8 @@ class Ref:
         if shim:
             L.ref_gpu_systematic_resample.restype = C.c_uint64
             L.ref_gpu_systematic_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64]
+            L.ref_gpu_resample_method.restype = C.c_uint64
+            L.ref_gpu_resample_method.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64]
         L.ref_last_error.restype = C.c_char_p
         L.ref_omp_threads.restype = C.c_uint
         L.ref_map_create.restype = C.c_void_p
@@ -254,6 +279,10 @@ class Ref:
         L.ref_pose_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
         L.ref_systematic_resample.restype = C.c_uint64
         L.ref_systematic_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.ref_resample_method.restype = C.c_uint64
+        L.ref_resample_method.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.ref_uniform_index_draws.restype = None
+        L.ref_uniform_index_draws.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
 
         if not shim:
             L.ref_reduce_scan.restype = C.c_int64
@@ -385,6 +414,32 @@ class Ref:
         pts = np.ascontiguousarray(points, dtype=np.float32)
         out = np.empty(mats.shape[0], dtype=np.float32)
         self.lib.ref_pose_weights(e, _fp(mats), mats.shape[0], _fp(pts), pts.shape[0], _fp(out))
+        return out
+
+    def resample_method(self, method, particles, seed, cap=None):
+        """The verbatim ResidualResampler (method 1) / ResidualSystematicResampler (method 2) with a seeded generator:
+        (length, particles out, the uniform(0,1) draw of method 2)."""
+        ps = np.ascontiguousarray(particles, dtype=np.float32)
+        n = ps.shape[0]
+        cap = cap or (2 * n + 64)
+        out = np.empty((cap, 7), dtype=np.float32)
+        u = C.c_float(0)
+        m = int(self.lib.ref_resample_method(method, _fp(ps), n, seed, _fp(out), cap, C.byref(u)))
+        return m, out[:min(m, cap)], u.value
+
+    def gpu_resample_method(self, method, particles, seed, cap=None):
+        ps = np.ascontiguousarray(particles, dtype=np.float32)
+        n = ps.shape[0]
+        cap = cap or (2 * n + 64)
+        out = np.empty((cap, 7), dtype=np.float32)
+        m = int(self.lib.ref_gpu_resample_method(method, _fp(ps), n, seed, _fp(out), cap))
+        if m == 2 ** 64 - 1:
+            raise RuntimeError(self.last_error())
+        return m, out[:min(m, cap)]
+
+    def uniform_index_draws(self, seed, n, count):
+        out = np.empty(count, dtype=np.uint64)
+        self.lib.ref_uniform_index_draws(seed, n, count, _fp(out))
         return out
 
     def systematic_resample(self, particles, seed, cap=None):

@@ -323,21 +323,66 @@ def test_spatial_evaluation_order_changes_nothing():
     assert results[1][4] > results[0][4]            # the sort kernels really ran
 
 
-def test_gpu_map_ingest_equals_host_ingest():
-    """tsdfloc_map_from_chunks_gpu against tsdfloc_map_from_chunks (which tests/test_map_ingest.py pins against the reference's
-    createTSDFMap): geometry, brick table, voxels and free-space points byte-identical, incl. negative chunk coordinates and a
-    chunk order that differs from the name order."""
-    from test_map_ingest import synthetic_chunks
+def test_gpu_map_ingest_equals_reference_createTSDFMap():
+    """tsdfloc_map_from_chunks_gpu against the UNMODIFIED reference createTSDFMap (map_util.h:17-154, compiled into oracle/_ref
+    over an in-memory HighFive stand-in) DIRECTLY: geometry, brick table, voxels and free-space points byte-identical, incl.
+    negative chunk coordinates and a chunk order that differs from the name order. The host ingest must agree as well."""
+    from oracle_lib import Ref, ref_available
+    from test_map_ingest import assert_same_map, synthetic_chunks
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    ref = Ref()
     for chunk_pos, centre in (([(0, 0, 0)], (1000.0, 2000.0, 500.0)),
                               ([(-1, 0, 0), (0, 0, -1), (0, 0, 0), (-1, -1, -1), (1, 0, 0)], (1000.0, 2000.0, 500.0)),
                               ([(2, 1, 0), (10, 1, 0), (3, 1, 0)], (9000.0, 6000.0, 2000.0))):
         data = synthetic_chunks(chunk_pos, seed=len(chunk_pos), centre_mm=centre)
-        host = CudaSubVoxelMap.from_chunks(chunk_pos, data, 0.1)
+        h, free_ref = ref.create_tsdf_map(chunk_pos, data, 0.1)
         gpu = CudaSubVoxelMap.from_chunks(chunk_pos, data, 0.1, device=0)
-        a, b = host.coef(), gpu.coef()
-        assert bytes(a) == bytes(b)
-        assert np.array_equal(host.rawGridOcc(), gpu.rawGridOcc())
-        assert host.rawData().tobytes() == gpu.rawData().tobytes() and host.rawData().size > 0
-        assert host.free_map().tobytes() == gpu.free_map().tobytes() and len(host.free_map()) > 0
+        assert_same_map(ref, h, gpu)
+        assert gpu.rawData().size > 0 and len(free_ref) > 0
+        assert gpu.free_map().tobytes() == free_ref.tobytes()
+        host = CudaSubVoxelMap.from_chunks(chunk_pos, data, 0.1)
+        assert bytes(host.coef()) == bytes(gpu.coef()) and host.rawData().tobytes() == gpu.rawData().tobytes()
+        ref.map_destroy(h)
     with pytest.raises(ValueError):
         CudaSubVoxelMap.from_chunks([(0, 0, 0), (0, 0, 0)], np.zeros((2, 64 ** 3), dtype=np.uint32), device=0)
+
+
+def test_device_resident_ingest_feeds_the_evaluator(oracle):
+    """tsdfloc_create_from_chunks: chunks -> bricks -> evaluation context on the device, the voxels never visiting the host.
+    Checked against the reference's createTSDFMap arrays: an evaluator built from THOSE arrays (tsdfloc_create) and the oracle
+    on those arrays give the same flat indices, hit counts and raw weights, bit for bit; the free-space points kept on the
+    device initialise the same particles as the reference's list handed in from the host."""
+    from oracle_lib import Ref, ref_available
+    from test_map_ingest import synthetic_chunks
+    from tsdf_localization_b200 import ParticleCloud
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    ref = Ref()
+    chunk_pos = [(-1, 0, 0), (0, 0, -1), (0, 0, 0), (-1, -1, -1), (1, 0, 0)]
+    data = synthetic_chunks(chunk_pos, seed=5)
+    h, free_ref = ref.create_tsdf_map(chunk_pos, data, 0.1)
+    coef, occ, vox = ref.map_arrays(h)
+    resident = CudaEvaluator.from_chunks(chunk_pos, data, 0.1)
+    uploaded = CudaEvaluator(CudaSubVoxelMap.from_arrays(coef, occ, vox))
+    assert bytes(resident.map_desc()) == bytes(uploaded.map_desc())
+    assert resident.free_map_size() == len(free_ref) and uploaded.free_map_size() == 0
+    om = oracle.map_from_arrays(coef, occ, vox)
+    rng = np.random.default_rng(2)
+    # a "scan" of points on the sphere the chunks encode (radius 2.5 m around (1, 2, 0.5)), seen from poses near its centre
+    d = rng.normal(size=(3000, 3))
+    pts = (2.5 * d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    ps = np.zeros((96, 7), dtype=np.float32)
+    ps[:, :3] = np.array([1.0, 2.0, 0.5]) + rng.normal(scale=0.05, size=(96, 3))
+    ps[:, 3:6] = rng.normal(scale=0.05, size=(96, 3))
+    want = oracle.evaluate(om, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF, want_idx=True)
+    assert want["hits"].sum() > 0.5 * want["idx"].size
+    for e in (resident, uploaded):
+        idx, hits, raw = e.debug_eval(ps, pts, syn.IDENTITY_TF)
+        assert np.array_equal(idx, want["idx"]) and np.array_equal(hits, want["hits"]) and raw.tobytes() == want["raw"].tobytes()
+    a = ParticleCloud(resident, seed=9).initialize(5000, (0, 0, 0, 0, 0, 0), (0, 0, 0, 0.1, 0.1, 3.0), mode=capi.INIT_FREE_MAP)
+    b = ParticleCloud(uploaded, seed=9).initialize(5000, (0, 0, 0, 0, 0, 0), (0, 0, 0, 0.1, 0.1, 3.0), mode=capi.INIT_FREE_MAP, free_map=free_ref)
+    assert a.tobytes() == b.tobytes()
+    resident.close()
+    uploaded.close()
+    ref.map_destroy(h)

@@ -100,6 +100,27 @@ def test_gpu_resampler_subclass_matches_reference_resampler(shim, small_map, n):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("method", [1, 2], ids=["residual", "residual_systematic"])
+@pytest.mark.parametrize("n", [500, 4096, 100000])
+def test_gpu_residual_resamplers_match_reference_classes(shim, small_map, n, method):
+    """GpuResidualResampler / GpuResidualSystematicResampler (shim/tsdfloc_shim.h: host recurrence + device expansion) through
+    the reference's Resampler interface against the reference's own ResidualResampler / ResidualSystematicResampler
+    (novel_resampling.h:9-36, 76-104 — the methods a default-configured node selects) with equal seeds: identical outputs."""
+    ev = shim.eval_create(small_map)
+    rng = np.random.default_rng(n + method)
+    ps = np.zeros((n, 7), dtype=np.float32)
+    ps[:, :6] = rng.normal(size=(n, 6))
+    w = rng.exponential(size=n) ** 2
+    ps[:, 6] = (w / w.sum()).astype(np.float32)
+    for seed in (1, 7):
+        m_ref, out_ref, _ = shim.resample_method(method, ps, seed)
+        m_gpu, out_gpu = shim.gpu_resample_method(method, ps, seed)
+        assert m_gpu == m_ref
+        assert np.array_equal(out_gpu, out_ref)
+    shim.eval_destroy(ev)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("near", [0, 400])
 def test_reference_evaluateParticles_gpu_branch_matches_its_cpu_branch(shim, small_map, near):
     """TSDFEvaluatorB200::evaluateParticles (GPU scan reduction + evaluation, the reduced scan never leaves the device)

@@ -38,7 +38,7 @@ def _stale(target: Path, sources) -> bool:
 def build_variant(name: str, defs, verbose: bool = False) -> Path:
     """Tuning experiments: lib/libtsdfloc_<name>.so built with extra -D flags (select with TSDFLOC_LIB=<path>)."""
     out = LIB.parent / f"libtsdfloc_{name}.so"
-    sources = [CSRC / "tsdfloc_api.cu", CSRC / "host_map.cpp", CSRC / "host_motion.cpp"]
+    sources = [CSRC / "tsdfloc_api.cu", CSRC / "host_map.cpp", CSRC / "host_motion.cpp", CSRC / "host_resample.cpp"]
     cmd = [_nvcc(), "-ccbin", "/usr/bin/g++", *NVCC_FLAGS, *defs, *(["-Xptxas", "-v"] if verbose else []), "-o", str(out), *map(str, sources)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -50,8 +50,8 @@ def build_variant(name: str, defs, verbose: bool = False) -> Path:
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source of the package for sm_100a into lib/libtsdfloc.so."""
-    sources = [CSRC / "tsdfloc_api.cu", CSRC / "host_map.cpp", CSRC / "host_motion.cpp"]
-    deps = sources + [CSRC / "tsdfloc_kernels.cuh", CSRC / "tsdfloc_eval2.cuh", CSRC / "tsdfloc_device.cuh", CSRC / "tsdfloc_reduce.cuh",
+    sources = [CSRC / "tsdfloc_api.cu", CSRC / "host_map.cpp", CSRC / "host_motion.cpp", CSRC / "host_resample.cpp"]
+    deps = sources + [CSRC / "tsdfloc_kernels.cuh", CSRC / "tsdfloc_eval.cuh", CSRC / "tsdfloc_device.cuh", CSRC / "tsdfloc_reduce.cuh",
                       CSRC / "tsdfloc_motion.cuh", CSRC / "tsdfloc_sort.cuh", CSRC / "tsdfloc_multi.inc", CSRC / "tsdfloc_ingest.inc", CSRC / "tsdfloc_host_map.h", ROOT / "include" / "tsdfloc.h"]
     if not force and not _stale(LIB, deps):
         return LIB

@@ -16,6 +16,8 @@ INIT_NORMAL, INIT_UNIFORM, INIT_FREE_MAP = range(3)
 NEG_MISS, NEG_SATURATE_LIKE_REF_GPU = range(2)
 TUNE_SPATIAL_ORDER, TUNE_EVAL_PAIRING, TUNE_DIVISION = range(3)
 DIV_IEEE, DIV_THREE, DIV_BRACKET = range(3)
+RESAMPLE_SYSTEMATIC, RESAMPLE_RESIDUAL, RESAMPLE_RESIDUAL_SYSTEMATIC = range(3)
+INDEX_DRAW_FN = C.CFUNCTYPE(C.c_uint64, C.c_void_p)
 
 
 class LibraryNotBuilt(RuntimeError):
@@ -67,6 +69,19 @@ SIGNATURES = {
     "tsdfloc_map_from_chunks": (C.c_int, [_vp, _vp, _u64, C.c_float, C.POINTER(_vp)]),
     "tsdfloc_map_from_chunks_gpu": (C.c_int, [_vp, _vp, _u64, C.c_float, C.c_int, C.POINTER(_vp)]),
     "tsdfloc_map_free_points": (_fp, [_vp, C.POINTER(_u64)]),
+    "tsdfloc_create_from_chunks": (C.c_int, [_vp, _vp, _u64, C.c_float, C.POINTER(Params), C.c_int, C.POINTER(_vp)]),
+    "tsdfloc_map_desc_of": (C.c_int, [_vp, C.POINTER(MapDesc)]),
+    "tsdfloc_free_map_device": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_u64)]),
+    "tsdfloc_mcl_read": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "tsdfloc_mcl_free": (None, [_vp]),
+    "tsdfloc_mcl_n_points": (_u64, [_vp]),
+    "tsdfloc_mcl_n_particles": (_u64, [_vp]),
+    "tsdfloc_mcl_points": (_fp, [_vp]),
+    "tsdfloc_mcl_rings": (_i32p, [_vp]),
+    "tsdfloc_mcl_particles": (_fp, [_vp]),
+    "tsdfloc_mcl_tf": (_fp, [_vp]),
+    "tsdfloc_mcl_pose": (_fp, [_vp]),
+    "tsdfloc_mcl_write": (C.c_int, [C.c_char_p, _vp, _vp, _u64, _vp, _u64, _fp, _fp]),
     "tsdfloc_likelihood_value": (C.c_float, [C.c_float, C.c_float]),
     "tsdfloc_likelihood_init": (C.c_float, [C.c_float]),
     "tsdfloc_create": (C.c_int, [C.POINTER(MapDesc), _vp, _vp, C.POINTER(Params), C.c_int, C.POINTER(_vp)]),
@@ -74,6 +89,11 @@ SIGNATURES = {
     "tsdfloc_sensor_update": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _fp, _fp]),
     "tsdfloc_resample_systematic": (C.c_int, [_vp, C.c_float, _vp, _u64, C.POINTER(_u64), _vp]),
     "tsdfloc_resample_particles": (C.c_int, [_vp, _vp, _u64, C.c_float, _vp, _u64, C.POINTER(_u64), _vp]),
+    "tsdfloc_residual_systematic_counts": (C.c_int, [_vp, _u64, _u64, C.c_float, _vp, C.POINTER(_u64)]),
+    "tsdfloc_residual_runs": (C.c_int, [_vp, _u64, _u64, INDEX_DRAW_FN, _vp, _u64, _vp, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
+    "tsdfloc_resample_expand": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _u64, C.POINTER(_u64), _vp]),
+    "tsdfloc_resample_expand_device": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp, C.POINTER(_vp), C.c_uint32, _vp, _vp]),
+    "tsdfloc_resample": (C.c_int, [_vp, C.c_int, _vp, _u64, C.c_float, INDEX_DRAW_FN, _vp, _vp, _u64, C.POINTER(_u64), _vp]),
     "tsdfloc_cdf_device": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
     "tsdfloc_debug_eval": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _fp, _vp, _vp, _vp]),
     "tsdfloc_set_scan_device": (C.c_int, [_vp, _vp, _u64, _vp]),

@@ -12,6 +12,9 @@
 #include "tsdfloc_sort.cuh"
 
 #include <algorithm>
+#include <cctype>
+#include <cerrno>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -57,6 +60,8 @@ struct tsdfloc_ctx
   // map
   int32_t* d_table = nullptr;
   float* d_voxels = nullptr;
+  float* d_free_map = nullptr;   // free-space points of a map ingested on the device (tsdfloc_create_from_chunks)
+  uint64_t n_free_map = 0;
 
   // scan
   DevBuf d_xyz_stage, d_pts;
@@ -93,6 +98,9 @@ struct tsdfloc_ctx
   int sort_mode = -1;       // -1: automatic (map larger than L2 and enough particles); 0 / 1: tsdfloc_tune(TSDFLOC_TUNE_SPATIAL_ORDER)
   size_t l2_bytes = 0;
   SortArgs sort_args{};
+
+  // run expansion (Residual / ResidualSystematic resamplers)
+  DevBuf d_run_off, d_run_parent, d_wpack;
 
   // motion update
   DevBuf d_draws;
@@ -263,9 +271,10 @@ void launch_eval_mode(const tsdfloc_ctx* c, int div, const EvalArgs& a, cudaStre
     k_eval<BS, kDivIeee, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
 }
 
-// Point pairs double the number of warps: taken while particle pairs would leave the machine short of kPairWaves full waves
-// of one-warp CTAs (32 per SM). Measured on B200, profiles/r02_eval_pairing.md.
-constexpr uint32_t kPairWaves = 2;
+// Point pairs double the number of warps but read the scan once per particle instead of once per pair (+15 % at full
+// occupancy): they win only while particle pairs would fill less than half of the machine's warp slots (32 one-warp CTAs per
+// SM). Measured on B200 (profiles/r02_eval_pairing.md): 500 particles x 131,072 points 1.24 -> 0.90 ms, 2,000: 1.36 -> 1.26,
+// 5,000 x 30,000: 0.50 = 0.50, 8,192: 2.80 vs 2.96, 65,536: 18.0 vs 21.2.
 
 void launch_eval(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s, bool dump)
 {
@@ -276,7 +285,7 @@ void launch_eval(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s, bool d
     if (div == kDivBracket && !c->bracket_ok) div = c->map.div_mode;   // never run an unproven mode
     if (div != kDivIeee && !c->three_ok) div = kDivIeee;
   }
-  bool pp = static_cast<uint64_t>((a.n_local + 1u) / 2u) < static_cast<uint64_t>(c->sm_count) * 32u * kPairWaves;
+  bool pp = static_cast<uint64_t>(a.n_local) < static_cast<uint64_t>(c->sm_count) * 32u;
   if (c->tune_shape == 1) pp = false;
   if (c->tune_shape == 2) pp = true;
   if (pp)
@@ -608,12 +617,26 @@ const char* tsdfloc_last_error(const tsdfloc_ctx* ctx) { return ctx ? ctx->err.c
 
 uint64_t tsdfloc_kernel_launches(const tsdfloc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const float* data, const tsdfloc_params* params, int device,
-                   tsdfloc_ctx** out)
+// Voxels that are already on the device (map ingested there): the ctx adopts the buffer (allocated with room for the miss
+// brick behind data_size) and the free-space points; value range of the payload for the summation planning.
+struct AdoptedVoxels
+{
+  float* d_voxels = nullptr;
+  float vmin = 0.0f, vmax = 0.0f;
+  bool finite = true;
+  float* d_free = nullptr;
+  uint64_t n_free = 0;
+};
+
+// in-brick offsets the index arithmetic can produce past a brick's end (sub coordinate == sub_dim): size of the miss brick
+static uint64_t miss_brick_size(const tsdfloc_map_desc* map) { return map->sub_dim * (1 + map->sub_dim + map->sub_dim_2) + 1; }
+
+static int create_impl(const tsdfloc_map_desc* map, const int32_t* grid_occ, const float* data, const AdoptedVoxels* adopt,
+                       const tsdfloc_params* params, int device, tsdfloc_ctx** out)
 {
   if (!out) return fail(nullptr, TSDFLOC_E_BAD_ARG, "out is NULL");
   *out = nullptr;
-  if (!map || !grid_occ || (!data && map->data_size)) return fail(nullptr, TSDFLOC_E_BAD_ARG, "map, grid_occ and data are required");
+  if (!map || !grid_occ || (!data && !adopt && map->data_size)) return fail(nullptr, TSDFLOC_E_BAD_ARG, "map, grid_occ and data are required");
   std::string why;
   if (!valid_desc(map, why)) return fail(nullptr, TSDFLOC_E_BAD_ARG, "invalid map description: " + why);
 
@@ -631,6 +654,11 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
   DeviceGuard guard(device);
   auto bail = [&](int code, const std::string& msg) {
     g_create_error = msg;
+    if (adopt)   // the caller still owns the adopted buffers when creation fails
+    {
+      c->d_voxels = nullptr;
+      c->d_free_map = nullptr;
+    }
     tsdfloc_destroy(c);
     return code;
   };
@@ -672,7 +700,7 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
   if (table_n >= (1ull << 31)) return bail(TSDFLOC_E_BAD_ARG, "padded brick table too large");
   const uint64_t sub_n = map->sub_dim * map->sub_dim * map->sub_dim;
   // miss brick: large enough for the largest in-brick offset the index arithmetic can produce (sub coordinate == sub_dim)
-  const uint64_t miss_n = map->sub_dim * (1 + map->sub_dim + map->sub_dim_2) + 1;
+  const uint64_t miss_n = miss_brick_size(map);
   const uint64_t miss_offset = map->data_size;
   if (miss_offset + miss_n + sub_n >= (1ull << 32)) return bail(TSDFLOC_E_BAD_ARG, "voxel array too large");
   std::vector<int32_t> table(table_n, static_cast<int32_t>(miss_offset));
@@ -693,9 +721,18 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
   (void)bricks;
   CU_CREATE(cudaMalloc(&c->d_table, sizeof(int32_t) * table_n), "cudaMalloc(brick table)");
   CU_CREATE(cudaMemcpy(c->d_table, table.data(), sizeof(int32_t) * table_n, cudaMemcpyHostToDevice), "upload brick table");
-  CU_CREATE(cudaMalloc(&c->d_voxels, sizeof(float) * (miss_offset + miss_n)), "cudaMalloc(voxels)");
-  if (map->data_size)
-    CU_CREATE(cudaMemcpy(c->d_voxels, data, sizeof(float) * map->data_size, cudaMemcpyHostToDevice), "upload voxels");
+  if (adopt)
+  {
+    c->d_voxels = adopt->d_voxels;      // ingested on this device: the bricks never visited the host
+    c->d_free_map = adopt->d_free;
+    c->n_free_map = adopt->n_free;
+  }
+  else
+  {
+    CU_CREATE(cudaMalloc(&c->d_voxels, sizeof(float) * (miss_offset + miss_n)), "cudaMalloc(voxels)");
+    if (map->data_size)
+      CU_CREATE(cudaMemcpy(c->d_voxels, data, sizeof(float) * map->data_size, cudaMemcpyHostToDevice), "upload voxels");
+  }
   {
     std::vector<float> miss(miss_n, map->init_value);
     CU_CREATE(cudaMemcpy(c->d_voxels + miss_offset, miss.data(), sizeof(float) * miss_n, cudaMemcpyHostToDevice), "upload miss brick");
@@ -760,13 +797,20 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
   {
     float vmax = map->init_value, vmin = map->init_value;
     bool finite = std::isfinite(map->init_value);
-    for (uint64_t i = 0; i < map->data_size; ++i)
+    if (adopt)
     {
-      const float v = data[i];
-      if (!std::isfinite(v)) { finite = false; break; }
-      vmax = std::max(vmax, v);
-      vmin = std::min(vmin, v);
+      finite = finite && adopt->finite;
+      vmax = std::max(vmax, adopt->vmax);
+      vmin = std::min(vmin, adopt->vmin);
     }
+    else
+      for (uint64_t i = 0; i < map->data_size; ++i)
+      {
+        const float v = data[i];
+        if (!std::isfinite(v)) { finite = false; break; }
+        vmax = std::max(vmax, v);
+        vmin = std::min(vmin, v);
+      }
     const float c_in = c->prm.a_range * static_cast<float>(1.0 / c->prm.max_range);
     const float c_out = c->prm.a_max;
     const bool nonneg = finite && vmin >= 0.0f && c->prm.a_hit >= 0.0f && c_in >= 0.0f && c_out >= 0.0f &&
@@ -821,6 +865,27 @@ int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const f
   return TSDFLOC_OK;
 }
 
+int tsdfloc_create(const tsdfloc_map_desc* map, const int32_t* grid_occ, const float* data, const tsdfloc_params* params, int device,
+                   tsdfloc_ctx** out)
+{
+  return create_impl(map, grid_occ, data, nullptr, params, device, out);
+}
+
+int tsdfloc_map_desc_of(const tsdfloc_ctx* c, tsdfloc_map_desc* desc)
+{
+  if (!c || !desc) return TSDFLOC_E_BAD_ARG;
+  *desc = c->desc;
+  return TSDFLOC_OK;
+}
+
+int tsdfloc_free_map_device(const tsdfloc_ctx* c, const float** d_points, uint64_t* n_points)
+{
+  if (!c || !d_points || !n_points) return TSDFLOC_E_BAD_ARG;
+  *d_points = c->d_free_map;
+  *n_points = c->n_free_map;
+  return TSDFLOC_OK;
+}
+
 void tsdfloc_destroy(tsdfloc_ctx* c)
 {
   if (!c) return;
@@ -829,11 +894,13 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
   DevBuf* bufs[] = {&c->d_xyz_stage, &c->d_pts, &c->d_particles, &c->d_particles_out, &c->d_mats,
                     &c->d_raw, &c->d_cdf, &c->d_tile_total, &c->d_tile_offset, &c->d_tile_moments, &c->d_tile_best, &c->d_parents, &c->d_idx, &c->d_hits,
                     &c->d_red_in_xyz, &c->d_red_in_ring, &c->d_red_key4, &c->d_red_table, &c->d_red_cta, &c->d_red_hist, &c->d_red_win,
-                    &c->d_red_rank, &c->d_red_out, &c->d_red_src, &c->d_draws, &c->d_sort_keys, &c->d_sort_hist, &c->d_perm};
+                    &c->d_red_rank, &c->d_red_out, &c->d_red_src, &c->d_draws, &c->d_sort_keys, &c->d_sort_hist, &c->d_perm,
+                    &c->d_run_off, &c->d_run_parent, &c->d_wpack};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->d_table) cudaFree(c->d_table);
   if (c->d_voxels) cudaFree(c->d_voxels);
+  if (c->d_free_map) cudaFree(c->d_free_map);
   if (c->d_mean) cudaFree(c->d_mean);
   if (c->d_segs) cudaFree(c->d_segs);
   if (c->d_eval_stats) cudaFree(c->d_eval_stats);
@@ -1049,10 +1116,18 @@ int tsdfloc_init_particles(tsdfloc_ctx* c, float* particles, uint64_t n, int mod
   const float* d_free = nullptr;
   if (mode == kInitFreeMap)
   {
-    if (!free_map || n_free == 0) return fail(c, TSDFLOC_E_BAD_ARG, "free map required");
-    if ((rc = ensure(c, c->d_draws, sizeof(float) * 3 * n_free, "cudaMalloc(free map)"))) return rc;
-    CU_TRY(c, cudaMemcpyAsync(c->d_draws.p, free_map, sizeof(float) * 3 * n_free, cudaMemcpyHostToDevice, s), "H2D free map");
-    d_free = static_cast<const float*>(c->d_draws.p);
+    if (!free_map && c->d_free_map && c->n_free_map)
+    {
+      d_free = c->d_free_map;      // the map was ingested on this device: its free-space points never left it
+      n_free = c->n_free_map;
+    }
+    else
+    {
+      if (!free_map || n_free == 0) return fail(c, TSDFLOC_E_BAD_ARG, "free map required");
+      if ((rc = ensure(c, c->d_draws, sizeof(float) * 3 * n_free, "cudaMalloc(free map)"))) return rc;
+      CU_TRY(c, cudaMemcpyAsync(c->d_draws.p, free_map, sizeof(float) * 3 * n_free, cudaMemcpyHostToDevice, s), "H2D free map");
+      d_free = static_cast<const float*>(c->d_draws.p);
+    }
   }
   float* d_p = static_cast<float*>(c->d_particles.p);
   if ((rc = stage_init(c, d_p, n, mode, mean, spread, d_free, n_free, seed, sequence, s))) return rc;
@@ -1260,12 +1335,163 @@ int tsdfloc_resample_particles(tsdfloc_ctx* c, const float* particles, uint64_t 
   return tsdfloc_resample_systematic(c, u0, particles_out, cap, n_out, parents);
 }
 
+// ---- Residual / ResidualSystematic resampling: host recurrence + device expansion --------------------------------
+
+int tsdfloc_resample_expand_device(tsdfloc_ctx* c, const float* d_particles, const uint32_t* d_run_off, const uint32_t* d_run_parent,
+                                   uint64_t n_runs, uint64_t first_out, uint64_t count_out, float* d_particles_out,
+                                   float* const* d_out_peers, uint32_t n_peers, uint32_t* d_parents, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!d_particles || !d_run_off || (count_out && !d_particles_out) || (n_peers && !d_out_peers)) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (n_runs == 0 || n_runs > (1ull << 24)) return fail(c, TSDFLOC_E_BAD_ARG, "n_runs must be in [1, 2^24]");
+  if (n_peers > static_cast<uint32_t>(kMaxPeers)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 8 peer buffers");
+  if (count_out == 0) return TSDFLOC_OK;
+  DeviceGuard guard(c->device);
+  DrawPeers peers{};
+  for (uint32_t r = 0; r < n_peers; ++r)
+    if (d_out_peers[r] && d_out_peers[r] != d_particles_out) peers.out[peers.n++] = d_out_peers[r];
+  k_expand_runs<<<static_cast<unsigned>((count_out + 255) / 256), 256, 0, pick(c, stream)>>>(
+      d_particles, d_run_off, d_run_parent, static_cast<uint32_t>(n_runs), first_out, static_cast<uint32_t>(count_out), d_particles_out,
+      d_parents, peers);
+  return launch_check(c, "k_expand_runs");
+}
+
+int tsdfloc_resample_expand(tsdfloc_ctx* c, const uint32_t* run_parent, const uint32_t* run_count, uint64_t n_runs, float* particles_out,
+                            uint64_t cap, uint64_t* n_out, uint32_t* parents)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!run_count || !particles_out || !n_out) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (c->n_resident == 0) return fail(c, TSDFLOC_E_STATE, "resample_expand needs a particle set on the device (sensor_update / resample_particles)");
+  if (n_runs == 0 || n_runs > (1ull << 24)) return fail(c, TSDFLOC_E_BAD_ARG, "n_runs must be in [1, 2^24]");
+  const uint64_t n = c->n_resident;
+  uint64_t total = 0;
+  for (uint64_t r = 0; r < n_runs; ++r)
+  {
+    total += run_count[r];
+    if ((run_parent ? run_parent[r] : r) >= n) return fail(c, TSDFLOC_E_BAD_ARG, "run names a particle outside the resident set");
+  }
+  *n_out = total;
+  if (total > cap) return fail(c, TSDFLOC_E_CAPACITY, "resampling emits " + std::to_string(total) + " particles, capacity is " + std::to_string(cap));
+  if (total == 0) return TSDFLOC_OK;
+  if (total >= (1ull << 32)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 2^32 output particles");
+  DeviceGuard guard(c->device);
+  cudaStream_t s = c->stream;
+  int rc;
+  const size_t off_bytes = sizeof(uint32_t) * (n_runs + 1), par_bytes = run_parent ? sizeof(uint32_t) * n_runs : 0;
+  const size_t out_bytes = sizeof(float) * 7 * total, pidx_bytes = parents ? sizeof(uint32_t) * total : 0;
+  if ((rc = ensure(c, c->d_run_off, off_bytes, "cudaMalloc(run offsets)"))) return rc;
+  if (run_parent && (rc = ensure(c, c->d_run_parent, par_bytes, "cudaMalloc(run parents)"))) return rc;
+  if ((rc = ensure(c, c->d_particles_out, out_bytes, "cudaMalloc(resampled particles)"))) return rc;
+  if (parents && (rc = ensure(c, c->d_parents, pidx_bytes, "cudaMalloc(parents)"))) return rc;
+  if ((rc = ensure_host(c, std::max(off_bytes + par_bytes, out_bytes + pidx_bytes)))) return rc;
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");   // the pinned buffer may still feed an earlier copy
+  uint32_t* h_off = static_cast<uint32_t*>(c->h_stage);
+  uint32_t acc = 0;
+  for (uint64_t r = 0; r < n_runs; ++r)
+  {
+    h_off[r] = acc;
+    acc += run_count[r];
+  }
+  h_off[n_runs] = acc;
+  CU_TRY(c, cudaMemcpyAsync(c->d_run_off.p, h_off, off_bytes, cudaMemcpyHostToDevice, s), "H2D run offsets");
+  if (run_parent)
+  {
+    uint32_t* h_par = h_off + n_runs + 1;
+    std::memcpy(h_par, run_parent, par_bytes);
+    CU_TRY(c, cudaMemcpyAsync(c->d_run_parent.p, h_par, par_bytes, cudaMemcpyHostToDevice, s), "H2D run parents");
+  }
+  if ((rc = tsdfloc_resample_expand_device(c, static_cast<const float*>(c->d_particles.p), static_cast<const uint32_t*>(c->d_run_off.p),
+                                           run_parent ? static_cast<const uint32_t*>(c->d_run_parent.p) : nullptr, n_runs, 0, total,
+                                           static_cast<float*>(c->d_particles_out.p), nullptr, 0,
+                                           parents ? static_cast<uint32_t*>(c->d_parents.p) : nullptr, s)))
+    return rc;
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");   // the offsets have left the pinned buffer; it now receives the output
+  CU_TRY(c, cudaMemcpyAsync(c->h_stage, c->d_particles_out.p, out_bytes, cudaMemcpyDeviceToHost, s), "D2H resampled particles");
+  uint32_t* h_pidx = reinterpret_cast<uint32_t*>(static_cast<char*>(c->h_stage) + out_bytes);
+  if (parents) CU_TRY(c, cudaMemcpyAsync(h_pidx, c->d_parents.p, pidx_bytes, cudaMemcpyDeviceToHost, s), "D2H parents");
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  std::memcpy(particles_out, c->h_stage, out_bytes);
+  if (parents) std::memcpy(parents, h_pidx, pidx_bytes);
+  return TSDFLOC_OK;
+}
+
+// Weights of the resident particle set -> host (4 B per particle).
+static int resident_weights_to_host(tsdfloc_ctx* c, std::vector<float>& w)
+{
+  const uint64_t n = c->n_resident;
+  cudaStream_t s = c->stream;
+  int rc;
+  if ((rc = ensure(c, c->d_wpack, sizeof(float) * n, "cudaMalloc(packed weights)"))) return rc;
+  if ((rc = ensure_host(c, sizeof(float) * n))) return rc;
+  k_pack_weights<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(static_cast<const float*>(c->d_particles.p), static_cast<uint32_t>(n),
+                                                                     static_cast<float*>(c->d_wpack.p));
+  if ((rc = launch_check(c, "k_pack_weights"))) return rc;
+  CU_TRY(c, cudaMemcpyAsync(c->h_stage, c->d_wpack.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s), "D2H weights");
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  w.assign(static_cast<const float*>(c->h_stage), static_cast<const float*>(c->h_stage) + n);
+  return TSDFLOC_OK;
+}
+
+int tsdfloc_resample(tsdfloc_ctx* c, int method, const float* particles, uint64_t n, float u, tsdfloc_index_draw_fn draw, void* user,
+                     float* particles_out, uint64_t cap, uint64_t* n_out, uint32_t* parents)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!particles_out || !n_out) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (method == TSDFLOC_RESAMPLE_SYSTEMATIC)
+    return particles ? tsdfloc_resample_particles(c, particles, n, u, particles_out, cap, n_out, parents)
+                     : tsdfloc_resample_systematic(c, u, particles_out, cap, n_out, parents);
+  if (method != TSDFLOC_RESAMPLE_RESIDUAL && method != TSDFLOC_RESAMPLE_RESIDUAL_SYSTEMATIC) return fail(c, TSDFLOC_E_BAD_ARG, "unknown resampling method");
+  if (method == TSDFLOC_RESAMPLE_RESIDUAL && !draw) return fail(c, TSDFLOC_E_BAD_ARG, "the residual resampler needs an index draw callback");
+  DeviceGuard guard(c->device);
+  int rc;
+  std::vector<float> w;
+  if (particles)
+  {
+    // Resampler::resample(ParticleCloud&) on a weighted host cloud: upload it, keep the weights here
+    if (n == 0 || n > (1ull << 24)) return fail(c, TSDFLOC_E_BAD_ARG, "particle count must be in [1, 2^24]");
+    const size_t pbytes = sizeof(float) * 7 * n;
+    if ((rc = ensure(c, c->d_particles, pbytes, "cudaMalloc(particles)"))) return rc;
+    if ((rc = ensure_host(c, pbytes))) return rc;
+    c->have_cdf = false;
+    c->n_resident = 0;
+    CU_TRY(c, cudaStreamSynchronize(c->stream), "stream sync");
+    std::memcpy(c->h_stage, particles, pbytes);
+    CU_TRY(c, cudaMemcpyAsync(c->d_particles.p, c->h_stage, pbytes, cudaMemcpyHostToDevice, c->stream), "H2D particles");
+    w.resize(n);
+    for (uint64_t i = 0; i < n; ++i) w[i] = particles[7 * i + 6];
+    c->n_resident = n;
+  }
+  else
+  {
+    if (c->n_resident == 0) return fail(c, TSDFLOC_E_STATE, "resample needs a preceding successful sensor_update");
+    n = c->n_resident;
+    if ((rc = resident_weights_to_host(c, w))) return rc;
+  }
+  std::vector<uint32_t> counts, run_parent;
+  uint64_t n_runs = 0;
+  if (method == TSDFLOC_RESAMPLE_RESIDUAL_SYSTEMATIC)
+  {
+    counts.resize(n);
+    uint64_t total = 0;
+    if (tsdfloc_residual_systematic_counts(w.data(), 1, n, u, counts.data(), &total) != TSDFLOC_OK)
+      return fail(c, TSDFLOC_E_BAD_ARG, "residual-systematic resampling: negative or non-finite weight");
+    n_runs = n;
+    return tsdfloc_resample_expand(c, nullptr, counts.data(), n_runs, particles_out, cap, n_out, parents);
+  }
+  counts.resize(n);
+  run_parent.resize(n);   // every run emits >= 1 of the n output particles
+  rc = tsdfloc_residual_runs(w.data(), 1, n, draw, user, 64ull * n + 1024ull, run_parent.data(), counts.data(), n, &n_runs, nullptr);
+  if (rc == TSDFLOC_E_CAPACITY) return fail(c, TSDFLOC_E_NO_VALID_PARTICLE, "residual resampling: the weights do not fill the output (all zero?)");
+  if (rc != TSDFLOC_OK) return fail(c, rc, "residual resampling: bad index draw");
+  return tsdfloc_resample_expand(c, run_parent.data(), counts.data(), n_runs, particles_out, cap, n_out, parents);
+}
+
 int tsdfloc_debug_eval(tsdfloc_ctx* c, const float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],
                        uint32_t* idx, uint32_t* hits, float* raw_weights)
 {
   if (!c) return TSDFLOC_E_BAD_ARG;
   if (!particles || !points || !tf || n == 0 || p == 0) return fail(c, TSDFLOC_E_BAD_ARG, "NULL or empty argument");
-  if (n * p >= (1ull << 32)) return fail(c, TSDFLOC_E_BAD_ARG, "debug dump limited to n*p < 2^32 pairs");
+  if (idx && n * p >= (1ull << 32)) return fail(c, TSDFLOC_E_BAD_ARG, "index dump limited to n*p < 2^32 pairs");
   DeviceGuard guard(c->device);
   cudaStream_t s = c->stream;
   int rc;
@@ -1404,3 +1630,4 @@ uint64_t tsdfloc_host_u_sequence(float u0, uint64_t n, double limit, float* out,
 #include "tsdfloc_multi.inc"
 #include "tsdfloc_host_map.h"
 #include "tsdfloc_ingest.inc"
+#include "tsdfloc_mcl.inc"

@@ -70,12 +70,15 @@ __device__ __forceinline__ void store_weight(const EvalArgs& A, uint32_t slot, f
 // The BS steps of one summation block: transform, index, gather, x = fl(fl(a_hit*v) + term), integer rounding at ulp 1/iu.
 // Leaves the block's x values in xa / xb (first / second half of every pair), the per-lane integer sums in acc0 / acc1 and
 // the largest |rounding residue| in mr0 / mr1 (0.5 = an exact tie). Returns the bracket-mismatch bits (kDiv == kDivBracket).
+// kDump (parity tests): also records every flat voxel index and counts the lookups that hit an allocated brick.
 template <int BS, int kDiv, bool kPP, bool kDump>
 __device__ __forceinline__ uint32_t eval_block(const MapDev& M, const EvalArgs& A, const float2 (&mm)[12], const float4* __restrict__ bp,
                                                uint32_t lane, float2 iu, float2 one, float2 ah, float (&xa)[BS], float (&xb)[BS],
-                                               uint32_t& acc0, uint32_t& acc1, float& mr0, float& mr1, uint32_t part0, uint32_t point0)
+                                               uint32_t& acc0, uint32_t& acc1, float& mr0, float& mr1, uint32_t part0, uint32_t point0,
+                                               uint32_t& hit0, uint32_t& hit1)
 {
   uint32_t mism = 0u;
+  hit0 = hit1 = 0u;
   acc0 = acc1 = 0u;
   mr0 = mr1 = 0.0f;
 #pragma unroll(BS)
@@ -115,16 +118,8 @@ __device__ __forceinline__ uint32_t eval_block(const MapDev& M, const EvalArgs& 
         if (va) A.idx_out[static_cast<size_t>(pa) * A.n_points + qa] = ha ? ia : M.data_size;
         if (vb) A.idx_out[static_cast<size_t>(pb) * A.n_points + qb] = hb ? ib : M.data_size;
       }
-      const uint32_t ca = __popc(__ballot_sync(0xffffffffu, ha)), cb = __popc(__ballot_sync(0xffffffffu, hb));
-      if (lane == 0 && A.hits_out)
-      {
-        if (kPP) { if (ca + cb) atomicAdd(A.hits_out + pa, ca + cb); }
-        else
-        {
-          if (ca) atomicAdd(A.hits_out + pa, ca);
-          if (cb) atomicAdd(A.hits_out + pb, cb);
-        }
-      }
+      hit0 += __popc(__ballot_sync(0xffffffffu, ha));   // committed by the caller once the block is accepted
+      hit1 += __popc(__ballot_sync(0xffffffffu, hb));
     }
     const float2 v = make_float2(__ldg(M.voxels + ia), __ldg(M.voxels + ib));
     const float2 x = __ffma2_rn(__fmul2_rn(ah, v), one, term);       // fl(fl(a_hit*v) + term)
@@ -218,8 +213,18 @@ __device__ __forceinline__ bool eval_commit_block(const MapDev& M, const EvalArg
   float xa[BS], xb[BS];
   uint32_t acc0, acc1;
   float mr0, mr1;
-  const uint32_t mism = eval_block<BS, kDiv, kPP, kDump>(M, A, mm, bp, lane, iu, one, ah, xa, xb, acc0, acc1, mr0, mr1, part0, point0);
+  uint32_t hit0, hit1;
+  const uint32_t mism = eval_block<BS, kDiv, kPP, kDump>(M, A, mm, bp, lane, iu, one, ah, xa, xb, acc0, acc1, mr0, mr1, part0, point0, hit0, hit1);
   if (kDiv == kDivBracket && __any_sync(0xffffffffu, mism != 0u)) return false;
+  if (kDump && lane == 0 && A.hits_out)
+  {
+    if (kPP) { if (part0 < A.n_local && hit0 + hit1) atomicAdd(A.hits_out + part0, hit0 + hit1); }
+    else
+    {
+      if (part0 < A.n_local && hit0) atomicAdd(A.hits_out + part0, hit0);
+      if (part0 + 1u < A.n_local && hit1) atomicAdd(A.hits_out + part0 + 1u, hit1);
+    }
+  }
 
   const bool whole = point0 + kBlockPoints <= A.n_points;   // only the scan's last block can be short
   const int left = static_cast<int>(min(kBlockPoints, A.n_points - point0));

@@ -618,4 +618,55 @@ __global__ void k_draw(const float* __restrict__ particles, const double* __rest
   if (parents) parents[t] = parent;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Run expansion — the device half of the Residual / ResidualSystematic resamplers (novel_resampling.h:27-30, 95-98: the
+// `new_particles.push_back(particle)` loops). The host recurrence (host_resample.cpp) decides how many copies of which
+// particle follow each other; run r covers output slots [run_off[r], run_off[r + 1]) and copies particle run_parent[r]
+// (run_parent == nullptr: particle r itself). One thread per output slot: binary search of its run, 28 B copy.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_expand_runs(const float* __restrict__ particles, const uint32_t* __restrict__ run_off, const uint32_t* __restrict__ run_parent,
+                              uint32_t n_runs, unsigned long long first_out, uint32_t count_out, float* __restrict__ out,
+                              uint32_t* __restrict__ parents, const DrawPeers peers)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count_out) return;
+  const unsigned long long total = run_off[n_runs];
+  unsigned long long j = first_out + t;
+  uint32_t parent = 0;
+  if (total != 0ull)
+  {
+    if (j >= total) j = total - 1;  // padding slots repeat the last valid copy
+    uint32_t lo = 0, hi = n_runs;   // last run r in [0, n_runs) with run_off[r] <= j (empty runs share an offset with their successor)
+    while (hi - lo > 1)
+    {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (run_off[mid] <= j) lo = mid; else hi = mid;
+    }
+    parent = run_parent ? run_parent[lo] : lo;
+  }
+  const float* src = particles + 7ull * parent;
+  float* dst = out + 7ull * t;
+  float v[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) v[k] = src[k];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) dst[k] = v[k];
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (static_cast<uint32_t>(r) < peers.n)
+    {
+      float* pd = peers.out[r] + 7ull * t;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) pd[k] = v[k];
+    }
+  if (parents) parents[t] = parent;
+}
+
+// weights (slot 6 of the AoS particles) -> a contiguous vector, for the host recurrences
+__global__ void k_pack_weights(const float* __restrict__ particles, uint32_t n, float* __restrict__ w)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) w[i] = particles[7ull * i + 6];
+}
+
 }  // namespace tsdfloc

@@ -178,6 +178,38 @@ class CudaEvaluator:
         self.device = device
         self.data_size = int(desc.data_size)
 
+    @classmethod
+    def from_chunks(cls, chunk_pos, chunk_data, sigma: float = 0.1, per_point: bool = False, a_hit: float = 0.9, a_range: float = 0.1,
+                    a_max: float = 0.0, max_range: float = 100.0, device: int = 0, neg_policy: int = capi.NEG_MISS) -> "CudaEvaluator":
+        """createTSDFMap + the constructor in one step on the GPU (tsdfloc_create_from_chunks): the bricks are built on
+        `device` and never visit the host; the free-space points stay there for ParticleCloud.initialize(free-map mode)."""
+        pos = np.ascontiguousarray(chunk_pos, dtype=np.int32).reshape(-1, 3)
+        dat = np.ascontiguousarray(chunk_data, dtype=np.uint32).reshape(len(pos), -1)
+        if dat.shape[1] != 64 ** 3:
+            raise ValueError("every chunk must hold 64^3 words")
+        self = cls.__new__(cls)
+        self._lib = capi.load_library()
+        self._ctx = C.c_void_p()
+        prm = capi.Params(a_hit, a_range, a_max, max_range, int(per_point), int(neg_policy))
+        rc = self._lib.tsdfloc_create_from_chunks(pos.ctypes.data_as(C.c_void_p), dat.ctypes.data_as(C.c_void_p), len(pos), C.c_float(sigma),
+                                                  C.byref(prm), int(device), C.byref(self._ctx))
+        if rc != capi.OK:
+            raise RuntimeError("Error while creating the CUDA context for the map! " + self._lib.tsdfloc_last_error(None).decode())
+        self.device = device
+        self.data_size = int(self.map_desc().data_size)
+        return self
+
+    def map_desc(self) -> capi.MapDesc:
+        d = capi.MapDesc()
+        capi.check(self._lib, self._ctx, self._lib.tsdfloc_map_desc_of(self._ctx, C.byref(d)))
+        return d
+
+    def free_map_size(self) -> int:
+        """Free-space points resident on the device (maps ingested by from_chunks)."""
+        p, n = C.c_void_p(), C.c_uint64(0)
+        capi.check(self._lib, self._ctx, self._lib.tsdfloc_free_map_device(self._ctx, C.byref(p), C.byref(n)))
+        return int(n.value)
+
     # -- reference interface -------------------------------------------------------------------------------------
     def evaluate(self, particles: np.ndarray, points, tf_matrix) -> PoseWithCovariance:
         """evaluate(std::vector<Particle>&, const std::vector<CudaPoint>&, FLOAT_T tf_matrix[16]).
@@ -547,3 +579,68 @@ class SystematicResampler:
         if u0 is None:
             u0 = self.draw_u0(n)
         return self._ev.resample_systematic(u0, capacity=n + n // 8 + 64, want_parents=want_parents)
+
+
+class _RunResampler:
+    """Shared plumbing of the two resamplers whose recurrence runs on the host (tsdfloc_resample)."""
+
+    METHOD = None
+
+    def __init__(self, evaluator, seed: Optional[int] = None):
+        self._ev = evaluator.cuda_evaluator_ if isinstance(evaluator, TSDFEvaluator) else evaluator
+        self._rng = np.random.default_rng(seed)
+
+    def _call(self, particle_cloud, n, u, draw_cb, cap, want_parents):
+        lib = self._ev._lib
+        ps = None if particle_cloud is None else _f32(particle_cloud, 7, "particle_cloud")
+        if ps is not None:
+            n = ps.shape[0]
+        out = np.empty((cap, 7), dtype=np.float32)
+        parents = np.empty(cap, dtype=np.uint32) if want_parents else None
+        n_out = C.c_uint64(0)
+        rc = lib.tsdfloc_resample(self._ev.ctx, self.METHOD, ps.ctypes.data_as(C.c_void_p) if ps is not None else None, n, C.c_float(u),
+                                  draw_cb if draw_cb is not None else C.cast(None, capi.INDEX_DRAW_FN), None,
+                                  out.ctypes.data_as(C.c_void_p), cap, C.byref(n_out),
+                                  parents.ctypes.data_as(C.c_void_p) if want_parents else None)
+        capi.check(lib, self._ev.ctx, rc)
+        m = int(n_out.value)
+        return (out[:m], parents[:m]) if want_parents else out[:m]
+
+
+class ResidualSystematicResampler(_RunResampler):
+    """ResidualSystematicResampler (novel_resampling.h:76-104), mcl_3d's compiled-in default (src/mcl_3d.cpp:765): the fp32
+    remainder recurrence runs on the host over the weights, the copies are made on the GPU. ``u0`` is the reference's
+    uniform_real_distribution<float>(0, 1) draw (from a seeded numpy Generator when not given)."""
+
+    METHOD = capi.RESAMPLE_RESIDUAL_SYSTEMATIC
+
+    def resample(self, particle_cloud: np.ndarray, u0: Optional[float] = None, want_parents: bool = False):
+        u = float(np.float32(self._rng.random())) if u0 is None else u0
+        return self._call(particle_cloud, 0, u, None, 2 * len(particle_cloud) + 64, want_parents)
+
+    def resample_resident(self, n: int, u0: Optional[float] = None, want_parents: bool = False):
+        u = float(np.float32(self._rng.random())) if u0 is None else u0
+        return self._call(None, n, u, None, 2 * n + 64, want_parents)
+
+
+class ResidualResampler(_RunResampler):
+    """ResidualResampler (novel_resampling.h:9-36), the dynamic-reconfigure default (cfg/MCL.cfg:54): uniformly drawn
+    particles are copied ceil(w * N) times until N slots are filled. ``index_draws``: the uniform index stream to consume (the
+    reference's std::uniform_int_distribution<size_t>(0, N-1) draws, for parity); default: a seeded numpy Generator."""
+
+    METHOD = capi.RESAMPLE_RESIDUAL
+
+    def _draw_cb(self, n, index_draws):
+        if index_draws is None:
+            rng = self._rng
+            return capi.INDEX_DRAW_FN(lambda _user: int(rng.integers(0, n)))
+        it = iter(np.asarray(index_draws, dtype=np.uint64).tolist())
+        return capi.INDEX_DRAW_FN(lambda _user: next(it, n))      # n = "out of draws": rejected by the library as a bad draw
+
+    def resample(self, particle_cloud: np.ndarray, index_draws=None, want_parents: bool = False):
+        n = len(particle_cloud)
+        return self._call(particle_cloud, 0, 0.0, self._draw_cb(n, index_draws), n, want_parents)
+
+    def resample_resident(self, n: int, index_draws=None, want_parents: bool = False):
+        return self._call(None, n, 0.0, self._draw_cb(n, index_draws), n, want_parents)
+

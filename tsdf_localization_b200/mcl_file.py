@@ -11,14 +11,17 @@ num_particles_eval / cuda_test_eval / snap_vis_node). Whitespace-separated text:
     "x y z q1 q2 q3 q4"     reference pose
 
 Numbers are formatted like the reference's ``ostream << float`` (``%g``, 6 significant digits) so files written here are
-byte-identical to the reference's for the same values; reading accepts anything ``istream >> float`` accepts.
+byte-identical to the reference's for the same values; reading accepts anything ``istream >> float`` accepts. The work is
+done by the C library (``tsdfloc_mcl_read`` / ``tsdfloc_mcl_write``, include/tsdfloc.h), which the C++ host side binds too.
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
-from pathlib import Path
 
 import numpy as np
+
+from . import capi
 
 
 @dataclass
@@ -30,63 +33,46 @@ class MCLSnapshot:
     pose: np.ndarray          # float32 [7]  x y z q1 q2 q3 q4
 
 
-def _g(v) -> str:
-    return "%g" % float(v)
-
-
 class MCLFile:
+    """Thin binding of tsdfloc_mcl_read / tsdfloc_mcl_write (csrc/tsdfloc_mcl.inc): the parsing and formatting happen in the
+    C library, so the C++ host side and Python read and write the same bytes."""
+
     def __init__(self, file_name):
         self.name_ = str(file_name)
 
     def write(self, points, rings, particles, tf, x, y, z, q_1, q_2, q_3, q_4) -> None:
-        pts = np.asarray(points, dtype=np.float32).reshape(-1, 3)
-        rg = np.asarray(rings).reshape(-1)
-        ps = np.asarray(particles, dtype=np.float32).reshape(-1, 7)
-        tfm = np.asarray(tf, dtype=np.float32).reshape(-1)
+        lib = capi.load_library()
+        pts = np.ascontiguousarray(np.asarray(points, dtype=np.float32).reshape(-1, 3))
+        rg = np.ascontiguousarray(np.asarray(rings).reshape(-1), dtype=np.int32)
+        ps = np.ascontiguousarray(np.asarray(particles, dtype=np.float32).reshape(-1, 7))
+        tfm = np.ascontiguousarray(np.asarray(tf, dtype=np.float32).reshape(-1))
         if len(rg) != len(pts) or len(tfm) != 16:
             raise ValueError("rings must match points; tf must hold 16 values")
-        out = [f"{len(pts)}\n\n"]
-        out += [f"{_g(p[0])} {_g(p[1])} {_g(p[2])}\n" for p in pts]
-        out += [f"{int(r)}\n" for r in rg]
-        out.append(f"{len(ps)}\n")
-        out += [" ".join(_g(v) for v in p[:6]) + "  " + _g(p[6]) + "\n" for p in ps]
-        out.append("\n")
-        out.append("".join(_g(v) + " " for v in tfm))
-        out.append("\n")
-        out.append(" ".join(_g(np.float32(v)) for v in (x, y, z, q_1, q_2, q_3, q_4)))
-        try:
-            Path(self.name_).write_text("".join(out))
-        except OSError as e:
-            raise OSError("Error while opening file for writing") from e
+        pose = np.array([x, y, z, q_1, q_2, q_3, q_4], dtype=np.float32)
+        rc = lib.tsdfloc_mcl_write(self.name_.encode(), pts.ctypes.data_as(C.c_void_p), rg.ctypes.data_as(C.c_void_p), len(pts),
+                                   ps.ctypes.data_as(C.c_void_p), len(ps), tfm.ctypes.data_as(C.POINTER(C.c_float)),
+                                   pose.ctypes.data_as(C.POINTER(C.c_float)))
+        if rc != capi.OK:
+            raise OSError(lib.tsdfloc_last_error(None).decode())
 
     def read(self) -> MCLSnapshot:
+        lib = capi.load_library()
+        h = C.c_void_p()
+        rc = lib.tsdfloc_mcl_read(self.name_.encode(), C.byref(h))
+        if rc == capi.E_STATE:
+            raise OSError(lib.tsdfloc_last_error(None).decode())
+        if rc != capi.OK:
+            raise ValueError(lib.tsdfloc_last_error(None).decode())
         try:
-            tokens = Path(self.name_).read_text().split()
-        except OSError as e:
-            raise OSError("Error while opening file for reading") from e
-        pos = 0
+            n_points, n_particles = int(lib.tsdfloc_mcl_n_points(h)), int(lib.tsdfloc_mcl_n_particles(h))
 
-        def take(n, dtype):
-            nonlocal pos
-            if pos + n > len(tokens):
-                raise ValueError("Error: Could not read mcl data from file")
-            try:
-                vals = np.array(tokens[pos:pos + n], dtype=np.float64).astype(dtype) if dtype != np.int32 else \
-                    np.array([int(t) for t in tokens[pos:pos + n]], dtype=np.int32)
-            except ValueError as e:
-                raise ValueError("Error: Could not read mcl data from file") from e
-            pos += n
-            return vals
+            def arr(ptr, shape, dtype):
+                if int(np.prod(shape)) == 0:
+                    return np.zeros(shape, dtype=dtype)
+                return np.ctypeslib.as_array(ptr, shape=shape).astype(dtype, copy=True)
 
-        try:
-            n_points = int(tokens[0])
-        except (IndexError, ValueError) as e:
-            raise ValueError("Error: Could not read mcl data from file") from e
-        pos = 1
-        points = take(3 * n_points, np.float32).reshape(n_points, 3)
-        rings = take(n_points, np.int32)
-        n_particles = int(take(1, np.int32)[0])
-        particles = take(7 * n_particles, np.float32).reshape(n_particles, 7)
-        tf = take(16, np.float32)
-        pose = take(7, np.float32)
-        return MCLSnapshot(points, rings, particles, tf, pose)
+            return MCLSnapshot(arr(lib.tsdfloc_mcl_points(h), (n_points, 3), np.float32), arr(lib.tsdfloc_mcl_rings(h), (n_points,), np.int32),
+                               arr(lib.tsdfloc_mcl_particles(h), (n_particles, 7), np.float32), arr(lib.tsdfloc_mcl_tf(h), (16,), np.float32),
+                               arr(lib.tsdfloc_mcl_pose(h), (7,), np.float32))
+        finally:
+            lib.tsdfloc_mcl_free(h)

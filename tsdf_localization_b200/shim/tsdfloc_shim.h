@@ -94,4 +94,73 @@ private:
   tsdfloc_ctx* ctx_;
 };
 
+// The reference's other two resamplers on the same split (host recurrence over the weights, device expansion of the
+// particles): drop-ins for `new ResidualResampler()` / `new ResidualSystematicResampler()` in src/mcl_3d.cpp:243-263,765.
+// The random draws come from the base class's mt19937 through the very distribution objects the reference constructs
+// (novel_resampling.h:14, 81), so equal seeds give equal outputs.
+class GpuResidualSystematicResampler : public Resampler
+{
+public:
+  explicit GpuResidualSystematicResampler(tsdfloc_ctx* ctx = nullptr) : ctx_(ctx) {}
+
+  void resample(ParticleCloud& particle_cloud) override
+  {
+    tsdfloc_ctx* ctx = ctx_ ? ctx_ : tsdfloc_shim_context();
+    if (!ctx) throw std::runtime_error("GpuResidualSystematicResampler: no CudaEvaluator context alive");
+    const std::size_t n = particle_cloud.size();
+    if (n == 0) return;
+    std::uniform_real_distribution<FLOAT_T> uniform_distribution(0.0, 1.0);
+    const FLOAT_T u = uniform_distribution(*m_generator_ptr);
+    std::vector<Particle> new_particles(2 * n + 64);
+    uint64_t n_out = 0;
+    const int rc = tsdfloc_resample(ctx, TSDFLOC_RESAMPLE_RESIDUAL_SYSTEMATIC, reinterpret_cast<const float*>(particle_cloud.particles().data()),
+                                    n, u, nullptr, nullptr, reinterpret_cast<float*>(new_particles.data()), new_particles.size(), &n_out, nullptr);
+    if (rc != TSDFLOC_OK) throw std::runtime_error(std::string("GpuResidualSystematicResampler: ") + tsdfloc_last_error(ctx));
+    new_particles.resize(n_out);
+    particle_cloud.particles() = std::move(new_particles);
+  }
+
+  void seed(uint32_t s) { m_generator_ptr.reset(new std::mt19937(s)); }
+
+private:
+  tsdfloc_ctx* ctx_;
+};
+
+class GpuResidualResampler : public Resampler
+{
+public:
+  explicit GpuResidualResampler(tsdfloc_ctx* ctx = nullptr) : ctx_(ctx) {}
+
+  void resample(ParticleCloud& particle_cloud) override
+  {
+    tsdfloc_ctx* ctx = ctx_ ? ctx_ : tsdfloc_shim_context();
+    if (!ctx) throw std::runtime_error("GpuResidualResampler: no CudaEvaluator context alive");
+    const std::size_t n = particle_cloud.size();
+    if (n == 0) return;
+    Draw d{m_generator_ptr.get(), std::uniform_int_distribution<size_t>(0, n - 1)};
+    std::vector<Particle> new_particles(n);
+    uint64_t n_out = 0;
+    const int rc = tsdfloc_resample(ctx, TSDFLOC_RESAMPLE_RESIDUAL, reinterpret_cast<const float*>(particle_cloud.particles().data()), n, 0.0f,
+                                    &Draw::next, &d, reinterpret_cast<float*>(new_particles.data()), new_particles.size(), &n_out, nullptr);
+    if (rc != TSDFLOC_OK) throw std::runtime_error(std::string("GpuResidualResampler: ") + tsdfloc_last_error(ctx));
+    new_particles.resize(n_out);
+    particle_cloud.particles() = std::move(new_particles);
+  }
+
+  void seed(uint32_t s) { m_generator_ptr.reset(new std::mt19937(s)); }
+
+private:
+  struct Draw
+  {
+    std::mt19937* gen;
+    std::uniform_int_distribution<size_t> dist;
+    static uint64_t next(void* self)
+    {
+      Draw* d = static_cast<Draw*>(self);
+      return d->dist(*d->gen);
+    }
+  };
+  tsdfloc_ctx* ctx_;
+};
+
 }  // namespace tsdf_localization
