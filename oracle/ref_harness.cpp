@@ -19,7 +19,9 @@
 //     src/particle_cloud.cpp drags in tf2/ROS-time code unrelated to this path
 //     (reference: src/particle_cloud.cpp:11-15, 619-632).
 //   * CudaEvaluator's four symbols are defined as "no CUDA" stubs unless TSDF_REF_WITH_B200_SHIM is set,
-//     in which case the B200 drop-in shim provides them (tsdf_evaluator.h:78 constructs it unconditionally).
+//     in which case the B200 drop-in shim provides them (tsdf_evaluator.h:78 constructs it unconditionally), or
+//     TSDF_REF_WITH_REF_CUDA, in which case the reference's OWN CUDA evaluator (src/cuda/*.cu, compiled unmodified by nvcc)
+//     provides them: libtsdf_ref_cuda.so, the reference GPU arm of bench.py.
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -61,7 +63,7 @@ std::size_t ParticleCloud::size() const
   return m_particles.size();
 }
 
-#ifndef TSDF_REF_WITH_B200_SHIM
+#if !defined(TSDF_REF_WITH_B200_SHIM) && !defined(TSDF_REF_WITH_REF_CUDA)
 // --- glue: CPU-only build has no CUDA back-end; mirror the base class behaviour ----------------
 CudaEvaluator::CudaEvaluator(CudaSubVoxelMap<FLOAT_T, FLOAT_T>&, bool per_point, FLOAT_T a_hit, FLOAT_T a_range, FLOAT_T a_max, FLOAT_T max_range)
 : d_map_(nullptr), per_point_(per_point), d_grid_occ_(nullptr), d_data_(nullptr), d_particles_(nullptr), d_particles_ordered_(nullptr),
@@ -258,6 +260,29 @@ int ref_map_set_data(void* h, const float* cells, uint64_t n)
       data.push_back(std::make_tuple(cells[4 * i], cells[4 * i + 1], cells[4 * i + 2], cells[4 * i + 3]));
     }
     static_cast<MapHandle*>(h)->map->setData(data);
+    return 0;
+  }
+  catch (std::exception& e)
+  {
+    g_last_error = e.what();
+    return 1;
+  }
+}
+
+// Large synthetic maps (BASELINE configs C4 / C5: 1.4 GB of bricks) are generated as arrays, not as 3.5e8 tuples: hand the
+// reference's map object the two arrays setData would have produced (layout of cuda_sub_voxel_map.tcc:196-224), through its
+// own public accessors (rawGridOcc(), rawDataPtr(), coef(); cuda_sub_voxel_map.h:92-125, 271). Lookups then run verbatim.
+int ref_map_adopt_arrays(void* h, const int32_t* grid_occ, const float* data, uint64_t data_size)
+{
+  try
+  {
+    RefMap& m = *static_cast<MapHandle*>(h)->map;
+    std::memcpy(m.rawGridOcc(), grid_occ, m.gridOccBytes());
+    float** slot = m.rawDataPtr();
+    delete[] *slot;
+    *slot = new float[data_size ? data_size : 1];
+    std::memcpy(*slot, data, sizeof(float) * data_size);
+    m.coef().data_size_ = data_size;
     return 0;
   }
   catch (std::exception& e)
@@ -627,6 +652,11 @@ uint64_t ref_gpu_resample_method(int method, const float* particles, uint64_t n,
 int ref_has_b200_shim() { return 1; }
 #else
 int ref_has_b200_shim() { return 0; }
+#endif
+#ifdef TSDF_REF_WITH_REF_CUDA
+int ref_has_reference_cuda() { return 1; }
+#else
+int ref_has_reference_cuda() { return 0; }
 #endif
 
 }  // extern "C"

@@ -241,13 +241,19 @@ def ref_shim_path() -> Path:
     return ORACLE_DIR / "_ref" / "libtsdf_ref_shim.so"
 
 
+def ref_cuda_path() -> Path:
+    """The reference's OWN CUDA evaluator (src/cuda/*.cu compiled unmodified for sm_100a) behind the same harness."""
+    return ORACLE_DIR / "_ref" / "libtsdf_ref_cuda.so"
+
+
 class Ref:
     """The verbatim reference (oracle/ref_harness.cpp)."""
 
-    def __init__(self, threads: int | None = None, shim: bool = False):
+    def __init__(self, threads: int | None = None, shim: bool = False, cuda: bool = False):
         """shim=True: the same reference classes linked against the product's drop-in CudaEvaluator shim + libtsdfloc.so
-        (evaluate(use_cuda=True) and GpuSystematicResampler then run on the B200)."""
-        self.lib = C.CDLL(str(ref_shim_path() if shim else ref_lib_path(threads)))
+        (evaluate(use_cuda=True) and GpuSystematicResampler then run on the B200).
+        cuda=True: linked against the reference's own CUDA evaluator (evaluate(use_cuda=True) runs the reference's kernels)."""
+        self.lib = C.CDLL(str(ref_cuda_path() if cuda else ref_shim_path() if shim else ref_lib_path(threads)))
         L = self.lib
         if shim:
             L.ref_gpu_systematic_resample.restype = C.c_uint64
@@ -260,6 +266,7 @@ class Ref:
         L.ref_map_create.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float]
         L.ref_map_destroy.argtypes = [C.c_void_p]
         L.ref_map_set_data.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.ref_map_adopt_arrays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.ref_map_get_coef.argtypes = [C.c_void_p, C.POINTER(Coef)]
         L.ref_map_grid_occ.restype = C.POINTER(C.c_int32)
         L.ref_map_grid_occ.argtypes = [C.c_void_p]
@@ -310,6 +317,17 @@ class Ref:
     def map_set_data(self, m, cells):
         cells = np.ascontiguousarray(cells, dtype=np.float32)
         return self.lib.ref_map_set_data(m, _fp(cells), cells.shape[0])
+
+    def map_adopt_arrays(self, m, grid_occ, data):
+        """Hand the reference's map the arrays setData would have built (large synthetic maps)."""
+        g = np.ascontiguousarray(grid_occ, dtype=np.int32)
+        d = np.ascontiguousarray(data, dtype=np.float32)
+        return self.lib.ref_map_adopt_arrays(m, _fp(g), _fp(d), d.shape[0])
+
+    def map_coef(self, m):
+        c = Coef()
+        self.lib.ref_map_get_coef(m, C.byref(c))
+        return c
 
     def map_arrays(self, m):
         c = Coef()

@@ -69,22 +69,25 @@ def test_c1_indices_hits_weights(oracle, omap, evaluator, tf):
 
 
 def test_c1_reference_gpu_semantics_all_particles(oracle, omap, room):
-    """C1 with neg_policy = SATURATE_LIKE_REF_GPU: all 500 particles — the 10 with a lookup below map.min included — match
-    the reference CUDA evaluator's device semantics (oracle mode NEG_REF_DEVICE_SAT, cuda_eval_particles.h:12-67) bit for
-    bit: 512,000 flat indices, hit counts, raw weights; normalised weights within the north star's 1e-5."""
+    """C1 with neg_policy = SATURATE_LIKE_REF_GPU: all 500 particles — the 10 that have a lookup below map.min included
+    (tests/golden: negband_particles) — match the reference CUDA evaluator's device semantics (oracle mode
+    NEG_REF_DEVICE_SAT, cuda_eval_particles.h:12-67) bit for bit: 512,000 flat indices, hit counts, raw weights; normalised
+    weights within the north star's 1e-5. (On this map the saturated lookups land in unallocated border cells, so the default
+    MISS policy produces the same bits; tests/test_gpu_edges.py has the map where the two policies differ on 25 % of the pairs.)"""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "c1_reference.npz")
     ps, pts, _ = common.config_c1()
-    ref = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF, mode=NEG_REF_DEVICE_SAT, want_idx=True)
-    miss = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.IDENTITY_TF, mode=NEG_AS_MISS, want_idx=True)
-    band = (ref["idx"] != miss["idx"]).any(axis=1)
-    assert band.sum() > 0, "C1 no longer has a negative band: the test would be vacuous"
-    ev = CudaEvaluator(room[1], neg_policy=capi.NEG_SATURATE_LIKE_REF_GPU)
-    idx, hits, raw = ev.debug_eval(ps, pts, syn.IDENTITY_TF)
-    assert np.array_equal(idx, ref["idx"]) and np.array_equal(hits, ref["hits"])
-    assert raw.tobytes() == ref["raw"].tobytes()
-    mine = ps.copy()
-    ev.evaluate(mine, pts, syn.IDENTITY_TF)
-    assert common.rel_err(mine[:, 6], ref["particles"][:, 6]).max() <= WEIGHT_RTOL
-    ev.close()
+    assert ps.tobytes() == g["particles"].tobytes() and int(g["negband_particles_identity"].sum()) >= 10
+    for tf in (syn.IDENTITY_TF, syn.CALIB_TF):
+        ref = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, tf, mode=NEG_REF_DEVICE_SAT, want_idx=True)
+        ev = CudaEvaluator(room[1], neg_policy=capi.NEG_SATURATE_LIKE_REF_GPU)
+        idx, hits, raw = ev.debug_eval(ps, pts, tf)
+        assert np.array_equal(idx, ref["idx"]) and np.array_equal(hits, ref["hits"])
+        assert raw.tobytes() == ref["raw"].tobytes()
+        mine = ps.copy()
+        ev.evaluate(mine, pts, tf)
+        assert common.rel_err(mine[:, 6], ref["particles"][:, 6]).max() <= WEIGHT_RTOL
+        ev.close()
 
 
 def test_c1_resample_parents_identical(oracle, evaluator):

@@ -164,7 +164,11 @@ class ShardedSensorUpdate:
         elif want and W > 1:
             raise RuntimeError("fused=True needs CUDA devices, torch.distributed collectives and peer-capable stages")
         self.raw = torch.zeros(W * chunk, **f32)              # un-normalised weights, slice r at [r*chunk, (r+1)*chunk)
-        self.out = torch.zeros((ocap, 7), **f32)              # resampled particles, slice r at [r*ochunk, (r+1)*ochunk)
+        # resampled particles, slice r at [r*ochunk, (r+1)*ochunk); two copies used alternately, so that the set a step
+        # returns (a view into one copy) can be fed straight back in as the next step's `particles`
+        self._out2 = torch.zeros((2, ocap, 7), **f32)
+        self.out = self._out2[0]
+        self._out_tick = 0
 
     def _setup_symmetric(self, n_raw: int, ocap: int) -> None:
         """Weight vector and output particle buffer in symmetric memory: every rank maps every peer's copy."""
@@ -182,7 +186,8 @@ class ShardedSensorUpdate:
         self._raw2, self._out2 = raw, out
         self.raw, self.out = raw[0], out[0]
         self._symm = (h_raw, h_out, [int(p) for p in h_raw.buffer_ptrs], [int(p) for p in h_out.buffer_ptrs])
-        self._tick = 0
+        self._raw_tick = 0
+        self._out_tick = 0
         torch.cuda.synchronize(self.device)
         h_raw.barrier(channel=0)
 
@@ -198,12 +203,14 @@ class ShardedSensorUpdate:
         chunk, first, count = shard(n, W, r)
         ocap = output_capacity(n, W)
         ochunk = ocap // W
+        which_out = self._select_out()
+        self._check_not_aliased(particles, n, ocap)
         if self._symm is not None:
             h_raw, h_out, raw_ptrs, out_ptrs = self._symm
-            which = self._select_copy()
+            which = self._select_raw()
             out = self.out[:ocap]
             raw_off = which * self._raw2.shape[1] * 4
-            out_off = which * self._out2.shape[1] * 28 + r * ochunk * 28
+            out_off = which_out * self._out2.shape[1] * 28 + r * ochunk * 28
             # The kernels themselves do the "all-gather" (P2P stores into every peer's copy); the two barriers only say
             # "all weights have landed everywhere" and "all resampled slices have landed everywhere".
             self.stages.eval_peers(particles, n, first, count, tf, self.raw, [p + raw_off for p in raw_ptrs])
@@ -225,12 +232,30 @@ class ShardedSensorUpdate:
             raise RuntimeError(f"resampling emits {n_out} particles, capacity is {ocap}")
         return out[:n_out], self.mean[:6], n_out, wsum
 
-    def _select_copy(self) -> int:
-        """Alternate between the two symmetric-memory copies of the weight vector / output buffer."""
-        which = self._tick & 1
-        self._tick += 1
-        self.raw, self.out = self._raw2[which], self._out2[which]
+    def _select_raw(self) -> int:
+        """Alternate between the two symmetric-memory copies of the weight vector (every update that evaluates)."""
+        which = self._raw_tick & 1
+        self._raw_tick += 1
+        self.raw = self._raw2[which]
         return which
+
+    def _select_out(self) -> int:
+        """Alternate between the two copies of the output particle buffer (every update that resamples): the set returned
+        by step k lives in the copy step k + 1 does NOT write, so it may be passed back in as `particles`."""
+        which = self._out_tick & 1
+        self._out_tick += 1
+        self.out = self._out2[which]
+        return which
+
+    def _check_not_aliased(self, particles: torch.Tensor, n: int, ocap: int) -> None:
+        """The draw kernel reads parents from `particles` while it (and the exchange) writes `self.out`: overlapping the two
+        would corrupt the resampled set silently."""
+        if particles.device != self.out.device:
+            return
+        a0, a1 = particles.data_ptr(), particles.data_ptr() + n * 28
+        b0, b1 = self.out.data_ptr(), self.out.data_ptr() + ocap * 28
+        if a0 < b1 and b0 < a1:
+            raise RuntimeError("particles overlaps the output buffer this step writes (pass a copy, or the set the previous step returned)")
 
     def evaluate_only(self, particles: torch.Tensor, n: int, tf):
         """Evaluation + normalisation without resampling (what the reference's evaluate() covers). Returns
@@ -240,7 +265,7 @@ class ShardedSensorUpdate:
         chunk, first, count = shard(n, W, r)
         if self._symm is not None:
             h_raw, _, raw_ptrs, _ = self._symm
-            raw_off = self._select_copy() * self._raw2.shape[1] * 4
+            raw_off = self._select_raw() * self._raw2.shape[1] * 4
             self.stages.eval_peers(particles, n, first, count, tf, self.raw, [p + raw_off for p in raw_ptrs])
             h_raw.barrier(channel=0)
         else:
