@@ -163,7 +163,9 @@ int tsdfloc_sensor_update(tsdfloc_ctx* ctx, float* particles, uint64_t n, const 
  * offset u0 in [0, 1/n) supplied by the caller (the reference draws it from std::mt19937, novel_resampling.h:49).
  * Reproduces the reference's fp32 running-U / fp64 running-sum recurrence exactly, including output lengths
  * != n. particles_out: capacity `cap` x 7 fp32; copies keep the parent's normalised weight. parents (optional):
- * index of the source particle per output slot. */
+ * index of the source particle per output slot. Only entries [0, *n_out) are meaningful; entries up to min(cap, n) may be
+ * written. Page-locked output buffers (cudaMallocHost / cudaHostRegister) are filled by the copy engine directly, pageable
+ * ones through the ctx's staging buffer; the same holds for the input buffers of tsdfloc_sensor_update. */
 int tsdfloc_resample_systematic(tsdfloc_ctx* ctx, float u0, float* particles_out, uint64_t cap, uint64_t* n_out,
                                 uint32_t* parents);
 
@@ -429,9 +431,22 @@ enum tsdfloc_tune_knob
 {
   TSDFLOC_TUNE_SPATIAL_ORDER = 0,
   TSDFLOC_TUNE_EVAL_PAIRING = 1,
-  TSDFLOC_TUNE_DIVISION = 2
+  TSDFLOC_TUNE_DIVISION = 2,
+  TSDFLOC_TUNE_STAGE_TIMERS = 3   /* 0 off (default), 1 record CUDA events around the stages (tsdfloc_stage_times) */
 };
 int tsdfloc_tune(tsdfloc_ctx* ctx, int knob, int value);
+
+/* Per-stage device times of the most recent update, the counterpart of the reference's RuntimeEvaluator tasks
+ * (src/util/runtime_evaluator.cpp:130-149; src/cuda/cuda_evaluator.cu:127,299,362): ms[0] init_kernel (scan preparation,
+ * spatial order, pose matrices), ms[1] exec_kernel (k_eval), ms[2] weight_update (normalisation + moments + CDF), ms[3]
+ * resampling (draw); 0 for a stage that did not run. Needs TSDFLOC_TUNE_STAGE_TIMERS = 1; synchronises the device. The host
+ * side of every stage is also an NVTX range ("tsdfloc:prep_scan", ":eval", ":weight_update", ":resample") for Nsight Systems. */
+int tsdfloc_stage_times(tsdfloc_ctx* ctx, float ms[4]);
+
+/* 1 when every fp64 addition of the parallel CDF scan of the last update / resampling call was exact (the result then cannot
+ * depend on the order), 0 when one rounded and the CDF was redone in the reference's serial order (k_cdf_exact), -1 without
+ * a ctx. Reflects the status block of the last call that read it back. */
+int tsdfloc_last_cdf_was_exact(const tsdfloc_ctx* ctx);
 
 /* Quotient mode tsdfloc_create proved for the map's resolution (0 IEEE, 1 three-instruction, 2 bracket); *open_brackets =
  * how many of the 2^30 floats in [0, 1) leave the bracket open (those blocks are evaluated twice). */

@@ -386,3 +386,51 @@ def test_device_resident_ingest_feeds_the_evaluator(oracle):
     resident.close()
     uploaded.close()
     ref.map_destroy(h)
+
+
+@pytest.mark.parametrize("n", [1000, 70001, 1 << 20])
+def test_cdf_with_rounding_additions_follows_the_reference_order(oracle, ev, n):
+    """Weights spanning 80 binades: the fp64 running sum `s += particle.second` (novel_resampling.h:57) rounds, so its value
+    depends on the order of the additions. The parallel scan notices (exactness check) and the CDF is redone in the
+    reference's serial order: parents identical to the oracle's serial loop; leading zeros, ties and huge jumps included."""
+    rng = np.random.default_rng(n)
+    w = 10.0 ** rng.uniform(-24.0, 0.0, n)
+    w[: n // 7] = 0.0                                # leading run of zero weights
+    w[n // 2] = 0.0
+    w = (w / w.sum()).astype(np.float32)
+    w[n // 3] = np.float32(2.0 ** -30)               # exact powers of two produce rounding ties
+    w[n // 3 + 1] = np.float32(2.0 ** -31)
+    ps = np.zeros((n, 7), dtype=np.float32)
+    ps[:, 0] = np.arange(n)
+    ps[:, 6] = w
+    for u0 in (0.0, 0.37 / n):
+        out, parents = SystematicResampler(ev).resample(ps, u0=u0, want_parents=True)
+        m_ref, parents_ref = oracle.systematic_resample(w, u0)
+        assert len(out) == m_ref and np.array_equal(parents, parents_ref)
+    assert capi.load_library().tsdfloc_last_cdf_was_exact(ev.ctx) == 0, "the weights were meant to make the parallel scan round"
+    ok = np.full(n, 1.0 / n, dtype=np.float32) if n & (n - 1) == 0 else None
+    if ok is not None:
+        ps[:, 6] = ok
+        SystematicResampler(ev).resample(ps, u0=0.0)
+        assert capi.load_library().tsdfloc_last_cdf_was_exact(ev.ctx) == 1
+
+
+def test_stage_times_mirror_the_reference_tasks(ev):
+    """tsdfloc_stage_times: init_kernel / exec_kernel / weight_update (cuda_evaluator.cu:127,299,362) + resampling."""
+    lib = capi.load_library()
+    ps = syn.tracking_particles(2000, GT, sigma_xy=0.2)
+    pts = _scan(8000)
+    ms = (C.c_float * 4)()
+    assert lib.tsdfloc_stage_times(ev.ctx, ms) == capi.E_STATE          # timers are off by default
+    ev.tune(capi.TUNE_STAGE_TIMERS, 1)
+    try:
+        mine = ps.copy()
+        ev.evaluate(mine, pts, syn.IDENTITY_TF)
+        ev.resample_systematic(0.1 / len(ps), capacity=len(ps) + 400)
+        capi.check(lib, ev.ctx, lib.tsdfloc_stage_times(ev.ctx, ms))
+        init, exe, upd, res = list(ms)
+        assert 0 < init < 5 and 0 < exe < 50 and 0 < upd < 5 and 0 < res < 5
+        assert exe > init and exe > upd
+    finally:
+        ev.tune(capi.TUNE_STAGE_TIMERS, 0)
+

@@ -11,6 +11,8 @@
 #include "tsdfloc_motion.cuh"
 #include "tsdfloc_sort.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <cctype>
 #include <cerrno>
@@ -56,6 +58,13 @@ struct tsdfloc_ctx
   unsigned long long bracket_open = 0;         // floats in [0, 1) whose bracket is open (statistics)
   cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;  // bracket the last k_eval launch (tsdfloc_last_eval_ms)
   bool eval_timed = false;
+  // optional per-stage timing (tsdfloc_tune(TSDFLOC_TUNE_STAGE_TIMERS, 1)): the reference's RuntimeEvaluator tasks
+  // init_kernel / exec_kernel / weight_update (src/cuda/cuda_evaluator.cu:127,299,362) + the resampling stage
+  enum { kEvPrep0, kEvPrep1, kEvInit0, kEvNorm0, kEvNorm1, kEvDraw0, kEvDraw1, kEvCount };
+  cudaEvent_t ev_stage[kEvCount] = {};
+  bool stage_timers = false;
+  uint32_t stage_seen = 0;     // bit k: ev_stage[k] was recorded since the timers were switched on
+  int norm_max_ctas = 0;       // co-resident CTAs of the cooperative normalisation kernel
 
   // map
   int32_t* d_table = nullptr;
@@ -71,7 +80,6 @@ struct tsdfloc_ctx
   DevBuf d_particles, d_particles_out, d_mats, d_raw, d_cdf, d_tile_total, d_tile_offset, d_tile_moments, d_tile_best, d_parents,
       d_idx, d_hits;
   float* d_mean = nullptr;
-  USeg* d_segs = nullptr;
   unsigned long long* d_eval_stats = nullptr;  // k_eval block statistics (cumulative)
   Status* d_status = nullptr;
   uint64_t n_resident = 0;  // particles left on the device by tsdfloc_sensor_update
@@ -164,6 +172,19 @@ int ensure_host(tsdfloc_ctx* c, size_t bytes)
 
 cudaStream_t pick(tsdfloc_ctx* c, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : c->stream; }
 
+// Page-locked caller memory (cudaMallocHost / cudaHostRegister) is copied from / to directly; pageable memory goes through
+// the ctx's pinned staging buffer.
+bool is_pinned(const void* p)
+{
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 struct DeviceGuard
 {
   int prev = -1;
@@ -206,24 +227,53 @@ int launch_check(tsdfloc_ctx* c, const char* what)
 
 // ---- stages (device pointers) ----------------------------------------------------------------------------
 
-int stage_prep_scan(tsdfloc_ctx* c, const float* d_xyz, uint64_t p, cudaStream_t s)
+// Optional stage timers: record event k on s.
+int mark(tsdfloc_ctx* c, int k, cudaStream_t s)
+{
+  if (!c->stage_timers) return TSDFLOC_OK;
+  CU_TRY(c, cudaEventRecord(c->ev_stage[k], s), "event record");
+  c->stage_seen |= 1u << k;
+  return TSDFLOC_OK;
+}
+
+// NVTX range over a host-side stage (visible in Nsight Systems; a no-op without a profiler attached)
+struct Range
+{
+  explicit Range(const char* name) { nvtxRangePushA(name); }
+  ~Range() { nvtxRangePop(); }
+};
+
+// The prepared scan: padded to whole summation blocks (+ one block), the pad written as zero points by the kernel itself.
+int scan_layout(tsdfloc_ctx* c, const float* d_xyz, uint64_t p, PrepArgs* a)
 {
   if (p > 0x7fffffffull) return fail(c, TSDFLOC_E_BAD_ARG, "scan larger than 2^31 points");
-  int rc;
-  // the evaluation kernel reads whole summation blocks: pad to a block multiple (+ one block) and keep the pad defined
   const uint64_t padded = (p + kEvalPadPoints - 1) / kEvalPadPoints * kEvalPadPoints + kEvalPadPoints;
+  int rc;
   if ((rc = ensure(c, c->d_pts, sizeof(float4) * padded, "cudaMalloc(scan)"))) return rc;
   c->n_points = p;
+  a->xyz = d_xyz;
+  a->out = static_cast<float4*>(c->d_pts.p);
+  a->p = static_cast<uint32_t>(p);
+  a->padded = static_cast<uint32_t>(padded);
+  a->a_range_term = c->prm.a_range * static_cast<float>(1.0 / c->prm.max_range);
+  a->a_max = c->prm.a_max;
+  a->max_range_sq = c->prm.max_range * c->prm.max_range;
+  return TSDFLOC_OK;
+}
+
+unsigned scan_ctas(const PrepArgs& a) { return static_cast<unsigned>(std::min<uint64_t>((static_cast<uint64_t>(a.padded) + 255) / 256, 1024)); }
+
+int stage_prep_scan(tsdfloc_ctx* c, const float* d_xyz, uint64_t p, cudaStream_t s)
+{
+  Range r("tsdfloc:prep_scan");
+  PrepArgs a{};
+  int rc;
+  if ((rc = scan_layout(c, d_xyz, p, &a))) return rc;
   if (p == 0) return TSDFLOC_OK;
-  {
-    cudaError_t me = cudaMemsetAsync(static_cast<float4*>(c->d_pts.p) + p, 0, sizeof(float4) * (padded - p), s);
-    if (me != cudaSuccess) return fail(c, TSDFLOC_E_CUDA, std::string("memset(scan pad): ") + cudaGetErrorString(me));
-  }
-  const float a_range_term = c->prm.a_range * static_cast<float>(1.0 / c->prm.max_range);
-  const unsigned nb = static_cast<unsigned>(std::min<uint64_t>((p + 255) / 256, 1024));
-  k_prep_scan<<<nb, 256, 0, s>>>(d_xyz, static_cast<uint32_t>(p), static_cast<float4*>(c->d_pts.p), a_range_term, c->prm.a_max,
-                                 c->prm.max_range * c->prm.max_range);
-  return launch_check(c, "k_prep_scan");
+  if ((rc = mark(c, tsdfloc_ctx::kEvPrep0, s))) return rc;
+  k_prep_scan<<<scan_ctas(a), 256, 0, s>>>(a);
+  if ((rc = launch_check(c, "k_prep_scan"))) return rc;
+  return mark(c, tsdfloc_ctx::kEvPrep1, s);
 }
 
 // Device copy of a set of peer pointers. The sets repeat from update to update (two per buffer with double buffering), so
@@ -322,32 +372,50 @@ int stage_sort(tsdfloc_ctx* c, const float* d_particles, uint64_t first, uint64_
   return TSDFLOC_OK;
 }
 
+// K0, or — fused_scan != nullptr — scan preparation + K0 in one launch (the host-buffer update issues both together).
 int stage_matrices(tsdfloc_ctx* c, const float* d_particles, uint64_t first, uint64_t count, const float tf[16], cudaStream_t s,
-                   const uint32_t* perm)
+                   const uint32_t* perm, const PrepArgs* fused_scan = nullptr)
 {
   int rc;
   if ((rc = ensure(c, c->d_mats, sizeof(float) * 12 * count, "cudaMalloc(matrices)"))) return rc;
   Tf12 t;
   std::memcpy(t.m, tf, sizeof(t.m));
-  k_pose_matrices<<<static_cast<unsigned>((count + 127) / 128), 128, 0, s>>>(d_particles, static_cast<uint32_t>(first),
-                                                                            static_cast<uint32_t>(count), t,
-                                                                            static_cast<float*>(c->d_mats.p), perm);
+  const unsigned mat_ctas = static_cast<unsigned>((count + 255) / 256);
+  if (fused_scan)
+  {
+    const unsigned sc = scan_ctas(*fused_scan);
+    k_prepare<<<sc + mat_ctas, 256, 0, s>>>(*fused_scan, sc, d_particles, static_cast<uint32_t>(first), static_cast<uint32_t>(count), t,
+                                            static_cast<float*>(c->d_mats.p), perm);
+    return launch_check(c, "k_prepare");
+  }
+  k_pose_matrices<<<mat_ctas, 256, 0, s>>>(d_particles, static_cast<uint32_t>(first), static_cast<uint32_t>(count), t,
+                                           static_cast<float*>(c->d_mats.p), perm);
   return launch_check(c, "k_pose_matrices");
 }
 
 int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint64_t first, uint64_t count, const float tf[16],
                float* d_raw, cudaStream_t s, float* const* d_raw_peers = nullptr, uint32_t n_peers = 0, bool dump = false,
-               uint32_t* d_idx = nullptr, uint32_t* d_hits = nullptr)
+               uint32_t* d_idx = nullptr, uint32_t* d_hits = nullptr, const PrepArgs* fused_scan = nullptr)
 {
+  Range r("tsdfloc:eval");
   if (n_peers > static_cast<uint32_t>(kMaxPeers)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 8 peer buffers");
   if (first + count > n_total) return fail(c, TSDFLOC_E_BAD_ARG, "particle slice exceeds n_total");
   if (n_total > (1ull << 24)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 2^24 particles: the reference's fp32 U recurrence stalls");
   if (c->n_points == 0) return fail(c, TSDFLOC_E_EMPTY_SCAN, "empty scan");
-  if (count == 0) return TSDFLOC_OK;
   int rc;
+  if (count == 0)
+  {
+    if (fused_scan)   // this rank evaluates nothing but still needs the prepared scan
+    {
+      k_prep_scan<<<scan_ctas(*fused_scan), 256, 0, s>>>(*fused_scan);
+      return launch_check(c, "k_prep_scan");
+    }
+    return TSDFLOC_OK;
+  }
+  if ((rc = mark(c, tsdfloc_ctx::kEvInit0, s))) return rc;
   const uint32_t* perm = nullptr;
   if ((rc = stage_sort(c, d_particles, first, count, s, &perm))) return rc;
-  if ((rc = stage_matrices(c, d_particles, first, count, tf, s, perm))) return rc;
+  if ((rc = stage_matrices(c, d_particles, first, count, tf, s, perm, fused_scan))) return rc;
   EvalArgs a{};
   a.perm = perm;
   a.pts = static_cast<const float4*>(c->d_pts.p);
@@ -376,9 +444,9 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   a.s_min = 32.0f * c->x_bound;
   a.stats = c->d_eval_stats;
   a.force_seq = c->force_seq;
-  CU_TRY(c, cudaEventRecord(c->ev_eval0, s), "event record");
   a.idx_out = d_idx;
   a.hits_out = d_hits;
+  CU_TRY(c, cudaEventRecord(c->ev_eval0, s), "event record");
   launch_eval(c, a, s, dump);
   if ((rc = launch_check(c, "k_eval"))) return rc;
   CU_TRY(c, cudaEventRecord(c->ev_eval1, s), "event record");
@@ -386,54 +454,77 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   return TSDFLOC_OK;
 }
 
-int stage_normalize(tsdfloc_ctx* c, float* d_particles, uint64_t n, const float* d_raw, float* d_mean, cudaStream_t s)
+int stage_normalize(tsdfloc_ctx* c, float* d_particles, uint64_t n, const float* d_raw, float* d_mean, cudaStream_t s, float* d_w_out = nullptr)
 {
+  Range r("tsdfloc:weight_update");
   if (n == 0) return fail(c, TSDFLOC_E_BAD_ARG, "no particles");
   if (n > (1ull << 24)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 2^24 particles: the reference's fp32 U recurrence stalls");
   const uint32_t tiles = static_cast<uint32_t>((n + kScanTile - 1) / kScanTile);
   int rc;
   if ((rc = ensure(c, c->d_cdf, sizeof(double) * n, "cudaMalloc(cdf)"))) return rc;
   if ((rc = ensure(c, c->d_tile_total, sizeof(double) * tiles, "cudaMalloc(tile totals)"))) return rc;
-  if ((rc = ensure(c, c->d_tile_offset, sizeof(double) * tiles, "cudaMalloc(tile offsets)"))) return rc;
+  if ((rc = ensure(c, c->d_tile_offset, sizeof(double) * tiles, "cudaMalloc(tile sums)"))) return rc;
   if ((rc = ensure(c, c->d_tile_moments, sizeof(double) * 9 * tiles, "cudaMalloc(tile moments)"))) return rc;
   if ((rc = ensure(c, c->d_tile_best, sizeof(unsigned long long) * tiles, "cudaMalloc(tile arg-max)"))) return rc;
-  const uint32_t n32 = static_cast<uint32_t>(n);
-  // d_raw == nullptr: scan the weights the particles already carry (slot 6, stride 7) without normalising them
-  k_weight_sum<<<tiles, kScanThreads, 0, s>>>(d_raw ? d_raw : d_particles + 6, d_raw ? 1u : 7u, n32,
-                                              static_cast<double*>(c->d_tile_total.p), c->d_status);
-  if ((rc = launch_check(c, "k_weight_sum"))) return rc;
-  k_normalise_scan<<<tiles, kScanThreads, 0, s>>>(d_particles, d_raw, n32, c->d_status, static_cast<double*>(c->d_cdf.p),
-                                                  static_cast<double*>(c->d_tile_total.p), static_cast<double*>(c->d_tile_moments.p),
-                                                  static_cast<unsigned long long*>(c->d_tile_best.p));
-  if ((rc = launch_check(c, "k_normalise_scan"))) return rc;
-  k_scan_tiles<<<1, 32, 0, s>>>(static_cast<const double*>(c->d_tile_total.p), static_cast<double*>(c->d_tile_offset.p), tiles,
-                                static_cast<const double*>(c->d_tile_moments.p), d_mean, c->d_status,
-                                static_cast<const unsigned long long*>(c->d_tile_best.p), d_particles);
-  if ((rc = launch_check(c, "k_scan_tiles"))) return rc;
-  k_cdf_finalize<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(static_cast<double*>(c->d_cdf.p),
-                                                                       static_cast<const double*>(c->d_tile_offset.p), n32, c->d_status);
-  if ((rc = launch_check(c, "k_cdf_finalize"))) return rc;
+  if ((rc = mark(c, tsdfloc_ctx::kEvNorm0, s))) return rc;
+  NormArgs a{};
+  a.particles = d_particles;
+  a.raw = d_raw;      // nullptr: scan the weights the particles already carry (slot 6) without normalising them
+  a.n = static_cast<uint32_t>(n);
+  a.st = c->d_status;
+  a.cdf = static_cast<double*>(c->d_cdf.p);
+  a.tile_sum = static_cast<double*>(c->d_tile_offset.p);
+  a.tile_total = static_cast<double*>(c->d_tile_total.p);
+  a.tile_moments = static_cast<double*>(c->d_tile_moments.p);
+  a.tile_best = static_cast<unsigned long long*>(c->d_tile_best.p);
+  a.mean_pose = d_mean;
+  a.w_out = d_w_out;
+  // cooperative launch: the grid must be co-resident; a CTA walks several tiles when there are more tiles than that
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, static_cast<uint64_t>(c->norm_max_ctas)));
+  void* args[] = {&a};
+  CU_TRY(c, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_normalise_cdf), dim3(grid), dim3(kScanThreads), args, 0, s),
+         "launch of k_normalise_cdf");
+  if ((rc = launch_check(c, "k_normalise_cdf"))) return rc;
+  // the exact-order redo, taken only when a parallel fp64 addition rounded (the kernel returns at once otherwise)
+  k_cdf_fallback<<<1, 32, 0, s>>>(d_particles, static_cast<double*>(c->d_cdf.p), static_cast<uint32_t>(n), c->d_status);
+  if ((rc = launch_check(c, "k_cdf_fallback"))) return rc;
+  if ((rc = mark(c, tsdfloc_ctx::kEvNorm1, s))) return rc;
   c->have_cdf = true;
   return TSDFLOC_OK;
+}
+
+// The reference's fp32 U recurrence as a table of exact linear runs, built here on the host: it depends only on u0 and N.
+void host_u_table(float u0, uint64_t n, UTable* t)
+{
+  unsigned long long below = 0;
+  uint32_t flags = 0;
+  // no limit: the table covers every U_j the recurrence can emit before 2N + 64 outputs; the draw kernel cuts it at s_last
+  t->n_segs = build_u_table(u0, 1.0 / static_cast<double>(n), HUGE_VAL, t->segs, kMaxUSegs, &below, 2ull * n + 64ull, &flags);
+  t->n_elems = below;
+  t->flags = flags;
 }
 
 int stage_draw(tsdfloc_ctx* c, const float* d_particles, uint64_t n, float u0, uint64_t first_out, uint64_t count_out, float* d_out,
                uint32_t* d_parents, cudaStream_t s, float* const* d_out_peers = nullptr, uint32_t n_peers = 0)
 {
+  Range r("tsdfloc:resample");
   if (n_peers > static_cast<uint32_t>(kMaxPeers)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 8 peer buffers");
   DrawPeers peers{};
   for (uint32_t r = 0; r < n_peers; ++r)
     if (d_out_peers[r] && d_out_peers[r] != d_out) peers.out[peers.n++] = d_out_peers[r];
   if (!c->have_cdf) return fail(c, TSDFLOC_E_STATE, "draw before normalize");
   if (!(u0 >= 0.0f)) return fail(c, TSDFLOC_E_BAD_ARG, "u0 must be >= 0");
-  k_finish_cdf_utable<<<1, 32, 0, s>>>(d_particles, static_cast<double*>(c->d_cdf.p), static_cast<uint32_t>(n), u0, c->d_segs, c->d_status);
+  if (count_out >= (1ull << 32)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 2^32 output slots");
   int rc;
-  if ((rc = launch_check(c, "k_finish_cdf_utable"))) return rc;
-  if (count_out == 0) return TSDFLOC_OK;
-  k_draw<<<static_cast<unsigned>((count_out + 255) / 256), 256, 0, s>>>(d_particles, static_cast<const double*>(c->d_cdf.p),
-                                                                       static_cast<uint32_t>(n), c->d_segs, c->d_status, first_out,
-                                                                       static_cast<uint32_t>(count_out), d_out, d_parents, peers);
-  return launch_check(c, "k_draw");
+  if ((rc = mark(c, tsdfloc_ctx::kEvDraw0, s))) return rc;
+  UTable t;
+  host_u_table(u0, n, &t);
+  // count_out == 0 still publishes n_out (one CTA)
+  const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, (count_out + 255) / 256));
+  k_draw<<<grid, 256, 0, s>>>(d_particles, static_cast<const double*>(c->d_cdf.p), static_cast<uint32_t>(n), t, c->d_status, first_out,
+                              static_cast<uint32_t>(count_out), d_out, d_parents, peers);
+  if ((rc = launch_check(c, "k_draw"))) return rc;
+  return mark(c, tsdfloc_ctx::kEvDraw1, s);
 }
 
 // Scan reduction (tsdfloc_reduce.cuh). All pointers are device pointers.
@@ -685,6 +776,15 @@ static int create_impl(const tsdfloc_map_desc* map, const int32_t* grid_occ, con
   CU_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
   CU_CREATE(cudaEventCreate(&c->ev_eval0), "cudaEventCreate");
   CU_CREATE(cudaEventCreate(&c->ev_eval1), "cudaEventCreate");
+  for (cudaEvent_t& e : c->ev_stage) CU_CREATE(cudaEventCreate(&e), "cudaEventCreate");
+  {
+    int per_sm = 0;
+    CU_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_normalise_cdf, kScanThreads, 0), "occupancy(k_normalise_cdf)");
+    int coop = 0;
+    CU_CREATE(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device), "cudaDeviceGetAttribute");
+    if (!coop || per_sm < 1) return bail(TSDFLOC_E_CUDA, "device does not support cooperative launches");
+    c->norm_max_ctas = per_sm * c->sm_count;
+  }
 
   // ---- padded brick table ------------------------------------------------------------------------------------
   uint32_t thr[3];
@@ -822,7 +922,6 @@ static int create_impl(const tsdfloc_map_desc* map, const int32_t* grid_occ, con
 
   // ---- small fixed buffers -------------------------------------------------------------------------------------
   CU_CREATE(cudaMalloc(&c->d_mean, sizeof(float) * 8), "cudaMalloc(mean pose)");
-  CU_CREATE(cudaMalloc(&c->d_segs, sizeof(USeg) * kMaxUSegs), "cudaMalloc(U table)");
   CU_CREATE(cudaMalloc(&c->d_eval_stats, sizeof(unsigned long long) * 4), "cudaMalloc(eval stats)");
   CU_CREATE(cudaMemset(c->d_eval_stats, 0, sizeof(unsigned long long) * 4), "memset(eval stats)");
   CU_CREATE(cudaMalloc(&c->d_status, sizeof(Status)), "cudaMalloc(status)");
@@ -902,7 +1001,6 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
   if (c->d_voxels) cudaFree(c->d_voxels);
   if (c->d_free_map) cudaFree(c->d_free_map);
   if (c->d_mean) cudaFree(c->d_mean);
-  if (c->d_segs) cudaFree(c->d_segs);
   if (c->d_eval_stats) cudaFree(c->d_eval_stats);
   if (c->d_status) cudaFree(c->d_status);
   if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -912,6 +1010,8 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
     if (t.dev) cudaFree(t.dev);
   if (c->d_red_status) cudaFree(c->d_red_status);
   if (c->h_red_status) cudaFreeHost(c->h_red_status);
+  for (cudaEvent_t e : c->ev_stage)
+    if (e) cudaEventDestroy(e);
   if (c->ev_eval0) cudaEventDestroy(c->ev_eval0);
   if (c->ev_eval1) cudaEventDestroy(c->ev_eval1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1154,30 +1254,39 @@ int tsdfloc_best_particle(tsdfloc_ctx* c, int64_t* index, float pose[6], float* 
 
 // ---- (A) host-buffer calls ---------------------------------------------------------------------------------------
 
-// Second half of a host-buffer sensor update: the prepared scan is resident in c->d_pts (stage_prep_scan was enqueued on s).
-static int update_with_resident_scan(tsdfloc_ctx* c, float* particles, uint64_t n, const float tf[16], float mean_pose[6], cudaStream_t s)
+// Host-buffer sensor update behind the scan upload: particles up, (scan preparation +) evaluation, normalisation, weights
+// back. fused_scan != nullptr: the raw scan is already on its way to the device on s and is prepared in the same launch that
+// builds the matrices; nullptr: the prepared scan is resident (tsdfloc_sensor_update_cloud).
+static int update_with_scan(tsdfloc_ctx* c, float* particles, uint64_t n, const float tf[16], float mean_pose[6], cudaStream_t s,
+                            const PrepArgs* fused_scan, size_t stage_off)
 {
   int rc;
   const size_t pbytes = sizeof(float) * 7 * n;
   if ((rc = ensure(c, c->d_particles, pbytes, "cudaMalloc(particles)"))) return rc;
   if ((rc = ensure(c, c->d_raw, sizeof(float) * n, "cudaMalloc(raw weights)"))) return rc;
-  if ((rc = ensure_host(c, pbytes))) return rc;
-  // the first pbytes of the pinned buffer are free here: tsdfloc_sensor_update stages the scan BEHIND them, and
-  // tsdfloc_sensor_update_cloud has synchronised the stream when it read the reduced scan's size
-  std::memcpy(c->h_stage, particles, pbytes);
+  if ((rc = ensure(c, c->d_wpack, sizeof(float) * n, "cudaMalloc(packed weights)"))) return rc;
   float* d_p = static_cast<float*>(c->d_particles.p);
-  CU_TRY(c, cudaMemcpyAsync(d_p, c->h_stage, pbytes, cudaMemcpyHostToDevice, s), "H2D particles");
-
-  if ((rc = stage_eval(c, d_p, n, 0, n, tf, static_cast<float*>(c->d_raw.p), s))) return rc;
-  if ((rc = stage_normalize(c, d_p, n, static_cast<const float*>(c->d_raw.p), c->d_mean, s))) return rc;
-  CU_TRY(c, cudaMemcpyAsync(c->h_stage, d_p, pbytes, cudaMemcpyDeviceToHost, s), "D2H particles");
-  CU_TRY(c, cudaMemcpyAsync(c->h_mean, c->d_mean, sizeof(float) * 6, cudaMemcpyDeviceToHost, s), "D2H mean pose");
+  char* stage = static_cast<char*>(c->h_stage) + stage_off;   // [stage_off, stage_off + pbytes) of the pinned buffer is ours
+  {
+    Range r("tsdfloc:init");
+    if (is_pinned(particles))
+      CU_TRY(c, cudaMemcpyAsync(d_p, particles, pbytes, cudaMemcpyHostToDevice, s), "H2D particles");
+    else
+    {
+      std::memcpy(stage, particles, pbytes);
+      CU_TRY(c, cudaMemcpyAsync(d_p, stage, pbytes, cudaMemcpyHostToDevice, s), "H2D particles");
+    }
+  }
+  if ((rc = stage_eval(c, d_p, n, 0, n, tf, static_cast<float*>(c->d_raw.p), s, nullptr, 0, false, nullptr, nullptr, fused_scan))) return rc;
+  float* d_w = static_cast<float*>(c->d_wpack.p);
+  if ((rc = stage_normalize(c, d_p, n, static_cast<const float*>(c->d_raw.p), c->d_status->mean, s, d_w))) return rc;
+  // 4 B per particle come back (the caller's poses are untouched, cuda_evaluator.cu:405-408) + the status block with the mean
+  CU_TRY(c, cudaMemcpyAsync(stage, d_w, sizeof(float) * n, cudaMemcpyDeviceToHost, s), "D2H weights");
   if ((rc = read_status(c, s))) return rc;
   if (c->h_status->zero_sum) return fail(c, TSDFLOC_E_NO_VALID_PARTICLE, "No particle is valid!");
-  // only the weight slot is written back: the caller's poses are untouched (cuda_evaluator.cu:405-408)
-  const float* h = static_cast<const float*>(c->h_stage);
-  for (uint64_t i = 0; i < n; ++i) particles[7 * i + 6] = h[7 * i + 6];
-  if (mean_pose) std::memcpy(mean_pose, c->h_mean, sizeof(float) * 6);
+  const float* h = reinterpret_cast<const float*>(stage);
+  for (uint64_t i = 0; i < n; ++i) particles[7 * i + 6] = h[i];
+  if (mean_pose) std::memcpy(mean_pose, c->h_status->mean, sizeof(float) * 6);
   c->n_resident = n;
   return TSDFLOC_OK;
 }
@@ -1192,19 +1301,26 @@ int tsdfloc_sensor_update(tsdfloc_ctx* c, float* particles, uint64_t n, const fl
   DeviceGuard guard(c->device);
   cudaStream_t s = c->stream;
   int rc;
-  // one pinned buffer, two regions: [particles | scan] — no host sync between the two uploads
+  // one pinned buffer, two regions: [particles / weights | scan] — no host sync between the two uploads
   const size_t scan_off = (sizeof(float) * 7 * n + 255) / 256 * 256;
   if ((rc = ensure_host(c, scan_off + sizeof(float) * 3 * p))) return rc;
   c->have_cdf = false;
   c->n_resident = 0;
-
-  // scan: host -> pinned -> device, then prep
-  char* h_scan = static_cast<char*>(c->h_stage) + scan_off;
-  std::memcpy(h_scan, points, sizeof(float) * 3 * p);
   if ((rc = ensure(c, c->d_xyz_stage, sizeof(float) * 3 * (p + 1), "cudaMalloc(scan staging)"))) return rc;
-  CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, h_scan, sizeof(float) * 3 * p, cudaMemcpyHostToDevice, s), "H2D scan");
-  if ((rc = stage_prep_scan(c, static_cast<const float*>(c->d_xyz_stage.p), p, s))) return rc;
-  return update_with_resident_scan(c, particles, n, tf, mean_pose, s);
+  {
+    Range r("tsdfloc:init");
+    if (is_pinned(points))
+      CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, points, sizeof(float) * 3 * p, cudaMemcpyHostToDevice, s), "H2D scan");
+    else
+    {
+      char* h_scan = static_cast<char*>(c->h_stage) + scan_off;
+      std::memcpy(h_scan, points, sizeof(float) * 3 * p);
+      CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, h_scan, sizeof(float) * 3 * p, cudaMemcpyHostToDevice, s), "H2D scan");
+    }
+  }
+  PrepArgs scan{};
+  if ((rc = scan_layout(c, static_cast<const float*>(c->d_xyz_stage.p), p, &scan))) return rc;
+  return update_with_scan(c, particles, n, tf, mean_pose, s, &scan, 0);
 }
 
 // ---- scan reduction -----------------------------------------------------------------------------------------------
@@ -1281,7 +1397,8 @@ int tsdfloc_sensor_update_cloud(tsdfloc_ctx* c, float* particles, uint64_t n, co
   if (n_points_used) *n_points_used = m;
   if (m == 0) return fail(c, TSDFLOC_E_EMPTY_SCAN, "empty scan after reduction: weights left untouched");
   if ((rc = stage_prep_scan(c, static_cast<const float*>(c->d_red_out.p), m, s))) return rc;
-  return update_with_resident_scan(c, particles, n, tf, mean_pose, s);
+  if ((rc = ensure_host(c, sizeof(float) * 7 * n))) return rc;
+  return update_with_scan(c, particles, n, tf, mean_pose, s, nullptr, 0);
 }
 
 int tsdfloc_resample_systematic(tsdfloc_ctx* c, float u0, float* particles_out, uint64_t cap, uint64_t* n_out, uint32_t* parents)
@@ -1295,18 +1412,45 @@ int tsdfloc_resample_systematic(tsdfloc_ctx* c, float u0, float* particles_out, 
   int rc;
   if ((rc = ensure(c, c->d_particles_out, sizeof(float) * 7 * cap, "cudaMalloc(resampled particles)"))) return rc;
   if (parents && (rc = ensure(c, c->d_parents, sizeof(uint32_t) * cap, "cudaMalloc(parents)"))) return rc;
-  if ((rc = ensure_host(c, sizeof(float) * 7 * cap + sizeof(uint32_t) * cap))) return rc;
   float* d_p = static_cast<float*>(c->d_particles.p);
   if ((rc = stage_draw(c, d_p, n, u0, 0, cap, static_cast<float*>(c->d_particles_out.p), parents ? static_cast<uint32_t*>(c->d_parents.p) : nullptr, s)))
     return rc;
-  CU_TRY(c, cudaMemcpyAsync(c->h_stage, c->d_particles_out.p, sizeof(float) * 7 * cap, cudaMemcpyDeviceToHost, s), "D2H resampled particles");
-  uint32_t* h_par = reinterpret_cast<uint32_t*>(static_cast<char*>(c->h_stage) + sizeof(float) * 7 * cap);
-  if (parents) CU_TRY(c, cudaMemcpyAsync(h_par, c->d_parents.p, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, s), "D2H parents");
+  // Page-locked output: the first min(cap, n) particles (the usual output length) go straight into the caller's buffer, in
+  // flight together with the status read-back; whatever the recurrence emitted beyond n follows once n_out is known.
+  // Pageable output: everything through the staging buffer.
+  const bool direct = is_pinned(particles_out) && (!parents || is_pinned(parents));
+  const uint64_t first = std::min<uint64_t>(cap, n);
+  uint32_t* h_par = nullptr;
+  if (direct)
+  {
+    CU_TRY(c, cudaMemcpyAsync(particles_out, c->d_particles_out.p, sizeof(float) * 7 * first, cudaMemcpyDeviceToHost, s), "D2H resampled particles");
+    if (parents) CU_TRY(c, cudaMemcpyAsync(parents, c->d_parents.p, sizeof(uint32_t) * first, cudaMemcpyDeviceToHost, s), "D2H parents");
+  }
+  else
+  {
+    if ((rc = ensure_host(c, sizeof(float) * 7 * cap + sizeof(uint32_t) * cap))) return rc;
+    h_par = reinterpret_cast<uint32_t*>(static_cast<char*>(c->h_stage) + sizeof(float) * 7 * cap);
+    CU_TRY(c, cudaMemcpyAsync(c->h_stage, c->d_particles_out.p, sizeof(float) * 7 * cap, cudaMemcpyDeviceToHost, s), "D2H resampled particles");
+    if (parents) CU_TRY(c, cudaMemcpyAsync(h_par, c->d_parents.p, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, s), "D2H parents");
+  }
   if ((rc = read_status(c, s))) return rc;
   if (c->h_status->table_overflow & 7u) return fail(c, TSDFLOC_E_CAPACITY, overflow_text(c->h_status->table_overflow));
   const uint64_t m = c->h_status->n_out;
   *n_out = m;
   if (m > cap) return fail(c, TSDFLOC_E_CAPACITY, "resampling emits " + std::to_string(m) + " particles, capacity is " + std::to_string(cap));
+  if (direct)
+  {
+    if (m > first)
+    {
+      CU_TRY(c, cudaMemcpyAsync(particles_out + 7 * first, static_cast<const float*>(c->d_particles_out.p) + 7 * first,
+                                sizeof(float) * 7 * (m - first), cudaMemcpyDeviceToHost, s), "D2H resampled particles (tail)");
+      if (parents)
+        CU_TRY(c, cudaMemcpyAsync(parents + first, static_cast<const uint32_t*>(c->d_parents.p) + first, sizeof(uint32_t) * (m - first),
+                                  cudaMemcpyDeviceToHost, s), "D2H parents (tail)");
+      CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+    }
+    return TSDFLOC_OK;
+  }
   std::memcpy(particles_out, c->h_stage, sizeof(float) * 7 * m);
   if (parents) std::memcpy(parents, h_par, sizeof(uint32_t) * m);
   return TSDFLOC_OK;
@@ -1579,9 +1723,38 @@ int tsdfloc_tune(tsdfloc_ctx* c, int knob, int value)
       if (value < -1 || value > kDivBracket) return fail(c, TSDFLOC_E_BAD_ARG, "division: -1 automatic, 0 IEEE, 1 three-instruction, 2 bracket");
       c->tune_div = value;
       return TSDFLOC_OK;
+    case TSDFLOC_TUNE_STAGE_TIMERS:
+      c->stage_timers = value != 0;
+      c->stage_seen = 0;
+      return TSDFLOC_OK;
     default: return fail(c, TSDFLOC_E_BAD_ARG, "unknown tuning knob");
   }
 }
+
+int tsdfloc_stage_times(tsdfloc_ctx* c, float ms[4])
+{
+  if (!c || !ms) return TSDFLOC_E_BAD_ARG;
+  if (!c->stage_timers) return fail(c, TSDFLOC_E_STATE, "stage timers are off: tsdfloc_tune(ctx, TSDFLOC_TUNE_STAGE_TIMERS, 1)");
+  DeviceGuard guard(c->device);
+  CU_TRY(c, cudaStreamSynchronize(c->stream), "stream sync");
+  CU_TRY(c, cudaDeviceSynchronize(), "device sync");
+  auto span = [&](int a, int b, float* out) {
+    *out = 0.0f;
+    if ((c->stage_seen >> a & 1u) && (c->stage_seen >> b & 1u)) cudaEventElapsedTime(out, c->ev_stage[a], c->ev_stage[b]);
+  };
+  float prep = 0.0f, mats = 0.0f;
+  span(tsdfloc_ctx::kEvPrep0, tsdfloc_ctx::kEvPrep1, &prep);
+  if ((c->stage_seen >> tsdfloc_ctx::kEvInit0 & 1u) && c->eval_timed) cudaEventElapsedTime(&mats, c->ev_stage[tsdfloc_ctx::kEvInit0], c->ev_eval0);
+  ms[0] = prep + mats;                                                       // init_kernel: scan preparation + spatial order + matrices
+  ms[1] = 0.0f;
+  if (c->eval_timed) cudaEventElapsedTime(&ms[1], c->ev_eval0, c->ev_eval1);  // exec_kernel: k_eval
+  span(tsdfloc_ctx::kEvNorm0, tsdfloc_ctx::kEvNorm1, &ms[2]);                  // weight_update: K2 (+ K3)
+  span(tsdfloc_ctx::kEvDraw0, tsdfloc_ctx::kEvDraw1, &ms[3]);                  // resampling: K4
+  cudaGetLastError();
+  return TSDFLOC_OK;
+}
+
+int tsdfloc_last_cdf_was_exact(const tsdfloc_ctx* c) { return (c && c->h_status) ? (c->h_status->inexact ? 0 : 1) : -1; }
 
 int tsdfloc_division_mode(tsdfloc_ctx* c, uint64_t* open_brackets)
 {

@@ -8,6 +8,7 @@
 #pragma once
 #include "tsdfloc_device.cuh"
 #include "tsdfloc_eval.cuh"
+#include <cooperative_groups.h>
 #include <cstring>
 
 namespace tsdfloc
@@ -28,12 +29,13 @@ struct Status
   uint32_t inexact;       // 1: a parallel fp64 add was inexact -> sequential fallback ran
   uint32_t n_segs;
   unsigned long long n_out;  // particles the reference recurrence emits
-  uint32_t ticket;        // last-block-done counter of k_weight_sum (self-resetting)
+  uint32_t ticket;        // (unused)
   uint32_t table_overflow;   // build_u_table flags: 1 table full, 2 stalled recurrence, 4 max_j reached
   unsigned long long best_key;  // arg-max of the weights: (weight bits << 32) | ~index; 0 = no particle with weight > 0
   float best_pose[6];        // pose of that particle
   float best_weight;
   uint32_t pad;
+  float mean[8];             // weighted mean pose when the caller did not supply its own device buffer: one read-back gets all
 };
 
 // Arg-max key of mcl_3d.cpp:382-395 (`if (value > max_value)` from max_value = 0: the FIRST particle carrying the largest
@@ -93,15 +95,32 @@ __global__ void __launch_bounds__(256) k_probe_gather(const float* __restrict__ 
 // Scan preparation: xyz -> float4 with w = the point's range term
 //   |p|^2 < max_range^2 ? a_range * (1/max_range) : a_max     (tsdf_evaluator.cpp:56-65, cuda_eval_particles.h:200-209)
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_prep_scan(const float* __restrict__ xyz, uint32_t p, float4* __restrict__ out, float a_range_term, float a_max,
-                            float max_range_sq)
+struct PrepArgs
 {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p; i += gridDim.x * blockDim.x)
+  const float* __restrict__ xyz;   // [p][3]
+  float4* __restrict__ out;        // [padded]
+  uint32_t p, padded;              // points beyond p are written as zero points (the evaluation reads whole blocks)
+  float a_range_term, a_max, max_range_sq;
+};
+
+__device__ __forceinline__ void prep_scan_points(const PrepArgs& A, uint32_t first_thread, uint32_t n_threads)
+{
+  for (uint32_t i = first_thread; i < A.padded; i += n_threads)
   {
-    const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
-    const float sq = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
-    out[i] = make_float4(x, y, z, sq < max_range_sq ? a_range_term : a_max);
+    if (i < A.p)
+    {
+      const float x = A.xyz[3 * i], y = A.xyz[3 * i + 1], z = A.xyz[3 * i + 2];
+      const float sq = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+      A.out[i] = make_float4(x, y, z, sq < A.max_range_sq ? A.a_range_term : A.a_max);
+    }
+    else
+      A.out[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   }
+}
+
+__global__ void __launch_bounds__(256) k_prep_scan(const PrepArgs A)
+{
+  prep_scan_points(A, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -114,11 +133,9 @@ struct Tf12
 };
 
 // perm (optional): matrix i belongs to particle first + perm[i] (spatial evaluation order, tsdfloc_sort.cuh).
-__global__ void k_pose_matrices(const float* __restrict__ particles, uint32_t first, uint32_t count, Tf12 tf, float* __restrict__ mats,
-                                const uint32_t* __restrict__ perm)
+__device__ __forceinline__ void pose_matrix(const float* __restrict__ particles, uint32_t first, uint32_t i, const Tf12& tf, float* __restrict__ mats,
+                                            const uint32_t* __restrict__ perm)
 {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
   const float* p = particles + 7ull * (first + (perm ? perm[i] : i));
   double sd, cd;
   sincos(static_cast<double>(p[3]), &sd, &cd);
@@ -154,6 +171,27 @@ __global__ void k_pose_matrices(const float* __restrict__ particles, uint32_t fi
   }
 }
 
+__global__ void __launch_bounds__(256) k_pose_matrices(const float* __restrict__ particles, uint32_t first, uint32_t count, Tf12 tf,
+                                                      float* __restrict__ mats, const uint32_t* __restrict__ perm)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) pose_matrix(particles, first, i, tf, mats, perm);
+}
+
+// Scan preparation and pose matrices in ONE launch (the host-buffer update issues them together): CTAs [0, scan_ctas) prepare
+// the scan, the rest build matrices.
+__global__ void __launch_bounds__(256) k_prepare(const PrepArgs A, uint32_t scan_ctas, const float* __restrict__ particles, uint32_t first,
+                                                uint32_t count, Tf12 tf, float* __restrict__ mats, const uint32_t* __restrict__ perm)
+{
+  if (blockIdx.x < scan_ctas)
+    prep_scan_points(A, blockIdx.x * blockDim.x + threadIdx.x, scan_ctas * blockDim.x);
+  else
+  {
+    const uint32_t i = (blockIdx.x - scan_ctas) * blockDim.x + threadIdx.x;
+    if (i < count) pose_matrix(particles, first, i, tf, mats, perm);
+  }
+}
+
 // Exhaustive proof obligations of the sub-voxel quotient for ONE resolution, over every float a in [0, 1):
 //   out[0]  a where the 3-instruction quotient's floor differs from floor(fl(a / res))            (0 = kDivThree is exact)
 //   out[1]  a where floor(a * lo1) <= floor(fl(a / res)) <= floor(a * hi1) is VIOLATED             (0 = the bracket holds)
@@ -181,49 +219,6 @@ __global__ void k_check_div(MapDev M, float lo1, float hi1, float lo2, float hi2
   if (open2) atomicAdd(out + 4, open2);
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// K2a: sum of raw weights in fp64, fixed order (block tree, then the last block adds the block sums in index order).
-// ------------------------------------------------------------------------------------------------------------
-__global__ void k_weight_sum(const float* __restrict__ raw, uint32_t stride, uint32_t n, double* __restrict__ block_sums,
-                             Status* __restrict__ st)
-{
-  __shared__ double s_part[kScanThreads / 32];
-  __shared__ bool s_last;
-  const uint32_t base = blockIdx.x * kScanTile;
-  double acc = 0.0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k)
-  {
-    const uint32_t i = base + threadIdx.x * kScanItems + k;
-    if (i < n) acc += static_cast<double>(raw[static_cast<size_t>(i) * stride]);
-  }
-  for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0)
-  {
-    double t = 0.0;
-    for (int w = 0; w < kScanThreads / 32; ++w) t += s_part[w];
-    block_sums[blockIdx.x] = t;
-    __threadfence();
-    const uint32_t ticket = atomicAdd(&st->ticket, 1u);
-    s_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x == 0)
-  {
-    __threadfence();
-    double t = 0.0;
-    for (uint32_t b = 0; b < gridDim.x; ++b) t += reinterpret_cast<volatile double*>(block_sums)[b];
-    st->weight_sum = t;
-    st->weight_sum_f = static_cast<float>(t);
-    st->zero_sum = (t == 0.0) ? 1u : 0u;
-    st->inexact = 0u;
-    st->table_overflow = 0u;
-    st->ticket = 0u;
-  }
-}
-
 // exact-add check: returns a+b and sets `bad` if the fp64 addition rounded.
 __device__ __forceinline__ double add_checked(double a, double b, bool& bad)
 {
@@ -235,196 +230,256 @@ __device__ __forceinline__ double add_checked(double a, double b, bool& bad)
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K2b: normalise (w /= (float)sum, cuda_eval_particles.h:556), per-tile fp64 inclusive scan of the normalised
-// weights, per-tile weighted moments (x y z, sin/cos of the three angles; tsdf_evaluator.cpp:203-217).
-// raw == nullptr: the particles already carry their weights (Resampler::resample on a weighted cloud): they are
-// scanned as they are and not rewritten.
+// K2: ONE cooperative kernel (grid-wide syncs instead of kernel boundaries) for everything between the evaluation and the
+// draw. Replaces weightSum x10, weight_particles, the host atan2s (cuda_evaluator.cu:364-392, cuda_sum.cu,
+// cuda_eval_particles.h:521-557) and the arg-max loop of the node (mcl_3d.cpp:382-399):
+//   A  per-tile fp64 sums of the raw weights (fixed order)                                  | grid sync
+//   B  sum of the tile sums (fixed order, every CTA redundantly) -> the fp32 divisor; normalise (w /= (float)sum,
+//      cuda_eval_particles.h:556), tile-local fp64 inclusive scan, weighted moments (tsdf_evaluator.cpp:203-217), arg-max
+//      (raw == nullptr: the particles already carry their weights — Resampler::resample on a weighted cloud — they are scanned
+//      as they are and nothing is rewritten)                                                | grid sync
+//   C  tile offsets (exactness-checked fp64: when every addition is exact the order is irrelevant; one that rounds raises
+//      st->inexact and k_cdf_fallback redoes the CDF in the reference's own order) -> global CDF s_m = sum_{i<=m} w_i;
+//      CTA 0: moments -> mean pose, best particle.
+// A CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the grid is sized to be co-resident (cooperative launch).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kScanThreads) k_normalise_scan(float* __restrict__ particles, const float* __restrict__ raw, uint32_t n,
-                                                                 Status* __restrict__ st, double* __restrict__ cdf,
-                                                                 double* __restrict__ tile_total, double* __restrict__ tile_moments,
-                                                                 unsigned long long* __restrict__ tile_best)
+struct NormArgs
 {
-  __shared__ double s_warp[kScanThreads / 32];
-  __shared__ double s_mom[kScanThreads / 32][9];
-  __shared__ unsigned long long s_best[kScanThreads / 32];
-  unsigned long long best = 0ull;
-  const float inv_den = st->weight_sum_f;
-  const bool dead = st->zero_sum != 0u;
-  const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-  bool bad = false;
+  float* particles;               // [n][7]; slot 6 receives the normalised weight (raw != nullptr)
+  const float* raw;               // [n] un-normalised weights, or nullptr
+  uint32_t n;
+  Status* st;
+  double* cdf;                    // [n]
+  double* tile_sum;               // [tiles] phase A
+  double* tile_total;             // [tiles] phase B: sum of the tile's normalised weights
+  double* tile_moments;           // [tiles][9]
+  unsigned long long* tile_best;  // [tiles]
+  float* mean_pose;               // [6] or nullptr
+  float* w_out;                   // [n] or nullptr: the normalised weights once more as a contiguous vector (4 B per particle
+                                  //     for the host write-back instead of the 28 B particles)
+};
 
-  double loc[kScanItems];
-  double mom[9];
-#pragma unroll
-  for (int q = 0; q < 9; ++q) mom[q] = 0.0;
-  double run = 0.0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k)
-  {
-    const uint32_t i = base + k;
-    float w = 0.0f;
-    if (i < n)
-    {
-      float* p = particles + 7ull * i;
-      if (raw)
-      {
-        w = dead ? 0.0f : __fdiv_rn(raw[i], inv_den);
-        p[6] = w;
-      }
-      else
-      {
-        w = p[6];
-      }
-      const unsigned long long key = best_key_of(w, i);
-      best = key > best ? key : best;
-      const float x = p[0], y = p[1], z = p[2];
-      mom[0] += static_cast<double>(__fmul_rn(x, w));
-      mom[1] += static_cast<double>(__fmul_rn(y, w));
-      mom[2] += static_cast<double>(__fmul_rn(z, w));
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-      {
-        double sd, cd;
-        sincos(static_cast<double>(p[3 + a]), &sd, &cd);
-        mom[3 + 2 * a] += sd * static_cast<double>(w);
-        mom[4 + 2 * a] += cd * static_cast<double>(w);
-      }
-    }
-    run = add_checked(run, static_cast<double>(w), bad);
-    loc[k] = run;
-  }
-
-  // inclusive scan of the per-thread totals across the warp, then across warps
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  double incl = run;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1)
-  {
-    const double up = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= static_cast<uint32_t>(o)) incl = add_checked(incl, up, bad);
-  }
-  double lane_excl = __shfl_up_sync(0xffffffffu, incl, 1);  // exclusive prefix over lanes: an already-checked sum
-  if (lane == 0) lane_excl = 0.0;
-  if (lane == 31) s_warp[warp] = incl;
-#pragma unroll
-  for (int q = 0; q < 9; ++q)
-  {
-    double v = mom[q];
-    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) s_mom[warp][q] = v;
-  }
-  for (int o = 16; o; o >>= 1)
-  {
-    const unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
-    best = other > best ? other : best;
-  }
-  if (lane == 0) s_best[warp] = best;
+__device__ __forceinline__ double block_sum_fixed(double v, double* s_part)
+{
+  // fixed order: shuffle tree inside each warp, then thread 0 adds the warp sums in warp order
+  for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
   __syncthreads();
-  double warp_off = 0.0;
-  for (uint32_t w = 0; w < warp; ++w) warp_off = add_checked(warp_off, s_warp[w], bad);
-  const double excl = add_checked(warp_off, lane_excl, bad);
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k)
-  {
-    const uint32_t i = base + k;
-    if (i < n) cdf[i] = add_checked(excl, loc[k], bad);
-  }
-  if (threadIdx.x == kScanThreads - 1) tile_total[blockIdx.x] = add_checked(excl, run, bad);
-  if (threadIdx.x < 9)
-  {
-    double v = 0.0;
-    for (int w = 0; w < kScanThreads / 32; ++w) v += s_mom[w][threadIdx.x];
-    tile_moments[static_cast<size_t>(blockIdx.x) * 9 + threadIdx.x] = v;
-  }
-  if (threadIdx.x == 9)
-  {
-    unsigned long long b = 0ull;
-    for (int w = 0; w < kScanThreads / 32; ++w) b = s_best[w] > b ? s_best[w] : b;
-    tile_best[blockIdx.x] = b;
-  }
-  if (bad) atomicOr(&st->inexact, 1u);
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < kScanThreads / 32; ++w) t += s_part[w];
+  __syncthreads();
+  return t;   // valid in thread 0
 }
 
-// K2c: one warp. Exclusive scan of the tile totals (fp64, exactness-checked: when every addition is exact the result does
-// not depend on the order, so the warp scans 32 tiles at a time instead of one thread walking them; an inexact addition
-// raises st->inexact and K3 redoes the CDF sequentially), moments -> mean pose, per-tile arg-max -> best particle.
-__global__ void __launch_bounds__(32) k_scan_tiles(const double* __restrict__ tile_total, double* __restrict__ tile_offset, uint32_t n_tiles,
-                                                   const double* __restrict__ tile_moments, float* __restrict__ mean_pose,
-                                                   Status* __restrict__ st, const unsigned long long* __restrict__ tile_best,
-                                                   const float* __restrict__ particles)
+__global__ void __launch_bounds__(kScanThreads) k_normalise_cdf(const NormArgs A)
 {
-  const uint32_t lane = threadIdx.x;
-  bool bad = false;
-  double carry = 0.0;
-  double mom[9];
-#pragma unroll
-  for (int q = 0; q < 9; ++q) mom[q] = 0.0;
-  unsigned long long best = 0ull;
-  for (uint32_t base = 0; base < n_tiles; base += 32u)
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ double s_part[kScanThreads / 32];
+  __shared__ double s_mom[kScanThreads / 32][9];
+  __shared__ unsigned long long s_best[kScanThreads / 32];
+  __shared__ double s_bcast;
+  const uint32_t n = A.n;
+  const uint32_t n_tiles = (n + kScanTile - 1) / kScanTile;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t stride = A.raw ? 1u : 7u;
+  const float* __restrict__ src = A.raw ? A.raw : A.particles + 6;
+
+  // ---- A: tile sums ------------------------------------------------------------------------------------------
+  if (blockIdx.x == 0 && threadIdx.x == 0) A.st->inexact = 0u;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
   {
-    const uint32_t t = base + lane;
-    const bool live = t < n_tiles;
-    const double v = live ? tile_total[t] : 0.0;
-    double incl = v;
+    const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (base + k < n) acc += static_cast<double>(src[static_cast<size_t>(base + k) * stride]);
+    const double t = block_sum_fixed(acc, s_part);
+    if (threadIdx.x == 0) A.tile_sum[tile] = t;
+  }
+  grid.sync();
+
+  // ---- B: total (every CTA, same order), normalise + tile-local scan + moments + arg-max ------------------------
+  {
+    double acc = 0.0;
+    for (uint32_t i = threadIdx.x; i < n_tiles; i += kScanThreads) acc += A.tile_sum[i];
+    const double t = block_sum_fixed(acc, s_part);
+    if (threadIdx.x == 0) s_bcast = t;
+    __syncthreads();
+  }
+  const double total = s_bcast;
+  const float den = static_cast<float>(total);
+  const bool dead = (total == 0.0);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    A.st->weight_sum = total;
+    A.st->weight_sum_f = den;
+    A.st->zero_sum = dead ? 1u : 0u;
+  }
+  bool bad = false;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  {
+    const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
+    unsigned long long best = 0ull;
+    double loc[kScanItems];
+    double mom[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) mom[q] = 0.0;
+    double run = 0.0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+    {
+      const uint32_t i = base + k;
+      float w = 0.0f;
+      if (i < n)
+      {
+        float* p = A.particles + 7ull * i;
+        if (A.raw)
+        {
+          w = dead ? 0.0f : __fdiv_rn(A.raw[i], den);
+          p[6] = w;
+        }
+        else
+          w = p[6];
+        if (A.w_out) A.w_out[i] = w;
+        const unsigned long long key = best_key_of(w, i);
+        best = key > best ? key : best;
+        const float x = p[0], y = p[1], z = p[2];
+        mom[0] += static_cast<double>(__fmul_rn(x, w));
+        mom[1] += static_cast<double>(__fmul_rn(y, w));
+        mom[2] += static_cast<double>(__fmul_rn(z, w));
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+          double sd, cd;
+          sincos(static_cast<double>(p[3 + a]), &sd, &cd);
+          mom[3 + 2 * a] += sd * static_cast<double>(w);
+          mom[4 + 2 * a] += cd * static_cast<double>(w);
+        }
+      }
+      run = add_checked(run, static_cast<double>(w), bad);
+      loc[k] = run;
+    }
+    // inclusive scan of the per-thread totals across the warp, then across warps
+    double incl = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
     {
       const double up = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= static_cast<uint32_t>(o)) incl = add_checked(incl, up, bad);
     }
-    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) excl = 0.0;
-    if (live) tile_offset[t] = add_checked(carry, excl, bad);
-    carry = add_checked(carry, __shfl_sync(0xffffffffu, incl, 31), bad);
-    if (live)
-    {
-      // per-lane partial sums in a fixed (tile-index) order; combined below in a fixed tree order -> deterministic
+    double lane_excl = __shfl_up_sync(0xffffffffu, incl, 1);  // exclusive prefix over lanes: an already-checked sum
+    if (lane == 0) lane_excl = 0.0;
+    __syncthreads();   // s_part / s_mom / s_best of the previous tile have been consumed
+    if (lane == 31) s_part[warp] = incl;
 #pragma unroll
-      for (int q = 0; q < 9; ++q) mom[q] += tile_moments[static_cast<size_t>(t) * 9 + q];
-      const unsigned long long b = tile_best[t];
+    for (int q = 0; q < 9; ++q)
+    {
+      double v = mom[q];
+      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) s_mom[warp][q] = v;
+    }
+    for (int o = 16; o; o >>= 1)
+    {
+      const unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+    double warp_off = 0.0;
+    for (uint32_t w = 0; w < warp; ++w) warp_off = add_checked(warp_off, s_part[w], bad);
+    const double excl = add_checked(warp_off, lane_excl, bad);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (base + k < n) A.cdf[base + k] = add_checked(excl, loc[k], bad);
+    if (threadIdx.x == kScanThreads - 1) A.tile_total[tile] = add_checked(excl, run, bad);
+    if (threadIdx.x < 9)
+    {
+      double v = 0.0;
+      for (int w = 0; w < kScanThreads / 32; ++w) v += s_mom[w][threadIdx.x];
+      A.tile_moments[static_cast<size_t>(tile) * 9 + threadIdx.x] = v;
+    }
+    if (threadIdx.x == 9)
+    {
+      unsigned long long b = 0ull;
+      for (int w = 0; w < kScanThreads / 32; ++w) b = s_best[w] > b ? s_best[w] : b;
+      A.tile_best[tile] = b;
+    }
+  }
+  grid.sync();
+
+  // ---- C: tile offsets -> global CDF; CTA 0: mean pose + best particle ----------------------------------------------
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  {
+    if (tile == 0) continue;
+    // offset = sum of the totals of all earlier tiles, every addition checked for exactness
+    double part = 0.0;
+    for (uint32_t i = threadIdx.x; i < tile; i += kScanThreads) part = add_checked(part, A.tile_total[i], bad);
+    for (int o = 16; o; o >>= 1)
+    {
+      const double other = __shfl_down_sync(0xffffffffu, part, o);
+      part = add_checked(part, other, bad);
+    }
+    __syncthreads();
+    if (lane == 0) s_part[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      double t = 0.0;
+      for (int w = 0; w < kScanThreads / 32; ++w) t = add_checked(t, s_part[w], bad);
+      s_bcast = t;
+    }
+    __syncthreads();
+    const double off = s_bcast;
+    const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (base + k < n) A.cdf[base + k] = add_checked(off, A.cdf[base + k], bad);
+  }
+  if (bad) atomicOr(&A.st->inexact, 1u);
+
+  if (blockIdx.x == 0 && warp == 0)
+  {
+    // per-lane partial sums in a fixed (tile-index) order, combined in a fixed tree order -> deterministic
+    double mom[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) mom[q] = 0.0;
+    unsigned long long best = 0ull;
+    for (uint32_t t = lane; t < n_tiles; t += 32u)
+    {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) mom[q] += A.tile_moments[static_cast<size_t>(t) * 9 + q];
+      const unsigned long long b = A.tile_best[t];
       best = b > best ? b : best;
     }
-  }
 #pragma unroll
-  for (int q = 0; q < 9; ++q)
-    for (int o = 16; o; o >>= 1) mom[q] += __shfl_down_sync(0xffffffffu, mom[q], o);
-  for (int o = 16; o; o >>= 1)
-  {
-    const unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
-    best = other > best ? other : best;
-  }
-  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&st->inexact, 1u);
-  if (lane == 0)
-  {
-    if (mean_pose)
+    for (int q = 0; q < 9; ++q)
+      for (int o = 16; o; o >>= 1) mom[q] += __shfl_down_sync(0xffffffffu, mom[q], o);
+    for (int o = 16; o; o >>= 1)
     {
-      mean_pose[0] = static_cast<float>(mom[0]);
-      mean_pose[1] = static_cast<float>(mom[1]);
-      mean_pose[2] = static_cast<float>(mom[2]);
-      mean_pose[3] = static_cast<float>(atan2(mom[3], mom[4]));
-      mean_pose[4] = static_cast<float>(atan2(mom[5], mom[6]));
-      mean_pose[5] = static_cast<float>(atan2(mom[7], mom[8]));
+      const unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
     }
-    st->best_key = best;
-    if (best)
+    if (lane == 0)
     {
-      const uint32_t i = ~static_cast<uint32_t>(best & 0xffffffffull);
-      for (int k = 0; k < 6; ++k) st->best_pose[k] = particles[7ull * i + k];
-      st->best_weight = particles[7ull * i + 6];
+      if (A.mean_pose)
+      {
+        A.mean_pose[0] = static_cast<float>(mom[0]);
+        A.mean_pose[1] = static_cast<float>(mom[1]);
+        A.mean_pose[2] = static_cast<float>(mom[2]);
+        A.mean_pose[3] = static_cast<float>(atan2(mom[3], mom[4]));
+        A.mean_pose[4] = static_cast<float>(atan2(mom[5], mom[6]));
+        A.mean_pose[5] = static_cast<float>(atan2(mom[7], mom[8]));
+      }
+      A.st->best_key = best;
+      if (best)
+      {
+        const uint32_t i = ~static_cast<uint32_t>(best & 0xffffffffull);
+        for (int k = 0; k < 6; ++k) A.st->best_pose[k] = A.particles[7ull * i + k];
+        A.st->best_weight = A.particles[7ull * i + 6];
+      }
     }
   }
-}
-
-// K2d: add the tile offsets (exactness-checked) -> global fp64 CDF s_m = sum_{i<=m} w_i.
-__global__ void k_cdf_finalize(double* __restrict__ cdf, const double* __restrict__ tile_offset, uint32_t n, Status* __restrict__ st)
-{
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  bool bad = false;
-  const uint32_t tile = i / kScanTile;
-  if (tile) cdf[i] = add_checked(tile_offset[tile], cdf[i], bad);
-  if (bad) atomicOr(&st->inexact, 1u);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -539,32 +594,40 @@ __host__ __device__ inline float u_at(const USeg* segs, uint32_t n_segs, unsigne
   return static_cast<float>(static_cast<double>(s.u_start) + static_cast<double>(j - s.j0) * static_cast<double>(s.step));
 }
 
-// K3: one warp. If the parallel scan was inexact, thread 0 redoes the CDF sequentially (the reference's own
-// order of fp64 additions); then builds the U table and n_out.
-__global__ void k_finish_cdf_utable(const float* __restrict__ particles, double* __restrict__ cdf, uint32_t n, float u0,
-                                    USeg* __restrict__ segs, Status* __restrict__ st)
+// The U table of one resampling call, built on the HOST (it depends only on u0 and N: build_u_table with no limit) and handed
+// to the draw kernel BY VALUE as a kernel parameter: no device-side table builder, no copy to order against the launch.
+struct UTable
 {
-  if (threadIdx.x != 0) return;
-  if (st->inexact)
+  USeg segs[kMaxUSegs];
+  unsigned long long n_elems;   // U_j is covered for j < n_elems
+  uint32_t n_segs;
+  uint32_t flags;               // build_u_table flags (1 table full, 2 stalled recurrence, 4 max_j reached)
+};
+
+// #{j < n_elems : U_j < limit}: U_j is non-decreasing in j, so a binary search over j with the exact u_at().
+__device__ inline unsigned long long u_count_below(const USeg* segs, uint32_t n_segs, unsigned long long n_elems, double limit)
+{
+  unsigned long long lo = 0, hi = n_elems;   // first j with U_j >= limit
+  while (lo < hi)
   {
-    double s = 0.0;
-    for (uint32_t i = 0; i < n; ++i)
-    {
-      s += static_cast<double>(particles[7ull * i + 6]);
-      cdf[i] = s;
-    }
+    const unsigned long long mid = (lo + hi) >> 1;
+    if (static_cast<double>(u_at(segs, n_segs, mid)) < limit) lo = mid + 1; else hi = mid;
   }
-  const double s_last = n ? cdf[n - 1] : 0.0;
-  st->s_last = s_last;
-  unsigned long long n_below = 0;
-  const double inv_m = 1.0 / static_cast<double>(n);
-  // the recurrence cannot emit more than ~ s_last * N + 1 elements; 2N + 64 bounds any sane weight vector
-  const unsigned long long max_j = 2ull * n + 64ull;
-  uint32_t flags = 0;
-  const uint32_t ns = build_u_table(u0, inv_m, s_last, segs, kMaxUSegs, &n_below, max_j, &flags);
-  st->n_segs = ns;
-  st->n_out = st->zero_sum ? 0ull : n_below;
-  st->table_overflow = flags;
+  return lo;
+}
+
+// K3: runs only when a parallel fp64 addition of K2 rounded (st->inexact): the CDF is then redone in the reference's own
+// order of additions, s += w_m, m = 0 .. n-1 (novel_resampling.h:57). With normalised weights from one sensor update the
+// additions are exact (the weights span a few binades); clouds with a very wide dynamic range take this path.
+__global__ void k_cdf_fallback(const float* __restrict__ particles, double* __restrict__ cdf, uint32_t n, const Status* __restrict__ st)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0 || !st->inexact) return;
+  double s = 0.0;
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    s += static_cast<double>(particles[7ull * i + 6]);
+    cdf[i] = s;
+  }
 }
 
 // Multi-GPU: the same output slice inside every other rank's particle buffer (peer-mapped); n == 0 on one GPU.
@@ -574,18 +637,35 @@ struct DrawPeers
   uint32_t n;
 };
 
-// K4: draw. Output slot j copies the first particle m with s_m > U_j (strict, novel_resampling.h:59).
-__global__ void k_draw(const float* __restrict__ particles, const double* __restrict__ cdf, uint32_t n, const USeg* __restrict__ segs,
-                       const Status* __restrict__ st, unsigned long long first_out, uint32_t count_out, float* __restrict__ out,
-                       uint32_t* __restrict__ parents, const DrawPeers peers)
+// K4: draw. Output slot j copies the first particle m with s_m > U_j (strict, novel_resampling.h:59). Every CTA derives the
+// output length n_out = #{j : U_j < s_last} itself (the `while (s > U)` loop of the reference ends there); CTA 0 publishes it.
+__global__ void __launch_bounds__(256) k_draw(const float* __restrict__ particles, const double* __restrict__ cdf, uint32_t n,
+                                              const __grid_constant__ UTable T, Status* __restrict__ st, unsigned long long first_out,
+                                              uint32_t count_out, float* __restrict__ out, uint32_t* __restrict__ parents, const DrawPeers peers)
 {
   __shared__ USeg s_segs[kMaxUSegs];
-  const uint32_t ns = st->n_segs;
-  for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) s_segs[i] = segs[i];
+  __shared__ unsigned long long s_n_out;
+  const uint32_t ns = T.n_segs;
+  for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) s_segs[i] = T.segs[i];
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    const double s_last = n ? cdf[n - 1] : 0.0;
+    const unsigned long long below = (ns && !st->zero_sum) ? u_count_below(s_segs, ns, T.n_elems, s_last) : 0ull;
+    s_n_out = below;
+    if (blockIdx.x == 0)
+    {
+      st->s_last = s_last;
+      st->n_segs = ns;
+      st->n_out = below;
+      // the table ended before U reached s_last: it was full, the recurrence stalled, or the weights sum to more than 2
+      st->table_overflow = (below >= T.n_elems && ns && !st->zero_sum) ? (T.flags ? T.flags : 4u) : 0u;
+    }
+  }
   __syncthreads();
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count_out) return;
-  const unsigned long long n_out = st->n_out;
+  const unsigned long long n_out = s_n_out;
   unsigned long long j = first_out + t;
   uint32_t parent = 0;
   if (n_out != 0ull && ns != 0u)
