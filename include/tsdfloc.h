@@ -307,6 +307,14 @@ int tsdfloc_multi_sensor_update(tsdfloc_multi* m, float* particles, uint64_t n, 
                                 float mean_pose[6]);
 int tsdfloc_multi_resample_systematic(tsdfloc_multi* m, float u0, float* particles_out, uint64_t cap, uint64_t* n_out);
 
+/* The whole update on device pointers in one call and four kernels (scan preparation + pose matrices, evaluation,
+ * normalisation + mean + CDF, draw) on `stream`, without a host synchronisation: d_points_xyz p x 3 fp32; d_particles n x 7
+ * (slot 6 receives the normalised weights); output slots [0, count_out) of the systematic resampling with offset u0 go to
+ * d_particles_out; d_mean_pose (optional) 6 fp32. Outcome (n_out, zero weight sum) through tsdfloc_check. The single-GPU
+ * form of the stage calls below; replaces CudaEvaluator::evaluate + SystematicResampler::resample for a device-resident filter. */
+int tsdfloc_update_device(tsdfloc_ctx* ctx, const float* d_points_xyz, uint64_t p, float* d_particles, uint64_t n, const float tf[16],
+                          float u0, float* d_particles_out, uint64_t count_out, float* d_mean_pose, void* stream);
+
 /* Synchronises `stream` and reports what the device recorded for the last normalize/draw:
  * n_out = number of particles the reference recurrence emits; returns TSDFLOC_E_NO_VALID_PARTICLE if sum == 0. */
 int tsdfloc_check(tsdfloc_ctx* ctx, uint64_t* n_out, double* weight_sum, void* stream);

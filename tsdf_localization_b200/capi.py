@@ -111,6 +111,7 @@ SIGNATURES = {
     "tsdfloc_normalize_device": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "tsdfloc_draw_device": (C.c_int, [_vp, _vp, _u64, C.c_float, _u64, _u64, _vp, _vp, _vp]),
     "tsdfloc_check": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double), _vp]),
+    "tsdfloc_update_device": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _fp, C.c_float, _vp, _u64, _vp, _vp]),
     "tsdfloc_reduce_scan_device": (C.c_int, [_vp, _vp, _vp, _u64, C.c_double, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "tsdfloc_reduce_result": (C.c_int, [_vp, C.POINTER(_u64), _vp]),
     "tsdfloc_reduce_scan": (C.c_int, [_vp, _vp, _u64, _vp, _u64, C.c_int, _u64, C.c_double, C.c_uint32, C.c_uint32, _vp, _vp, _u64,

@@ -64,7 +64,7 @@ struct tsdfloc_ctx
   cudaEvent_t ev_stage[kEvCount] = {};
   bool stage_timers = false;
   uint32_t stage_seen = 0;     // bit k: ev_stage[k] was recorded since the timers were switched on
-  int norm_max_ctas = 0;       // co-resident CTAs of the cooperative normalisation kernel
+  int norm_max_ctas = 0, exact_max_ctas = 0;   // co-resident CTAs of the cooperative kernels k_normalise_cdf / k_cdf_exact
 
   // map
   int32_t* d_table = nullptr;
@@ -485,9 +485,21 @@ int stage_normalize(tsdfloc_ctx* c, float* d_particles, uint64_t n, const float*
   CU_TRY(c, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_normalise_cdf), dim3(grid), dim3(kScanThreads), args, 0, s),
          "launch of k_normalise_cdf");
   if ((rc = launch_check(c, "k_normalise_cdf"))) return rc;
-  // the exact-order redo, taken only when a parallel fp64 addition rounded (the kernel returns at once otherwise)
-  k_cdf_fallback<<<1, 32, 0, s>>>(d_particles, static_cast<double*>(c->d_cdf.p), static_cast<uint32_t>(n), c->d_status);
-  if ((rc = launch_check(c, "k_cdf_fallback"))) return rc;
+  // the serial-order CDF, computed only when a parallel fp64 addition rounded (every CTA returns at once otherwise); K2's
+  // per-tile scratch is free again and is reused
+  ExactArgs x{};
+  x.particles = d_particles;
+  x.n = static_cast<uint32_t>(n);
+  x.st = c->d_status;
+  x.cdf = static_cast<double*>(c->d_cdf.p);
+  x.tile_units = static_cast<long long*>(c->d_tile_moments.p);   // 9 doubles per tile: room for 2 x int64
+  x.tile_flag = static_cast<uint32_t*>(c->d_tile_best.p);
+  x.tile_start = static_cast<double*>(c->d_tile_total.p);
+  const unsigned xgrid = static_cast<unsigned>(std::min<uint64_t>(tiles, static_cast<uint64_t>(c->exact_max_ctas)));
+  void* xargs[] = {&x};
+  CU_TRY(c, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_cdf_exact), dim3(xgrid), dim3(kScanThreads), xargs, 0, s),
+         "launch of k_cdf_exact");
+  if ((rc = launch_check(c, "k_cdf_exact"))) return rc;
   if ((rc = mark(c, tsdfloc_ctx::kEvNorm1, s))) return rc;
   c->have_cdf = true;
   return TSDFLOC_OK;
@@ -784,6 +796,9 @@ static int create_impl(const tsdfloc_map_desc* map, const int32_t* grid_occ, con
     CU_CREATE(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device), "cudaDeviceGetAttribute");
     if (!coop || per_sm < 1) return bail(TSDFLOC_E_CUDA, "device does not support cooperative launches");
     c->norm_max_ctas = per_sm * c->sm_count;
+    CU_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cdf_exact, kScanThreads, 0), "occupancy(k_cdf_exact)");
+    if (per_sm < 1) return bail(TSDFLOC_E_CUDA, "k_cdf_exact cannot be made resident");
+    c->exact_max_ctas = per_sm * c->sm_count;
   }
 
   // ---- padded brick table ------------------------------------------------------------------------------------
@@ -1091,6 +1106,25 @@ int tsdfloc_draw_device(tsdfloc_ctx* c, const float* d_particles, uint64_t n_tot
   if (!d_particles || (count_out && !d_particles_out)) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
   DeviceGuard guard(c->device);
   return stage_draw(c, d_particles, n_total, u0, first_out, count_out, d_particles_out, d_parents, pick(c, stream));
+}
+
+int tsdfloc_update_device(tsdfloc_ctx* c, const float* d_points_xyz, uint64_t p, float* d_particles, uint64_t n, const float tf[16], float u0,
+                          float* d_particles_out, uint64_t count_out, float* d_mean_pose, void* stream)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!d_points_xyz || !d_particles || !tf || (count_out && !d_particles_out)) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (p == 0) return fail(c, TSDFLOC_E_EMPTY_SCAN, "empty scan");
+  if (n == 0) return fail(c, TSDFLOC_E_BAD_ARG, "no particles");
+  DeviceGuard guard(c->device);
+  cudaStream_t s = pick(c, stream);
+  int rc;
+  if ((rc = ensure(c, c->d_raw, sizeof(float) * n, "cudaMalloc(raw weights)"))) return rc;
+  c->have_cdf = false;
+  PrepArgs scan{};
+  if ((rc = scan_layout(c, d_points_xyz, p, &scan))) return rc;
+  if ((rc = stage_eval(c, d_particles, n, 0, n, tf, static_cast<float*>(c->d_raw.p), s, nullptr, 0, false, nullptr, nullptr, &scan))) return rc;
+  if ((rc = stage_normalize(c, d_particles, n, static_cast<const float*>(c->d_raw.p), d_mean_pose ? d_mean_pose : c->d_mean, s))) return rc;
+  return stage_draw(c, d_particles, n, u0, 0, count_out, d_particles_out, nullptr, s);
 }
 
 int tsdfloc_check(tsdfloc_ctx* c, uint64_t* n_out, double* weight_sum, void* stream)

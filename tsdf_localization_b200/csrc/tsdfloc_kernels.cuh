@@ -616,17 +616,264 @@ __device__ inline unsigned long long u_count_below(const USeg* segs, uint32_t n_
   return lo;
 }
 
-// K3: runs only when a parallel fp64 addition of K2 rounded (st->inexact): the CDF is then redone in the reference's own
-// order of additions, s += w_m, m = 0 .. n-1 (novel_resampling.h:57). With normalised weights from one sensor update the
-// additions are exact (the weights span a few binades); clouds with a very wide dynamic range take this path.
-__global__ void k_cdf_fallback(const float* __restrict__ particles, double* __restrict__ cdf, uint32_t n, const Status* __restrict__ st)
+// ------------------------------------------------------------------------------------------------------------
+// K3: the CDF in the reference's own order of additions — s += w_m, m = 0 .. n-1, in fp64 (novel_resampling.h:57) — for
+// weight vectors whose fp64 sum ROUNDS (st->inexact: a parallel addition of K2 was inexact, so the order matters). With the
+// normalised weights of one sensor update the additions are exact and every CTA returns at once; clouds whose weights span
+// dozens of binades take this path (a serial loop costs 38 ms at 2^20 particles).
+// The serial sum is reproduced in parallel. While the running sum s = S * u stays inside one binade (ulp u, S an integer)
+// and the addends are >= 0, RN(s + w) adds RN(w / u) units — except for an exact TIE (w / u = k + 1/2), which
+// round-half-even resolves by the parity of S + k: it adds k + ((S + k) mod 2) and leaves S EVEN. So the only state a weight
+// needs from its predecessors is the parity of S, and every weight is a map {parity in} -> {units added, parity out}; those
+// maps compose associatively, which makes the whole thing a parallel scan (struct ParityMap). Per 1,024-particle tile:
+//   1  (all tiles in parallel) guess the tile's binade from K2's approximate scan, compose the tile's maps: units added and
+//      parity out for both start parities; a tile with a negative / non-finite / huge addend or a binade change is "complex"
+//   2  (one thread, tile by tile, exact) take the units for the parity of the exact s; accept s + units * u iff the exact s
+//      really lies in the guessed binade and the result still does; otherwise the tile's additions are done one after the other
+//      (s doubles at most ~80 times between the smallest fp32 weight and 1: a few dozen serial tiles at worst)
+//   3  (accepted tiles in parallel) cdf[m] = s_tile + u * units(prefix up to m), exact
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kTileComplex = 0u, kTileSimple = 1u, kTileZero = 2u;
+
+struct ParityMap
 {
-  if (threadIdx.x != 0 || blockIdx.x != 0 || !st->inexact) return;
-  double s = 0.0;
-  for (uint32_t i = 0; i < n; ++i)
+  long long d0, d1;   // units added when the running sum's parity on entry is 0 / 1
+  uint32_t o;         // bit 0 / bit 1: parity on exit for parity 0 / 1 on entry
+};
+
+__device__ __forceinline__ ParityMap pm_identity() { return ParityMap{0ll, 0ll, 2u}; }
+
+// f first, then g
+__device__ __forceinline__ ParityMap pm_then(const ParityMap& f, const ParityMap& g)
+{
+  const uint32_t f0 = f.o & 1u, f1 = (f.o >> 1) & 1u;
+  ParityMap r;
+  r.d0 = f.d0 + (f0 ? g.d1 : g.d0);
+  r.d1 = f.d1 + (f1 ? g.d1 : g.d0);
+  r.o = ((g.o >> f0) & 1u) | (((g.o >> f1) & 1u) << 1);
+  return r;
+}
+
+// the map of one weight at ulp 1 / inv_u; `bad` flags what the scheme cannot express
+__device__ __forceinline__ ParityMap pm_of_weight(float wf, double inv_u, bool& bad, bool& nonzero)
+{
+  nonzero |= (wf != 0.0f);
+  const double q = static_cast<double>(wf) * inv_u;     // exact: a power-of-two scaling
+  const bool ok = (q < 4503599627370496.0) && (wf >= 0.0f);   // < 2^52, finite, not NaN; negative addends break monotonicity
+  bad |= !ok;
+  if (!ok) return pm_identity();
+  const double fl = floor(q);
+  const long long k = __double2ll_rd(q);
+  const uint32_t kp = static_cast<uint32_t>(k) & 1u;
+  if (q - fl == 0.5)     // exact tie: to even
+    return ParityMap{k + static_cast<long long>(kp), k + static_cast<long long>(kp ^ 1u), 0u};
+  const long long r = __double2ll_rn(q);
+  const uint32_t x = static_cast<uint32_t>(r) & 1u;
+  return ParityMap{r, r, x | ((x ^ 1u) << 1)};
+}
+
+__device__ __forceinline__ ParityMap pm_shfl_up(const ParityMap& m, int delta)
+{
+  ParityMap r;
+  r.d0 = __shfl_up_sync(0xffffffffu, m.d0, delta);
+  r.d1 = __shfl_up_sync(0xffffffffu, m.d1, delta);
+  r.o = __shfl_up_sync(0xffffffffu, m.o, delta);
+  return r;
+}
+
+struct ExactArgs
+{
+  const float* particles;
+  uint32_t n;
+  const Status* st;
+  double* cdf;            // in: K2's scan (approximate where additions rounded); out: the serial-order CDF
+  long long* tile_units;  // [tiles][2] units the tile adds for start parity 0 / 1, at the tile's guessed ulp
+  uint32_t* tile_flag;    // [tiles] kind | exit parities << 4 | biased exponent of the guessed binade << 8
+  double* tile_start;     // [tiles] exact running sum in front of the tile
+};
+
+__device__ __forceinline__ uint32_t f64_exp(double x) { return static_cast<uint32_t>(__double_as_longlong(x) >> 52) & 0x7ffu; }
+
+// Inclusive scan of the tile's maps: returns the composition of all maps of the items BEFORE this thread's first item
+// (exclusive prefix) and leaves the thread's own per-item inclusive compositions (relative to that prefix) in loc[].
+__device__ __forceinline__ ParityMap tile_scan(const ExactArgs& A, uint32_t base, double inv_u, ParityMap (&loc)[kScanItems], bool& bad,
+                                               bool& nonzero, ParityMap* s_warp, ParityMap& tile_total)
+{
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  ParityMap run = pm_identity();
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
   {
-    s += static_cast<double>(particles[7ull * i + 6]);
-    cdf[i] = s;
+    if (base + k < A.n) run = pm_then(run, pm_of_weight(A.particles[7ull * (base + k) + 6], inv_u, bad, nonzero));
+    loc[k] = run;
+  }
+  ParityMap incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const ParityMap up = pm_shfl_up(incl, o);
+    if (lane >= static_cast<uint32_t>(o)) incl = pm_then(up, incl);
+  }
+  ParityMap excl = pm_shfl_up(incl, 1);
+  if (lane == 0) excl = pm_identity();
+  __syncthreads();
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  ParityMap off = pm_identity();
+  for (uint32_t w = 0; w < warp; ++w) off = pm_then(off, s_warp[w]);
+  tile_total = off;
+  for (uint32_t w = warp; w < kScanThreads / 32; ++w) tile_total = pm_then(tile_total, s_warp[w]);
+  return pm_then(off, excl);
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_cdf_exact(const ExactArgs A)
+{
+  if (!A.st->inexact) return;   // uniform over the grid: nobody reaches a grid sync
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ ParityMap s_warp[kScanThreads / 32];
+  __shared__ uint32_t s_flags;
+  const uint32_t n = A.n;
+  const uint32_t n_tiles = (n + kScanTile - 1) / kScanTile;
+
+  // ---- 1: the tile's map at the guessed ulp ---------------------------------------------------------------------------
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  {
+    const uint32_t first = tile * kScanTile, last = min(first + kScanTile, n) - 1u;
+    const double s_lo = tile ? A.cdf[first - 1u] : 0.0, s_hi = A.cdf[last];
+    const uint32_t e = f64_exp(s_lo);
+    const bool cand = s_lo > 0.0 && e == f64_exp(s_hi) && e >= 64u && e < 0x7ffu;
+    const double inv_u = __longlong_as_double(static_cast<long long>(2098u - min(max(e, 64u), 2046u)) << 52);   // 2^(52 - (e - 1023))
+    bool bad = false, nonzero = false;
+    ParityMap loc[kScanItems], total;
+    if (threadIdx.x == 0) s_flags = 0u;
+    tile_scan(A, first + threadIdx.x * kScanItems, inv_u, loc, bad, nonzero, s_warp, total);
+    if (bad) atomicOr(&s_flags, 1u);
+    if (nonzero) atomicOr(&s_flags, 2u);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      const uint32_t kind = !(s_flags & 2u) ? kTileZero : (cand && !(s_flags & 1u)) ? kTileSimple : kTileComplex;
+      A.tile_units[2ull * tile] = total.d0;
+      A.tile_units[2ull * tile + 1] = total.d1;
+      A.tile_flag[tile] = kind | ((total.o & 3u) << 4) | (e << 8);
+    }
+    __syncthreads();
+  }
+  grid.sync();
+
+  // ---- 2: the exact running sum in front of every tile (CTA 0) ---------------------------------------------------------
+  // Thread 0 walks the tiles; their flags / unit counts are staged in shared memory a chunk at a time so that the walk is a
+  // chain of arithmetic, not of L2 round trips. A tile that needs its additions done one after the other is staged through
+  // shared memory by the whole CTA (coalesced loads and stores around thread 0's 1,024 dependent additions).
+  if (blockIdx.x == 0)
+  {
+    constexpr uint32_t kChunk = 512;
+    __shared__ uint32_t s_flag[kChunk];
+    __shared__ long long s_u0[kChunk], s_u1[kChunk];
+    __shared__ float s_w[kScanTile];
+    __shared__ double s_c[kScanTile];
+    __shared__ double s_run;
+    __shared__ uint32_t s_stop;     // next tile to be done serially (or end of chunk)
+    if (threadIdx.x == 0) s_run = 0.0;
+    for (uint32_t chunk0 = 0; chunk0 < n_tiles; chunk0 += kChunk)
+    {
+      const uint32_t chunk_n = min(kChunk, n_tiles - chunk0);
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < chunk_n; i += kScanThreads)
+      {
+        s_flag[i] = A.tile_flag[chunk0 + i];
+        s_u0[i] = A.tile_units[2ull * (chunk0 + i)];
+        s_u1[i] = A.tile_units[2ull * (chunk0 + i) + 1];
+      }
+      __syncthreads();
+      uint32_t pos = 0;   // uniform: every thread follows s_stop
+      while (pos < chunk_n)
+      {
+        if (threadIdx.x == 0)
+        {
+          double s = s_run;
+          uint32_t i = pos;
+          for (; i < chunk_n; ++i)
+          {
+            A.tile_start[chunk0 + i] = s;
+            const uint32_t flag = s_flag[i], kind = flag & 0xfu, e = flag >> 8;
+            if (kind == kTileZero) continue;
+            bool ok = false;
+            if (kind == kTileSimple && f64_exp(s) == e)
+            {
+              const uint32_t parity = static_cast<uint32_t>(__double_as_longlong(s)) & 1u;   // S = s / u: the mantissa's last bit
+              const long long T = parity ? s_u1[i] : s_u0[i];
+              if (T < (1ll << 53))
+              {
+                const double u = __longlong_as_double(static_cast<long long>(e - 52u) << 52);
+                const double next = s + static_cast<double>(T) * u;   // exact when it stays inside the binade
+                if (f64_exp(next) == e)
+                {
+                  s = next;
+                  ok = true;
+                }
+              }
+            }
+            if (!ok) break;
+          }
+          s_run = s;
+          s_stop = i;
+        }
+        __syncthreads();
+        const uint32_t stop = s_stop;
+        if (stop >= chunk_n) break;
+        // tile chunk0 + stop: serial additions
+        const uint32_t tile = chunk0 + stop, first = tile * kScanTile, cnt = min(static_cast<uint32_t>(kScanTile), n - first);
+        for (uint32_t i = threadIdx.x; i < cnt; i += kScanThreads) s_w[i] = A.particles[7ull * (first + i) + 6];
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+          A.tile_flag[tile] = kTileComplex | (s_flag[stop] & ~0xffu);
+          double s = s_run;
+          for (uint32_t i = 0; i < cnt; ++i)
+          {
+            s += static_cast<double>(s_w[i]);
+            s_c[i] = s;
+          }
+          s_run = s;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += kScanThreads) A.cdf[first + i] = s_c[i];
+        pos = stop + 1;
+        __syncthreads();
+      }
+    }
+  }
+  grid.sync();
+
+  // ---- 3: accepted tiles: start + u * units(prefix) -------------------------------------------------------------------
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  {
+    const uint32_t flag = A.tile_flag[tile], kind = flag & 0xfu, e = flag >> 8;
+    if (kind == kTileComplex) continue;
+    const double start = A.tile_start[tile];
+    const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
+    if (kind == kTileZero)
+    {
+#pragma unroll
+      for (int k = 0; k < kScanItems; ++k)
+        if (base + k < n) A.cdf[base + k] = start;
+      continue;
+    }
+    const double inv_u = __longlong_as_double(static_cast<long long>(2098u - e) << 52);
+    const double u = __longlong_as_double(static_cast<long long>(e - 52u) << 52);
+    const uint32_t parity = static_cast<uint32_t>(__double_as_longlong(start)) & 1u;
+    bool bad = false, nonzero = false;
+    ParityMap loc[kScanItems], total;
+    const ParityMap excl = tile_scan(A, base, inv_u, loc, bad, nonzero, s_warp, total);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (base + k < n)
+      {
+        const ParityMap m = pm_then(excl, loc[k]);
+        A.cdf[base + k] = start + static_cast<double>(parity ? m.d1 : m.d0) * u;
+      }
+    __syncthreads();
   }
 }
 

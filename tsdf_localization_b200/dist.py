@@ -76,6 +76,13 @@ class GpuStages:
                                                                          first_out, count_out, C.c_void_p(d_out.data_ptr()), arr,
                                                                          len(peer_out_ptrs), None, self._stream()))
 
+    def update_fused(self, d_points, d_particles, n, tf, u0, d_out, count_out, d_mean) -> None:
+        """Single-GPU update in one call (tsdfloc_update_device): scan preparation + matrices, evaluation, normalisation, draw."""
+        tfc = (C.c_float * 16)(*[float(v) for v in tf])
+        capi.check(self.lib, self.ctx, self.lib.tsdfloc_update_device(
+            self.ctx, C.c_void_p(d_points.data_ptr()), d_points.shape[0], C.c_void_p(d_particles.data_ptr()), n, tfc, C.c_float(u0),
+            C.c_void_p(d_out.data_ptr()), count_out, C.c_void_p(d_mean.data_ptr()), self._stream()))
+
     def normalize(self, d_particles, n, d_raw, d_mean) -> None:
         capi.check(self.lib, self.ctx, self.lib.tsdfloc_normalize_device(self.ctx, C.c_void_p(d_particles.data_ptr()), n,
                                                                         C.c_void_p(d_raw.data_ptr()), C.c_void_p(d_mean.data_ptr()),
@@ -192,6 +199,12 @@ class ShardedSensorUpdate:
         h_raw.barrier(channel=0)
 
     def set_scan(self, d_points: torch.Tensor) -> None:
+        """The scan of the next step(s). One GPU with fused stages: only remembered here — step() prepares it in the same
+        launch that builds the pose matrices (the tensor must stay unchanged until then)."""
+        if self.world == 1 and hasattr(self.stages, "update_fused"):
+            self._pending_scan = d_points
+            return
+        self._pending_scan = None
         self.stages.set_scan(d_points)
 
     def step(self, particles: torch.Tensor, n: int, tf, u0: float):
@@ -205,6 +218,13 @@ class ShardedSensorUpdate:
         ochunk = ocap // W
         which_out = self._select_out()
         self._check_not_aliased(particles, n, ocap)
+        if W == 1 and getattr(self, "_pending_scan", None) is not None:
+            out = self.out[:ocap]
+            self.stages.update_fused(self._pending_scan, particles, n, tf, u0, out, ocap, self.mean)
+            n_out, wsum = self.stages.check()
+            if n_out > ocap:
+                raise RuntimeError(f"resampling emits {n_out} particles, capacity is {ocap}")
+            return out[:n_out], self.mean[:6], n_out, wsum
         if self._symm is not None:
             h_raw, h_out, raw_ptrs, out_ptrs = self._symm
             which = self._select_raw()
@@ -263,6 +283,9 @@ class ShardedSensorUpdate:
         W, r = self.world, self.rank
         self._reserve(n)
         chunk, first, count = shard(n, W, r)
+        if getattr(self, "_pending_scan", None) is not None:      # the staged calls below need the prepared scan
+            self.stages.set_scan(self._pending_scan)
+            self._pending_scan = None
         if self._symm is not None:
             h_raw, _, raw_ptrs, _ = self._symm
             raw_off = self._select_raw() * self._raw2.shape[1] * 4
