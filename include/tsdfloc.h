@@ -302,6 +302,11 @@ int tsdfloc_multi_device_count(const tsdfloc_multi* m);
 const char* tsdfloc_multi_last_error(const tsdfloc_multi* m);
 /* The single-device context of rank `rank` (owned by m), e.g. for tsdfloc_resample_particles / tsdfloc_reduce_scan. */
 tsdfloc_ctx* tsdfloc_multi_ctx(tsdfloc_multi* m, int rank);
+/* tsdfloc_sensor_update_cloud over all devices (TSDFEvaluator::evaluateParticles, tsdf_evaluator.cpp:247-378): the first device
+ * reduces the raw cloud, the reduced scan reaches the others over NVLink, then the sharded update. */
+int tsdfloc_multi_sensor_update_cloud(tsdfloc_multi* m, float* particles, uint64_t n, const void* xyz_base, uint64_t xyz_stride,
+                                      const void* ring_base, uint64_t ring_stride, int ring_bytes, uint64_t n_points, double cell_size,
+                                      uint32_t n_rings, uint32_t flags, const float tf[16], float mean_pose[6], uint64_t* n_points_used);
 /* tsdfloc_sensor_update / tsdfloc_resample_systematic over all devices (same arguments and status codes). */
 int tsdfloc_multi_sensor_update(tsdfloc_multi* m, float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],
                                 float mean_pose[6]);

@@ -187,3 +187,41 @@ def test_single_process_multi_gpu_equals_single_gpu(n):
     with pytest.raises(RuntimeError, match="No particle is valid!"):
         mev.evaluate(far, pts, tf)
     mev.close()
+
+
+def test_single_process_multi_gpu_cloud_equals_single_gpu():
+    """tsdfloc_multi_sensor_update_cloud (TSDFEvaluator::evaluateParticles over several devices): reduction on the first device,
+    reduced scan to the others, sharded update — bit-identical to tsdfloc_sensor_update_cloud on one GPU."""
+    import torch
+    from tsdf_localization_b200 import CudaEvaluator, MultiGpuEvaluator
+    from test_reduce_oracle import scan_with_rings
+    _, m = common.box_room()
+    pts, ring = scan_with_rings("vlp16", near=200, shuffle=True)
+    n = 3001
+    ps = syn.tracking_particles(n, syn.GT_POSE)
+    tf, u0 = syn.CALIB_TF, 0.41 / n
+    ev = CudaEvaluator(m)
+    want = ps.copy()
+    pose1, used1 = ev.evaluate_cloud(want, pts, ring, tf, n_rings=16)
+    out1 = ev.resample_systematic(u0, capacity=n + n // 8 + 64)
+    ev.close()
+    assert used1 > 0
+    layouts = [[0, 0, 0]]
+    if torch.cuda.device_count() >= 2:
+        layouts.append(list(range(min(torch.cuda.device_count(), 8))))
+    for devices in layouts:
+        mev = MultiGpuEvaluator(m, devices)
+        for _ in range(2):
+            got = ps.copy()
+            pose, used = mev.evaluate_cloud(got, pts, ring, tf, n_rings=16)
+            out = mev.resample_systematic(u0, capacity=n + n // 8 + 64)
+            assert used == used1
+            assert got.tobytes() == want.tobytes(), f"normalised weights differ on devices {devices}"
+            assert out.tobytes() == out1.tobytes(), f"resampled particles differ on devices {devices}"
+            assert pose.position == pose1.position and pose.rpy == pose1.rpy
+        # a cloud whose every point is nearer than 1 m reduces to nothing: weights untouched, default pose
+        near = (pts[:50] * 0.0 + 0.1).astype(np.float32)
+        got = ps.copy()
+        pose, used = mev.evaluate_cloud(got, near, ring[:50], tf, n_rings=16)
+        assert used == 0 and got.tobytes() == ps.tobytes()
+        mev.close()

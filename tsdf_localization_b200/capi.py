@@ -108,6 +108,8 @@ SIGNATURES = {
     "tsdfloc_multi_ctx": (_vp, [_vp, C.c_int]),
     "tsdfloc_multi_sensor_update": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _fp, _fp]),
     "tsdfloc_multi_resample_systematic": (C.c_int, [_vp, C.c_float, _vp, _u64, C.POINTER(_u64)]),
+    "tsdfloc_multi_sensor_update_cloud": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _vp, _u64, C.c_int, _u64, C.c_double, C.c_uint32, C.c_uint32,
+                                                    _fp, _fp, C.POINTER(_u64)]),
     "tsdfloc_normalize_device": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp]),
     "tsdfloc_draw_device": (C.c_int, [_vp, _vp, _u64, C.c_float, _u64, _u64, _vp, _vp, _vp]),
     "tsdfloc_check": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double), _vp]),

@@ -20,8 +20,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <string>
 #include <vector>
 

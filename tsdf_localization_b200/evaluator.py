@@ -391,6 +391,25 @@ class MultiGpuEvaluator:
                                                           pts.ctypes.data_as(C.c_void_p), pts.shape[0], tf, mean))
         return PoseWithCovariance.from_mean(list(mean))
 
+    def evaluate_cloud(self, particles: np.ndarray, points, ring, tf_matrix, cell_size: float = 0.064, n_rings: int = 128,
+                       ring_desync_like_reference: bool = False):
+        """TSDFEvaluator::evaluateParticles over all devices: the first device reduces the raw cloud, the reduced scan goes to the
+        others over NVLink, then the sharded update. Returns (pose, reduced scan size) like CudaEvaluator.evaluate_cloud."""
+        if not (isinstance(particles, np.ndarray) and particles.dtype == np.float32 and particles.ndim == 2
+                and particles.shape[1] == 7 and particles.flags.c_contiguous):
+            raise ValueError("particles must be a C-contiguous float32[n, 7] array (it is updated in place)")
+        pts, rg, args = CudaEvaluator._cloud_args(points, ring)
+        tf = (C.c_float * 16)(*[float(v) for v in np.asarray(tf_matrix, dtype=np.float32).reshape(-1)[:16]])
+        mean = (C.c_float * 6)()
+        used = C.c_uint64(0)
+        flags = capi.REDUCE_RING_DESYNC_LIKE_REFERENCE if ring_desync_like_reference else 0
+        rc = self._lib.tsdfloc_multi_sensor_update_cloud(self._m, particles.ctypes.data_as(C.c_void_p), particles.shape[0], *args,
+                                                         C.c_double(cell_size), n_rings, flags, tf, mean, C.byref(used))
+        if rc == capi.E_EMPTY_SCAN:
+            return PoseWithCovariance(), 0
+        self._check(rc)
+        return PoseWithCovariance.from_mean(list(mean)), int(used.value)
+
     def resample_systematic(self, u0: float, capacity: int):
         out = np.empty((capacity, 7), dtype=np.float32)
         n_out = C.c_uint64(0)

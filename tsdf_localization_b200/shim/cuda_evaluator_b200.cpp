@@ -44,6 +44,7 @@ namespace
 {
 std::mutex g_ctx_mutex;
 tsdfloc_ctx* g_last_ctx = nullptr;
+tsdfloc_multi* g_last_multi = nullptr;
 
 inline tsdfloc_ctx* ctx_of(FLOAT_T* slot) { return reinterpret_cast<tsdfloc_ctx*>(slot); }
 inline tsdfloc_multi* multi_of(FLOAT_T* slot) { return reinterpret_cast<tsdfloc_multi*>(slot); }
@@ -71,6 +72,12 @@ tsdfloc_ctx* tsdfloc_shim_context()
 {
   std::lock_guard<std::mutex> lock(g_ctx_mutex);
   return g_last_ctx;
+}
+
+tsdfloc_multi* tsdfloc_shim_multi()
+{
+  std::lock_guard<std::mutex> lock(g_ctx_mutex);
+  return g_last_multi;
 }
 
 CudaEvaluator::CudaEvaluator(CudaSubVoxelMap<FLOAT_T, FLOAT_T>& map, bool per_point, FLOAT_T a_hit, FLOAT_T a_range, FLOAT_T a_max, FLOAT_T max_range)
@@ -132,6 +139,7 @@ CudaEvaluator::CudaEvaluator(CudaSubVoxelMap<FLOAT_T, FLOAT_T>& map, bool per_po
   d_transform_ = reinterpret_cast<FLOAT_T*>(ctx);
   std::lock_guard<std::mutex> lock(g_ctx_mutex);
   g_last_ctx = ctx;
+  g_last_multi = d_new_weights_ ? multi_of(d_new_weights_) : nullptr;
 }
 
 CudaEvaluator::~CudaEvaluator()
@@ -139,7 +147,11 @@ CudaEvaluator::~CudaEvaluator()
   tsdfloc_ctx* ctx = ctx_of(d_transform_);
   {
     std::lock_guard<std::mutex> lock(g_ctx_mutex);
-    if (g_last_ctx == ctx) g_last_ctx = nullptr;
+    if (g_last_ctx == ctx)
+    {
+      g_last_ctx = nullptr;
+      g_last_multi = nullptr;
+    }
   }
   if (d_new_weights_)
   {
@@ -161,6 +173,12 @@ uint32_t field_offset(const sensor_msgs::PointCloud2& cloud, const std::string& 
   for (const auto& f : cloud.fields)
     if (f.name == name) return f.offset;
   throw std::runtime_error("Field " + name + " does not exist");
+}
+
+void throw_multi_error(tsdfloc_multi* multi, int rc)
+{
+  if (rc == TSDFLOC_E_NO_VALID_PARTICLE) throw std::runtime_error("No particle is valid!");
+  throw std::runtime_error(std::string("Error occured during the sensor update on the gpu! ") + tsdfloc_multi_last_error(multi));
 }
 
 void throw_update_error(tsdfloc_ctx* ctx, int rc)
@@ -198,6 +216,16 @@ geometry_msgs::PoseWithCovariance CudaEvaluator::evaluate(std::vector<Particle>&
   field_offset(real_cloud, "ring");  // the reference's iterator throws when the field is missing
   tsdfloc_ctx* ctx = ctx_of(d_transform_);
   float mean[6] = {0, 0, 0, 0, 0, 0};
+  if (d_new_weights_)   // TSDFLOC_DEVICES names several GPUs: reduce on the first, evaluate on all
+  {
+    tsdfloc_multi* multi = multi_of(d_new_weights_);
+    const int rc = tsdfloc_multi_sensor_update_cloud(multi, reinterpret_cast<float*>(particles.data()), particles.size(),
+                                                     real_cloud.data.data() + field_offset(real_cloud, "x"), real_cloud.point_step, nullptr, 0, 4,
+                                                     n_points, 0.064, 1, TSDFLOC_REDUCE_EMIT_CENTRES, tf_matrix, mean, nullptr);
+    if (rc == TSDFLOC_E_EMPTY_SCAN) return geometry_msgs::PoseWithCovariance();
+    if (rc != TSDFLOC_OK) throw_multi_error(multi, rc);
+    return tsdfloc_shim_pose(mean);
+  }
   const int rc = tsdfloc_sensor_update_cloud(ctx, reinterpret_cast<float*>(particles.data()), particles.size(),
                                              real_cloud.data.data() + field_offset(real_cloud, "x"), real_cloud.point_step, nullptr, 0, 4,
                                              n_points, 0.064, 1, TSDFLOC_REDUCE_EMIT_CENTRES, tf_matrix, mean, nullptr);
@@ -238,6 +266,17 @@ geometry_msgs::PoseWithCovariance TSDFEvaluatorB200::evaluateParticles(ParticleC
   float mean[6] = {0, 0, 0, 0, 0, 0};
   last_reduced_ = 0;
   // x y z are read as three consecutive floats at the "x" field (iter_x[0..2], :311-315), the ring as a short (:305)
+  if (multi_)   // TSDFLOC_DEVICES names several GPUs: reduce on the first, evaluate on all
+  {
+    const int rc = tsdfloc_multi_sensor_update_cloud(multi_, reinterpret_cast<float*>(particles.data()), particles.size(),
+                                                     base + field_offset(real_cloud, "x"), real_cloud.point_step,
+                                                     base + field_offset(real_cloud, "ring"), real_cloud.point_step, 2, n_points, cell_, n_rings,
+                                                     ring_desync_like_reference ? TSDFLOC_REDUCE_RING_DESYNC_LIKE_REFERENCE : 0u, tf_matrix,
+                                                     mean, &last_reduced_);
+    if (rc == TSDFLOC_E_EMPTY_SCAN) return geometry_msgs::PoseWithCovariance();
+    if (rc != TSDFLOC_OK) throw_multi_error(multi_, rc);
+    return tsdfloc_shim_pose(mean);
+  }
   const int rc = tsdfloc_sensor_update_cloud(ctx_, reinterpret_cast<float*>(particles.data()), particles.size(),
                                              base + field_offset(real_cloud, "x"), real_cloud.point_step,
                                              base + field_offset(real_cloud, "ring"), real_cloud.point_step, 2, n_points, cell_, n_rings,

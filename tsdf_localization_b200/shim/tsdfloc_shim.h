@@ -26,6 +26,8 @@ namespace tsdf_localization
 // Context of the most recently constructed CudaEvaluator (the reference keeps one per process, cuda_data.h:17-26);
 // nullptr when none is alive.
 tsdfloc_ctx* tsdfloc_shim_context();
+// The multi-GPU handle of that evaluator when TSDFLOC_DEVICES names several devices, else nullptr.
+tsdfloc_multi* tsdfloc_shim_multi();
 
 // geometry_msgs::PoseWithCovariance from (x y z roll pitch yaw): position + setRPY quaternion, covariance 0, exactly what
 // CudaEvaluator::evaluate returns (src/cuda/cuda_evaluator.cu:410-423).
@@ -37,7 +39,8 @@ public:
   TSDFEvaluatorB200(const std::shared_ptr<CudaSubVoxelMap<FLOAT_T, FLOAT_T>>& map_ptr, bool per_point = false, FLOAT_T a_hit = 0.9,
                     FLOAT_T a_range = 0.1, FLOAT_T a_max = 0.0, FLOAT_T max_range = 100.0, FLOAT_T reduction_cell_size = 0.064)
   : TSDFEvaluator(map_ptr, per_point, a_hit, a_range, a_max, max_range, reduction_cell_size), cell_(reduction_cell_size),
-    ctx_(tsdfloc_shim_context())  // the CudaEvaluator the base class just constructed (tsdf_evaluator.h:78)
+    ctx_(tsdfloc_shim_context()),  // the CudaEvaluator the base class just constructed (tsdf_evaluator.h:78)
+    multi_(tsdfloc_shim_multi())
   {
   }
 
@@ -59,6 +62,7 @@ public:
 private:
   FLOAT_T cell_;
   tsdfloc_ctx* ctx_;
+  tsdfloc_multi* multi_;
   uint64_t last_reduced_ = 0;
 };
 
