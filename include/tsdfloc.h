@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TSDFLOC_ABI_VERSION 4
+#define TSDFLOC_ABI_VERSION 3
 
 typedef struct tsdfloc_ctx tsdfloc_ctx;
 
@@ -72,10 +72,6 @@ typedef struct tsdfloc_params
   float max_range; /* default 100  (util.h:13); the range term uses 1/max_range like the CPU evaluator (tsdf_evaluator.cpp:60) */
   int32_t per_point; /* accepted for signature parity; both reference variants compute the same weights, one kernel serves both */
   int32_t neg_policy; /* enum tsdfloc_neg_policy: lookups below map.min on an axis */
-  uint64_t dense_budget_bytes; /* device layout of the voxels: when the resolution is aligned (sub_dim * resolution = 1) and the
-                                * map's bounding box, one float per voxel, fits in this many bytes, the bricks are laid out DENSE
-                                * (no brick table, no dependent gather; the evaluation kernel's speculative index needs it).
-                                * 0 = automatic (a quarter of the device's memory), 1 = never. Results are identical either way. */
 } tsdfloc_params;
 
 /* Lookups whose offset x - map.min is negative on some axis. The reference converts the negative float to unsigned, which
@@ -438,30 +434,18 @@ int tsdfloc_probe_gather(tsdfloc_ctx* ctx, uint64_t bytes, uint32_t spread_secto
  * because a bracketed sub-voxel quotient was open. */
 int tsdfloc_eval_stats(tsdfloc_ctx* ctx, uint64_t out[4]);
 
-/* Cumulative statistics of the evaluation kernel's speculative voxel index (synchronises the device):
- * out[0] = steps (64 evaluations each) evaluated speculatively, out[1] = of those re-evaluated through the exact path because
- * a lane's voxel was not certified, out[2] = warps (particle pairs) that were not eligible and ran the exact loop,
- * out[3] = bit 0: the dense layout was built for this map (aligned resolution, bounding box within the budget), bit 1: the
- * speculative index is proven for it (lattice proof passed, MISS policy). */
-int tsdfloc_spec_stats(tsdfloc_ctx* ctx, uint64_t out[4]);
-
 /* Test / tuning hook (never needed for correct results: every setting produces the same bits). No environment variables
  * are read anywhere in the library.
  *   TSDFLOC_TUNE_SPATIAL_ORDER  -1 automatic (map larger than L2 and >= 16,384 particles), 0 off, 1 on (tsdfloc_sort.cuh)
  *   TSDFLOC_TUNE_EVAL_PAIRING    0 automatic, 1 two particles per warp, 2 two points per lane (tsdfloc_eval.cuh)
  *   TSDFLOC_TUNE_DIVISION       -1 what tsdfloc_create proved for the resolution, 0 IEEE division, 1 three-instruction
- *                                quotient, 2 bracketed quotient (an unproven mode is never run)
- *   TSDFLOC_TUNE_SPECULATE      -1 automatic, 0 off, 1 on: certified speculative voxel index (only where tsdfloc_create
- *                                proved it: dense layout, MISS policy)
- *   TSDFLOC_TUNE_DENSE          -1 automatic, 0 brick layout even where the dense one was built                            */
+ *                                quotient, 2 bracketed quotient (an unproven mode is never run)                            */
 enum tsdfloc_tune_knob
 {
   TSDFLOC_TUNE_SPATIAL_ORDER = 0,
   TSDFLOC_TUNE_EVAL_PAIRING = 1,
   TSDFLOC_TUNE_DIVISION = 2,
-  TSDFLOC_TUNE_STAGE_TIMERS = 3,  /* 0 off (default), 1 record CUDA events around the stages (tsdfloc_stage_times) */
-  TSDFLOC_TUNE_SPECULATE = 4,
-  TSDFLOC_TUNE_DENSE = 5          /* -1 automatic (dense layout where tsdfloc_create built it), 0 evaluate on the brick layout */
+  TSDFLOC_TUNE_STAGE_TIMERS = 3   /* 0 off (default), 1 record CUDA events around the stages (tsdfloc_stage_times) */
 };
 int tsdfloc_tune(tsdfloc_ctx* ctx, int knob, int value);
 

@@ -21,11 +21,6 @@ else:
     pts, _ = syn.make_scan(kind, syn.GT_POSE)
     ps = syn.tracking_particles(n, syn.GT_POSE)
 ev = CudaEvaluator(m)
-# optional 4th / 5th argument: TSDFLOC_TUNE_DENSE / TSDFLOC_TUNE_SPECULATE values (-1 automatic, 0 off)
-if len(sys.argv) > 4:
-    ev.tune(capi.TUNE_DENSE, int(sys.argv[4]))
-if len(sys.argv) > 5:
-    ev.tune(capi.TUNE_SPECULATE, int(sys.argv[5]))
 lib = capi.load_library()
 dev = torch.device("cuda:0")
 d_ps = torch.from_numpy(ps).to(dev)

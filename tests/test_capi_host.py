@@ -30,7 +30,7 @@ def test_header_symbols_exported_and_typed(lib):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/tsdfloc.h but not exported by libtsdfloc.so"
     assert declared == set(capi.SIGNATURES), "ctypes binding and header disagree"
-    assert lib.tsdfloc_abi_version() == 4
+    assert lib.tsdfloc_abi_version() == 3
 
 
 def test_status_strings_and_defaults(lib):

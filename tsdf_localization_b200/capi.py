@@ -14,7 +14,7 @@ REDUCE_RING_DESYNC_LIKE_REFERENCE, REDUCE_EMIT_CENTRES = 1, 2
 MOTION_NOISE, MOTION_ODOM, MOTION_IMU, MOTION_NOISE_IMU = range(4)
 INIT_NORMAL, INIT_UNIFORM, INIT_FREE_MAP = range(3)
 NEG_MISS, NEG_SATURATE_LIKE_REF_GPU = range(2)
-TUNE_SPATIAL_ORDER, TUNE_EVAL_PAIRING, TUNE_DIVISION, TUNE_STAGE_TIMERS, TUNE_SPECULATE, TUNE_DENSE = range(6)
+TUNE_SPATIAL_ORDER, TUNE_EVAL_PAIRING, TUNE_DIVISION, TUNE_STAGE_TIMERS = range(4)
 DIV_IEEE, DIV_THREE, DIV_BRACKET = range(3)
 RESAMPLE_SYSTEMATIC, RESAMPLE_RESIDUAL, RESAMPLE_RESIDUAL_SYSTEMATIC = range(3)
 INDEX_DRAW_FN = C.CFUNCTYPE(C.c_uint64, C.c_void_p)
@@ -41,7 +41,7 @@ class MapDesc(C.Structure):
 
 class Params(C.Structure):
     _fields_ = [("a_hit", C.c_float), ("a_range", C.c_float), ("a_max", C.c_float), ("max_range", C.c_float),
-                ("per_point", C.c_int32), ("neg_policy", C.c_int32), ("dense_budget_bytes", C.c_uint64)]
+                ("per_point", C.c_int32), ("neg_policy", C.c_int32)]
 
 
 def lib_path() -> Path:
@@ -129,7 +129,6 @@ SIGNATURES = {
     "tsdfloc_host_u_sequence": (_u64, [C.c_float, _u64, C.c_double, _vp, _u64, _u32p, _u32p]),
     "tsdfloc_probe_gather": (C.c_int, [_vp, _u64, C.c_uint32, C.c_uint32, _fp, C.POINTER(_u64)]),
     "tsdfloc_eval_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
-    "tsdfloc_spec_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "tsdfloc_tune": (C.c_int, [_vp, C.c_int, C.c_int]),
     "tsdfloc_stage_times": (C.c_int, [_vp, _fp]),
     "tsdfloc_last_cdf_was_exact": (C.c_int, [_vp]),

@@ -58,12 +58,6 @@ struct tsdfloc_ctx
   uint64_t launches = 0;
   int tune_shape = 0;       // tsdfloc_tune(TSDFLOC_TUNE_EVAL_PAIRING): 0 automatic, 1 particle pairs, 2 point pairs
   int tune_div = -1;        // tsdfloc_tune(TSDFLOC_TUNE_DIVISION): -1 what k_check_div proved, else kDivIeee / kDivThree / kDivBracket
-  int tune_spec = -1;       // tsdfloc_tune(TSDFLOC_TUNE_SPECULATE): -1 automatic (on where proven), 0 off, 1 on (where proven)
-  int tune_dense = -1;      // tsdfloc_tune(TSDFLOC_TUNE_DENSE): -1 automatic (dense layout where built), 0 brick layout
-  bool spec_proven = false; // dense layout + lattice proof + 3-instruction quotient + MISS policy
-  SpecPrep spec_prep{};     // what K0 needs for the speculative rows
-  uint32_t* d_scan_sq = nullptr;   // [2] max |p|^2 of the prepared scan, two slots used alternately (k_prep_scan zeroes the next one)
-  uint32_t scan_slot = 0;
   bool three_ok = false, bracket_ok = false;   // what k_check_div proved for this resolution
   unsigned long long bracket_open = 0;         // floats in [0, 1) whose bracket is open (statistics)
   cudaEvent_t ev_eval0 = nullptr, ev_eval1 = nullptr;  // bracket the last k_eval launch (tsdfloc_last_eval_ms)
@@ -78,8 +72,6 @@ struct tsdfloc_ctx
 
   // map
   int32_t* d_table = nullptr;
-  float* d_dense = nullptr;      // dense layout (MapDev::dense): bounding box + one-voxel border, built by k_build_dense
-  uint32_t dense_n[3] = {0, 0, 0};
   float* d_voxels = nullptr;
   float* d_free_map = nullptr;   // free-space points of a map ingested on the device (tsdfloc_create_from_chunks)
   uint64_t n_free_map = 0;
@@ -270,9 +262,6 @@ int scan_layout(tsdfloc_ctx* c, const float* d_xyz, uint64_t p, PrepArgs* a)
   a->a_range_term = c->prm.a_range * static_cast<float>(1.0 / c->prm.max_range);
   a->a_max = c->prm.a_max;
   a->max_range_sq = c->prm.max_range * c->prm.max_range;
-  if (p) c->scan_slot ^= 1u;   // stream order: the previous preparation zeroed this slot
-  a->sq_max = c->d_scan_sq + c->scan_slot;
-  a->sq_next = c->d_scan_sq + (c->scan_slot ^ 1u);
   return TSDFLOC_OK;
 }
 
@@ -324,24 +313,16 @@ int peer_table(tsdfloc_ctx* c, float* const* want, uint32_t n, cudaStream_t s, f
 // Launches the evaluation kernel: pairing (two particles per warp, or two points per lane), quotient mode and — parity
 // dumps only — the index-recording instantiation of the very same code.
 template <bool kPP, bool kDump>
-void launch_eval_mode(const tsdfloc_ctx* c, int div, bool dense, bool spec, const EvalArgs& a, cudaStream_t s)
+void launch_eval_mode(const tsdfloc_ctx* c, int div, const EvalArgs& a, cudaStream_t s)
 {
   const uint32_t grid = kPP ? a.n_local : (a.n_local + 1u) / 2u;
   constexpr int BS = kEvalBlockSteps;
-  if (spec)   // dense layout, speculative index; warps that are not eligible run the plain exact loop (no bracket: one loop body less)
-    k_eval<BS, kDivThree, false, true, true, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
-  else if (dense && div == kDivBracket)
-    k_eval<BS, kDivThree, true, true, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
-  else if (dense && div == kDivThree)
-    k_eval<BS, kDivThree, false, true, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
-  else if (dense)
-    k_eval<BS, kDivIeee, false, true, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
-  else if (div == kDivBracket)
-    k_eval<BS, kDivThree, true, false, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
+  if (div == kDivBracket)
+    k_eval<BS, kDivThree, true, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
   else if (div == kDivThree)
-    k_eval<BS, kDivThree, false, false, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
+    k_eval<BS, kDivThree, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
   else
-    k_eval<BS, kDivIeee, false, false, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
+    k_eval<BS, kDivIeee, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
 }
 
 // Point pairs double the number of warps but read the scan once per particle instead of once per pair (+15 % at full
@@ -358,16 +339,13 @@ void launch_eval(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s, bool d
     if (div == kDivBracket && !c->bracket_ok) div = c->map.div_mode;   // never run an unproven mode
     if (div != kDivIeee && !c->three_ok) div = kDivIeee;
   }
-  const bool dense = c->map.dense_ok && c->tune_dense != 0;
-  // the speculative index needs the dense layout, its proofs (tsdfloc_create) and the 3-instruction quotient for the steps it redoes
-  const bool spec = dense && c->spec_proven && c->tune_spec != 0 && div != kDivIeee;
   bool pp = static_cast<uint64_t>(a.n_local) < static_cast<uint64_t>(c->sm_count) * 32u;
   if (c->tune_shape == 1) pp = false;
   if (c->tune_shape == 2) pp = true;
   if (pp)
-    dump ? launch_eval_mode<true, true>(c, div, dense, spec, a, s) : launch_eval_mode<true, false>(c, div, dense, spec, a, s);
+    dump ? launch_eval_mode<true, true>(c, div, a, s) : launch_eval_mode<true, false>(c, div, a, s);
   else
-    dump ? launch_eval_mode<false, true>(c, div, dense, spec, a, s) : launch_eval_mode<false, false>(c, div, dense, spec, a, s);
+    dump ? launch_eval_mode<false, true>(c, div, a, s) : launch_eval_mode<false, false>(c, div, a, s);
 }
 
 // Spatial evaluation order of particles [first, first + count): *perm = device permutation, or nullptr when ordering is off
@@ -403,7 +381,7 @@ int stage_matrices(tsdfloc_ctx* c, const float* d_particles, uint64_t first, uin
                    const uint32_t* perm, const PrepArgs* fused_scan = nullptr)
 {
   int rc;
-  if ((rc = ensure(c, c->d_mats, sizeof(float) * kMatStride * count, "cudaMalloc(matrices)"))) return rc;
+  if ((rc = ensure(c, c->d_mats, sizeof(float) * 12 * count, "cudaMalloc(matrices)"))) return rc;
   Tf12 t;
   std::memcpy(t.m, tf, sizeof(t.m));
   const unsigned mat_ctas = static_cast<unsigned>((count + 255) / 256);
@@ -411,10 +389,10 @@ int stage_matrices(tsdfloc_ctx* c, const float* d_particles, uint64_t first, uin
   {
     const unsigned sc = scan_ctas(*fused_scan);
     k_prepare<<<sc + mat_ctas, 256, 0, s>>>(*fused_scan, sc, d_particles, static_cast<uint32_t>(first), static_cast<uint32_t>(count), t,
-                                            c->spec_prep, static_cast<float*>(c->d_mats.p), perm);
+                                            static_cast<float*>(c->d_mats.p), perm);
     return launch_check(c, "k_prepare");
   }
-  k_pose_matrices<<<mat_ctas, 256, 0, s>>>(d_particles, static_cast<uint32_t>(first), static_cast<uint32_t>(count), t, c->spec_prep,
+  k_pose_matrices<<<mat_ctas, 256, 0, s>>>(d_particles, static_cast<uint32_t>(first), static_cast<uint32_t>(count), t,
                                            static_cast<float*>(c->d_mats.p), perm);
   return launch_check(c, "k_pose_matrices");
 }
@@ -469,7 +447,6 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   a.one = 1.0f;
   a.s_min = 32.0f * c->x_bound;
   a.stats = c->d_eval_stats;
-  a.scan_sq = c->d_scan_sq + c->scan_slot;
   a.force_seq = c->force_seq;
   a.idx_out = d_idx;
   a.hits_out = d_hits;
@@ -724,7 +701,6 @@ void tsdfloc_default_params(tsdfloc_params* p)
   p->max_range = 100.0f;
   p->per_point = 0;
   p->neg_policy = TSDFLOC_NEG_MISS;
-  p->dense_budget_bytes = 0;
 }
 
 int tsdfloc_abi_version(void) { return TSDFLOC_ABI_VERSION; }
@@ -884,7 +860,6 @@ static int create_impl(const tsdfloc_map_desc* map, const int32_t* grid_occ, con
   MapDev& M = c->map;
   M.table = c->d_table;
   M.voxels = c->d_voxels;
-
   for (int a = 0; a < 3; ++a)
   {
     M.min[a] = map->min[a];
@@ -908,61 +883,6 @@ static int create_impl(const tsdfloc_map_desc* map, const int32_t* grid_occ, con
   M.data_size = static_cast<uint32_t>(map->data_size);
   M.table_bias = kMagicBits * (1u + M.pad_x + M.pad_xy);
   M.sub_bias = kMagicBits * (1u + M.sub_dim + M.sub_dim_2);
-
-  // ---- dense layout + speculative index (tsdfloc_device.cuh) ----------------------------------------------------------------
-  // Needs an ALIGNED resolution (sub_dim * res = 1 up to 2^-18: the voxel faces of neighbouring cells form one lattice; 0.05,
-  // 0.1, 0.125, 0.25 ... are, 0.064 is not) and a bounding box that fits the budget (default: a quarter of the device's memory
-  // — HBM capacity buys the removal of the brick-table gather). Otherwise the brick layout above serves every lookup.
-  {
-    const double sd = static_cast<double>(map->sub_dim);
-    const double rho = std::fabs(1.0 / (static_cast<double>(map->resolution) * sd) - 1.0);
-    uint64_t n[3];
-    for (int a = 0; a < 3; ++a) n[a] = static_cast<uint64_t>(thr[a]) * map->sub_dim + 2ull;
-    // rows padded to whole 128 B lines plus one 32 B sector, slices to whole rows plus one line: neighbouring rows / slices never
-    // start in the same L1 / L2 set (a power-of-two stride measured 45 % slower: profiles/r02_dense_layout.md)
-    const uint64_t row = (n[0] + 31) / 32 * 32 + 8, slice = row * n[1] + 32;
-    const uint64_t dense_total = slice * n[2];
-    uint64_t budget = c->prm.dense_budget_bytes;
-    if (budget == 0)
-    {
-      size_t free_b = 0, total_b = 0;
-      CU_CREATE(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
-      budget = std::min<uint64_t>(total_b / 4, free_b / 2);
-    }
-    int j = 1;   // 2^-j in (res / 4, res / 2]: u = 1 lands this far inside the border voxel above the map
-    while (std::ldexp(1.0, -j) > 0.5 * map->resolution) ++j;
-    bool ok = map->sub_dim >= 2 && rho <= std::ldexp(1.0, -18) && j <= 12 && dense_total < (1ull << 32) && dense_total * 4ull <= budget &&
-              map->data_size > 0;
-    for (int a = 0; a < 3 && ok; ++a)
-    {
-      const double kd = static_cast<double>(thr[a]) * sd + 1.0 + sd * std::ldexp(1.0, -j);
-      M.kk[a] = static_cast<float>(kd);
-      ok = static_cast<double>(M.kk[a]) == kd && kd < static_cast<double>(1u << 21);   // exact in fp32, floors fit the 2^23 magic
-      c->spec_prep.inv_sp[a] = sd / kd;
-      c->spec_prep.min[a] = map->min[a];
-    }
-    c->spec_prep.off = 1.0 / sd;
-    if (ok)
-    {
-      CU_CREATE(cudaMalloc(&c->d_dense, sizeof(float) * dense_total), "cudaMalloc(dense voxels)");
-      for (int a = 0; a < 3; ++a) c->dense_n[a] = static_cast<uint32_t>(n[a]);
-      M.dense = c->d_dense;
-      M.nx = static_cast<uint32_t>(row);
-      M.nxy = static_cast<uint32_t>(slice);
-      M.dshift_y = 0;
-      while ((1ull << M.dshift_y) < row) ++M.dshift_y;
-      M.dshift_z = 0;
-      while ((1ull << M.dshift_z) < slice) ++M.dshift_z;
-      M.dense_bias = kMagicBits * (1u + M.nx + M.nxy);
-      M.g_const = static_cast<int32_t>((kMagicBits + 1u) * M.sub_dim + kMagicBits - 1u);
-      // gamma: lattice mismatch rho * (in-cell position < 1) + the division's rounding (2^-24 relative on a quotient < sub_dim,
-      // i.e. < 2^-24 m) with room; k_check_div then PROVES it for every float in [0, 1)
-      M.gamma = static_cast<float>((rho + std::ldexp(1.0, -22)) * 1.0001);
-      // a margin must leave the clamp points (u = 0: the border voxel below, u = 1: 2^-j into the border voxel above) certain
-      M.delta_max = static_cast<float>(0.125 * std::min(std::ldexp(1.0, -j), static_cast<double>(map->resolution) - std::ldexp(1.0, -j)));
-      M.dense_ok = 1u;   // withdrawn below if the lattice proof fails
-    }
-  }
 
   // ---- cell keys of the spatial evaluation order: cells of 2^k metres so that the key space stays <= 2^20 ------------------
   {
@@ -1021,10 +941,8 @@ static int create_impl(const tsdfloc_map_desc* map, const int32_t* grid_occ, con
 
   // ---- small fixed buffers -------------------------------------------------------------------------------------
   CU_CREATE(cudaMalloc(&c->d_mean, sizeof(float) * 8), "cudaMalloc(mean pose)");
-  CU_CREATE(cudaMalloc(&c->d_eval_stats, sizeof(unsigned long long) * 8), "cudaMalloc(eval stats)");
-  CU_CREATE(cudaMemset(c->d_eval_stats, 0, sizeof(unsigned long long) * 8), "memset(eval stats)");
-  CU_CREATE(cudaMalloc(&c->d_scan_sq, sizeof(uint32_t) * 2), "cudaMalloc(scan bound)");
-  CU_CREATE(cudaMemset(c->d_scan_sq, 0, sizeof(uint32_t) * 2), "memset(scan bound)");
+  CU_CREATE(cudaMalloc(&c->d_eval_stats, sizeof(unsigned long long) * 4), "cudaMalloc(eval stats)");
+  CU_CREATE(cudaMemset(c->d_eval_stats, 0, sizeof(unsigned long long) * 4), "memset(eval stats)");
   CU_CREATE(cudaMalloc(&c->d_status, sizeof(Status)), "cudaMalloc(status)");
   CU_CREATE(cudaMemset(c->d_status, 0, sizeof(Status)), "memset(status)");
   CU_CREATE(cudaMallocHost(&c->h_status, sizeof(Status)), "cudaMallocHost(status)");
@@ -1036,8 +954,8 @@ static int create_impl(const tsdfloc_map_desc* map, const int32_t* grid_occ, con
   // ---- prove the quotient shortcuts for this resolution (exhaustive over every float in [0, 1)) ------------------
   {
     unsigned long long* d_out = nullptr;
-    CU_CREATE(cudaMalloc(&d_out, sizeof(unsigned long long) * 6), "cudaMalloc(div check)");
-    CU_CREATE(cudaMemset(d_out, 0, sizeof(unsigned long long) * 6), "memset(div check)");
+    CU_CREATE(cudaMalloc(&d_out, sizeof(unsigned long long) * 5), "cudaMalloc(div check)");
+    CU_CREATE(cudaMemset(d_out, 0, sizeof(unsigned long long) * 5), "memset(div check)");
     const float inv = M.inv_res;
     const float lo1 = std::nextafterf(inv, 0.0f), hi1 = std::nextafterf(inv, INFINITY);
     const float lo2 = std::nextafterf(lo1, 0.0f), hi2 = std::nextafterf(hi1, INFINITY);
@@ -1049,7 +967,7 @@ static int create_impl(const tsdfloc_map_desc* map, const int32_t* grid_occ, con
       return bail(TSDFLOC_E_CUDA, std::string("kernel image not loadable on this device (built for sm_100a): ") + cudaGetErrorString(le));
     }
     ++c->launches;
-    unsigned long long h[6] = {};
+    unsigned long long h[5] = {};
     cudaError_t ce = cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
     cudaFree(d_out);
@@ -1059,16 +977,6 @@ static int create_impl(const tsdfloc_map_desc* map, const int32_t* grid_occ, con
     if (c->three_ok && h[1] == 0) { c->bracket_ok = true; M.inv_lo = lo1; M.inv_hi = hi1; c->bracket_open = h[2]; }
     else if (c->three_ok && h[3] == 0) { c->bracket_ok = true; M.inv_lo = lo2; M.inv_hi = hi2; c->bracket_open = h[4]; }
     M.div_mode = c->bracket_ok ? kDivBracket : c->three_ok ? kDivThree : kDivIeee;
-    // the speculative index redoes uncertain steps with the 3-instruction quotient and trusts gamma only when proven
-    c->spec_proven = M.dense_ok && c->three_ok && h[5] == 0 && c->prm.neg_policy == TSDFLOC_NEG_MISS;
-    if (M.dense_ok)
-    {
-      k_build_dense<<<c->sm_count * 16, 256, 0, c->stream>>>(M, c->dense_n[0], c->dense_n[1], c->dense_n[2], map->init_value, c->d_dense);
-      cudaError_t be = cudaGetLastError();
-      if (be == cudaSuccess) be = cudaStreamSynchronize(c->stream);
-      if (be != cudaSuccess) return bail(TSDFLOC_E_CUDA, std::string("dense layout build failed: ") + cudaGetErrorString(be));
-      ++c->launches;
-    }
   }
 #undef CU_CREATE
   *out = c;
@@ -1113,8 +1021,6 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
   if (c->d_free_map) cudaFree(c->d_free_map);
   if (c->d_mean) cudaFree(c->d_mean);
   if (c->d_eval_stats) cudaFree(c->d_eval_stats);
-  if (c->d_scan_sq) cudaFree(c->d_scan_sq);
-  if (c->d_dense) cudaFree(c->d_dense);
   if (c->d_status) cudaFree(c->d_status);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_status) cudaFreeHost(c->h_status);
@@ -1855,14 +1761,6 @@ int tsdfloc_tune(tsdfloc_ctx* c, int knob, int value)
       if (value < -1 || value > kDivBracket) return fail(c, TSDFLOC_E_BAD_ARG, "division: -1 automatic, 0 IEEE, 1 three-instruction, 2 bracket");
       c->tune_div = value;
       return TSDFLOC_OK;
-    case TSDFLOC_TUNE_DENSE:
-      if (value < -1 || value > 1) return fail(c, TSDFLOC_E_BAD_ARG, "dense: -1 automatic, 0 brick layout, 1 dense layout (where built)");
-      c->tune_dense = value;
-      return TSDFLOC_OK;
-    case TSDFLOC_TUNE_SPECULATE:
-      if (value < -1 || value > 1) return fail(c, TSDFLOC_E_BAD_ARG, "speculate: -1 automatic, 0 off, 1 on (where proven)");
-      c->tune_spec = value;
-      return TSDFLOC_OK;
     case TSDFLOC_TUNE_STAGE_TIMERS:
       c->stage_timers = value != 0;
       c->stage_seen = 0;
@@ -1911,20 +1809,6 @@ int tsdfloc_eval_stats(tsdfloc_ctx* c, uint64_t out[4])
   unsigned long long h[4];
   CU_TRY(c, cudaMemcpy(h, c->d_eval_stats, sizeof(h), cudaMemcpyDeviceToHost), "D2H eval stats");
   for (int i = 0; i < 4; ++i) out[i] = h[i];
-  return TSDFLOC_OK;
-}
-
-int tsdfloc_spec_stats(tsdfloc_ctx* c, uint64_t out[4])
-{
-  if (!c || !out) return TSDFLOC_E_BAD_ARG;
-  DeviceGuard guard(c->device);
-  CU_TRY(c, cudaDeviceSynchronize(), "device sync");
-  unsigned long long h[8];
-  CU_TRY(c, cudaMemcpy(h, c->d_eval_stats, sizeof(h), cudaMemcpyDeviceToHost), "D2H eval stats");
-  out[0] = h[4];
-  out[1] = h[5];
-  out[2] = h[6];
-  out[3] = (c->map.dense_ok ? 1u : 0u) | (c->spec_proven ? 2u : 0u);
   return TSDFLOC_OK;
 }
 

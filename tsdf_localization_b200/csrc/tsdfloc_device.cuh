@@ -50,19 +50,6 @@ struct MapDev
   uint32_t table_bias; // kMagicBits * (1 + pad_x + pad_xy)   (mod 2^32)
   uint32_t sub_bias;   // kMagicBits * (1 + sub_dim + sub_dim_2) (mod 2^32)
   int32_t div_mode;    // kDivIeee / kDivThree / kDivBracket: what k_check_div proved for this resolution
-  // DENSE layout (tsdfloc_create builds it when the resolution is aligned — sub_dim * res = 1 — and the bounding box fits the
-  // budget): one float per voxel of the bounding box plus a one-voxel border of init_value, x fastest. Coordinate G_a of a
-  // lookup = floor(sub_dim * offset_a) + 1, 0 and n_a - 1 being the border (every miss outside the map); unallocated cells hold
-  // init_value. No brick table, no dependent gather. The speculative index (voxel_index2_spec) exists for this layout only.
-  const float* __restrict__ dense;
-  uint32_t nx, nxy;      // strides of G_y and G_z: powers of two (shifts and adds on the ALU pipe, the FMA pipe is the busy one)
-  uint32_t dshift_y, dshift_z;   // log2(nx), log2(nxy)
-  uint32_t dense_bias;   // kMagicBits * (1 + nx + nxy)
-  int32_t g_const;       // exact path: G = bits(floor cell + 2^23 + 1) * sub_dim + bits(2^23 + q) - g_const
-  float kk[3];           // K_a = thr_a * sub_dim + 1 + sub_dim * 2^-j (exact): G = floor(K_a * u) for the normalised offset u in [0, 1]
-  float gamma;           // how far the reference's voxel lattice (fl(p / res) per cell) can sit from the ideal one, metres (k_check_div)
-  float delta_max;       // particles whose certified margin would exceed this are evaluated exactly
-  uint32_t dense_ok;     // 1: dense layout built and the lattice proof passed
 };
 
 constexpr int kDivIeee = 0;      // __fdiv_rn
@@ -165,23 +152,9 @@ __device__ __forceinline__ float2 sub_coord2(const MapDev& M, float2 a, uint32_t
   return __fadd2_rd(make_float2(__fdiv_rn(a.x, M.res), __fdiv_rn(a.y, M.res)), km);
 }
 
-// Reference flat index (brick offset + in-brick offset; data_size for every miss) of the dense coordinates G — parity dumps only.
-__device__ __forceinline__ uint32_t ref_index_of(const MapDev& M, uint32_t gx, uint32_t gy, uint32_t gz)
-{
-  if (gx == 0u || gy == 0u || gz == 0u) return M.data_size;   // the border below the map; the one above it is a border cell of the table
-  const uint32_t vx = gx - 1u, vy = gy - 1u, vz = gz - 1u;
-  const uint32_t cx = vx / M.sub_dim, cy = vy / M.sub_dim, cz = vz / M.sub_dim;
-  if (cx + 1u >= M.pad_x || cy + 1u >= M.pad_xy / M.pad_x) return M.data_size;
-  const uint32_t brick = static_cast<uint32_t>(__ldg(M.table + (cx + 1u) + (cy + 1u) * M.pad_x + (cz + 1u) * M.pad_xy));
-  const uint32_t idx = brick + (vx - cx * M.sub_dim) + (vy - cy * M.sub_dim) * M.sub_dim + (vz - cz * M.sub_dim) * M.sub_dim_2;
-  return idx < M.data_size ? idx : M.data_size;
-}
-
-// voxel_index for two evaluations at once; same arithmetic per half as voxel_index<>. ia / ib index the array the kernel
-// gathers from: M.voxels (brick layout) or — kDense — M.dense. kRef (parity dumps): ra / rb = the reference's flat index.
-template <int kDiv, bool kDense, bool kRef>
-__device__ __forceinline__ void voxel_index2(const MapDev& M, float2 tx, float2 ty, float2 tz, uint32_t& ia, uint32_t& ib, uint32_t& mism,
-                                             uint32_t& ra, uint32_t& rb)
+// voxel_index for two evaluations at once; same arithmetic per half as voxel_index<>.
+template <int kDiv>
+__device__ __forceinline__ void voxel_index2(const MapDev& M, float2 tx, float2 ty, float2 tz, uint32_t& ia, uint32_t& ib, uint32_t& mism)
 {
   const float2 ox = clamp2(__fadd2_rn(tx, dup2(-M.min[0])), M.clamp_lo, M.clamp_hi[0]);
   const float2 oy = clamp2(__fadd2_rn(ty, dup2(-M.min[1])), M.clamp_lo, M.clamp_hi[1]);
@@ -196,88 +169,16 @@ __device__ __forceinline__ void voxel_index2(const MapDev& M, float2 tx, float2 
   const float2 px = __fadd2_rn(ox, make_float2(-fx.x, -fx.y));
   const float2 py = __fadd2_rn(oy, make_float2(-fy.x, -fy.y));
   const float2 pz = __fadd2_rn(oz, make_float2(-fz.x, -fz.y));
-  const float2 qx = sub_coord2<kDiv>(M, px, mism);
-  const float2 qy = sub_coord2<kDiv>(M, py, mism);
-  const float2 qz = sub_coord2<kDiv>(M, pz, mism);
-  if (kDense)
-  {
-    // G = cell * sub_dim + q + 1, cell in [-1, thr]: the lower border cell collapses onto G = 0
-    // (unsigned wrap-around arithmetic; the result is a small signed number)
-    const uint32_t sd = M.sub_dim, gc = static_cast<uint32_t>(M.g_const);
-    const int32_t gxa = max(static_cast<int32_t>(__float_as_uint(bx.x) * sd + __float_as_uint(qx.x) - gc), 0);
-    const int32_t gya = max(static_cast<int32_t>(__float_as_uint(by.x) * sd + __float_as_uint(qy.x) - gc), 0);
-    const int32_t gza = max(static_cast<int32_t>(__float_as_uint(bz.x) * sd + __float_as_uint(qz.x) - gc), 0);
-    const int32_t gxb = max(static_cast<int32_t>(__float_as_uint(bx.y) * sd + __float_as_uint(qx.y) - gc), 0);
-    const int32_t gyb = max(static_cast<int32_t>(__float_as_uint(by.y) * sd + __float_as_uint(qy.y) - gc), 0);
-    const int32_t gzb = max(static_cast<int32_t>(__float_as_uint(bz.y) * sd + __float_as_uint(qz.y) - gc), 0);
-    ia = static_cast<uint32_t>(gxa) + static_cast<uint32_t>(gya) * M.nx + static_cast<uint32_t>(gza) * M.nxy;
-    ib = static_cast<uint32_t>(gxb) + static_cast<uint32_t>(gyb) * M.nx + static_cast<uint32_t>(gzb) * M.nxy;
-    if (kRef)
-    {
-      ra = ref_index_of(M, gxa, gya, gza);
-      rb = ref_index_of(M, gxb, gyb, gzb);
-    }
-    return;
-  }
   // padded strides are powers of two: shifts on the ALU pipe instead of IMADs on the FMA pipe
   const uint32_t ta = __float_as_uint(bx.x) + (__float_as_uint(by.x) << M.shift_x) + (__float_as_uint(bz.x) << M.shift_xy) - M.table_bias;
   const uint32_t tb = __float_as_uint(bx.y) + (__float_as_uint(by.y) << M.shift_x) + (__float_as_uint(bz.y) << M.shift_xy) - M.table_bias;
   const uint32_t brick_a = static_cast<uint32_t>(__ldg(M.table + ta));
   const uint32_t brick_b = static_cast<uint32_t>(__ldg(M.table + tb));
+  const float2 qx = sub_coord2<kDiv>(M, px, mism);
+  const float2 qy = sub_coord2<kDiv>(M, py, mism);
+  const float2 qz = sub_coord2<kDiv>(M, pz, mism);
   ia = brick_a + __float_as_uint(qx.x) + __float_as_uint(qy.x) * M.sub_dim + __float_as_uint(qz.x) * M.sub_dim_2 - M.sub_bias;
   ib = brick_b + __float_as_uint(qx.y) + __float_as_uint(qy.y) * M.sub_dim + __float_as_uint(qz.y) * M.sub_dim_2 - M.sub_bias;
-  if (kRef)
-  {
-    ra = ia;
-    rb = ib;
-  }
-}
-
-// ---- speculative voxel index (certified), dense layout --------------------------------------------------------------
-//
-// The exact path above spends 36 of its 41 packed instructions per step reproducing the reference's separately rounded
-// transform and its floor / remainder / quotient per axis, plus twelve clamps. The speculative path computes, per axis, a
-// normalised offset
-//     u_lo = sat( fma(a0, x, fma(a1, y, fma(a2, z, a3))) ),   a_k = RN(m_k / S'),  a3 = RN((m3 - min + 1/sub_dim) / S') - delta_u
-//     u_hi = RU( u_lo + 2 delta_u )
-// (three fused multiply-adds, the last one saturating: the clamp is free) and the two floors
-//     G_lo = floor(K u_lo),  G_hi = floor(K u_hi),  K = S' * sub_dim   (one round-down FMA each: exact floors of exact products).
-// delta_u is chosen per particle and axis (SpecPlan, tsdfloc_eval.cuh) so that the reference's own rounded offset o_ref —
-// whatever its seven roundings did — satisfies  S' u_lo - 1/sub_dim <= o_ref - gamma  and  o_ref + gamma <= S' u_hi - 1/sub_dim.
-// The reference's voxel coordinate is monotone in o_ref and within gamma of the ideal lattice (k_check_div proves that
-// exhaustively for the map's resolution), so G_lo <= G_ref <= G_hi: where the floors agree that IS the reference's voxel,
-// bit for bit; where they differ (the point lies within ~1e-5 m of a voxel face: ~0.1 % of the evaluations) the caller
-// redoes the step with the exact path. Clamped coordinates need no compare: u = 0 is the border voxel below the map, u = 1
-// a point 2^-j m inside the border voxel above it, NaN saturates to 0 exactly where the exact path's fmaxf(NaN, -1) lands.
-__device__ __forceinline__ float2 spec_axis(const MapDev& M, int r, float2 a0, float2 a1, float2 a2, float2 a3, float2 two_delta, float2 xx,
-                                            float2 yy, float2 zz, uint32_t& mism)
-{
-  const float2 v1 = __ffma2_rn(a2, zz, a3);
-  const float2 v2 = __ffma2_rn(a1, yy, v1);
-  const float2 u = make_float2(__saturatef(__fmaf_rn(a0.x, xx.x, v2.x)), __saturatef(__fmaf_rn(a0.y, xx.y, v2.y)));
-  const float2 uh = __fadd2_ru(u, two_delta);
-  const float2 km = dup2(kMagic);
-  const float2 gl = __ffma2_rd(u, dup2(M.kk[r]), km);
-  const float2 gh = __ffma2_rd(uh, dup2(M.kk[r]), km);
-  mism |= (__float_as_uint(gl.x) ^ __float_as_uint(gh.x)) | (__float_as_uint(gl.y) ^ __float_as_uint(gh.y));
-  return gl;
-}
-
-// aa = the particle pair's speculative coefficients (rows of 4, slot 3 already lowered by delta_u), dl = 2 delta_u per axis.
-template <bool kRef>
-__device__ __forceinline__ void voxel_index2_spec(const MapDev& M, const float2 (&aa)[12], const float2 (&dl)[3], float2 xx, float2 yy, float2 zz,
-                                                  uint32_t& ia, uint32_t& ib, uint32_t& mism, uint32_t& ra, uint32_t& rb)
-{
-  const float2 gx = spec_axis(M, 0, aa[0], aa[1], aa[2], aa[3], dl[0], xx, yy, zz, mism);
-  const float2 gy = spec_axis(M, 1, aa[4], aa[5], aa[6], aa[7], dl[1], xx, yy, zz, mism);
-  const float2 gz = spec_axis(M, 2, aa[8], aa[9], aa[10], aa[11], dl[2], xx, yy, zz, mism);
-  ia = __float_as_uint(gx.x) + __float_as_uint(gy.x) * M.nx + __float_as_uint(gz.x) * M.nxy - M.dense_bias;
-  ib = __float_as_uint(gx.y) + __float_as_uint(gy.y) * M.nx + __float_as_uint(gz.y) * M.nxy - M.dense_bias;
-  if (kRef)
-  {
-    ra = ref_index_of(M, __float_as_uint(gx.x) - kMagicBits, __float_as_uint(gy.x) - kMagicBits, __float_as_uint(gz.x) - kMagicBits);
-    rb = ref_index_of(M, __float_as_uint(gx.y) - kMagicBits, __float_as_uint(gy.y) - kMagicBits, __float_as_uint(gz.y) - kMagicBits);
-  }
 }
 
 }  // namespace tsdfloc

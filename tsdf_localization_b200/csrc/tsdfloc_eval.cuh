@@ -25,11 +25,6 @@
 //   * The sub-voxel quotient floor(fl(p / res)) is bracketed by two round-down FMAs (tsdfloc_device.cuh); a block in which
 //     any quotient's bracket is open (~0.5 % of the blocks) is redone with the exact division. Exactness never depends on
 //     the bracket being tight — only speed does.
-//   * SPECULATIVE INDEX (kSpec): warps whose particles pass SpecPlan compute the voxel index from three fused multiply-adds
-//     per axis and a certified margin (voxel_index2_spec, tsdfloc_device.cuh): 26 packed instructions and no clamp per step
-//     instead of 41 + 12. A step in which any lane's voxel is uncertain (the point lies within the proven error bound of a
-//     voxel face) is redone with the exact path out of the exact matrices; the indices that reach the gathers are the
-//     reference's, bit for bit, by proof — not by sampling.
 #pragma once
 #include "tsdfloc_device.cuh"
 
@@ -43,19 +38,16 @@ constexpr float kRoundMagic = 12582912.0f;       // 1.5 * 2^23: x + magic rounds
 constexpr uint32_t kRoundMagicBits = 0x4B400000u;
 
 constexpr int kMaxPeers = 8;         // ranks of one NVSwitch domain
-constexpr int kMatStride = 24;       // floats per particle in EvalArgs::mats: exact rows [0, 12), speculative rows [12, 24)
 
 struct EvalArgs
 {
   const float4* __restrict__ pts;   // x y z term, padded with zero points to a multiple of kEvalPadPoints (+ one block)
-  const float* __restrict__ mats;   // [n_local][24]: the exact 3x4 rows, then the speculative rows (m_k / S', (m3 - min + 1) / S')
+  const float* __restrict__ mats;   // [n_local][12]
   float* raw_out;                   // [n_local] un-normalised weights (this rank's slice of its own weight vector)
   const uint32_t* perm;             // evaluation order: slot j is particle perm[j] (nullptr = identity), tsdfloc_sort.cuh
   float* const* peer_out;           // multi-GPU: device table of n_peer_out pointers = the same slice inside every OTHER
   uint32_t n_peer_out;              //            rank's weight vector (peer-mapped, NVLink); 0 / nullptr on one GPU
-  unsigned long long* __restrict__ stats;  // [8]: blocks, blocks folded sequentially, tie folds, blocks redone (open bracket),
-                                           //      steps evaluated speculatively, of those redone exactly, warps not eligible
-  const uint32_t* __restrict__ scan_sq;    // bit pattern of max(x^2 + y^2 + z^2) over the prepared scan (k_prep_scan); NaN/Inf poison it
+  unsigned long long* __restrict__ stats;  // [4]: blocks, blocks folded sequentially, tie folds, blocks redone (open bracket)
   uint32_t* idx_out;                // kDump only: [n_local][n_points] flat voxel index (data_size = miss)
   uint32_t* hits_out;               // kDump only: [n_local] lookups that hit an allocated brick
   uint32_t n_points;
@@ -79,7 +71,7 @@ __device__ __forceinline__ void store_weight(const EvalArgs& A, uint32_t slot, f
 // Leaves the block's x values in xa / xb (first / second half of every pair), the per-lane integer sums in acc0 / acc1 and
 // the largest |rounding residue| in mr0 / mr1 (0.5 = an exact tie). Returns the bracket-mismatch bits (kDiv == kDivBracket).
 // kDump (parity tests): also records every flat voxel index and counts the lookups that hit an allocated brick.
-template <int BS, int kDiv, bool kDense, bool kPP, bool kDump>
+template <int BS, int kDiv, bool kPP, bool kDump>
 __device__ __forceinline__ uint32_t eval_block(const MapDev& M, const EvalArgs& A, const float2 (&mm)[12], const float4* __restrict__ bp,
                                                uint32_t lane, float2 iu, float2 one, float2 ah, float (&xa)[BS], float (&xb)[BS],
                                                uint32_t& acc0, uint32_t& acc1, float& mr0, float& mr1, uint32_t part0, uint32_t point0,
@@ -112,25 +104,24 @@ __device__ __forceinline__ uint32_t eval_block(const MapDev& M, const EvalArgs& 
     const float2 tx = row_apply2(mm[0], mm[1], mm[2], mm[3], xx, yy, zz, one);
     const float2 ty = row_apply2(mm[4], mm[5], mm[6], mm[7], xx, yy, zz, one);
     const float2 tz = row_apply2(mm[8], mm[9], mm[10], mm[11], xx, yy, zz, one);
-    uint32_t ia, ib, ra = 0u, rb = 0u;
-    voxel_index2<kDiv, kDense, kDump>(M, tx, ty, tz, ia, ib, mism, ra, rb);
+    uint32_t ia, ib;
+    voxel_index2<kDiv>(M, tx, ty, tz, ia, ib, mism);
     if (kDump)
     {
       // (particle, point) of the two halves; identity evaluation order
       const uint32_t pa = part0, pb = kPP ? part0 : part0 + 1;
       const uint32_t qa = point0 + (kPP ? (b << 6) : (b << 5)) + lane, qb = kPP ? qa + 32u : qa;
       const bool va = pa < A.n_local && qa < A.n_points, vb = pb < A.n_local && qb < A.n_points && (kPP || pb != pa);
-      const bool ha = va && ra < M.data_size, hb = vb && rb < M.data_size;
+      const bool ha = va && ia < M.data_size, hb = vb && ib < M.data_size;
       if (A.idx_out)
       {
-        if (va) A.idx_out[static_cast<size_t>(pa) * A.n_points + qa] = ha ? ra : M.data_size;
-        if (vb) A.idx_out[static_cast<size_t>(pb) * A.n_points + qb] = hb ? rb : M.data_size;
+        if (va) A.idx_out[static_cast<size_t>(pa) * A.n_points + qa] = ha ? ia : M.data_size;
+        if (vb) A.idx_out[static_cast<size_t>(pb) * A.n_points + qb] = hb ? ib : M.data_size;
       }
       hit0 += __popc(__ballot_sync(0xffffffffu, ha));   // committed by the caller once the block is accepted
       hit1 += __popc(__ballot_sync(0xffffffffu, hb));
     }
-    const float* __restrict__ src = kDense ? M.dense : M.voxels;
-    const float2 v = make_float2(__ldg(src + ia), __ldg(src + ib));
+    const float2 v = make_float2(__ldg(M.voxels + ia), __ldg(M.voxels + ib));
     const float2 x = __ffma2_rn(__fmul2_rn(ah, v), one, term);       // fl(fl(a_hit*v) + term)
     xa[b] = x.x;
     xb[b] = x.y;
@@ -143,203 +134,6 @@ __device__ __forceinline__ uint32_t eval_block(const MapDev& M, const EvalArgs& 
     mr1 = fmaxf(mr1, fabsf(r.y));
   }
   return mism;
-}
-
-// The particle pair's matrices / coefficient rows as fp32x2 pairs {first half, second half}.
-__device__ __forceinline__ void load_rows(const float* __restrict__ rows_a, const float* __restrict__ rows_b, float2 (&cf)[12])
-{
-  const float4* __restrict__ a = reinterpret_cast<const float4*>(rows_a);
-  const float4* __restrict__ b = reinterpret_cast<const float4*>(rows_b);
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-  {
-    const float4 va = __ldg(a + r), vb = __ldg(b + r);
-    cf[4 * r + 0] = make_float2(va.x, vb.x);
-    cf[4 * r + 1] = make_float2(va.y, vb.y);
-    cf[4 * r + 2] = make_float2(va.z, vb.z);
-    cf[4 * r + 3] = make_float2(va.w, vb.w);
-  }
-}
-
-// SpecPlan: the certified margin of one particle and axis. With  T = |m0 x| + |m1 y| + |m2 z| <= |row| * |p|  (Cauchy-Schwarz),
-// D = |m3 - min + 1/sub_dim|  and every rounding bounded by 2^-24 times the magnitude of its result:
-//   reference offset  o_ref = fl(fl(fl(fl(fl(m0 x) + fl(m1 y)) + fl(m2 z)) + m3) - min):
-//       |o_ref - o*| <= 2^-24 (T + T + T + (T + |m3|) + (T + |m3| + |min|))            = 2^-24 (5 T + 2 |m3| + |min|)
-//   speculative offset  S' (u + delta_u) - 1  (three FMA roundings on magnitudes <= (T + D) / S' + delta_u, the coefficient
-//   roundings a_k = RN(m_k / S'), base3 = RN((m3 - min + 1/sub_dim) / S'), a3 = RN(base3 - delta_u)):
-//       |.. - o*| <= 2^-24 (3 (T + D) + T + D + D) + 2^-24 * 5 delta                    = 2^-24 (4 T + 5 D) + ..
-//   with |m3| <= D + |min| + 1 the sum is  2^-24 (9 T + 7 D + 3 |min| + 2) + ..; the plan uses  (10 T + 8 D + 4 |min| + 4) * 1.01
-//   (the slack pays for the (1 + 2^-24)^k factors, the fp64 roundings of the coefficient preparation and this computation's own
-//   fp32 roundings) plus gamma, the distance between the reference's per-cell voxel lattice and the ideal one.
-// Lowers slot 3 of every row by delta_u, returns 2 delta_u in dl and whether BOTH halves are eligible (finite bound, margin
-// below delta_max). All lanes compute the same values.
-__device__ __forceinline__ bool spec_plan(const MapDev& M, const EvalArgs& A, float2 (&cf)[12], float2 (&dl)[3])
-{
-  const float k1 = 1.0f + 0x1p-20f;
-  const float rho = __fsqrt_ru(__uint_as_float(__ldg(A.scan_sq)) * (1.0f + 0x1p-21f)) * k1;   // >= every |p| of the scan; NaN when poisoned
-  bool ok = rho <= 0x1p60f;
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-  {
-    const float sp = __fdiv_ru(M.kk[r], static_cast<float>(M.sub_dim)) * k1;   // >= S' (bounds), and
-    const float sp_lo = sp * (1.0f - 0x1p-18f);                                  // <= S' (the margin in units of u)
-    const float amin = fabsf(M.min[r]);
-    float du[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-    {
-      const float a0 = h ? cf[4 * r].y : cf[4 * r].x, a1 = h ? cf[4 * r + 1].y : cf[4 * r + 1].x, a2 = h ? cf[4 * r + 2].y : cf[4 * r + 2].x;
-      const float b = h ? cf[4 * r + 3].y : cf[4 * r + 3].x;
-      const float row = __fsqrt_ru(a0 * a0 + a1 * a1 + a2 * a2) * k1;
-      const float T = sp * row * rho * k1;
-      const float D = fabsf(b) * sp * k1;
-      const float delta = (10.0f * T + 8.0f * D + 4.0f * amin + 4.0f) * (1.01f * 0x1p-24f) + M.gamma;
-      ok = ok && (delta <= M.delta_max);
-      du[h] = __fdiv_ru(delta, sp_lo) * k1;
-    }
-    cf[4 * r + 3] = make_float2(__fsub_rn(cf[4 * r + 3].x, du[0]), __fsub_rn(cf[4 * r + 3].y, du[1]));
-    // the chain's first FMA takes two warp-uniform operands (a2, a3) and the packed instruction only one uniform register:
-    // keep a3 in ordinary registers (opaque to the uniform-datapath allocation) instead of two moves per axis and step
-    asm volatile("" : "+f"(cf[4 * r + 3].x), "+f"(cf[4 * r + 3].y));
-    dl[r] = make_float2(2.0f * du[0], 2.0f * du[1]);
-  }
-  return ok;
-}
-
-// One summation block through the speculative index: per-lane integer sums acc0 / acc1 and largest rounding residues
-// mr0 / mr1 like eval_block, but NO x values are kept (16 registers less in the hot loop): a block that cannot take the
-// integer shortcut is evaluated again by the caller through the exact path. Lanes whose voxel is uncertain in a step leave
-// that step out of their sums; the step is then redone through the exact transform and index (mats_a / mats_b = the two
-// halves' exact rows) and only those lanes add it. `redone` counts the redone steps.
-template <int BS, int kExact, bool kPP, bool kDump>
-__device__ __forceinline__ void eval_block_spec(const MapDev& M, const EvalArgs& A, const float2 (&cf)[12], const float2 (&dl)[3],
-                                                const float* __restrict__ mats_a, const float* __restrict__ mats_b,
-                                                const float4* __restrict__ bp, uint32_t lane, float2 iu, float2 one, float2 ah,
-                                                uint32_t& acc0, uint32_t& acc1, float& mr0, float& mr1, uint32_t part0, uint32_t point0,
-                                                uint32_t& hit0, uint32_t& hit1, uint32_t& redone)
-{
-  uint32_t lane_mask = 0u;
-  uint32_t ja[kDump ? BS : 1], jb[kDump ? BS : 1];
-  acc0 = acc1 = 0u;
-  mr0 = mr1 = 0.0f;
-#pragma unroll(BS)
-  for (int b = 0; b < BS; ++b)
-  {
-    float2 xx, yy, zz, term;
-    if (kPP)
-    {
-      const float4 p = __ldg(bp + (b << 6) + lane), q = __ldg(bp + (b << 6) + 32 + lane);
-      xx = make_float2(p.x, q.x);
-      yy = make_float2(p.y, q.y);
-      zz = make_float2(p.z, q.z);
-      term = make_float2(p.w, q.w);
-    }
-    else
-    {
-      const float4 p = __ldg(bp + (b << 5) + lane);
-      xx = dup2(p.x);
-      yy = dup2(p.y);
-      zz = dup2(p.z);
-      term = dup2(p.w);
-    }
-    uint32_t ia, ib, mism = 0u, ra = 0u, rb = 0u;
-    voxel_index2_spec<kDump>(M, cf, dl, xx, yy, zz, ia, ib, mism, ra, rb);
-    if (kDump)
-    {
-      ja[b] = ra;
-      jb[b] = rb;
-    }
-    const float2 v = make_float2(__ldg(M.dense + ia), __ldg(M.dense + ib));
-    const float2 x = __ffma2_rn(__fmul2_rn(ah, v), one, term);       // fl(fl(a_hit*v) + term)
-    const float2 tq = __ffma2_rn(x, iu, dup2(kRoundMagic));          // RN-even(x/u) in the low mantissa bits
-    const float2 tm = __fadd2_rn(tq, dup2(-kRoundMagic));
-    const float2 r = __ffma2_rn(x, iu, make_float2(-tm.x, -tm.y));   // exact rounding residue, |r| <= 0.5
-    if (mism == 0u)
-    {
-      acc0 += __float_as_uint(tq.x) - kRoundMagicBits;
-      acc1 += __float_as_uint(tq.y) - kRoundMagicBits;
-      mr0 = fmaxf(mr0, fabsf(r.x));
-      mr1 = fmaxf(mr1, fabsf(r.y));
-    }
-    else
-      lane_mask |= 1u << b;
-  }
-  const uint32_t redo = __reduce_or_sync(0xffffffffu, lane_mask);
-  if (redo)
-  {
-    redone += __popc(redo);
-#pragma unroll(BS)
-    for (int b = 0; b < BS; ++b)
-    {
-      if ((redo >> b) & 1u)
-      {
-        float2 xx, yy, zz, term;
-        if (kPP)
-        {
-          const float4 p = __ldg(bp + (b << 6) + lane), q = __ldg(bp + (b << 6) + 32 + lane);
-          xx = make_float2(p.x, q.x);
-          yy = make_float2(p.y, q.y);
-          zz = make_float2(p.z, q.z);
-          term = make_float2(p.w, q.w);
-        }
-        else
-        {
-          const float4 p = __ldg(bp + (b << 5) + lane);
-          xx = dup2(p.x);
-          yy = dup2(p.y);
-          zz = dup2(p.z);
-          term = dup2(p.w);
-        }
-        const float4* __restrict__ rows_a = reinterpret_cast<const float4*>(mats_a);
-        const float4* __restrict__ rows_b = reinterpret_cast<const float4*>(mats_b);
-        float2 t[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-        {
-          const float4 va = __ldg(rows_a + r), vb = __ldg(rows_b + r);
-          t[r] = row_apply2(make_float2(va.x, vb.x), make_float2(va.y, vb.y), make_float2(va.z, vb.z), make_float2(va.w, vb.w), xx, yy, zz, one);
-        }
-        uint32_t ia, ib, unused = 0u, ra = 0u, rb = 0u;
-        voxel_index2<kExact, true, kDump>(M, t[0], t[1], t[2], ia, ib, unused, ra, rb);
-        if (kDump)
-        {
-          ja[b] = ra;
-          jb[b] = rb;
-        }
-        const float2 v = make_float2(__ldg(M.dense + ia), __ldg(M.dense + ib));
-        const float2 x = __ffma2_rn(__fmul2_rn(ah, v), one, term);
-        const float2 tq = __ffma2_rn(x, iu, dup2(kRoundMagic));
-        const float2 tm = __fadd2_rn(tq, dup2(-kRoundMagic));
-        const float2 r = __ffma2_rn(x, iu, make_float2(-tm.x, -tm.y));
-        if ((lane_mask >> b) & 1u)
-        {
-          acc0 += __float_as_uint(tq.x) - kRoundMagicBits;
-          acc1 += __float_as_uint(tq.y) - kRoundMagicBits;
-          mr0 = fmaxf(mr0, fabsf(r.x));
-          mr1 = fmaxf(mr1, fabsf(r.y));
-        }
-      }
-    }
-  }
-  hit0 = hit1 = 0u;
-  if (kDump)
-  {
-#pragma unroll(BS)
-    for (int b = 0; b < BS; ++b)
-    {
-      const uint32_t pa = part0, pb = kPP ? part0 : part0 + 1;
-      const uint32_t qa = point0 + (kPP ? (b << 6) : (b << 5)) + lane, qb = kPP ? qa + 32u : qa;
-      const bool va = pa < A.n_local && qa < A.n_points, vb = pb < A.n_local && qb < A.n_points && (kPP || pb != pa);
-      const bool ha = va && ja[b] < M.data_size, hb = vb && jb[b] < M.data_size;
-      if (A.idx_out)
-      {
-        if (va) A.idx_out[static_cast<size_t>(pa) * A.n_points + qa] = ha ? ja[b] : M.data_size;
-        if (vb) A.idx_out[static_cast<size_t>(pb) * A.n_points + qb] = hb ? jb[b] : M.data_size;
-      }
-      hit0 += __popc(__ballot_sync(0xffffffffu, ha));
-      hit1 += __popc(__ballot_sync(0xffffffffu, hb));
-    }
-  }
 }
 
 // Sequential fp32 fold of one summation block in scan order, out of the lanes' registers.
@@ -408,20 +202,9 @@ struct WarpSums
 // running sums (integer-block shortcut where it provably equals the sequential fp32 sum, sequential fold otherwise).
 // kDiv == kDivBracket: returns false WITHOUT committing anything when a sub-voxel quotient's bracket is open — the caller
 // then runs the same block through an exact quotient mode.
-// kDiv == kDivSpec: mm holds the speculative coefficients, sp the rest of the plan; uncertain steps are redone inside
-// (through kExact), the block always commits.
-struct SpecState
-{
-  float2 dl[3];                      // 2 delta_u per axis and half
-  const float* __restrict__ mats_a;  // exact rows of the two halves
-  const float* __restrict__ mats_b;
-  uint32_t redone;                   // steps re-evaluated exactly
-};
-constexpr int kDivSpec = 3;
-
-template <int BS, int kDiv, int kExact, bool kDense, bool kPP, bool kDump>
-__device__ __forceinline__ bool eval_commit_block(const MapDev& M, const EvalArgs& A, const float2 (&mm)[12], SpecState& sp, uint32_t lane,
-                                                  float2 one, float2 ah, uint32_t part0, uint32_t point0, WarpSums& W)
+template <int BS, int kDiv, bool kPP, bool kDump>
+__device__ __forceinline__ bool eval_commit_block(const MapDev& M, const EvalArgs& A, const float2 (&mm)[12], uint32_t lane, float2 one,
+                                                  float2 ah, uint32_t part0, uint32_t point0, WarpSums& W)
 {
   constexpr uint32_t kBlockPoints = (kPP ? 64u : 32u) * BS;
   const float4* __restrict__ bp = A.pts + point0;
@@ -431,58 +214,9 @@ __device__ __forceinline__ bool eval_commit_block(const MapDev& M, const EvalArg
   uint32_t acc0, acc1;
   float mr0, mr1;
   uint32_t hit0, hit1;
-  bool dump_now = kDump;
-  if (kDiv == kDivSpec)
-  {
-    eval_block_spec<BS, kExact, kPP, kDump>(M, A, mm, sp.dl, sp.mats_a, sp.mats_b, bp, lane, iu, one, ah, acc0, acc1, mr0, mr1, part0, point0,
-                                            hit0, hit1, sp.redone);
-    // integer shortcut for every sum of the warp? then the block is done; otherwise (first blocks, binade crossing, tie: ~2 %)
-    // the whole block once more through the exact path, which keeps the x values for the sequential fold
-    const bool whole_blk = point0 + kBlockPoints <= A.n_points;
-    bool fast_ok;
-    float c0, c1 = 0.0f;
-    if (kPP)
-    {
-      const uint32_t tot = __reduce_add_sync(0xffffffffu, acc0 + acc1);
-      const bool any_tie = __any_sync(0xffffffffu, fmaxf(mr0, mr1) == 0.5f);
-      c0 = __fadd_rn(W.s0, __fmul_rn(static_cast<float>(tot), p0.u));
-      fast_ok = whole_blk && p0.fast && !any_tie && tot < (1u << 24) && c0 <= p0.limit;
-    }
-    else
-    {
-      const uint32_t tot0 = __reduce_add_sync(0xffffffffu, acc0), tot1 = __reduce_add_sync(0xffffffffu, acc1);
-      const bool any_tie = __any_sync(0xffffffffu, fmaxf(mr0, mr1) == 0.5f);
-      c0 = __fadd_rn(W.s0, __fmul_rn(static_cast<float>(tot0), p0.u));
-      c1 = __fadd_rn(W.s1, __fmul_rn(static_cast<float>(tot1), p1.u));
-      fast_ok = whole_blk && p0.fast && p1.fast && !any_tie && tot0 < (1u << 24) && tot1 < (1u << 24) && c0 <= p0.limit && c1 <= p1.limit;
-    }
-    if (kDump && lane == 0 && A.hits_out)
-    {
-      if (kPP) { if (part0 < A.n_local && hit0 + hit1) atomicAdd(A.hits_out + part0, hit0 + hit1); }
-      else
-      {
-        if (part0 < A.n_local && hit0) atomicAdd(A.hits_out + part0, hit0);
-        if (part0 + 1u < A.n_local && hit1) atomicAdd(A.hits_out + part0 + 1u, hit1);
-      }
-    }
-    if (fast_ok)
-    {
-      W.s0 = c0;
-      if (!kPP) W.s1 = c1;
-      return true;
-    }
-    float2 me[12];
-    load_rows(sp.mats_a, sp.mats_b, me);
-    eval_block<BS, kExact, true, kPP, false>(M, A, me, bp, lane, iu, one, ah, xa, xb, acc0, acc1, mr0, mr1, part0, point0, hit0, hit1);
-    dump_now = false;   // indices and hits of this block were recorded above
-  }
-  else
-  {
-    const uint32_t mism = eval_block<BS, kDiv == kDivSpec ? kExact : kDiv, kDense, kPP, kDump>(M, A, mm, bp, lane, iu, one, ah, xa, xb, acc0,
-                                                                                              acc1, mr0, mr1, part0, point0, hit0, hit1);
-    if (kDiv == kDivBracket && __any_sync(0xffffffffu, mism != 0u)) return false;
-  }
-  if (dump_now && lane == 0 && A.hits_out)
+  const uint32_t mism = eval_block<BS, kDiv, kPP, kDump>(M, A, mm, bp, lane, iu, one, ah, xa, xb, acc0, acc1, mr0, mr1, part0, point0, hit0, hit1);
+  if (kDiv == kDivBracket && __any_sync(0xffffffffu, mism != 0u)) return false;
+  if (kDump && lane == 0 && A.hits_out)
   {
     if (kPP) { if (part0 < A.n_local && hit0 + hit1) atomicAdd(A.hits_out + part0, hit0 + hit1); }
     else
@@ -542,10 +276,8 @@ __device__ __forceinline__ bool eval_commit_block(const MapDev& M, const EvalArg
   return true;
 }
 
-// kExact = kDivIeee or kDivThree (what k_check_div proved); kBracket: try the bracketed quotients first; kDense: the dense
-// layout — warps whose particles pass SpecPlan use the speculative index when kSpec, the others (and every warp when !kSpec)
-// run the bracketed / exact loop of the same kernel on the same array.
-template <int BS, int kExact, bool kBracket, bool kDense, bool kSpec, bool kPP, bool kDump>
+// kExact = kDivIeee or kDivThree (what k_check_div proved); kBracket: try the bracketed quotients first.
+template <int BS, int kExact, bool kBracket, bool kPP, bool kDump>
 __global__ void __launch_bounds__(32, 32) k_eval(const MapDev M, const EvalArgs A)
 {
   constexpr uint32_t kBlockPoints = (kPP ? 64u : 32u) * BS;
@@ -553,52 +285,32 @@ __global__ void __launch_bounds__(32, 32) k_eval(const MapDev M, const EvalArgs 
   const uint32_t part0 = kPP ? blockIdx.x : blockIdx.x * 2u;
   const uint32_t n_blocks_total = (A.n_points + kBlockPoints - 1u) / kBlockPoints;
 
-  // the rows as fp32x2 pairs: {particle A, particle B}, or {particle, particle}; a warp past the end re-does the last
+  // the matrices as fp32x2 pairs: {particle A, particle B}, or {particle, particle}; a warp past the end re-does the last
   // particle and stores nothing
-  const uint32_t pa = min(part0, A.n_local - 1u), pb = kPP ? pa : min(part0 + 1u, A.n_local - 1u);
-  const float* __restrict__ rows_a = A.mats + static_cast<size_t>(kMatStride) * pa;
-  const float* __restrict__ rows_b = A.mats + static_cast<size_t>(kMatStride) * pb;
   float2 mm[12];
-  SpecState sp;
-  sp.mats_a = rows_a;
-  sp.mats_b = rows_b;
-  sp.redone = 0u;
-  bool spec = false;
-  if (kSpec)
   {
-    load_rows(rows_a + 12, rows_b + 12, mm);
-    spec = spec_plan(M, A, mm, sp.dl);
+    const uint32_t pa = min(part0, A.n_local - 1u), pb = kPP ? pa : min(part0 + 1u, A.n_local - 1u);
+#pragma unroll
+    for (int e = 0; e < 12; ++e) mm[e] = make_float2(__ldg(A.mats + 12ull * pa + e), __ldg(A.mats + 12ull * pb + e));
   }
   WarpSums W{0.0f, 0.0f, 0u, 0u};
   uint32_t n_redo = 0;
   const float2 one = dup2(A.one);
   const float2 ah = dup2(A.a_hit);
 
-  if (kSpec && spec)
+  uint32_t blk = 0;
+  while (blk < n_blocks_total)
   {
+    // hot loop: bracketed quotients (or, where the bracket is unproven for this resolution, the exact mode directly)
 #pragma unroll 1
-    for (uint32_t blk = 0; blk < n_blocks_total; ++blk)
-      eval_commit_block<BS, kDivSpec, kExact, true, kPP, kDump>(M, A, mm, sp, lane, one, ah, part0, blk * kBlockPoints, W);
-  }
-  else
-  {
-    load_rows(rows_a, rows_b, mm);
-    uint32_t blk = 0;
-    while (blk < n_blocks_total)
+    for (; blk < n_blocks_total; ++blk)
+      if (!eval_commit_block<BS, kBracket ? kDivBracket : kExact, kPP, kDump>(M, A, mm, lane, one, ah, part0, blk * kBlockPoints, W)) break;
+    if (kBracket && blk < n_blocks_total)
     {
-      // hot loop: bracketed quotients (or, where the bracket is unproven for this resolution, the exact mode directly)
-#pragma unroll 1
-      for (; blk < n_blocks_total; ++blk)
-        if (!eval_commit_block<BS, kBracket ? kDivBracket : kExact, kExact, kDense, kPP, kDump>(M, A, mm, sp, lane, one, ah, part0,
-                                                                                                blk * kBlockPoints, W))
-          break;
-      if (kBracket && blk < n_blocks_total)
-      {
-        // cold: a quotient of this block sits within a few ulps of an integer — the same block with the exact division
-        eval_commit_block<BS, kExact, kExact, kDense, kPP, kDump>(M, A, mm, sp, lane, one, ah, part0, blk * kBlockPoints, W);
-        ++n_redo;
-        ++blk;
-      }
+      // cold: a quotient of this block sits within a few ulps of an integer — the same block with the exact division
+      eval_commit_block<BS, kExact, kPP, kDump>(M, A, mm, lane, one, ah, part0, blk * kBlockPoints, W);
+      ++n_redo;
+      ++blk;
     }
   }
 
@@ -612,13 +324,6 @@ __global__ void __launch_bounds__(32, 32) k_eval(const MapDev M, const EvalArgs 
       atomicAdd(A.stats + 1, static_cast<unsigned long long>(W.n_fold));
       atomicAdd(A.stats + 2, static_cast<unsigned long long>(W.n_tie));
       atomicAdd(A.stats + 3, static_cast<unsigned long long>(n_redo));
-      if (kSpec && spec)
-      {
-        atomicAdd(A.stats + 4, static_cast<unsigned long long>(n_blocks_total) * BS);
-        atomicAdd(A.stats + 5, static_cast<unsigned long long>(sp.redone));
-      }
-      else if (kSpec)
-        atomicAdd(A.stats + 6, 1ull);
     }
   }
 }

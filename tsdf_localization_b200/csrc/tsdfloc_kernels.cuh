@@ -101,13 +101,10 @@ struct PrepArgs
   float4* __restrict__ out;        // [padded]
   uint32_t p, padded;              // points beyond p are written as zero points (the evaluation reads whole blocks)
   float a_range_term, a_max, max_range_sq;
-  uint32_t* sq_max;                // bit pattern of max(x^2 + y^2 + z^2) over the scan (atomicMax; zero on entry); NaN/Inf poison it:
-  uint32_t* sq_next;               // the evaluation's SpecPlan reads it. sq_next = the slot of the NEXT scan, zeroed here.
 };
 
 __device__ __forceinline__ void prep_scan_points(const PrepArgs& A, uint32_t first_thread, uint32_t n_threads)
 {
-  uint32_t far = 0u;   // sq >= 0 or NaN: the bit patterns order like the values, NaN above everything
   for (uint32_t i = first_thread; i < A.padded; i += n_threads)
   {
     if (i < A.p)
@@ -115,14 +112,10 @@ __device__ __forceinline__ void prep_scan_points(const PrepArgs& A, uint32_t fir
       const float x = A.xyz[3 * i], y = A.xyz[3 * i + 1], z = A.xyz[3 * i + 2];
       const float sq = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
       A.out[i] = make_float4(x, y, z, sq < A.max_range_sq ? A.a_range_term : A.a_max);
-      far = max(far, __float_as_uint(sq) | (sq != sq ? 0x7fffffffu : 0u));
     }
     else
       A.out[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   }
-  far = __reduce_max_sync(0xffffffffu, far);
-  if ((threadIdx.x & 31u) == 0u && far) atomicMax(A.sq_max, far);
-  if (first_thread == 0u) *A.sq_next = 0u;
 }
 
 __global__ void __launch_bounds__(256) k_prep_scan(const PrepArgs A)
@@ -139,17 +132,9 @@ struct Tf12
   float m[12];
 };
 
-// What K0 needs to write the speculative rows next to the exact ones (tsdfloc_eval.cuh, SpecPlan).
-struct SpecPrep
-{
-  double inv_sp[3];   // 1 / S'_a, S'_a = K_a / sub_dim
-  double off;         // 1 / sub_dim: the dense layout's one-voxel border below the map
-  float min[3];
-};
-
 // perm (optional): matrix i belongs to particle first + perm[i] (spatial evaluation order, tsdfloc_sort.cuh).
-__device__ __forceinline__ void pose_matrix(const float* __restrict__ particles, uint32_t first, uint32_t i, const Tf12& tf, const SpecPrep& sp,
-                                            float* __restrict__ mats, const uint32_t* __restrict__ perm)
+__device__ __forceinline__ void pose_matrix(const float* __restrict__ particles, uint32_t first, uint32_t i, const Tf12& tf, float* __restrict__ mats,
+                                            const uint32_t* __restrict__ perm)
 {
   const float* p = particles + 7ull * (first + (perm ? perm[i] : i));
   double sd, cd;
@@ -174,65 +159,36 @@ __device__ __forceinline__ void pose_matrix(const float* __restrict__ particles,
   r[2][2] = __fmul_rn(ca, cb);
   r[2][3] = p[2];
 
-  float4* o = reinterpret_cast<float4*>(mats + 24ull * i);
+  float* o = mats + 12ull * i;
 #pragma unroll
   for (int k = 0; k < 3; ++k)
   {
     const float a = r[k][0], b = r[k][1], c = r[k][2], d = r[k][3];
-    float4 m;
-    m.x = __fadd_rn(__fadd_rn(__fmul_rn(a, tf.m[0]), __fmul_rn(b, tf.m[4])), __fmul_rn(c, tf.m[8]));
-    m.y = __fadd_rn(__fadd_rn(__fmul_rn(a, tf.m[1]), __fmul_rn(b, tf.m[5])), __fmul_rn(c, tf.m[9]));
-    m.z = __fadd_rn(__fadd_rn(__fmul_rn(a, tf.m[2]), __fmul_rn(b, tf.m[6])), __fmul_rn(c, tf.m[10]));
-    m.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, tf.m[3]), __fmul_rn(b, tf.m[7])), __fmul_rn(c, tf.m[11])), d);
-    o[k] = m;
-    // speculative row: a_k = RN(m_k / S'), base3 = RN((m3 - min + 1/sub_dim) / S'); the fp64 operations round too, 2^-53 relative
-    float4 q;
-    q.x = static_cast<float>(static_cast<double>(m.x) * sp.inv_sp[k]);
-    q.y = static_cast<float>(static_cast<double>(m.y) * sp.inv_sp[k]);
-    q.z = static_cast<float>(static_cast<double>(m.z) * sp.inv_sp[k]);
-    q.w = static_cast<float>((static_cast<double>(m.w) - static_cast<double>(sp.min[k]) + sp.off) * sp.inv_sp[k]);
-    o[3 + k] = q;
+    o[4 * k + 0] = __fadd_rn(__fadd_rn(__fmul_rn(a, tf.m[0]), __fmul_rn(b, tf.m[4])), __fmul_rn(c, tf.m[8]));
+    o[4 * k + 1] = __fadd_rn(__fadd_rn(__fmul_rn(a, tf.m[1]), __fmul_rn(b, tf.m[5])), __fmul_rn(c, tf.m[9]));
+    o[4 * k + 2] = __fadd_rn(__fadd_rn(__fmul_rn(a, tf.m[2]), __fmul_rn(b, tf.m[6])), __fmul_rn(c, tf.m[10]));
+    o[4 * k + 3] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, tf.m[3]), __fmul_rn(b, tf.m[7])), __fmul_rn(c, tf.m[11])), d);
   }
 }
 
-__global__ void __launch_bounds__(256) k_pose_matrices(const float* __restrict__ particles, uint32_t first, uint32_t count, Tf12 tf, SpecPrep sp,
+__global__ void __launch_bounds__(256) k_pose_matrices(const float* __restrict__ particles, uint32_t first, uint32_t count, Tf12 tf,
                                                       float* __restrict__ mats, const uint32_t* __restrict__ perm)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) pose_matrix(particles, first, i, tf, sp, mats, perm);
+  if (i < count) pose_matrix(particles, first, i, tf, mats, perm);
 }
 
 // Scan preparation and pose matrices in ONE launch (the host-buffer update issues them together): CTAs [0, scan_ctas) prepare
 // the scan, the rest build matrices.
 __global__ void __launch_bounds__(256) k_prepare(const PrepArgs A, uint32_t scan_ctas, const float* __restrict__ particles, uint32_t first,
-                                                uint32_t count, Tf12 tf, SpecPrep sp, float* __restrict__ mats, const uint32_t* __restrict__ perm)
+                                                uint32_t count, Tf12 tf, float* __restrict__ mats, const uint32_t* __restrict__ perm)
 {
   if (blockIdx.x < scan_ctas)
     prep_scan_points(A, blockIdx.x * blockDim.x + threadIdx.x, scan_ctas * blockDim.x);
   else
   {
     const uint32_t i = (blockIdx.x - scan_ctas) * blockDim.x + threadIdx.x;
-    if (i < count) pose_matrix(particles, first, i, tf, sp, mats, perm);
-  }
-}
-
-// Dense layout from the padded brick table + bricks (tsdfloc_device.cuh, MapDev::dense): one thread per dense voxel.
-__global__ void __launch_bounds__(256) k_build_dense(MapDev M, uint32_t nx, uint32_t ny, uint32_t nz, float init_value, float* __restrict__ dense)
-{
-  // (nx, ny, nz) = voxels per axis incl. the two border layers; rows and slices are padded to M.nx / M.nxy (left untouched)
-  const size_t total = static_cast<size_t>(nx) * ny * nz;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-  {
-    const uint32_t gx = static_cast<uint32_t>(i % nx), gy = static_cast<uint32_t>((i / nx) % ny), gz = static_cast<uint32_t>(i / (static_cast<size_t>(nx) * ny));
-    float v = init_value;
-    if (gx >= 1u && gy >= 1u && gz >= 1u && gx + 1u < nx && gy + 1u < ny && gz + 1u < nz)
-    {
-      const uint32_t vx = gx - 1u, vy = gy - 1u, vz = gz - 1u;
-      const uint32_t cx = vx / M.sub_dim, cy = vy / M.sub_dim, cz = vz / M.sub_dim;
-      const uint32_t brick = static_cast<uint32_t>(M.table[(cx + 1u) + (cy + 1u) * M.pad_x + (cz + 1u) * M.pad_xy]);
-      v = M.voxels[brick + (vx - cx * M.sub_dim) + (vy - cy * M.sub_dim) * M.sub_dim + (vz - cz * M.sub_dim) * M.sub_dim_2];
-    }
-    dense[static_cast<size_t>(gx) + static_cast<size_t>(gy) * M.nx + static_cast<size_t>(gz) * M.nxy] = v;
+    if (i < count) pose_matrix(particles, first, i, tf, mats, perm);
   }
 }
 
@@ -241,13 +197,9 @@ __global__ void __launch_bounds__(256) k_build_dense(MapDev M, uint32_t nx, uint
 //   out[1]  a where floor(a * lo1) <= floor(fl(a / res)) <= floor(a * hi1) is VIOLATED             (0 = the bracket holds)
 //   out[2]  a where that bracket is open (the two floors differ: the kernel redoes such a block exactly)
 //   out[3], out[4]  the same for the wider pair (lo2, hi2)
-//   out[5]  a where the reference's in-cell voxel floor(fl(a / res)) is NOT within gamma of the ideal lattice, i.e. where
-//           floor(sub_dim (a - gamma)) <= floor(fl(a / res)) <= floor(sub_dim (a + gamma))  fails, or the voxel reaches sub_dim
-//           (0 = the speculative index may trust gamma for this resolution; evaluated in fp64, exact for these magnitudes)
 __global__ void k_check_div(MapDev M, float lo1, float hi1, float lo2, float hi2, unsigned long long* __restrict__ out)
 {
-  unsigned long long bad3 = 0, bad1 = 0, open1 = 0, bad2 = 0, open2 = 0, badg = 0;
-  const double sd = static_cast<double>(M.sub_dim), gam = 0.99 * static_cast<double>(M.gamma);   // 1 % under what the kernel assumes: fp64 rounding cannot matter
+  unsigned long long bad3 = 0, bad1 = 0, open1 = 0, bad2 = 0, open2 = 0;
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < 0x3F800000u; b += gridDim.x * blockDim.x)
   {
     const float a = __uint_as_float(b);
@@ -259,15 +211,12 @@ __global__ void k_check_div(MapDev M, float lo1, float hi1, float lo2, float hi2
     open1 += (l1 != h1);
     bad2 += !(l2 <= ieee && ieee <= h2);
     open2 += (l2 != h2);
-    const double q = static_cast<double>(ieee - kMagicBits), ad = static_cast<double>(a);
-    badg += !(floor(sd * (ad - gam)) <= q && q <= floor(sd * (ad + gam)) && q < sd);
   }
   if (bad3) atomicAdd(out + 0, bad3);
   if (bad1) atomicAdd(out + 1, bad1);
   if (open1) atomicAdd(out + 2, open1);
   if (bad2) atomicAdd(out + 3, bad2);
   if (open2) atomicAdd(out + 4, open2);
-  if (badg) atomicAdd(out + 5, badg);
 }
 
 // exact-add check: returns a+b and sets `bad` if the fp64 addition rounded.

@@ -160,14 +160,12 @@ class CudaEvaluator:
     """GPU sensor update. Constructor uploads the map once (cuda_evaluator.cu:21-59)."""
 
     def __init__(self, map: CudaSubVoxelMap, per_point: bool = False, a_hit: float = 0.9, a_range: float = 0.1,
-                 a_max: float = 0.0, max_range: float = 100.0, device: int = 0, neg_policy: int = capi.NEG_MISS,
-                 dense_budget_bytes: int = 0):
+                 a_max: float = 0.0, max_range: float = 100.0, device: int = 0, neg_policy: int = capi.NEG_MISS):
         """neg_policy (not a reference argument): capi.NEG_MISS (default) or capi.NEG_SATURATE_LIKE_REF_GPU, which
-        reproduces the reference CUDA build's handling of lookups below map.min bit for bit (tsdfloc.h).
-        dense_budget_bytes: 0 = automatic, 1 = always the brick layout (tsdfloc_params.dense_budget_bytes)."""
+        reproduces the reference CUDA build's handling of lookups below map.min bit for bit (tsdfloc.h)."""
         self._lib = capi.load_library()
         self._ctx = C.c_void_p()
-        prm = capi.Params(a_hit, a_range, a_max, max_range, int(per_point), int(neg_policy), int(dense_budget_bytes))
+        prm = capi.Params(a_hit, a_range, a_max, max_range, int(per_point), int(neg_policy))
         desc = map.coef()
         occ = np.ascontiguousarray(map.rawGridOcc(), dtype=np.int32)
         data = np.ascontiguousarray(map.rawData(), dtype=np.float32)
@@ -343,11 +341,6 @@ class CudaEvaluator:
         st = (C.c_uint64 * 4)()
         capi.check(self._lib, self._ctx, self._lib.tsdfloc_eval_stats(self._ctx, st))
         return dict(blocks=int(st[0]), folded=int(st[1]), tie_folds=int(st[2]), redone=int(st[3]))
-
-    def spec_stats(self):
-        st = (C.c_uint64 * 4)()
-        capi.check(self._lib, self._ctx, self._lib.tsdfloc_spec_stats(self._ctx, st))
-        return dict(steps=int(st[0]), redone=int(st[1]), warps_not_eligible=int(st[2]), dense=bool(st[3] & 1), proven=bool(st[3] & 2))
 
     def close(self) -> None:
         if getattr(self, "_ctx", None):
