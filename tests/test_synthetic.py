@@ -36,3 +36,21 @@ def test_box_room_is_chunk_aligned_and_scan_hits_it():
     spec, m = common.box_room(small=True)
     assert spec.min == (-6.4, -3.2, -3.2) and spec.max == (6.4, 3.2, 6.4)
     assert (m.rawGridOcc() >= 0).sum() * 8000 == m.coef().data_size
+
+
+def test_committed_bench_lines_are_rank_count_invariant():
+    """The round-2 bench lines at 1, 2, 4 and 8 GPUs (profiles/r02_bench_c3*.json, written by `bench.py --gpus N` on the B200
+    box) carry sha256 digests of the normalised weight vector and of the resampled particle set, device-resident and through
+    the host-buffer C ABI: one update, whatever the number of ranks, produces the same bytes."""
+    import json
+    from pathlib import Path
+    prof = Path(__file__).resolve().parents[1] / "profiles"
+    lines = {n: json.loads((prof / name).read_text()) for n, name in
+             ((1, "r02_bench_c3.json"), (2, "r02_bench_c3_n2.json"), (4, "r02_bench_c3_n4.json"), (8, "r02_bench_c3_n8.json"))}
+    digests = set()
+    for n, d in lines.items():
+        assert d["n_gpus"] == n and d["config"]["particles"] == 65536 and d["config"]["points"] == 131072
+        c = d["config"]
+        digests.add((c["weights_sha256"], c["resampled_sha256"]))
+        digests.add((c["e2e_weights_sha256"], c["e2e_resampled_sha256"]))
+    assert len(digests) == 1, digests
