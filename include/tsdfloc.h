@@ -445,7 +445,8 @@ enum tsdfloc_tune_knob
   TSDFLOC_TUNE_SPATIAL_ORDER = 0,
   TSDFLOC_TUNE_EVAL_PAIRING = 1,
   TSDFLOC_TUNE_DIVISION = 2,
-  TSDFLOC_TUNE_STAGE_TIMERS = 3   /* 0 off (default), 1 record CUDA events around the stages (tsdfloc_stage_times) */
+  TSDFLOC_TUNE_STAGE_TIMERS = 3,  /* 0 off (default), 1 record CUDA events around the stages (tsdfloc_stage_times) */
+  TSDFLOC_TUNE_EVAL_REGISTERS = 4 /* 0 automatic (128 registers per thread up to 16,384 particles per device, 64 beyond), 1 64, 2 128 */
 };
 int tsdfloc_tune(tsdfloc_ctx* ctx, int knob, int value);
 

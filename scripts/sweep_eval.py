@@ -1,4 +1,4 @@
-"""Dev script: evaluation-kernel sweep over particle counts x pairing x quotient mode (tsdfloc_tune), CUDA events around
+"""Dev script: evaluation-kernel sweep over particle counts x pairing x register budget (tsdfloc_tune), CUDA events around
 tsdfloc_eval_device, L2 flushed before every timed launch. Writes one JSON line per cell; every cell must produce the same
 sha256 of the raw weight vector per particle count (all settings are bit-identical by construction).
 
@@ -45,9 +45,9 @@ def main():
             d_raw = torch.zeros(n, dtype=torch.float32, device=dev)
             shas = set()
             for pairing in (1, 2):
-                for div in (capi.DIV_THREE, capi.DIV_BRACKET):
+                for regs in (1, 2):
                     ev.tune(capi.TUNE_EVAL_PAIRING, pairing)
-                    ev.tune(capi.TUNE_DIVISION, div)
+                    ev.tune(capi.TUNE_EVAL_REGISTERS, regs)
                     times = []
                     for it in range(reps + 2):
                         flush.zero_()
@@ -60,7 +60,7 @@ def main():
                             times.append(e0.elapsed_time(e1))
                     sha = hashlib.sha256(d_raw.cpu().numpy().tobytes()).hexdigest()[:16]
                     shas.add(sha)
-                    row = dict(particles=n, points=P, pairing={1: "particles", 2: "points"}[pairing], division={1: "three", 2: "bracket"}[div],
+                    row = dict(particles=n, points=P, pairing={1: "particles", 2: "points"}[pairing], registers={1: 64, 2: 128}[regs],
                                ms_min=min(times), ms_med=float(np.median(times)), gevals_per_s=n * P / min(times) / 1e6, raw_sha=sha)
                     f.write(json.dumps(row) + "\n")
                     f.flush()

@@ -43,21 +43,24 @@ def _scan(p):
                                  (2, 512), (5, 513), (33, 1000), (4, 1025), (64, 4097), (257, 511)])
 def test_ragged_shapes_bit_exact(oracle, omap, ev, n, p):
     """P not a multiple of the 32- / 64-point step or of the 256- / 512-point summation block; odd particle counts (the
-    particle-pair shape pairs particles); both pairings of the evaluation kernel."""
+    particle-pair shape pairs particles); both pairings and both register budgets of the evaluation kernel."""
     ps = syn.tracking_particles(n, GT, sigma_xy=0.2, seed=n + p)
     pts = _scan(p)
     ref = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.CALIB_TF, want_idx=True)
     try:
         for pairing in (1, 2):
-            ev.tune(capi.TUNE_EVAL_PAIRING, pairing)
-            idx, hits, raw = ev.debug_eval(ps, pts, syn.CALIB_TF)
-            assert np.array_equal(idx, ref["idx"]) and np.array_equal(hits, ref["hits"])
-            assert raw.tobytes() == ref["raw"].tobytes()
-            mine = ps.copy()
-            ev.evaluate(mine, pts, syn.CALIB_TF)
-            assert common.rel_err(mine[:, 6], ref["particles"][:, 6]).max() <= 1e-5
+            for registers in (1, 2):          # the 64- and the 128-register build of the kernel
+                ev.tune(capi.TUNE_EVAL_PAIRING, pairing)
+                ev.tune(capi.TUNE_EVAL_REGISTERS, registers)
+                idx, hits, raw = ev.debug_eval(ps, pts, syn.CALIB_TF)
+                assert np.array_equal(idx, ref["idx"]) and np.array_equal(hits, ref["hits"])
+                assert raw.tobytes() == ref["raw"].tobytes()
+                mine = ps.copy()
+                ev.evaluate(mine, pts, syn.CALIB_TF)
+                assert common.rel_err(mine[:, 6], ref["particles"][:, 6]).max() <= 1e-5
     finally:
         ev.tune(capi.TUNE_EVAL_PAIRING, 0)
+        ev.tune(capi.TUNE_EVAL_REGISTERS, 0)
 
 
 @pytest.mark.parametrize("pairing", [1, 2], ids=["particle_pairs", "point_pairs"])

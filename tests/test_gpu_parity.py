@@ -114,3 +114,21 @@ def test_c2_hits_and_weights(oracle, omap, evaluator):
     mine = ps.copy()
     evaluator.evaluate(mine, pts, syn.IDENTITY_TF)
     assert common.rel_err(mine[:, 6], ref["particles"][:, 6]).max() <= WEIGHT_RTOL
+
+
+def test_c1_both_register_budgets_bit_exact(oracle, omap, evaluator):
+    """The kernel ships at two register budgets (64: 32 CTAs per SM; 128: 16 CTAs per SM, chosen for slices of at most 16,384
+    particles): same code, same bits — indices, hit counts, raw weights against the oracle for both, both pairings."""
+    ps, pts, _ = common.config_c1()
+    ref = oracle.evaluate(omap, common.DEFAULT_PARAMS, ps, pts, syn.CALIB_TF, mode=NEG_AS_MISS, want_idx=True)
+    try:
+        for registers in (1, 2):
+            for pairing in (1, 2):
+                evaluator.tune(capi.TUNE_EVAL_REGISTERS, registers)
+                evaluator.tune(capi.TUNE_EVAL_PAIRING, pairing)
+                idx, hits, raw = evaluator.debug_eval(ps, pts, syn.CALIB_TF)
+                assert np.array_equal(idx, ref["idx"]) and np.array_equal(hits, ref["hits"]), (registers, pairing)
+                assert raw.tobytes() == ref["raw"].tobytes(), (registers, pairing)
+    finally:
+        evaluator.tune(capi.TUNE_EVAL_REGISTERS, 0)
+        evaluator.tune(capi.TUNE_EVAL_PAIRING, 0)

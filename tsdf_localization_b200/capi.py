@@ -14,7 +14,7 @@ REDUCE_RING_DESYNC_LIKE_REFERENCE, REDUCE_EMIT_CENTRES = 1, 2
 MOTION_NOISE, MOTION_ODOM, MOTION_IMU, MOTION_NOISE_IMU = range(4)
 INIT_NORMAL, INIT_UNIFORM, INIT_FREE_MAP = range(3)
 NEG_MISS, NEG_SATURATE_LIKE_REF_GPU = range(2)
-TUNE_SPATIAL_ORDER, TUNE_EVAL_PAIRING, TUNE_DIVISION, TUNE_STAGE_TIMERS = range(4)
+TUNE_SPATIAL_ORDER, TUNE_EVAL_PAIRING, TUNE_DIVISION, TUNE_STAGE_TIMERS, TUNE_EVAL_REGISTERS = range(5)
 DIV_IEEE, DIV_THREE, DIV_BRACKET = range(3)
 RESAMPLE_SYSTEMATIC, RESAMPLE_RESIDUAL, RESAMPLE_RESIDUAL_SYSTEMATIC = range(3)
 INDEX_DRAW_FN = C.CFUNCTYPE(C.c_uint64, C.c_void_p)

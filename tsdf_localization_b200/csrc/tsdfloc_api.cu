@@ -57,6 +57,7 @@ struct tsdfloc_ctx
   uint32_t force_seq = 0;   // 1: contributions may be negative / non-finite -> always fold sequentially
   uint64_t launches = 0;
   int tune_shape = 0;       // tsdfloc_tune(TSDFLOC_TUNE_EVAL_PAIRING): 0 automatic, 1 particle pairs, 2 point pairs
+  int tune_regs = 0;        // tsdfloc_tune(TSDFLOC_TUNE_EVAL_REGISTERS): 0 automatic, 1 64 registers (32 CTAs/SM), 2 128 registers (16 CTAs/SM)
   int tune_div = -1;        // tsdfloc_tune(TSDFLOC_TUNE_DIVISION): -1 what k_check_div proved, else kDivIeee / kDivThree / kDivBracket
   bool three_ok = false, bracket_ok = false;   // what k_check_div proved for this resolution
   unsigned long long bracket_open = 0;         // floats in [0, 1) whose bracket is open (statistics)
@@ -312,23 +313,32 @@ int peer_table(tsdfloc_ctx* c, float* const* want, uint32_t n, cudaStream_t s, f
 
 // Launches the evaluation kernel: pairing (two particles per warp, or two points per lane), quotient mode and — parity
 // dumps only — the index-recording instantiation of the very same code.
-template <bool kPP, bool kDump>
+template <bool kPP, bool kDump, int kMinCtas>
 void launch_eval_mode(const tsdfloc_ctx* c, int div, const EvalArgs& a, cudaStream_t s)
 {
   const uint32_t grid = kPP ? a.n_local : (a.n_local + 1u) / 2u;
   constexpr int BS = kEvalBlockSteps;
   if (div == kDivBracket)
-    k_eval<BS, kDivThree, true, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
+    k_eval<BS, kDivThree, true, kPP, kDump, kMinCtas><<<grid, 32, 0, s>>>(c->map, a);
   else if (div == kDivThree)
-    k_eval<BS, kDivThree, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
+    k_eval<BS, kDivThree, false, kPP, kDump, kMinCtas><<<grid, 32, 0, s>>>(c->map, a);
   else
-    k_eval<BS, kDivIeee, false, kPP, kDump><<<grid, 32, 0, s>>>(c->map, a);
+    k_eval<BS, kDivIeee, false, kPP, kDump, kMinCtas><<<grid, 32, 0, s>>>(c->map, a);
+}
+
+template <int kMinCtas>
+void launch_eval_budget(const tsdfloc_ctx* c, int div, bool pp, bool dump, const EvalArgs& a, cudaStream_t s)
+{
+  if (pp)
+    dump ? launch_eval_mode<true, true, kMinCtas>(c, div, a, s) : launch_eval_mode<true, false, kMinCtas>(c, div, a, s);
+  else
+    dump ? launch_eval_mode<false, true, kMinCtas>(c, div, a, s) : launch_eval_mode<false, false, kMinCtas>(c, div, a, s);
 }
 
 // Point pairs double the number of warps but read the scan once per particle instead of once per pair (+15 % at full
-// occupancy): they win only while particle pairs would fill less than half of the machine's warp slots (32 one-warp CTAs per
-// SM). Measured on B200 (profiles/r02_eval_pairing.md): 500 particles x 131,072 points 1.24 -> 0.90 ms, 2,000: 1.36 -> 1.26,
-// 5,000 x 30,000: 0.50 = 0.50, 8,192: 2.80 vs 2.96, 65,536: 18.0 vs 21.2.
+// occupancy): they win only while particle pairs would leave most of the machine's warp slots empty. Measured on B200 at the
+// 128-register budget (profiles/r02_eval_registers.md, r02_eval_sweep_*.jsonl): 500 particles x 131,072 points 0.79 -> 0.50 ms,
+// 2,000: 1.07 -> 0.97, 5,000 x 30,000: 0.49 -> 0.465, 8,192: 2.69 vs 2.83, 65,536 (64 registers): 17.7 vs 20.2.
 
 void launch_eval(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s, bool dump)
 {
@@ -339,13 +349,19 @@ void launch_eval(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s, bool d
     if (div == kDivBracket && !c->bracket_ok) div = c->map.div_mode;   // never run an unproven mode
     if (div != kDivIeee && !c->three_ok) div = kDivIeee;
   }
-  bool pp = static_cast<uint64_t>(a.n_local) < static_cast<uint64_t>(c->sm_count) * 32u;
+  bool pp = static_cast<uint64_t>(a.n_local) * 4u < static_cast<uint64_t>(c->sm_count) * 32u * 5u;   // < 5,920 particles on 148 SMs
   if (c->tune_shape == 1) pp = false;
   if (c->tune_shape == 2) pp = true;
-  if (pp)
-    dump ? launch_eval_mode<true, true>(c, div, a, s) : launch_eval_mode<true, false>(c, div, a, s);
+  // Register budget: 128 registers (16 CTAs per SM) while the slice is at most 16,384 particles — a warp on its own runs 1.6x
+  // faster with the deeper budget and such a grid is at most ~3 waves of it —, 64 registers (32 CTAs per SM) beyond.
+  // Measured on B200 (profiles/r02_eval_registers.md): 8,192 particles 2.80 -> 2.69 ms, 16,384: 5.00 = 4.97, 32,768: 9.15 vs 9.36.
+  bool deep = a.n_local <= 16384u;
+  if (c->tune_regs == 1) deep = false;
+  if (c->tune_regs == 2) deep = true;
+  if (deep)
+    launch_eval_budget<16>(c, div, pp, dump, a, s);
   else
-    dump ? launch_eval_mode<false, true>(c, div, a, s) : launch_eval_mode<false, false>(c, div, a, s);
+    launch_eval_budget<32>(c, div, pp, dump, a, s);
 }
 
 // Spatial evaluation order of particles [first, first + count): *perm = device permutation, or nullptr when ordering is off
@@ -1760,6 +1776,10 @@ int tsdfloc_tune(tsdfloc_ctx* c, int knob, int value)
     case TSDFLOC_TUNE_DIVISION:
       if (value < -1 || value > kDivBracket) return fail(c, TSDFLOC_E_BAD_ARG, "division: -1 automatic, 0 IEEE, 1 three-instruction, 2 bracket");
       c->tune_div = value;
+      return TSDFLOC_OK;
+    case TSDFLOC_TUNE_EVAL_REGISTERS:
+      if (value < 0 || value > 2) return fail(c, TSDFLOC_E_BAD_ARG, "registers: 0 automatic, 1 64 per thread, 2 128 per thread");
+      c->tune_regs = value;
       return TSDFLOC_OK;
     case TSDFLOC_TUNE_STAGE_TIMERS:
       c->stage_timers = value != 0;

@@ -22,6 +22,10 @@
 //     afterwards, no lane saw an exact tie and the sum stayed below the top of the binade; otherwise (binade crossing, tie, or
 //     the first steps while s is small: ~2 % of the blocks) the block is folded truly sequentially with warp shuffles out of
 //     the lanes' registers. A tree sum would differ from the reference by up to 1e-3 at P = 131k.
+//   * Two REGISTER BUDGETS of the same code (kMinCtas): 64 registers = 32 one-warp CTAs per SM, the fastest once the grid is
+//     several waves deep (>= 32,768 particles); 128 registers = 16 CTAs per SM, where ptxas keeps more of a block's gathers in
+//     flight: a warp walks the scan 1.6x faster on its own, which is what a shard that cannot fill the machine needs
+//     (profiles/r02_eval_registers.md: 500 particles 0.90 -> 0.49 ms, 8,192: 2.80 -> 2.69 ms, 65,536: 17.6 vs 18.3 ms).
 //   * The sub-voxel quotient floor(fl(p / res)) is bracketed by two round-down FMAs (tsdfloc_device.cuh); a block in which
 //     any quotient's bracket is open (~0.5 % of the blocks) is redone with the exact division. Exactness never depends on
 //     the bracket being tight — only speed does.
@@ -277,8 +281,8 @@ __device__ __forceinline__ bool eval_commit_block(const MapDev& M, const EvalArg
 }
 
 // kExact = kDivIeee or kDivThree (what k_check_div proved); kBracket: try the bracketed quotients first.
-template <int BS, int kExact, bool kBracket, bool kPP, bool kDump>
-__global__ void __launch_bounds__(32, 32) k_eval(const MapDev M, const EvalArgs A)
+template <int BS, int kExact, bool kBracket, bool kPP, bool kDump, int kMinCtas>
+__global__ void __launch_bounds__(32, kMinCtas) k_eval(const MapDev M, const EvalArgs A)
 {
   constexpr uint32_t kBlockPoints = (kPP ? 64u : 32u) * BS;
   const uint32_t lane = threadIdx.x;
