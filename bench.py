@@ -386,6 +386,8 @@ def _run_b200_arm(args, guard):
     m = product_map(args.workload)
     n, p = len(ps), len(pts)
     ev = CudaEvaluator(m, device=local)
+    if args.registers:
+        ev.tune(capi.TUNE_EVAL_REGISTERS, args.registers)
     lib = capi.load_library()
     stages = GpuStages(ev)
     fused = {"auto": None, "nccl": False, "fused": True}[args.transport]
@@ -608,6 +610,8 @@ def main():
     ap.add_argument("--transport", choices=("auto", "nccl", "fused"), default="auto",
                     help="multi-GPU exchange: fused = kernels store straight into the peers' buffers (default when available); nccl = all-gathers")
     ap.add_argument("--particles", type=int, default=0, help="development: override the particle count of c1-c3 (not a BASELINE config)")
+    ap.add_argument("--registers", type=int, default=0, choices=(0, 1, 2),
+                    help="development: force the evaluation kernel's register budget (1: 64, 2: 128; 0 = the library's own rule)")
     args = ap.parse_args()
     global PARTICLES_OVERRIDE
     PARTICLES_OVERRIDE = args.particles
