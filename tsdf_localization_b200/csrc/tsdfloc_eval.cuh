@@ -35,7 +35,10 @@
 namespace tsdfloc
 {
 
-constexpr int kEvalBlockSteps = 8;   // steps per summation block (all 16 table loads / 16 gathers of a block are independent)
+#ifndef TSDFLOC_EVAL_BLOCK_STEPS
+#define TSDFLOC_EVAL_BLOCK_STEPS 8   // tuning builds only (scripts/probes): 4 / 6 / 12 / 16 measured slower, profiles/r02_eval_registers.md
+#endif
+constexpr int kEvalBlockSteps = TSDFLOC_EVAL_BLOCK_STEPS;   // steps per summation block (all 16 table loads / 16 gathers of a block are independent)
 constexpr int kEvalPadPoints = 64 * kEvalBlockSteps;   // the prepared scan is padded to whole blocks of the widest step
 
 constexpr float kRoundMagic = 12582912.0f;       // 1.5 * 2^23: x + magic rounds x to an integer (RN-even) for 0 <= x < 2^22
