@@ -326,6 +326,13 @@ void launch_eval_mode(const tsdfloc_ctx* c, int div, const EvalArgs& a, cudaStre
     k_eval<BS, kDivIeee, false, kPP, kDump, kMinCtas><<<grid, 32, 0, s>>>(c->map, a);
 }
 
+#ifndef TSDFLOC_EVAL_CTAS_SHALLOW
+#define TSDFLOC_EVAL_CTAS_SHALLOW 32   // one-warp CTAs per SM of the two register budgets (64 | 128 registers); tuning builds only
+#endif
+#ifndef TSDFLOC_EVAL_CTAS_DEEP
+#define TSDFLOC_EVAL_CTAS_DEEP 16
+#endif
+
 template <int kMinCtas>
 void launch_eval_budget(const tsdfloc_ctx* c, int div, bool pp, bool dump, const EvalArgs& a, cudaStream_t s)
 {
@@ -359,9 +366,9 @@ void launch_eval(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s, bool d
   if (c->tune_regs == 1) deep = false;
   if (c->tune_regs == 2) deep = true;
   if (deep)
-    launch_eval_budget<16>(c, div, pp, dump, a, s);
+    launch_eval_budget<TSDFLOC_EVAL_CTAS_DEEP>(c, div, pp, dump, a, s);
   else
-    launch_eval_budget<32>(c, div, pp, dump, a, s);
+    launch_eval_budget<TSDFLOC_EVAL_CTAS_SHALLOW>(c, div, pp, dump, a, s);
 }
 
 // Spatial evaluation order of particles [first, first + count): *perm = device permutation, or nullptr when ordering is off
