@@ -509,8 +509,11 @@ int stage_normalize(tsdfloc_ctx* c, float* d_particles, uint64_t n, const float*
   // cooperative launch: the grid must be co-resident; a CTA walks several tiles when there are more tiles than that
   const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, static_cast<uint64_t>(c->norm_max_ctas)));
   void* args[] = {&a};
-  CU_TRY(c, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_normalise_cdf), dim3(grid), dim3(kScanThreads), args, 0, s),
-         "launch of k_normalise_cdf");
+  if (tiles == 1)   // one CTA: no grid barrier needed, an ordinary launch
+    k_normalise_cdf<false><<<1, kScanThreads, 0, s>>>(a);
+  else
+    CU_TRY(c, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_normalise_cdf<true>), dim3(grid), dim3(kScanThreads), args, 0, s),
+           "launch of k_normalise_cdf");
   if ((rc = launch_check(c, "k_normalise_cdf"))) return rc;
   // the serial-order CDF, computed only when a parallel fp64 addition rounded (every CTA returns at once otherwise); K2's
   // per-tile scratch is free again and is reused
@@ -524,8 +527,11 @@ int stage_normalize(tsdfloc_ctx* c, float* d_particles, uint64_t n, const float*
   x.tile_start = static_cast<double*>(c->d_tile_total.p);
   const unsigned xgrid = static_cast<unsigned>(std::min<uint64_t>(tiles, static_cast<uint64_t>(c->exact_max_ctas)));
   void* xargs[] = {&x};
-  CU_TRY(c, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_cdf_exact), dim3(xgrid), dim3(kScanThreads), xargs, 0, s),
-         "launch of k_cdf_exact");
+  if (tiles == 1)
+    k_cdf_exact<false><<<1, kScanThreads, 0, s>>>(x);
+  else
+    CU_TRY(c, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_cdf_exact<true>), dim3(xgrid), dim3(kScanThreads), xargs, 0, s),
+           "launch of k_cdf_exact");
   if ((rc = launch_check(c, "k_cdf_exact"))) return rc;
   if ((rc = mark(c, tsdfloc_ctx::kEvNorm1, s))) return rc;
   c->have_cdf = true;
@@ -818,12 +824,12 @@ static int create_impl(const tsdfloc_map_desc* map, const int32_t* grid_occ, con
   for (cudaEvent_t& e : c->ev_stage) CU_CREATE(cudaEventCreate(&e), "cudaEventCreate");
   {
     int per_sm = 0;
-    CU_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_normalise_cdf, kScanThreads, 0), "occupancy(k_normalise_cdf)");
+    CU_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_normalise_cdf<true>, kScanThreads, 0), "occupancy(k_normalise_cdf)");
     int coop = 0;
     CU_CREATE(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device), "cudaDeviceGetAttribute");
     if (!coop || per_sm < 1) return bail(TSDFLOC_E_CUDA, "device does not support cooperative launches");
     c->norm_max_ctas = per_sm * c->sm_count;
-    CU_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cdf_exact, kScanThreads, 0), "occupancy(k_cdf_exact)");
+    CU_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cdf_exact<true>, kScanThreads, 0), "occupancy(k_cdf_exact)");
     if (per_sm < 1) return bail(TSDFLOC_E_CUDA, "k_cdf_exact cannot be made resident");
     c->exact_max_ctas = per_sm * c->sm_count;
   }

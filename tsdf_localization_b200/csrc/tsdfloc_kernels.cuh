@@ -272,9 +272,20 @@ __device__ __forceinline__ double block_sum_fixed(double v, double* s_part)
   return t;   // valid in thread 0
 }
 
+// Grid-wide barrier of the two kernels below. kCoop = false: the launch is ONE CTA (at most 1,024 particles: C1) and an
+// ordinary launch — a block barrier orders its global writes, and the cooperative launch's extra latency is saved.
+template <bool kCoop>
+__device__ __forceinline__ void grid_barrier()
+{
+  if (kCoop)
+    cooperative_groups::this_grid().sync();
+  else
+    __syncthreads();
+}
+
+template <bool kCoop>
 __global__ void __launch_bounds__(kScanThreads) k_normalise_cdf(const NormArgs A)
 {
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   __shared__ double s_part[kScanThreads / 32];
   __shared__ double s_mom[kScanThreads / 32][9];
   __shared__ unsigned long long s_best[kScanThreads / 32];
@@ -297,7 +308,7 @@ __global__ void __launch_bounds__(kScanThreads) k_normalise_cdf(const NormArgs A
     const double t = block_sum_fixed(acc, s_part);
     if (threadIdx.x == 0) A.tile_sum[tile] = t;
   }
-  grid.sync();
+  grid_barrier<kCoop>();
 
   // ---- B: total (every CTA, same order), normalise + tile-local scan + moments + arg-max ------------------------
   {
@@ -406,7 +417,7 @@ __global__ void __launch_bounds__(kScanThreads) k_normalise_cdf(const NormArgs A
       A.tile_best[tile] = b;
     }
   }
-  grid.sync();
+  grid_barrier<kCoop>();
 
   // ---- C: tile offsets -> global CDF; CTA 0: mean pose + best particle ----------------------------------------------
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
@@ -726,10 +737,10 @@ __device__ __forceinline__ ParityMap tile_scan(const ExactArgs& A, uint32_t base
   return pm_then(off, excl);
 }
 
+template <bool kCoop>
 __global__ void __launch_bounds__(kScanThreads) k_cdf_exact(const ExactArgs A)
 {
   if (!A.st->inexact) return;   // uniform over the grid: nobody reaches a grid sync
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   __shared__ ParityMap s_warp[kScanThreads / 32];
   __shared__ uint32_t s_flags;
   const uint32_t n = A.n;
@@ -759,7 +770,7 @@ __global__ void __launch_bounds__(kScanThreads) k_cdf_exact(const ExactArgs A)
     }
     __syncthreads();
   }
-  grid.sync();
+  grid_barrier<kCoop>();
 
   // ---- 2: the exact running sum in front of every tile (CTA 0) ---------------------------------------------------------
   // Thread 0 walks the tiles; their flags / unit counts are staged in shared memory a chunk at a time so that the walk is a
@@ -844,7 +855,7 @@ __global__ void __launch_bounds__(kScanThreads) k_cdf_exact(const ExactArgs A)
       }
     }
   }
-  grid.sync();
+  grid_barrier<kCoop>();
 
   // ---- 3: accepted tiles: start + u * units(prefix) -------------------------------------------------------------------
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
