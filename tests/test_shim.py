@@ -177,3 +177,28 @@ def test_reference_facade_over_several_devices(shim, small_map, monkeypatch):
     m_gpu, out_gpu = shim.gpu_systematic_resample(many, 3)      # the resampler borrows rank 0's context
     assert m_gpu == m_ref and np.array_equal(out_gpu, out_ref)
     shim.eval_destroy(ev)
+
+
+@pytest.mark.gpu
+def test_reference_evaluateParticles_over_several_devices(shim, small_map, monkeypatch):
+    """The call mcl_3d actually makes — TSDFEvaluator::evaluateParticles(cloud) — with TSDFLOC_DEVICES naming several GPUs:
+    the first device reduces the cloud, every device evaluates its particle slice (tsdfloc_multi_sensor_update_cloud). Same
+    bytes as the single-device run, same reduced scan size."""
+    import torch
+    gt = (0.4, -0.3, 1.2, 0.01, -0.02, 0.4)
+    pts, ring = syn.make_scan("vlp16", gt, room_lo=(-3.0, -2.5, 0.0), room_hi=(3.0, 2.5, 3.0))
+    ps = syn.tracking_particles(301, gt, sigma_xy=0.05, sigma_z=0.05, sigma_yaw=0.03)
+    ev = shim.eval_create_cell(small_map, 0.064)
+    assert ev, shim.last_error()
+    rc, one, pose_one, err, used_one = shim.evaluate_cloud(ev, ps, pts, ring, use_cuda=True, desync=False, n_rings=64)
+    assert rc == 0, err
+    shim.eval_destroy(ev)
+    monkeypatch.setenv("TSDFLOC_DEVICES", "0,1,0" if torch.cuda.device_count() >= 2 else "0,0,0")
+    ev = shim.eval_create_cell(small_map, 0.064)
+    assert ev, shim.last_error()
+    for _ in range(2):
+        rc, many, pose_many, err, used_many = shim.evaluate_cloud(ev, ps, pts, ring, use_cuda=True, desync=False, n_rings=64)
+        assert rc == 0, err
+        assert used_many == used_one and 0 < used_one < len(pts)
+        assert many.tobytes() == one.tobytes() and pose_many.tobytes() == pose_one.tobytes()
+    shim.eval_destroy(ev)
