@@ -388,6 +388,10 @@ def _run_b200_arm(args, guard):
     ev = CudaEvaluator(m, device=local)
     if args.registers:
         ev.tune(capi.TUNE_EVAL_REGISTERS, args.registers)
+    if not args.graphs:
+        ev.tune(capi.TUNE_GRAPHS, 0)
+    if args.chunks:
+        ev.tune(capi.TUNE_EVAL_CHUNKS, args.chunks)
     lib = capi.load_library()
     stages = GpuStages(ev)
     fused = {"auto": None, "nccl": False, "fused": True}[args.transport]
@@ -588,7 +592,7 @@ def _run_b200_arm(args, guard):
                            else f"tsdfloc_multi_sensor_update + tsdfloc_multi_resample_systematic from rank 0 over {world} devices (host buffers)"
                            if via_multi else f"pinned H2D + ShardedSensorUpdate.step + pinned D2H per rank (tsdfloc_multi unavailable: {multi_err})",
                     "per_process_ms_per_step": (pp_total_ms / K) if world > 1 else None},
-            "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step_incl_flush": wall_ms / K,
+            "gpu_launches": int(launches), "graphs": dict(zip(("recordings", "replays", "note"), ev.graph_stats())), "clocks": clocks, "wall_ms_per_step_incl_flush": wall_ms / K,
         }
         guard.emit(json.dumps(line))
     if multi is not None:
@@ -612,6 +616,10 @@ def main():
     ap.add_argument("--particles", type=int, default=0, help="development: override the particle count of c1-c3 (not a BASELINE config)")
     ap.add_argument("--registers", type=int, default=0, choices=(0, 1, 2),
                     help="development: force the evaluation kernel's register budget (1: 64, 2: 128; 0 = the library's own rule)")
+    ap.add_argument("--chunks", type=int, default=0,
+                    help="development: scan chunks per particle in the evaluation kernel (1 = whole scans; 0 = the library's own rule)")
+    ap.add_argument("--graphs", type=int, default=1, choices=(0, 1),
+                    help="development: 0 = launch every update kernel by kernel (A/B against the steady-state CUDA graphs)")
     args = ap.parse_args()
     global PARTICLES_OVERRIDE
     PARTICLES_OVERRIDE = args.particles

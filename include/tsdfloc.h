@@ -446,7 +446,9 @@ enum tsdfloc_tune_knob
   TSDFLOC_TUNE_EVAL_PAIRING = 1,
   TSDFLOC_TUNE_DIVISION = 2,
   TSDFLOC_TUNE_STAGE_TIMERS = 3,  /* 0 off (default), 1 record CUDA events around the stages (tsdfloc_stage_times) */
-  TSDFLOC_TUNE_EVAL_REGISTERS = 4 /* 0 automatic (128 registers per thread up to 16,384 particles per device, 64 beyond), 1 64, 2 128 */
+  TSDFLOC_TUNE_EVAL_REGISTERS = 4, /* 0 automatic (128 registers per thread up to 16,384 particles per device, 64 beyond), 1 64, 2 128 */
+  TSDFLOC_TUNE_GRAPHS = 5,         /* 1 (default) replay fixed-shape device-resident updates as CUDA graphs, 0 always launch kernel by kernel */
+  TSDFLOC_TUNE_EVAL_CHUNKS = 6     /* 0 automatic, 1 every warp walks the whole scan, 2..64 chained scan chunks per particle (tsdfloc_eval.cuh) */
 };
 int tsdfloc_tune(tsdfloc_ctx* ctx, int knob, int value);
 
@@ -456,6 +458,17 @@ int tsdfloc_tune(tsdfloc_ctx* ctx, int knob, int value);
  * resampling (draw); 0 for a stage that did not run. Needs TSDFLOC_TUNE_STAGE_TIMERS = 1; synchronises the device. The host
  * side of every stage is also an NVTX range ("tsdfloc:prep_scan", ":eval", ":weight_update", ":resample") for Nsight Systems. */
 int tsdfloc_stage_times(tsdfloc_ctx* ctx, float ms[4]);
+
+/* Steady-state CUDA graphs. tsdfloc_update_device records its whole chain of launches the second time it is called with the
+ * same buffers, sizes and tuning modes, and replays it with one cudaGraphLaunch from then on (the sensor transform and u0 may
+ * differ from call to call: they are patched into the recorded kernel nodes; up to four buffer sets are remembered, so
+ * double-buffered outputs are steady state too). This replaces the per-scan re-issue of src/cuda/cuda_evaluator.cu:118-428;
+ * results are bit-identical to the kernel-by-kernel launches. A call whose shape was not seen before runs kernel by kernel
+ * at no extra cost. The host-buffer calls (tsdfloc_sensor_update) are launched kernel by kernel on purpose: their caller
+ * waits for the result and a graph launch measured slower there (profiles/r02_graphs.md). out[0] = recordings made, out[1] =
+ * updates served by a graph launch; *note (optional) = why the last recording attempt was abandoned, "" if none was (the
+ * update then ran kernel by kernel — still on the GPU; there is no CPU path). */
+int tsdfloc_graph_stats(const tsdfloc_ctx* ctx, uint64_t out[2], const char** note);
 
 /* 1 when every fp64 addition of the parallel CDF scan of the last update / resampling call was exact (the result then cannot
  * depend on the order), 0 when one rounded and the CDF was redone in the reference's serial order (k_cdf_exact), -1 without

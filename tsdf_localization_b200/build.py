@@ -52,7 +52,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source of the package for sm_100a into lib/libtsdfloc.so."""
     sources = [CSRC / "tsdfloc_api.cu", CSRC / "host_map.cpp", CSRC / "host_motion.cpp", CSRC / "host_resample.cpp"]
     deps = sources + [CSRC / "tsdfloc_kernels.cuh", CSRC / "tsdfloc_eval.cuh", CSRC / "tsdfloc_device.cuh", CSRC / "tsdfloc_reduce.cuh",
-                      CSRC / "tsdfloc_motion.cuh", CSRC / "tsdfloc_sort.cuh", CSRC / "tsdfloc_multi.inc", CSRC / "tsdfloc_ingest.inc", CSRC / "tsdfloc_host_map.h", ROOT / "include" / "tsdfloc.h"]
+                      CSRC / "tsdfloc_motion.cuh", CSRC / "tsdfloc_sort.cuh", CSRC / "tsdfloc_multi.inc", CSRC / "tsdfloc_ingest.inc", CSRC / "tsdfloc_graph.inc", CSRC / "tsdfloc_mcl.inc", CSRC / "tsdfloc_host_map.h", ROOT / "include" / "tsdfloc.h"]
     if not force and not _stale(LIB, deps):
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)

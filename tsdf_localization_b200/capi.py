@@ -14,7 +14,7 @@ REDUCE_RING_DESYNC_LIKE_REFERENCE, REDUCE_EMIT_CENTRES = 1, 2
 MOTION_NOISE, MOTION_ODOM, MOTION_IMU, MOTION_NOISE_IMU = range(4)
 INIT_NORMAL, INIT_UNIFORM, INIT_FREE_MAP = range(3)
 NEG_MISS, NEG_SATURATE_LIKE_REF_GPU = range(2)
-TUNE_SPATIAL_ORDER, TUNE_EVAL_PAIRING, TUNE_DIVISION, TUNE_STAGE_TIMERS, TUNE_EVAL_REGISTERS = range(5)
+TUNE_SPATIAL_ORDER, TUNE_EVAL_PAIRING, TUNE_DIVISION, TUNE_STAGE_TIMERS, TUNE_EVAL_REGISTERS, TUNE_GRAPHS, TUNE_EVAL_CHUNKS = range(7)
 DIV_IEEE, DIV_THREE, DIV_BRACKET = range(3)
 RESAMPLE_SYSTEMATIC, RESAMPLE_RESIDUAL, RESAMPLE_RESIDUAL_SYSTEMATIC = range(3)
 INDEX_DRAW_FN = C.CFUNCTYPE(C.c_uint64, C.c_void_p)
@@ -131,6 +131,7 @@ SIGNATURES = {
     "tsdfloc_eval_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "tsdfloc_tune": (C.c_int, [_vp, C.c_int, C.c_int]),
     "tsdfloc_stage_times": (C.c_int, [_vp, _fp]),
+    "tsdfloc_graph_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_char_p)]),
     "tsdfloc_last_cdf_was_exact": (C.c_int, [_vp]),
     "tsdfloc_division_mode": (C.c_int, [_vp, C.POINTER(_u64)]),
     "tsdfloc_last_eval_ms": (C.c_int, [_vp, _fp]),

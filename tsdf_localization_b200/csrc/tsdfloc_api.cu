@@ -42,6 +42,25 @@ struct DevBuf
   size_t bytes = 0;
 };
 
+// One cached CUDA graph of a fixed-shape update (tsdfloc_graph.inc): the whole launch chain replayed with one
+// cudaGraphLaunch; only the sensor transform (k_prepare) and the U table (k_draw) change between replays and are patched into
+// their kernel nodes.
+struct GraphSlot
+{
+  std::vector<unsigned char> key;   // every pointer / size / mode the captured launches depend on
+  uint32_t seen = 0;                // consecutive eager calls with this key (the second one is captured)
+  bool failed = false;              // capture of this key failed once: stay eager
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t node_prepare = nullptr, node_draw = nullptr;
+  cudaKernelNodeParams kp_prepare{}, kp_draw{};
+  std::vector<void*> args_prepare, args_draw;
+  Tf12 tf{};
+  UTable ut{};
+  uint64_t n_kernels = 0;
+  uint64_t last_use = 0;            // recency (graph_tick) for recycling
+};
+
 }  // namespace
 
 struct tsdfloc_ctx
@@ -58,6 +77,7 @@ struct tsdfloc_ctx
   uint64_t launches = 0;
   int tune_shape = 0;       // tsdfloc_tune(TSDFLOC_TUNE_EVAL_PAIRING): 0 automatic, 1 particle pairs, 2 point pairs
   int tune_regs = 0;        // tsdfloc_tune(TSDFLOC_TUNE_EVAL_REGISTERS): 0 automatic, 1 64 registers (32 CTAs/SM), 2 128 registers (16 CTAs/SM)
+  int tune_chunks = 0;      // tsdfloc_tune(TSDFLOC_TUNE_EVAL_CHUNKS): 0 automatic, k >= 1 scan chunks per particle (1 = whole scans)
   int tune_div = -1;        // tsdfloc_tune(TSDFLOC_TUNE_DIVISION): -1 what k_check_div proved, else kDivIeee / kDivThree / kDivBracket
   bool three_ok = false, bracket_ok = false;   // what k_check_div proved for this resolution
   unsigned long long bracket_open = 0;         // floats in [0, 1) whose bracket is open (statistics)
@@ -71,6 +91,16 @@ struct tsdfloc_ctx
   uint32_t stage_seen = 0;     // bit k: ev_stage[k] was recorded since the timers were switched on
   int norm_max_ctas = 0, exact_max_ctas = 0;   // co-resident CTAs of the cooperative kernels k_normalise_cdf / k_cdf_exact
 
+  // steady-state CUDA graphs (tsdfloc_graph.inc): one slot per fixed-shape entry point
+  enum { kGraphUpdateDevice, kGraphCount, kGraphWays = 4 };
+  GraphSlot graphs[kGraphCount][kGraphWays];
+  uint64_t graph_tick = 0;
+  bool graphs_on = true;       // tsdfloc_tune(TSDFLOC_TUNE_GRAPHS)
+  bool capturing = false;      // the stages are being recorded into a graph: timing events become external event nodes
+  uint64_t alloc_epoch = 0;    // bumped whenever a device / pinned buffer is (re)allocated: cached graphs hold raw pointers
+  uint64_t graph_replays = 0, graph_captures = 0;
+  std::string graph_note;      // why the last capture attempt was abandoned (diagnostics)
+
   // map
   int32_t* d_table = nullptr;
   float* d_voxels = nullptr;
@@ -83,7 +113,7 @@ struct tsdfloc_ctx
 
   // particles / scratch
   DevBuf d_particles, d_particles_out, d_mats, d_raw, d_cdf, d_tile_total, d_tile_offset, d_tile_moments, d_tile_best, d_parents,
-      d_idx, d_hits;
+      d_idx, d_hits, d_chain;
   float* d_mean = nullptr;
   unsigned long long* d_eval_stats = nullptr;  // k_eval block statistics (cumulative)
   Status* d_status = nullptr;
@@ -156,6 +186,7 @@ int ensure(tsdfloc_ctx* c, DevBuf& b, size_t bytes, const char* what)
   size_t want = bytes + bytes / 4 + 256;
   CU_TRY(c, cudaMalloc(&b.p, want), what);
   b.bytes = want;
+  ++c->alloc_epoch;
   return TSDFLOC_OK;
 }
 
@@ -172,6 +203,7 @@ int ensure_host(tsdfloc_ctx* c, size_t bytes)
   size_t want = bytes + bytes / 4 + 4096;
   CU_TRY(c, cudaMallocHost(&c->h_stage, want), "cudaMallocHost(staging)");
   c->h_stage_bytes = want;
+  ++c->alloc_epoch;
   return TSDFLOC_OK;
 }
 
@@ -238,6 +270,13 @@ int mark(tsdfloc_ctx* c, int k, cudaStream_t s)
   if (!c->stage_timers) return TSDFLOC_OK;
   CU_TRY(c, cudaEventRecord(c->ev_stage[k], s), "event record");
   c->stage_seen |= 1u << k;
+  return TSDFLOC_OK;
+}
+
+// Timing events around k_eval: inside a graph capture they must be external event-record nodes.
+int record(tsdfloc_ctx* c, cudaEvent_t ev, cudaStream_t s)
+{
+  CU_TRY(c, c->capturing ? cudaEventRecordWithFlags(ev, s, cudaEventRecordExternal) : cudaEventRecord(ev, s), "event record");
   return TSDFLOC_OK;
 }
 
@@ -316,8 +355,22 @@ int peer_table(tsdfloc_ctx* c, float* const* want, uint32_t n, cudaStream_t s, f
 template <bool kPP, bool kDump, int kMinCtas>
 void launch_eval_mode(const tsdfloc_ctx* c, int div, const EvalArgs& a, cudaStream_t s)
 {
-  const uint32_t grid = kPP ? a.n_local : (a.n_local + 1u) / 2u;
   constexpr int BS = kEvalBlockSteps;
+  if constexpr (!kDump)
+  {
+    if (a.n_chunks > 1u)
+    {
+      const uint32_t grid = a.n_tasks * a.n_chunks;
+      if (div == kDivBracket)
+        k_eval<BS, kDivThree, true, kPP, false, kMinCtas, true><<<grid, 32, 0, s>>>(c->map, a);
+      else if (div == kDivThree)
+        k_eval<BS, kDivThree, false, kPP, false, kMinCtas, true><<<grid, 32, 0, s>>>(c->map, a);
+      else
+        k_eval<BS, kDivIeee, false, kPP, false, kMinCtas, true><<<grid, 32, 0, s>>>(c->map, a);
+      return;
+    }
+  }
+  const uint32_t grid = a.n_tasks;
   if (div == kDivBracket)
     k_eval<BS, kDivThree, true, kPP, kDump, kMinCtas><<<grid, 32, 0, s>>>(c->map, a);
   else if (div == kDivThree)
@@ -334,7 +387,7 @@ void launch_eval_mode(const tsdfloc_ctx* c, int div, const EvalArgs& a, cudaStre
 #endif
 
 template <int kMinCtas>
-void launch_eval_budget(const tsdfloc_ctx* c, int div, bool pp, bool dump, const EvalArgs& a, cudaStream_t s)
+void launch_eval_budget(const tsdfloc_ctx* c, bool pp, bool dump, int div, const EvalArgs& a, cudaStream_t s)
 {
   if (pp)
     dump ? launch_eval_mode<true, true, kMinCtas>(c, div, a, s) : launch_eval_mode<true, false, kMinCtas>(c, div, a, s);
@@ -342,33 +395,63 @@ void launch_eval_budget(const tsdfloc_ctx* c, int div, bool pp, bool dump, const
     dump ? launch_eval_mode<false, true, kMinCtas>(c, div, a, s) : launch_eval_mode<false, false, kMinCtas>(c, div, a, s);
 }
 
+// The shape of one evaluation launch: pairing, register budget, quotient mode, and how the scan is chunked.
+struct EvalShape
+{
+  int div = kDivIeee;
+  bool pp = false, deep = false;
+  uint32_t n_tasks = 0, n_chunks = 1, blocks_per_chunk = 0;
+};
+
 // Point pairs double the number of warps but read the scan once per particle instead of once per pair (+15 % at full
 // occupancy): they win only while particle pairs would leave most of the machine's warp slots empty. Measured on B200 at the
 // 128-register budget (profiles/r02_eval_registers.md, r02_eval_sweep_*.jsonl): 500 particles x 131,072 points 0.79 -> 0.50 ms,
 // 2,000: 1.07 -> 0.97, 5,000 x 30,000: 0.49 -> 0.465, 8,192: 2.69 vs 2.83, 65,536 (64 registers): 17.7 vs 20.2.
-
-void launch_eval(const tsdfloc_ctx* c, const EvalArgs& a, cudaStream_t s, bool dump)
+EvalShape eval_shape(const tsdfloc_ctx* c, uint32_t n_local, uint32_t n_points, bool dump)
 {
-  int div = c->map.div_mode;
+  EvalShape e;
+  e.div = c->map.div_mode;
   if (c->tune_div >= 0)
   {
-    div = c->tune_div;
-    if (div == kDivBracket && !c->bracket_ok) div = c->map.div_mode;   // never run an unproven mode
-    if (div != kDivIeee && !c->three_ok) div = kDivIeee;
+    e.div = c->tune_div;
+    if (e.div == kDivBracket && !c->bracket_ok) e.div = c->map.div_mode;   // never run an unproven mode
+    if (e.div != kDivIeee && !c->three_ok) e.div = kDivIeee;
   }
-  bool pp = static_cast<uint64_t>(a.n_local) * 4u < static_cast<uint64_t>(c->sm_count) * 32u * 5u;   // < 5,920 particles on 148 SMs
-  if (c->tune_shape == 1) pp = false;
-  if (c->tune_shape == 2) pp = true;
+  e.pp = static_cast<uint64_t>(n_local) * 4u < static_cast<uint64_t>(c->sm_count) * 32u * 5u;   // < 5,920 particles on 148 SMs
+  if (c->tune_shape == 1) e.pp = false;
+  if (c->tune_shape == 2) e.pp = true;
   // Register budget: 128 registers (16 CTAs per SM) while the slice is at most 16,384 particles — a warp on its own runs 1.6x
   // faster with the deeper budget and such a grid is at most ~3 waves of it —, 64 registers (32 CTAs per SM) beyond.
   // Measured on B200 (profiles/r02_eval_registers.md): 8,192 particles 2.80 -> 2.69 ms, 16,384: 5.00 = 4.97, 32,768: 9.15 vs 9.36.
-  bool deep = a.n_local <= 16384u;
-  if (c->tune_regs == 1) deep = false;
-  if (c->tune_regs == 2) deep = true;
-  if (deep)
-    launch_eval_budget<TSDFLOC_EVAL_CTAS_DEEP>(c, div, pp, dump, a, s);
+  e.deep = n_local <= 16384u;
+  if (c->tune_regs == 1) e.deep = false;
+  if (c->tune_regs == 2) e.deep = true;
+  e.n_tasks = e.pp ? n_local : (n_local + 1u) / 2u;
+  // Chained scan chunks (tsdfloc_eval.cuh): worth it when the grid is a few waves deep and the last one is far from full —
+  // 8,192 particles are 1.73 waves of the 128-register budget and cost 2 without chunks. At least 8 summation blocks per chunk.
+  const uint32_t block_points = (e.pp ? 64u : 32u) * static_cast<uint32_t>(kEvalBlockSteps);
+  const uint32_t n_blocks = (n_points + block_points - 1u) / block_points;
+  const uint64_t slots = static_cast<uint64_t>(c->sm_count) * (e.deep ? TSDFLOC_EVAL_CTAS_DEEP : TSDFLOC_EVAL_CTAS_SHALLOW);
+  uint32_t chunks = 1;
+  if (c->tune_chunks > 0) chunks = static_cast<uint32_t>(c->tune_chunks);
+  else if (e.n_tasks > slots && e.n_tasks < 12u * slots)
+  {
+    const uint64_t waves = (e.n_tasks + slots - 1u) / slots;
+    if (static_cast<double>(e.n_tasks) < 0.93 * static_cast<double>(waves * slots)) chunks = 8;
+  }
+  chunks = std::min(chunks, std::max(1u, n_blocks / 8u));
+  if (dump || static_cast<uint64_t>(e.n_tasks) * chunks >= (1ull << 31)) chunks = 1;
+  e.blocks_per_chunk = (n_blocks + chunks - 1u) / chunks;
+  e.n_chunks = e.blocks_per_chunk ? (n_blocks + e.blocks_per_chunk - 1u) / e.blocks_per_chunk : 1u;
+  return e;
+}
+
+void launch_eval(const tsdfloc_ctx* c, const EvalShape& e, const EvalArgs& a, cudaStream_t s, bool dump)
+{
+  if (e.deep)
+    launch_eval_budget<TSDFLOC_EVAL_CTAS_DEEP>(c, e.pp, dump, e.div, a, s);
   else
-    launch_eval_budget<TSDFLOC_EVAL_CTAS_SHALLOW>(c, div, pp, dump, a, s);
+    launch_eval_budget<TSDFLOC_EVAL_CTAS_SHALLOW>(c, e.pp, dump, e.div, a, s);
 }
 
 // Spatial evaluation order of particles [first, first + count): *perm = device permutation, or nullptr when ordering is off
@@ -473,10 +556,26 @@ int stage_eval(tsdfloc_ctx* c, const float* d_particles, uint64_t n_total, uint6
   a.force_seq = c->force_seq;
   a.idx_out = d_idx;
   a.hits_out = d_hits;
-  CU_TRY(c, cudaEventRecord(c->ev_eval0, s), "event record");
-  launch_eval(c, a, s, dump);
+  const EvalShape shape = eval_shape(c, a.n_local, a.n_points, dump);
+  a.n_tasks = shape.n_tasks;
+  a.n_chunks = shape.n_chunks;
+  a.blocks_per_chunk = shape.blocks_per_chunk;
+  a.chain = nullptr;
+  if (shape.n_chunks > 1u)
+  {
+    // ticket + per-task links of the chained chunks; zero when allocated, and every launch leaves it zero again
+    const size_t words = kChainHeader + static_cast<size_t>(kChainStride) * shape.n_tasks;
+    if (sizeof(uint32_t) * words > c->d_chain.bytes)
+    {
+      if ((rc = ensure(c, c->d_chain, sizeof(uint32_t) * words, "cudaMalloc(chunk chain)"))) return rc;
+      CU_TRY(c, cudaMemsetAsync(c->d_chain.p, 0, c->d_chain.bytes, s), "memset(chunk chain)");
+    }
+    a.chain = static_cast<uint32_t*>(c->d_chain.p);
+  }
+  if ((rc = record(c, c->ev_eval0, s))) return rc;
+  launch_eval(c, shape, a, s, dump);
   if ((rc = launch_check(c, "k_eval"))) return rc;
-  CU_TRY(c, cudaEventRecord(c->ev_eval1, s), "event record");
+  if ((rc = record(c, c->ev_eval1, s))) return rc;
   c->eval_timed = true;
   return TSDFLOC_OK;
 }
@@ -550,7 +649,8 @@ void host_u_table(float u0, uint64_t n, UTable* t)
 }
 
 int stage_draw(tsdfloc_ctx* c, const float* d_particles, uint64_t n, float u0, uint64_t first_out, uint64_t count_out, float* d_out,
-               uint32_t* d_parents, cudaStream_t s, float* const* d_out_peers = nullptr, uint32_t n_peers = 0)
+               uint32_t* d_parents, cudaStream_t s, float* const* d_out_peers = nullptr, uint32_t n_peers = 0,
+               const UTable* prebuilt = nullptr)
 {
   Range r("tsdfloc:resample");
   if (n_peers > static_cast<uint32_t>(kMaxPeers)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 8 peer buffers");
@@ -562,8 +662,9 @@ int stage_draw(tsdfloc_ctx* c, const float* d_particles, uint64_t n, float u0, u
   if (count_out >= (1ull << 32)) return fail(c, TSDFLOC_E_BAD_ARG, "more than 2^32 output slots");
   int rc;
   if ((rc = mark(c, tsdfloc_ctx::kEvDraw0, s))) return rc;
-  UTable t;
-  host_u_table(u0, n, &t);
+  UTable own;
+  if (!prebuilt) host_u_table(u0, n, &own);
+  const UTable& t = prebuilt ? *prebuilt : own;
   // count_out == 0 still publishes n_out (one CTA)
   const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, (count_out + 255) / 256));
   k_draw<<<grid, 256, 0, s>>>(d_particles, static_cast<const double*>(c->d_cdf.p), static_cast<uint32_t>(n), t, c->d_status, first_out,
@@ -571,6 +672,8 @@ int stage_draw(tsdfloc_ctx* c, const float* d_particles, uint64_t n, float u0, u
   if ((rc = launch_check(c, "k_draw"))) return rc;
   return mark(c, tsdfloc_ctx::kEvDraw1, s);
 }
+
+#include "tsdfloc_graph.inc"
 
 // Scan reduction (tsdfloc_reduce.cuh). All pointers are device pointers.
 int stage_reduce(tsdfloc_ctx* c, const float* d_xyz, const int32_t* d_ring, uint64_t n, double cell, uint32_t n_rings, uint32_t flags,
@@ -1038,8 +1141,9 @@ void tsdfloc_destroy(tsdfloc_ctx* c)
   if (!c) return;
   DeviceGuard guard(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  graph_drop_all(c);
   DevBuf* bufs[] = {&c->d_xyz_stage, &c->d_pts, &c->d_particles, &c->d_particles_out, &c->d_mats,
-                    &c->d_raw, &c->d_cdf, &c->d_tile_total, &c->d_tile_offset, &c->d_tile_moments, &c->d_tile_best, &c->d_parents, &c->d_idx, &c->d_hits,
+                    &c->d_raw, &c->d_cdf, &c->d_tile_total, &c->d_tile_offset, &c->d_tile_moments, &c->d_tile_best, &c->d_parents, &c->d_idx, &c->d_hits, &c->d_chain,
                     &c->d_red_in_xyz, &c->d_red_in_ring, &c->d_red_key4, &c->d_red_table, &c->d_red_cta, &c->d_red_hist, &c->d_red_win,
                     &c->d_red_rank, &c->d_red_out, &c->d_red_src, &c->d_draws, &c->d_sort_keys, &c->d_sort_hist, &c->d_perm,
                     &c->d_run_off, &c->d_run_parent, &c->d_wpack};
@@ -1148,6 +1252,7 @@ int tsdfloc_update_device(tsdfloc_ctx* c, const float* d_points_xyz, uint64_t p,
   if (!d_points_xyz || !d_particles || !tf || (count_out && !d_particles_out)) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
   if (p == 0) return fail(c, TSDFLOC_E_EMPTY_SCAN, "empty scan");
   if (n == 0) return fail(c, TSDFLOC_E_BAD_ARG, "no particles");
+  if (!(u0 >= 0.0f)) return fail(c, TSDFLOC_E_BAD_ARG, "u0 must be >= 0");
   DeviceGuard guard(c->device);
   cudaStream_t s = pick(c, stream);
   int rc;
@@ -1155,9 +1260,22 @@ int tsdfloc_update_device(tsdfloc_ctx* c, const float* d_points_xyz, uint64_t p,
   c->have_cdf = false;
   PrepArgs scan{};
   if ((rc = scan_layout(c, d_points_xyz, p, &scan))) return rc;
-  if ((rc = stage_eval(c, d_particles, n, 0, n, tf, static_cast<float*>(c->d_raw.p), s, nullptr, 0, false, nullptr, nullptr, &scan))) return rc;
-  if ((rc = stage_normalize(c, d_particles, n, static_cast<const float*>(c->d_raw.p), d_mean_pose ? d_mean_pose : c->d_mean, s))) return rc;
-  return stage_draw(c, d_particles, n, u0, 0, count_out, d_particles_out, nullptr, s);
+  UTable table;
+  host_u_table(u0, n, &table);
+  float* d_mean = d_mean_pose ? d_mean_pose : c->d_mean;
+  auto issue = [&]() -> int {
+    int r;
+    if ((r = stage_eval(c, d_particles, n, 0, n, tf, static_cast<float*>(c->d_raw.p), s, nullptr, 0, false, nullptr, nullptr, &scan))) return r;
+    if ((r = stage_normalize(c, d_particles, n, static_cast<const float*>(c->d_raw.p), d_mean, s))) return r;
+    return stage_draw(c, d_particles, n, u0, 0, count_out, d_particles_out, nullptr, s, nullptr, 0, &table);
+  };
+  // steady state (same buffers and sizes as the previous call): one graph launch instead of the five kernel launches
+  GraphKey key;
+  key.add(d_points_xyz).add(p).add(d_particles).add(n).add(d_particles_out).add(count_out).add(d_mean);
+  if ((rc = run_graphed(c, tsdfloc_ctx::kGraphUpdateDevice, key, s, tf, &table, issue))) return rc;
+  c->have_cdf = true;
+  c->eval_timed = true;
+  return TSDFLOC_OK;
 }
 
 int tsdfloc_check(tsdfloc_ctx* c, uint64_t* n_out, double* weight_sum, void* stream)
@@ -1321,41 +1439,92 @@ int tsdfloc_best_particle(tsdfloc_ctx* c, int64_t* index, float pose[6], float* 
 
 // ---- (A) host-buffer calls ---------------------------------------------------------------------------------------
 
-// Host-buffer sensor update behind the scan upload: particles up, (scan preparation +) evaluation, normalisation, weights
-// back. fused_scan != nullptr: the raw scan is already on its way to the device on s and is prepared in the same launch that
-// builds the matrices; nullptr: the prepared scan is resident (tsdfloc_sensor_update_cloud).
-static int update_with_scan(tsdfloc_ctx* c, float* particles, uint64_t n, const float tf[16], float mean_pose[6], cudaStream_t s,
-                            const PrepArgs* fused_scan, size_t stage_off)
+// Host-buffer sensor update in parts: prepare sizes the buffers and picks the upload sources (page-locked caller memory is
+// copied from directly, pageable memory goes through the pinned staging buffer); upload: scan + particles; kernels: (scan
+// preparation +) evaluation, normalisation; download: weights + status; finish waits, checks, scatters the weights into the
+// caller's particles. Launched kernel by kernel on purpose: here the caller waits for the result, so the host-side cost of a
+// graph launch sits on the critical path and outweighs the tighter kernel spacing — measured on B200 through this call, C1
+// 0.115 ms kernel by kernel, 0.119 ms with the kernel chain as a graph, 0.124 ms with the copies recorded as well; C2 0.576 /
+// 0.582 / 0.585 ms (profiles/r02_graphs.md). The device-resident update (tsdfloc_update_device) does replay a graph.
+struct HostUpdate
+{
+  float* particles = nullptr;
+  uint64_t n = 0;
+  const void* src_particles = nullptr;   // caller memory (page-locked) or the staging region
+  char* stage = nullptr;                  // staging region of this update: particles up (pageable callers), weights back
+  const void* src_scan = nullptr;         // raw scan upload (tsdfloc_sensor_update), nullptr when the prepared scan is resident
+  size_t scan_bytes = 0;
+  PrepArgs scan{};                        // valid when src_scan != nullptr
+};
+
+static int host_update_prepare(tsdfloc_ctx* c, float* particles, uint64_t n, size_t stage_off, HostUpdate* u)
 {
   int rc;
   const size_t pbytes = sizeof(float) * 7 * n;
   if ((rc = ensure(c, c->d_particles, pbytes, "cudaMalloc(particles)"))) return rc;
   if ((rc = ensure(c, c->d_raw, sizeof(float) * n, "cudaMalloc(raw weights)"))) return rc;
   if ((rc = ensure(c, c->d_wpack, sizeof(float) * n, "cudaMalloc(packed weights)"))) return rc;
-  float* d_p = static_cast<float*>(c->d_particles.p);
-  char* stage = static_cast<char*>(c->h_stage) + stage_off;   // [stage_off, stage_off + pbytes) of the pinned buffer is ours
+  u->particles = particles;
+  u->n = n;
+  u->stage = static_cast<char*>(c->h_stage) + stage_off;   // [stage_off, stage_off + pbytes) of the pinned buffer is ours
+  if (is_pinned(particles)) u->src_particles = particles;
+  else
   {
-    Range r("tsdfloc:init");
-    if (is_pinned(particles))
-      CU_TRY(c, cudaMemcpyAsync(d_p, particles, pbytes, cudaMemcpyHostToDevice, s), "H2D particles");
-    else
-    {
-      std::memcpy(stage, particles, pbytes);
-      CU_TRY(c, cudaMemcpyAsync(d_p, stage, pbytes, cudaMemcpyHostToDevice, s), "H2D particles");
-    }
+    std::memcpy(u->stage, particles, pbytes);
+    u->src_particles = u->stage;
   }
-  if ((rc = stage_eval(c, d_p, n, 0, n, tf, static_cast<float*>(c->d_raw.p), s, nullptr, 0, false, nullptr, nullptr, fused_scan))) return rc;
-  float* d_w = static_cast<float*>(c->d_wpack.p);
-  if ((rc = stage_normalize(c, d_p, n, static_cast<const float*>(c->d_raw.p), c->d_status->mean, s, d_w))) return rc;
-  // 4 B per particle come back (the caller's poses are untouched, cuda_evaluator.cu:405-408) + the status block with the mean
-  CU_TRY(c, cudaMemcpyAsync(stage, d_w, sizeof(float) * n, cudaMemcpyDeviceToHost, s), "D2H weights");
-  if ((rc = read_status(c, s))) return rc;
-  if (c->h_status->zero_sum) return fail(c, TSDFLOC_E_NO_VALID_PARTICLE, "No particle is valid!");
-  const float* h = reinterpret_cast<const float*>(stage);
-  for (uint64_t i = 0; i < n; ++i) particles[7 * i + 6] = h[i];
-  if (mean_pose) std::memcpy(mean_pose, c->h_status->mean, sizeof(float) * 6);
-  c->n_resident = n;
   return TSDFLOC_OK;
+}
+
+static int host_update_upload(tsdfloc_ctx* c, const HostUpdate& u, cudaStream_t s)
+{
+  Range r("tsdfloc:init");
+  if (u.src_scan) CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, u.src_scan, u.scan_bytes, cudaMemcpyHostToDevice, s), "H2D scan");
+  CU_TRY(c, cudaMemcpyAsync(c->d_particles.p, u.src_particles, sizeof(float) * 7 * u.n, cudaMemcpyHostToDevice, s), "H2D particles");
+  return TSDFLOC_OK;
+}
+
+static int host_update_kernels(tsdfloc_ctx* c, const HostUpdate& u, const float tf[16], cudaStream_t s)
+{
+  int rc;
+  float* d_p = static_cast<float*>(c->d_particles.p);
+  if ((rc = stage_eval(c, d_p, u.n, 0, u.n, tf, static_cast<float*>(c->d_raw.p), s, nullptr, 0, false, nullptr, nullptr,
+                       u.src_scan ? &u.scan : nullptr)))
+    return rc;
+  return stage_normalize(c, d_p, u.n, static_cast<const float*>(c->d_raw.p), c->d_status->mean, s, static_cast<float*>(c->d_wpack.p));
+}
+
+static int host_update_download(tsdfloc_ctx* c, const HostUpdate& u, cudaStream_t s)
+{
+  // 4 B per particle come back (the caller's poses are untouched, cuda_evaluator.cu:405-408) + the status block with the mean
+  CU_TRY(c, cudaMemcpyAsync(u.stage, c->d_wpack.p, sizeof(float) * u.n, cudaMemcpyDeviceToHost, s), "D2H weights");
+  CU_TRY(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(Status), cudaMemcpyDeviceToHost, s), "status readback");
+  return TSDFLOC_OK;
+}
+
+static int host_update_finish(tsdfloc_ctx* c, const HostUpdate& u, float mean_pose[6], cudaStream_t s)
+{
+  CU_TRY(c, cudaStreamSynchronize(s), "stream sync");
+  c->have_cdf = true;
+  c->eval_timed = true;
+  if (c->h_status->zero_sum) return fail(c, TSDFLOC_E_NO_VALID_PARTICLE, "No particle is valid!");
+  const float* h = reinterpret_cast<const float*>(u.stage);
+  for (uint64_t i = 0; i < u.n; ++i) u.particles[7 * i + 6] = h[i];
+  if (mean_pose) std::memcpy(mean_pose, c->h_status->mean, sizeof(float) * 6);
+  c->n_resident = u.n;
+  return TSDFLOC_OK;
+}
+
+// The prepared scan is resident (tsdfloc_sensor_update_cloud): the scan length differs from cloud to cloud, so no graph.
+static int update_with_scan(tsdfloc_ctx* c, float* particles, uint64_t n, const float tf[16], float mean_pose[6], cudaStream_t s, size_t stage_off)
+{
+  int rc;
+  HostUpdate u;
+  if ((rc = host_update_prepare(c, particles, n, stage_off, &u))) return rc;
+  if ((rc = host_update_upload(c, u, s))) return rc;
+  if ((rc = host_update_kernels(c, u, tf, s))) return rc;
+  if ((rc = host_update_download(c, u, s))) return rc;
+  return host_update_finish(c, u, mean_pose, s);
 }
 
 int tsdfloc_sensor_update(tsdfloc_ctx* c, float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],
@@ -1374,20 +1543,21 @@ int tsdfloc_sensor_update(tsdfloc_ctx* c, float* particles, uint64_t n, const fl
   c->have_cdf = false;
   c->n_resident = 0;
   if ((rc = ensure(c, c->d_xyz_stage, sizeof(float) * 3 * (p + 1), "cudaMalloc(scan staging)"))) return rc;
+  HostUpdate u;
+  u.scan_bytes = sizeof(float) * 3 * p;
+  if (is_pinned(points)) u.src_scan = points;
+  else
   {
-    Range r("tsdfloc:init");
-    if (is_pinned(points))
-      CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, points, sizeof(float) * 3 * p, cudaMemcpyHostToDevice, s), "H2D scan");
-    else
-    {
-      char* h_scan = static_cast<char*>(c->h_stage) + scan_off;
-      std::memcpy(h_scan, points, sizeof(float) * 3 * p);
-      CU_TRY(c, cudaMemcpyAsync(c->d_xyz_stage.p, h_scan, sizeof(float) * 3 * p, cudaMemcpyHostToDevice, s), "H2D scan");
-    }
+    char* h_scan = static_cast<char*>(c->h_stage) + scan_off;
+    std::memcpy(h_scan, points, u.scan_bytes);
+    u.src_scan = h_scan;
   }
-  PrepArgs scan{};
-  if ((rc = scan_layout(c, static_cast<const float*>(c->d_xyz_stage.p), p, &scan))) return rc;
-  return update_with_scan(c, particles, n, tf, mean_pose, s, &scan, 0);
+  if ((rc = scan_layout(c, static_cast<const float*>(c->d_xyz_stage.p), p, &u.scan))) return rc;
+  if ((rc = host_update_prepare(c, particles, n, 0, &u))) return rc;
+  if ((rc = host_update_upload(c, u, s))) return rc;
+  if ((rc = host_update_kernels(c, u, tf, s))) return rc;
+  if ((rc = host_update_download(c, u, s))) return rc;
+  return host_update_finish(c, u, mean_pose, s);
 }
 
 // ---- scan reduction -----------------------------------------------------------------------------------------------
@@ -1465,7 +1635,7 @@ int tsdfloc_sensor_update_cloud(tsdfloc_ctx* c, float* particles, uint64_t n, co
   if (m == 0) return fail(c, TSDFLOC_E_EMPTY_SCAN, "empty scan after reduction: weights left untouched");
   if ((rc = stage_prep_scan(c, static_cast<const float*>(c->d_red_out.p), m, s))) return rc;
   if ((rc = ensure_host(c, sizeof(float) * 7 * n))) return rc;
-  return update_with_scan(c, particles, n, tf, mean_pose, s, nullptr, 0);
+  return update_with_scan(c, particles, n, tf, mean_pose, s, 0);
 }
 
 int tsdfloc_resample_systematic(tsdfloc_ctx* c, float u0, float* particles_out, uint64_t cap, uint64_t* n_out, uint32_t* parents)
@@ -1794,9 +1964,22 @@ int tsdfloc_tune(tsdfloc_ctx* c, int knob, int value)
       if (value < 0 || value > 2) return fail(c, TSDFLOC_E_BAD_ARG, "registers: 0 automatic, 1 64 per thread, 2 128 per thread");
       c->tune_regs = value;
       return TSDFLOC_OK;
+    case TSDFLOC_TUNE_EVAL_CHUNKS:
+      if (value < 0 || value > 64) return fail(c, TSDFLOC_E_BAD_ARG, "chunks: 0 automatic, 1..64 scan chunks per particle");
+      c->tune_chunks = value;
+      return TSDFLOC_OK;
     case TSDFLOC_TUNE_STAGE_TIMERS:
       c->stage_timers = value != 0;
       c->stage_seen = 0;
+      return TSDFLOC_OK;
+    case TSDFLOC_TUNE_GRAPHS:
+      c->graphs_on = value != 0;
+      if (!c->graphs_on)
+      {
+        DeviceGuard guard(c->device);
+        cudaStreamSynchronize(c->stream);
+        graph_drop_all(c);
+      }
       return TSDFLOC_OK;
     default: return fail(c, TSDFLOC_E_BAD_ARG, "unknown tuning knob");
   }
@@ -1822,6 +2005,15 @@ int tsdfloc_stage_times(tsdfloc_ctx* c, float ms[4])
   span(tsdfloc_ctx::kEvNorm0, tsdfloc_ctx::kEvNorm1, &ms[2]);                  // weight_update: K2 (+ K3)
   span(tsdfloc_ctx::kEvDraw0, tsdfloc_ctx::kEvDraw1, &ms[3]);                  // resampling: K4
   cudaGetLastError();
+  return TSDFLOC_OK;
+}
+
+int tsdfloc_graph_stats(const tsdfloc_ctx* c, uint64_t out[2], const char** note)
+{
+  if (!c || !out) return TSDFLOC_E_BAD_ARG;
+  out[0] = c->graph_captures;
+  out[1] = c->graph_replays;
+  if (note) *note = c->graph_note.c_str();
   return TSDFLOC_OK;
 }
 

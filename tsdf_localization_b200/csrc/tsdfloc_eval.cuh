@@ -26,6 +26,13 @@
 //     several waves deep (>= 32,768 particles); 128 registers = 16 CTAs per SM, where ptxas keeps more of a block's gathers in
 //     flight: a warp walks the scan 1.6x faster on its own, which is what a shard that cannot fill the machine needs
 //     (profiles/r02_eval_registers.md: 500 particles 0.90 -> 0.49 ms, 8,192: 2.80 -> 2.69 ms, 65,536: 17.6 vs 18.3 ms).
+//   * CHAINED SCAN CHUNKS for grids that end in a long, half-empty last wave (kChain): a warp's unit of work is one CHUNK of
+//     the scan for its particle(s), not the whole scan. Units are handed out chunk-major through an atomic ticket (all
+//     particles' chunk 0, then everybody's chunk 1, ...); chunk k of a particle starts from the running sum chunk k - 1 left in
+//     global memory (it waits on a flag, but with tickets in chunk-major order the predecessor has long finished) — the sum is
+//     still the one sequential fp32 sum, bit for bit, only carried from warp to warp. The tail of the grid is then one chunk
+//     long instead of one scan long: 8,192 particles x 131,072 points are 1.73 waves of the 128-register budget and used to
+//     cost two full waves (profiles/r02_eval_chain.md).
 //   * The sub-voxel quotient floor(fl(p / res)) is bracketed by two round-down FMAs (tsdfloc_device.cuh); a block in which
 //     any quotient's bracket is open (~0.5 % of the blocks) is redone with the exact division. Exactness never depends on
 //     the bracket being tight — only speed does.
@@ -63,7 +70,16 @@ struct EvalArgs
   float one;                        // 1.0f, opaque to the compiler (see tsdfloc_device.cuh, packed path)
   float s_min;                      // integer-block summation is used once s >= s_min (= 32 * bound of one addend)
   uint32_t force_seq;               // 1: negative/non-finite addends possible -> always fold sequentially
+  // kChain only: the scan is cut into n_chunks chunks of blocks_per_chunk summation blocks; the grid holds n_tasks * n_chunks
+  // one-warp CTAs (n_tasks = particle pairs, or particles in the point-pair shape)
+  uint32_t* chain;                  // [kChainHeader + kChainStride * n_tasks]: ticket, finished units; per task: flag + carried state
+  uint32_t n_tasks;
+  uint32_t n_chunks;
+  uint32_t blocks_per_chunk;
 };
+
+constexpr uint32_t kChainHeader = 8;   // words: [0] ticket, [1] finished units (both back to 0 when the launch ends)
+constexpr uint32_t kChainStride = 8;   // words per task: [0] chunks committed (0 again after the last), [1..5] s0 s1 n_fold n_tie n_redo
 
 // Final store of a particle's weight: into this rank's vector and — fused all-gather — straight into every peer's
 // (P2P stores over NVLink; the kernel boundary + the driver's signal barrier order them before the peers' reads).
@@ -284,13 +300,29 @@ __device__ __forceinline__ bool eval_commit_block(const MapDev& M, const EvalArg
 }
 
 // kExact = kDivIeee or kDivThree (what k_check_div proved); kBracket: try the bracketed quotients first.
-template <int BS, int kExact, bool kBracket, bool kPP, bool kDump, int kMinCtas>
+// kChain: chained scan chunks (see the header); false = one warp walks the whole scan, task = blockIdx.x.
+template <int BS, int kExact, bool kBracket, bool kPP, bool kDump, int kMinCtas, bool kChain = false>
 __global__ void __launch_bounds__(32, kMinCtas) k_eval(const MapDev M, const EvalArgs A)
 {
+  static_assert(!(kChain && kDump), "the parity dumps walk whole scans");
   constexpr uint32_t kBlockPoints = (kPP ? 64u : 32u) * BS;
   const uint32_t lane = threadIdx.x;
-  const uint32_t part0 = kPP ? blockIdx.x : blockIdx.x * 2u;
   const uint32_t n_blocks_total = (A.n_points + kBlockPoints - 1u) / kBlockPoints;
+
+  uint32_t task = blockIdx.x, chunk = 0u, blk = 0u, blk_end = n_blocks_total;
+  if (kChain)
+  {
+    // units in the order in which their CTAs actually start: whoever holds (chunk, task) knows (chunk - 1, task) is running
+    // or done, so waiting for it cannot deadlock whatever order the hardware dispatches CTAs in
+    uint32_t t = 0u;
+    if (lane == 0) t = atomicAdd(A.chain, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    chunk = t / A.n_tasks;
+    task = t - chunk * A.n_tasks;
+    blk = chunk * A.blocks_per_chunk;
+    blk_end = min(n_blocks_total, blk + A.blocks_per_chunk);
+  }
+  const uint32_t part0 = kPP ? task : task * 2u;
 
   // the matrices as fp32x2 pairs: {particle A, particle B}, or {particle, particle}; a warp past the end re-does the last
   // particle and stores nothing
@@ -302,17 +334,30 @@ __global__ void __launch_bounds__(32, kMinCtas) k_eval(const MapDev M, const Eva
   }
   WarpSums W{0.0f, 0.0f, 0u, 0u};
   uint32_t n_redo = 0;
+  uint32_t* const link = kChain ? A.chain + kChainHeader + static_cast<size_t>(kChainStride) * task : nullptr;
+  if (kChain && chunk > 0u)
+  {
+    // the running sums chunk - 1 left behind (L2 reads: the writer sits on another SM)
+    if (lane == 0)
+      while (*reinterpret_cast<volatile uint32_t*>(link) < chunk) __nanosleep(200);
+    __syncwarp();
+    __threadfence();
+    W.s0 = __uint_as_float(__ldcg(link + 1));
+    W.s1 = __uint_as_float(__ldcg(link + 2));
+    W.n_fold = __ldcg(link + 3);
+    W.n_tie = __ldcg(link + 4);
+    n_redo = __ldcg(link + 5);
+  }
   const float2 one = dup2(A.one);
   const float2 ah = dup2(A.a_hit);
 
-  uint32_t blk = 0;
-  while (blk < n_blocks_total)
+  while (blk < blk_end)
   {
     // hot loop: bracketed quotients (or, where the bracket is unproven for this resolution, the exact mode directly)
 #pragma unroll 1
-    for (; blk < n_blocks_total; ++blk)
+    for (; blk < blk_end; ++blk)
       if (!eval_commit_block<BS, kBracket ? kDivBracket : kExact, kPP, kDump>(M, A, mm, lane, one, ah, part0, blk * kBlockPoints, W)) break;
-    if (kBracket && blk < n_blocks_total)
+    if (kBracket && blk < blk_end)
     {
       // cold: a quotient of this block sits within a few ulps of an integer — the same block with the exact division
       eval_commit_block<BS, kExact, kPP, kDump>(M, A, mm, lane, one, ah, part0, blk * kBlockPoints, W);
@@ -323,14 +368,39 @@ __global__ void __launch_bounds__(32, kMinCtas) k_eval(const MapDev M, const Eva
 
   if (lane == 0)
   {
-    if (part0 < A.n_local) store_weight(A, part0, W.s0);
-    if (!kPP && part0 + 1u < A.n_local) store_weight(A, part0 + 1u, W.s1);
-    if (A.stats && part0 < A.n_local)
+    if (kChain && chunk + 1u < A.n_chunks)
     {
-      atomicAdd(A.stats + 0, static_cast<unsigned long long>(n_blocks_total) * (kPP ? 1ull : 2ull));
-      atomicAdd(A.stats + 1, static_cast<unsigned long long>(W.n_fold));
-      atomicAdd(A.stats + 2, static_cast<unsigned long long>(W.n_tie));
-      atomicAdd(A.stats + 3, static_cast<unsigned long long>(n_redo));
+      // hand the running sums to the warp that takes this task's next chunk
+      __stcg(link + 1, __float_as_uint(W.s0));
+      __stcg(link + 2, __float_as_uint(W.s1));
+      __stcg(link + 3, W.n_fold);
+      __stcg(link + 4, W.n_tie);
+      __stcg(link + 5, n_redo);
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(link) = chunk + 1u;
+    }
+    else
+    {
+      if (part0 < A.n_local) store_weight(A, part0, W.s0);
+      if (!kPP && part0 + 1u < A.n_local) store_weight(A, part0 + 1u, W.s1);
+      if (A.stats && part0 < A.n_local)
+      {
+        atomicAdd(A.stats + 0, static_cast<unsigned long long>(n_blocks_total) * (kPP ? 1ull : 2ull));
+        atomicAdd(A.stats + 1, static_cast<unsigned long long>(W.n_fold));
+        atomicAdd(A.stats + 2, static_cast<unsigned long long>(W.n_tie));
+        atomicAdd(A.stats + 3, static_cast<unsigned long long>(n_redo));
+      }
+      if (kChain) *reinterpret_cast<volatile uint32_t*>(link) = 0u;   // the next launch finds the chain empty
+    }
+    if (kChain)
+    {
+      // the last unit to finish re-arms the ticket (every unit has drawn its ticket by then)
+      const uint32_t done = atomicAdd(A.chain + 1, 1u);
+      if (done + 1u == gridDim.x)
+      {
+        A.chain[1] = 0u;
+        A.chain[0] = 0u;
+      }
     }
   }
 }

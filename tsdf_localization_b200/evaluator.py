@@ -332,6 +332,13 @@ class CudaEvaluator:
         """Test / tuning hook (tsdfloc_tune): every setting produces the same bits."""
         capi.check(self._lib, self._ctx, self._lib.tsdfloc_tune(self._ctx, int(knob), int(value)))
 
+    def graph_stats(self):
+        """(recordings made, updates served by a graph launch, why the last recording attempt was abandoned)."""
+        st = (C.c_uint64 * 2)()
+        note = C.c_char_p()
+        capi.check(self._lib, self._ctx, self._lib.tsdfloc_graph_stats(self._ctx, st, C.byref(note)))
+        return int(st[0]), int(st[1]), (note.value or b"").decode()
+
     def division_mode(self):
         """(mode, open brackets): what tsdfloc_create proved for the map's resolution (capi.DIV_*)."""
         n = C.c_uint64(0)
