@@ -392,6 +392,8 @@ def _run_b200_arm(args, guard):
         ev.tune(capi.TUNE_GRAPHS, 0)
     if args.chunks:
         ev.tune(capi.TUNE_EVAL_CHUNKS, args.chunks)
+    if args.pairing:
+        ev.tune(capi.TUNE_EVAL_PAIRING, args.pairing)
     lib = capi.load_library()
     stages = GpuStages(ev)
     fused = {"auto": None, "nccl": False, "fused": True}[args.transport]
@@ -616,6 +618,8 @@ def main():
     ap.add_argument("--particles", type=int, default=0, help="development: override the particle count of c1-c3 (not a BASELINE config)")
     ap.add_argument("--registers", type=int, default=0, choices=(0, 1, 2),
                     help="development: force the evaluation kernel's register budget (1: 64, 2: 128; 0 = the library's own rule)")
+    ap.add_argument("--pairing", type=int, default=0, choices=(0, 1, 2),
+                    help="development: force the evaluation kernel's pairing (1: two particles per warp, 2: two points per lane)")
     ap.add_argument("--chunks", type=int, default=0,
                     help="development: scan chunks per particle in the evaluation kernel (1 = whole scans; 0 = the library's own rule)")
     ap.add_argument("--graphs", type=int, default=1, choices=(0, 1),

@@ -437,7 +437,8 @@ int tsdfloc_eval_stats(tsdfloc_ctx* ctx, uint64_t out[4]);
 /* Test / tuning hook (never needed for correct results: every setting produces the same bits). No environment variables
  * are read anywhere in the library.
  *   TSDFLOC_TUNE_SPATIAL_ORDER  -1 automatic (map larger than L2 and >= 16,384 particles), 0 off, 1 on (tsdfloc_sort.cuh)
- *   TSDFLOC_TUNE_EVAL_PAIRING    0 automatic, 1 two particles per warp, 2 two points per lane (tsdfloc_eval.cuh)
+ *   TSDFLOC_TUNE_EVAL_PAIRING    0 automatic (two points per lane while particle pairs would not fill the warp slots once),
+ *                                1 two particles per warp, 2 two points per lane (tsdfloc_eval.cuh)
  *   TSDFLOC_TUNE_DIVISION       -1 what tsdfloc_create proved for the resolution, 0 IEEE division, 1 three-instruction
  *                                quotient, 2 bracketed quotient (an unproven mode is never run)                            */
 enum tsdfloc_tune_knob
@@ -446,7 +447,7 @@ enum tsdfloc_tune_knob
   TSDFLOC_TUNE_EVAL_PAIRING = 1,
   TSDFLOC_TUNE_DIVISION = 2,
   TSDFLOC_TUNE_STAGE_TIMERS = 3,  /* 0 off (default), 1 record CUDA events around the stages (tsdfloc_stage_times) */
-  TSDFLOC_TUNE_EVAL_REGISTERS = 4, /* 0 automatic (128 registers per thread up to 16,384 particles per device, 64 beyond), 1 64, 2 128 */
+  TSDFLOC_TUNE_EVAL_REGISTERS = 4, /* 0 automatic (128 registers per thread below 1.5 waves of 64-register warps, 64 beyond), 1 64, 2 128 */
   TSDFLOC_TUNE_GRAPHS = 5,         /* 1 (default) replay fixed-shape device-resident updates as CUDA graphs, 0 always launch kernel by kernel */
   TSDFLOC_TUNE_EVAL_CHUNKS = 6     /* 0 automatic, 1 every warp walks the whole scan, 2..64 chained scan chunks per particle (tsdfloc_eval.cuh) */
 };

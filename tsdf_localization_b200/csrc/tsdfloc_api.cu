@@ -404,9 +404,10 @@ struct EvalShape
 };
 
 // Point pairs double the number of warps but read the scan once per particle instead of once per pair (+15 % at full
-// occupancy): they win only while particle pairs would leave most of the machine's warp slots empty. Measured on B200 at the
-// 128-register budget (profiles/r02_eval_registers.md, r02_eval_sweep_*.jsonl): 500 particles x 131,072 points 0.79 -> 0.50 ms,
-// 2,000: 1.07 -> 0.97, 5,000 x 30,000: 0.49 -> 0.465, 8,192: 2.69 vs 2.83, 65,536 (64 registers): 17.7 vs 20.2.
+// occupancy): they win only while particle pairs cannot even fill the machine's warp slots once. With chained chunks a grid
+// of a little more than one wave no longer costs two, so pairs take over as soon as there is more than one wave of them.
+// Measured on B200 (profiles/r02_eval_registers.md, r02_eval_chain.md): 500 particles x 131,072 points 0.79 (pairs) -> 0.50 ms
+// (point pairs), 2,000: 1.07 -> 0.97; 5,000: 1.64 (point pairs, chunked) vs 1.48 (pairs, chunked); 5,000 x 30,000: 0.418 vs 0.366.
 EvalShape eval_shape(const tsdfloc_ctx* c, uint32_t n_local, uint32_t n_points, bool dump)
 {
   EvalShape e;
@@ -417,21 +418,25 @@ EvalShape eval_shape(const tsdfloc_ctx* c, uint32_t n_local, uint32_t n_points, 
     if (e.div == kDivBracket && !c->bracket_ok) e.div = c->map.div_mode;   // never run an unproven mode
     if (e.div != kDivIeee && !c->three_ok) e.div = kDivIeee;
   }
-  e.pp = static_cast<uint64_t>(n_local) * 4u < static_cast<uint64_t>(c->sm_count) * 32u * 5u;   // < 5,920 particles on 148 SMs
+  const uint64_t slots_deep = static_cast<uint64_t>(c->sm_count) * TSDFLOC_EVAL_CTAS_DEEP;
+  const uint64_t slots_shallow = static_cast<uint64_t>(c->sm_count) * TSDFLOC_EVAL_CTAS_SHALLOW;
+  e.pp = (n_local + 1u) / 2u <= slots_deep;   // <= 4,736 particles on 148 SMs
   if (c->tune_shape == 1) e.pp = false;
   if (c->tune_shape == 2) e.pp = true;
-  // Register budget: 128 registers (16 CTAs per SM) while the slice is at most 16,384 particles — a warp on its own runs 1.6x
-  // faster with the deeper budget and such a grid is at most ~3 waves of it —, 64 registers (32 CTAs per SM) beyond.
-  // Measured on B200 (profiles/r02_eval_registers.md): 8,192 particles 2.80 -> 2.69 ms, 16,384: 5.00 = 4.97, 32,768: 9.15 vs 9.36.
-  e.deep = n_local <= 16384u;
+  e.n_tasks = e.pp ? n_local : (n_local + 1u) / 2u;
+  // Register budget: 128 registers (16 CTAs per SM) while the warps are fewer than 1.5 waves of the 64-register budget (32
+  // CTAs per SM) — a warp on its own runs 1.6x faster with the deeper budget —, 64 registers beyond. Measured on B200
+  // (profiles/r02_eval_registers.md, r02_eval_chain.md; chunked where the rule below says so): 8,192 particles 2.80 (64) vs
+  // 2.33 ms (128), 12,000: 3.38 (128), 16,384: 4.46 (64) vs 4.60 (128), 32,768: 8.84 (64) vs 9.36 (128).
+  e.deep = 2u * static_cast<uint64_t>(e.n_tasks) < 3u * slots_shallow;
   if (c->tune_regs == 1) e.deep = false;
   if (c->tune_regs == 2) e.deep = true;
-  e.n_tasks = e.pp ? n_local : (n_local + 1u) / 2u;
   // Chained scan chunks (tsdfloc_eval.cuh): worth it when the grid is a few waves deep and the last one is far from full —
-  // 8,192 particles are 1.73 waves of the 128-register budget and cost 2 without chunks. At least 8 summation blocks per chunk.
+  // 8,192 particles are 1.73 waves of the 128-register budget and cost 2 without chunks. At least 12 summation blocks per chunk
+  // (C2, 59 blocks: 4 chunks 0.419 ms, 7 chunks 0.428 ms, profiles/r02_eval_chain.md).
   const uint32_t block_points = (e.pp ? 64u : 32u) * static_cast<uint32_t>(kEvalBlockSteps);
   const uint32_t n_blocks = (n_points + block_points - 1u) / block_points;
-  const uint64_t slots = static_cast<uint64_t>(c->sm_count) * (e.deep ? TSDFLOC_EVAL_CTAS_DEEP : TSDFLOC_EVAL_CTAS_SHALLOW);
+  const uint64_t slots = e.deep ? slots_deep : slots_shallow;
   uint32_t chunks = 1;
   if (c->tune_chunks > 0) chunks = static_cast<uint32_t>(c->tune_chunks);
   else if (e.n_tasks > slots && e.n_tasks < 12u * slots)
@@ -439,7 +444,7 @@ EvalShape eval_shape(const tsdfloc_ctx* c, uint32_t n_local, uint32_t n_points, 
     const uint64_t waves = (e.n_tasks + slots - 1u) / slots;
     if (static_cast<double>(e.n_tasks) < 0.93 * static_cast<double>(waves * slots)) chunks = 8;
   }
-  chunks = std::min(chunks, std::max(1u, n_blocks / 8u));
+  chunks = std::min(chunks, std::max(1u, n_blocks / 12u));
   if (dump || static_cast<uint64_t>(e.n_tasks) * chunks >= (1ull << 31)) chunks = 1;
   e.blocks_per_chunk = (n_blocks + chunks - 1u) / chunks;
   e.n_chunks = e.blocks_per_chunk ? (n_blocks + e.blocks_per_chunk - 1u) / e.blocks_per_chunk : 1u;
