@@ -45,10 +45,13 @@ def test_committed_bench_lines_are_rank_count_invariant():
     import json
     from pathlib import Path
     prof = Path(__file__).resolve().parents[1] / "profiles"
-    lines = {n: json.loads((prof / name).read_text()) for n, name in
-             ((1, "r02_bench_c3.json"), (2, "r02_bench_c3_n2.json"), (4, "r02_bench_c3_n4.json"), (8, "r02_bench_c3_n8.json"))}
+    # r02b_*: the same command after the evaluation kernel learned chained scan chunks and the update its CUDA graph — other
+    # launches, same bytes
+    lines = [(n, json.loads((prof / name).read_text().strip().splitlines()[-1])) for n, name in
+             ((1, "r02_bench_c3.json"), (2, "r02_bench_c3_n2.json"), (4, "r02_bench_c3_n4.json"), (8, "r02_bench_c3_n8.json"),
+              (1, "r02b_bench_c3.json"), (2, "r02b_bench_c3_n2.json"), (8, "r02b_bench_c3_n8.json"))]
     digests = set()
-    for n, d in lines.items():
+    for n, d in lines:
         assert d["n_gpus"] == n and d["config"]["particles"] == 65536 and d["config"]["points"] == 131072
         c = d["config"]
         digests.add((c["weights_sha256"], c["resampled_sha256"]))

@@ -25,7 +25,8 @@
 //   * Two REGISTER BUDGETS of the same code (kMinCtas): 64 registers = 32 one-warp CTAs per SM, the fastest once the grid is
 //     several waves deep (>= 32,768 particles); 128 registers = 16 CTAs per SM, where ptxas keeps more of a block's gathers in
 //     flight: a warp walks the scan 1.6x faster on its own, which is what a shard that cannot fill the machine needs
-//     (profiles/r02_eval_registers.md: 500 particles 0.90 -> 0.49 ms, 8,192: 2.80 -> 2.69 ms, 65,536: 17.6 vs 18.3 ms).
+//     (profiles/r02_eval_registers.md: 500 particles 0.90 -> 0.49 ms, 8,192: 2.80 -> 2.69 ms, 65,536: 17.6 vs 18.3 ms). The host
+//     picks the budget, the pairing and the chunking per launch (eval_shape, tsdfloc_api.cu).
 //   * CHAINED SCAN CHUNKS for grids that end in a long, half-empty last wave (kChain): a warp's unit of work is one CHUNK of
 //     the scan for its particle(s), not the whole scan. Units are handed out chunk-major through an atomic ticket (all
 //     particles' chunk 0, then everybody's chunk 1, ...); chunk k of a particle starts from the running sum chunk k - 1 left in
