@@ -241,6 +241,49 @@ int tsdfloc_resample_expand_device(tsdfloc_ctx* ctx, const float* d_particles, c
 int tsdfloc_resample(tsdfloc_ctx* ctx, int method, const float* particles, uint64_t n, float u, tsdfloc_index_draw_fn draw, void* user,
                      float* particles_out, uint64_t cap, uint64_t* n_out, uint32_t* parents);
 
+/* ---- the three remaining choices of mcl_3d's resampling_method switch (src/mcl_3d.cpp:243-263) ---------------------
+ * Wheel (case 0), Metropolis (case 4) and Rejection (default) pick every output particle from random draws on the resampler's
+ * std::mt19937. The draws stay with the caller (callbacks, like the index draws of Residual) so that equal seeds give equal
+ * outputs; the host half turns weights + draws into one parent per output slot (4 B per particle on the host), the device
+ * copies the 28 B particles (k_expand_runs with runs of length one). */
+enum tsdfloc_resample_method_drawn
+{
+  TSDFLOC_RESAMPLE_WHEEL = 3,       /* WheelResampler       src/resampling/wheel_resampler.cpp:6-34 */
+  TSDFLOC_RESAMPLE_METROPOLIS = 4,  /* MetropolisResampler  novel_resampling.h:106-144              */
+  TSDFLOC_RESAMPLE_REJECTION = 5    /* RejectionResampler   novel_resampling.h:146-189              */
+};
+/* One uniform_real draw on [0, 1) already converted to the method's FLOAT_T: Metropolis / Rejection draw
+ * std::uniform_real_distribution<FLOAT_T>(0.0, 1.0) (novel_resampling.h:115, 151); Wheel draws
+ * std::uniform_real_distribution<>(0.0, 1.0) — a double — and narrows it to FLOAT_T (wheel_resampler.cpp:9, 15). */
+typedef float (*tsdfloc_real_draw_fn)(void* user);
+typedef struct tsdfloc_draws
+{
+  tsdfloc_real_draw_fn real;    /* all three methods */
+  tsdfloc_index_draw_fn index;  /* Metropolis, Rejection: std::uniform_int_distribution<size_t>(0, n - 1); NULL for Wheel */
+  void* user;                   /* handed to both callbacks */
+  uint64_t metropolis_steps;    /* MetropolisResampler's sampling_steps_ (mcl_3d passes 50, src/mcl_3d.cpp:258) */
+  uint64_t max_draws;           /* Rejection: give up (TSDFLOC_E_CAPACITY) after this many index draws; 0 = never, like the reference */
+} tsdfloc_draws;
+
+/* Host half of WheelResampler::resample: per output slot one draw u and the first index whose fp32 running weight sum (restarted
+ * at 0 for every slot in the reference, hence the same prefix array for all) reaches u; a slot whose u exceeds the last sum
+ * keeps its own particle (wheel_resampler.cpp:13-31 leaves particle_cloud[particle_index] untouched). O(n) instead of the
+ * reference's O(n^2): prefix once, guide table, bracketed search. Any finite weights are accepted (a running maximum makes
+ * "first index whose sum reaches u" searchable even where negative weights make the sums non-monotone). Pure host code. */
+int tsdfloc_wheel_parents(const float* weights, uint64_t stride, uint64_t n, tsdfloc_real_draw_fn real, void* user, uint32_t* parents);
+/* Host half of MetropolisResampler::resample: per output slot `steps` rounds of (u, j) draws, k = j whenever
+ * u <= w[j] / w[0] — the reference binds `particle_k` to particle 0 once (:125) and never rebinds it, so every ratio is
+ * against particle 0; reproduced as written. Pure host code. */
+int tsdfloc_metropolis_parents(const float* weights, uint64_t stride, uint64_t n, uint64_t steps, tsdfloc_real_draw_fn real,
+                               tsdfloc_index_draw_fn index, void* user, uint32_t* parents);
+/* Host half of RejectionResampler::resample: slot i proposes itself first, then uniformly drawn particles, until
+ * u <= w[j] / sup_w (fp64 quotient of an fp32 weight and the fp64 maximum, :157-180). *n_draws (optional) = index draws used. */
+int tsdfloc_rejection_parents(const float* weights, uint64_t stride, uint64_t n, tsdfloc_real_draw_fn real, tsdfloc_index_draw_fn index,
+                              void* user, uint64_t max_draws, uint32_t* parents, uint64_t* n_draws);
+/* Resampler::resample(ParticleCloud&) for the three drawn methods; particles / n / outputs as tsdfloc_resample (n_out = n). */
+int tsdfloc_resample_drawn(tsdfloc_ctx* ctx, int method, const float* particles, uint64_t n, const tsdfloc_draws* draws,
+                           float* particles_out, uint64_t cap, uint64_t* n_out, uint32_t* parents);
+
 /* ---- (B) device-pointer stage calls ---------------------------------------------------------------------
  * All pointers are device pointers on ctx's device; `stream` is a cudaStream_t passed as void* (NULL = the
  * ctx's own non-blocking stream; pass cudaStreamLegacy / cudaStreamPerThread explicitly for the default streams).

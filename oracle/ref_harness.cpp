@@ -36,6 +36,7 @@
 #include <tsdf_localization/evaluation/model/likelihood_evaluation.h>
 #include <tsdf_localization/map/map_util.h>
 #include <tsdf_localization/resampling/novel_resampling.h>
+#include <tsdf_localization/resampling/wheel_resampler.h>
 #include <tsdf_localization/util/constant.h>
 #include <tsdf_localization/util/mcl_file.h>
 #ifdef TSDF_REF_WITH_B200_SHIM
@@ -133,6 +134,37 @@ struct SeededResidualSystematic : public ResidualSystematicResampler
 {
   void seed(uint32_t s) { m_generator_ptr.reset(new std::mt19937(s)); }
 };
+// sampling_steps_ of the Metropolis resamplers constructed below (mcl_3d passes 50, src/mcl_3d.cpp:258)
+size_t g_metropolis_steps = 50;
+struct SeededWheel : public WheelResampler
+{
+  void seed(uint32_t s) { m_generator_ptr.reset(new std::mt19937(s)); }
+};
+struct SeededMetropolis : public MetropolisResampler
+{
+  SeededMetropolis() : MetropolisResampler(g_metropolis_steps) {}
+  void seed(uint32_t s) { m_generator_ptr.reset(new std::mt19937(s)); }
+};
+struct SeededRejection : public RejectionResampler
+{
+  void seed(uint32_t s) { m_generator_ptr.reset(new std::mt19937(s)); }
+};
+#ifdef TSDF_REF_WITH_B200_SHIM
+struct SeededGpuMetropolis : public GpuMetropolisResampler
+{
+  SeededGpuMetropolis() : GpuMetropolisResampler(g_metropolis_steps) {}
+};
+#endif
+// A seeded std::mt19937 with the distribution objects the reference's resamplers construct, behind C callbacks: feeds
+// restatements the very draws — in the very interleaving — the reference consumes.
+struct DrawSource
+{
+  std::mt19937 gen;
+  std::uniform_real_distribution<FLOAT_T> real;    // novel_resampling.h:115, 151
+  std::uniform_real_distribution<> real_wheel;     // wheel_resampler.cpp:9
+  std::uniform_int_distribution<size_t> index;     // novel_resampling.h:116, 152
+  uint64_t n_real = 0, n_index = 0;
+};
 
 struct MapHandle
 {
@@ -154,7 +186,8 @@ thread_local std::string g_last_error;
 using namespace tsdf_localization;
 
 // ResidualSystematicResampler::resample (novel_resampling.h:79-103) / ResidualResampler::resample (:12-34), verbatim, with a
-// seeded generator. method: 1 = Residual, 2 = ResidualSystematic. u_out: the uniform(0,1) draw of ResidualSystematic.
+// seeded generator. method: 1 = Residual, 2 = ResidualSystematic, 3 = Wheel, 4 = Metropolis, 5 = Rejection (the numbering of
+// include/tsdfloc.h). u_out: the uniform(0,1) draw of ResidualSystematic.
 template <typename R>
 static uint64_t run_seeded_resampler(const float* particles, uint64_t n, uint32_t seed, float* particles_out, uint64_t cap)
 {
@@ -515,7 +548,44 @@ uint64_t ref_resample_method(int method, const float* particles, uint64_t n, uin
   }
   if (method == 1) return run_seeded_resampler<SeededResidual>(particles, n, seed, particles_out, cap);
   if (method == 2) return run_seeded_resampler<SeededResidualSystematic>(particles, n, seed, particles_out, cap);
+  if (method == 3) return run_seeded_resampler<SeededWheel>(particles, n, seed, particles_out, cap);        // wheel_resampler.cpp:6-34
+  if (method == 4) return run_seeded_resampler<SeededMetropolis>(particles, n, seed, particles_out, cap);   // novel_resampling.h:106-144
+  if (method == 5) return run_seeded_resampler<SeededRejection>(particles, n, seed, particles_out, cap);    // novel_resampling.h:146-189
   return ~0ull;
+}
+void ref_set_metropolis_steps(uint64_t steps) { g_metropolis_steps = steps; }
+
+// Draw callbacks on a seeded generator (see DrawSource). `n` is the particle count of the index distribution.
+void* ref_draws_create(uint32_t seed, uint64_t n)
+{
+  return new DrawSource{std::mt19937(seed), std::uniform_real_distribution<FLOAT_T>(0.0, 1.0), std::uniform_real_distribution<>(0.0, 1.0),
+                        std::uniform_int_distribution<size_t>(0, n - 1)};
+}
+void ref_draws_destroy(void* d) { delete static_cast<DrawSource*>(d); }
+float ref_draw_real(void* p)
+{
+  DrawSource* d = static_cast<DrawSource*>(p);
+  ++d->n_real;
+  return d->real(d->gen);
+}
+float ref_draw_real_wheel(void* p)
+{
+  DrawSource* d = static_cast<DrawSource*>(p);
+  ++d->n_real;
+  const FLOAT_T random_value = d->real_wheel(d->gen);
+  return random_value;
+}
+uint64_t ref_draw_index(void* p)
+{
+  DrawSource* d = static_cast<DrawSource*>(p);
+  ++d->n_index;
+  return d->index(d->gen);
+}
+void ref_draws_used(void* p, uint64_t* n_real, uint64_t* n_index)
+{
+  DrawSource* d = static_cast<DrawSource*>(p);
+  *n_real = d->n_real;
+  *n_index = d->n_index;
 }
 
 // The first `count` draws of std::uniform_int_distribution<size_t>(0, n - 1) on std::mt19937(seed): the index stream
@@ -640,6 +710,9 @@ uint64_t ref_gpu_resample_method(int method, const float* particles, uint64_t n,
   {
     if (method == 1) return run_seeded_resampler<GpuResidualResampler>(particles, n, seed, particles_out, cap);
     if (method == 2) return run_seeded_resampler<GpuResidualSystematicResampler>(particles, n, seed, particles_out, cap);
+    if (method == 3) return run_seeded_resampler<GpuWheelResampler>(particles, n, seed, particles_out, cap);
+    if (method == 4) return run_seeded_resampler<SeededGpuMetropolis>(particles, n, seed, particles_out, cap);
+    if (method == 5) return run_seeded_resampler<GpuRejectionResampler>(particles, n, seed, particles_out, cap);
     g_last_error = "unknown method";
     return ~0ull;
   }

@@ -412,6 +412,119 @@ uint64_t oracle_residual_resample(const float* w, uint64_t n, const uint64_t* dr
   return out;
 }
 
+/* ---- Wheel / Metropolis / Rejection, statement by statement, with the draws handed in as callbacks ------- */
+
+void oracle_wheel_resample(const float* w, uint64_t n, oracle_real_draw_fn real, void* user, uint32_t* parents_out)
+{
+  /* src/resampling/wheel_resampler.cpp:13-32: one draw per output slot (a double narrowed to FLOAT_T, :15 — the callback
+   * returns it narrowed), a fresh fp32 running sum per slot, the first index whose sum reaches the draw; a slot no sum
+   * reaches keeps its own particle (:31 is commented out). O(n^2), like the reference. */
+  for (uint64_t particle_index = 0; particle_index < n; ++particle_index)
+  {
+    float random_value = real(user);
+    float weight_sum = 0.0f;
+    uint32_t parent = (uint32_t)particle_index;
+    for (uint64_t index = 0; index < n; ++index)
+    {
+      float current_weight = w[index];
+      weight_sum += current_weight;
+      if (random_value <= weight_sum)
+      {
+        parent = (uint32_t)index;
+        break;
+      }
+    }
+    parents_out[particle_index] = parent;
+  }
+}
+
+void oracle_metropolis_resample(const float* w, uint64_t n, uint64_t steps, oracle_real_draw_fn real, oracle_index_draw_fn index_draw,
+                                void* user, uint32_t* parents_out)
+{
+  /* novel_resampling.h:121-140. `auto& particle_k = particle_cloud[k]` (:125) is bound while k == 0 and a reference cannot
+   * be re-seated, so the acceptance ratio is always against particle 0's weight; u is drawn before j (:129-130). */
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    uint64_t k = 0;
+    const float* particle_k_second = &w[0];
+    for (uint64_t s = 0; s < steps; ++s)
+    {
+      float u = real(user);
+      uint64_t j = index_draw(user);
+      if (u <= w[j] / *particle_k_second) k = j;
+    }
+    parents_out[i] = (uint32_t)k;
+  }
+}
+
+void oracle_rejection_resample(const float* w, uint64_t n, oracle_real_draw_fn real, oracle_index_draw_fn index_draw, void* user,
+                               uint32_t* parents_out)
+{
+  /* novel_resampling.h:157-181. `auto sup_w = 0.0` is a double, so `second / sup_w` divides in fp64 and the float draw is
+   * widened for the comparison; inside the loop j is drawn before u (:176-177). */
+  double sup_w = 0.0;
+  for (uint64_t index = 0; index < n; ++index)
+  {
+    float wi = w[index];
+    if (sup_w < wi) sup_w = wi;
+  }
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    uint64_t j = i;
+    float u = real(user);
+    while (u > (w[j] / sup_w))
+    {
+      j = index_draw(user);
+      u = real(user);
+    }
+    parents_out[i] = (uint32_t)j;
+  }
+}
+
+/* A small deterministic draw source for tests that run where the reference's std::mt19937 is not at hand (splitmix64): equal
+ * seeds give equal streams, which is all a restatement-vs-product comparison needs. */
+typedef struct oracle_draws
+{
+  uint64_t state, n, n_real, n_index;
+} oracle_draws;
+
+static uint64_t splitmix64(uint64_t* s)
+{
+  uint64_t z = (*s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+void* oracle_draws_create(uint64_t seed, uint64_t n)
+{
+  oracle_draws* d = (oracle_draws*)malloc(sizeof(oracle_draws));
+  if (!d) return NULL;
+  d->state = seed;
+  d->n = n ? n : 1;
+  d->n_real = d->n_index = 0;
+  return d;
+}
+void oracle_draws_destroy(void* p) { free(p); }
+float oracle_draw_real(void* p)
+{
+  oracle_draws* d = (oracle_draws*)p;
+  ++d->n_real;
+  return (float)(splitmix64(&d->state) >> 40) * (1.0f / 16777216.0f); /* 24 bits: [0, 1) exactly representable */
+}
+uint64_t oracle_draw_index(void* p)
+{
+  oracle_draws* d = (oracle_draws*)p;
+  ++d->n_index;
+  return splitmix64(&d->state) % d->n;
+}
+void oracle_draws_used(void* p, uint64_t* n_real, uint64_t* n_index)
+{
+  oracle_draws* d = (oracle_draws*)p;
+  *n_real = d->n_real;
+  *n_index = d->n_index;
+}
+
 /* ---- scan reduction ---------------------------------------------------------------------------------- */
 
 typedef struct red_key

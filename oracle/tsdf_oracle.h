@@ -112,6 +112,26 @@ uint64_t oracle_residual_systematic_resample(const float* weights, uint64_t n, f
 uint64_t oracle_residual_resample(const float* weights, uint64_t n, const uint64_t* draws, uint64_t n_draws, uint32_t* parents_out,
                                   uint64_t* draws_used);
 
+/* The remaining resamplers of mcl_3d's switch (src/mcl_3d.cpp:243-263), every random draw handed in through callbacks:
+ * real() = one uniform_real draw as FLOAT_T, index_draw() = one uniform_int_distribution<size_t>(0, n - 1) draw.
+ * parents_out: n entries (all three emit exactly n particles).
+ *   WheelResampler::resample       src/resampling/wheel_resampler.cpp:6-34
+ *   MetropolisResampler::resample  include/tsdf_localization/resampling/novel_resampling.h:106-144
+ *   RejectionResampler::resample   include/tsdf_localization/resampling/novel_resampling.h:146-189 */
+typedef float (*oracle_real_draw_fn)(void* user);
+typedef uint64_t (*oracle_index_draw_fn)(void* user);
+void oracle_wheel_resample(const float* weights, uint64_t n, oracle_real_draw_fn real, void* user, uint32_t* parents_out);
+void oracle_metropolis_resample(const float* weights, uint64_t n, uint64_t steps, oracle_real_draw_fn real, oracle_index_draw_fn index_draw,
+                                void* user, uint32_t* parents_out);
+void oracle_rejection_resample(const float* weights, uint64_t n, oracle_real_draw_fn real, oracle_index_draw_fn index_draw, void* user,
+                               uint32_t* parents_out);
+/* Deterministic draw source for tests (splitmix64); pass the handle as `user`. */
+void* oracle_draws_create(uint64_t seed, uint64_t n);
+void oracle_draws_destroy(void* draws);
+float oracle_draw_real(void* draws);
+uint64_t oracle_draw_index(void* draws);
+void oracle_draws_used(void* draws, uint64_t* n_real, uint64_t* n_index);
+
 
 /* Scan reduction of TSDFEvaluator::evaluateParticles, src/evaluation/tsdf_evaluator.cpp:304-376: drop points nearer than
  * 1 m (:317-322), keep per (ring, reduction cell) the FIRST point in cloud order (unordered_set insert of SortClass keyed

@@ -76,6 +76,16 @@ class Oracle:
         L.oracle_residual_systematic_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.c_uint64]
         L.oracle_residual_resample.restype = C.c_uint64
         L.oracle_residual_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.oracle_wheel_resample.restype = None
+        L.oracle_wheel_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_metropolis_resample.restype = None
+        L.oracle_metropolis_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_rejection_resample.restype = None
+        L.oracle_rejection_resample.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_draws_create.restype = C.c_void_p
+        L.oracle_draws_create.argtypes = [C.c_uint64, C.c_uint64]
+        L.oracle_draws_destroy.argtypes = [C.c_void_p]
+        L.oracle_draws_used.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.oracle_motion_model.argtypes = [C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_motion_apply.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         L.oracle_reduce_scan.restype = C.c_int64
@@ -226,6 +236,68 @@ class Oracle:
         used = C.c_uint64(0)
         m = int(self.lib.oracle_residual_resample(_fp(w), n, _fp(d), d.shape[0], _fp(parents), C.byref(used)))
         return m, parents[:m], int(used.value)
+
+
+    def drawn_resample(self, method, weights, draws, steps=50):
+        """Parents of the Wheel (3) / Metropolis (4) / Rejection (5) resampler restatements fed the draws of a NativeDraws."""
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        n = w.shape[0]
+        parents = np.empty(n, dtype=np.uint32)
+        if method == 3:
+            self.lib.oracle_wheel_resample(_fp(w), n, draws.real_wheel_ptr, draws.handle, _fp(parents))
+        elif method == 4:
+            self.lib.oracle_metropolis_resample(_fp(w), n, steps, draws.real_ptr, draws.index_ptr, draws.handle, _fp(parents))
+        elif method == 5:
+            self.lib.oracle_rejection_resample(_fp(w), n, draws.real_ptr, draws.index_ptr, draws.handle, _fp(parents))
+        else:
+            raise ValueError(method)
+        return parents
+
+    def draws(self, seed, n):
+        """The oracle's own deterministic draw source (splitmix64), usable where oracle/_ref is not built."""
+        return NativeDraws(self.lib, "oracle", seed, n)
+
+
+class NativeDraws:
+    """A seeded native draw source behind C callbacks (`user` = handle): the oracle's splitmix64 ("oracle") or the reference's
+    std::mt19937 with its own distribution objects ("ref", oracle/ref_harness.cpp DrawSource). Feed two equally seeded
+    instances to two implementations to give them the same draws in the same interleaving."""
+
+    def __init__(self, lib, prefix, seed, n):
+        self._lib, self._prefix = lib, prefix
+        create = getattr(lib, f"{prefix}_draws_create")
+        create.restype = C.c_void_p
+        create.argtypes = [C.c_uint32 if prefix == "ref" else C.c_uint64, C.c_uint64]
+        getattr(lib, f"{prefix}_draws_destroy").argtypes = [C.c_void_p]
+        getattr(lib, f"{prefix}_draws_used").argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        self.handle = C.c_void_p(create(seed, n))
+        self.real_fn = getattr(lib, f"{prefix}_draw_real")
+        self.real_wheel_fn = getattr(lib, f"{prefix}_draw_real_wheel") if prefix == "ref" else self.real_fn
+        self.index_fn = getattr(lib, f"{prefix}_draw_index")
+        self.real_ptr = C.cast(self.real_fn, C.c_void_p)
+        self.real_wheel_ptr = C.cast(self.real_wheel_fn, C.c_void_p)
+        self.index_ptr = C.cast(self.index_fn, C.c_void_p)
+
+    def used(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        getattr(self._lib, f"{self._prefix}_draws_used")(self.handle, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    def source(self):
+        """As the product's DrawSource (tsdf_localization_b200.evaluator)."""
+        from tsdf_localization_b200 import DrawSource
+        return DrawSource(real=self.real_fn, index=self.index_fn, user=self.handle, wheel_real=self.real_wheel_fn)
+
+    def close(self):
+        if self.handle:
+            getattr(self._lib, f"{self._prefix}_draws_destroy")(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def ref_lib_path(threads: int | None = None) -> Path:
@@ -435,8 +507,9 @@ class Ref:
         return out
 
     def resample_method(self, method, particles, seed, cap=None):
-        """The verbatim ResidualResampler (method 1) / ResidualSystematicResampler (method 2) with a seeded generator:
-        (length, particles out, the uniform(0,1) draw of method 2)."""
+        """The verbatim ResidualResampler (method 1) / ResidualSystematicResampler (2) / WheelResampler (3) / MetropolisResampler
+        (4, steps via set_metropolis_steps) / RejectionResampler (5) with a seeded generator: (length, particles out, the
+        uniform(0,1) draw of method 2)."""
         ps = np.ascontiguousarray(particles, dtype=np.float32)
         n = ps.shape[0]
         cap = cap or (2 * n + 64)
@@ -454,6 +527,14 @@ class Ref:
         if m == 2 ** 64 - 1:
             raise RuntimeError(self.last_error())
         return m, out[:min(m, cap)]
+
+    def set_metropolis_steps(self, steps):
+        self.lib.ref_set_metropolis_steps.argtypes = [C.c_uint64]
+        self.lib.ref_set_metropolis_steps(steps)
+
+    def draws(self, seed, n):
+        """std::mt19937(seed) with the reference's distribution objects, as callbacks."""
+        return NativeDraws(self.lib, "ref", seed, n)
 
     def uniform_index_draws(self, seed, n, count):
         out = np.empty(count, dtype=np.uint64)

@@ -1,11 +1,15 @@
-"""Residual / ResidualSystematic resampling end to end on the GPU (host recurrence over the weights + k_expand_runs),
+"""Residual / ResidualSystematic / Wheel / Metropolis / Rejection resampling end to end on the GPU (host half over the weights +
+k_expand_runs),
 through the Python mirror of the reference classes, against the oracle (pinned to the verbatim reference classes in
 tests/test_resamplers_host.py): parents identical, copies are byte copies of the parents."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
 import common
-from tsdf_localization_b200 import CudaEvaluator, ResidualResampler, ResidualSystematicResampler, capi, synthetic as syn
+from tsdf_localization_b200 import (CudaEvaluator, MetropolisResampler, RejectionResampler, ResidualResampler, ResidualSystematicResampler,
+                                    WheelResampler, capi, synthetic as syn)
 from test_resamplers_host import weighted_cloud
 
 pytestmark = pytest.mark.gpu
@@ -40,6 +44,64 @@ def test_residual_weighted_cloud(oracle, ev, n, kind):
     m_ref, parents_ref, _ = oracle.residual_resample(ps[:, 6], draws)
     assert m_ref == n and len(out) == n and np.array_equal(parents, parents_ref)
     assert np.array_equal(out, ps[parents_ref])
+
+
+DRAWN = [(3, WheelResampler), (4, MetropolisResampler), (5, RejectionResampler)]
+
+
+@pytest.mark.parametrize("n", [1, 2, 500, 4097, 65536])
+@pytest.mark.parametrize("kind", ["flat", "uniform", "sparse"])
+@pytest.mark.parametrize("method,cls", DRAWN, ids=["wheel", "metropolis", "rejection"])
+def test_drawn_resamplers_weighted_cloud(oracle, ev, method, cls, n, kind):
+    """Wheel / Metropolis / Rejection end to end (host half over the weights + k_expand_runs) against the oracle's restatements
+    (pinned to the verbatim reference classes in tests/test_resamplers_host.py) on equally seeded draw sources."""
+    if method != 4 and n > 4097:
+        n = 16384          # the oracle walks the wheel in O(n^2) like the reference; sparse rejection needs ~20 draws per slot
+    ps = weighted_cloud(n, kind, n + method)
+    steps = 50 if n <= 500 else 5
+    rs = cls(ev, steps) if method == 4 else cls(ev)
+    d_o, d_p = oracle.draws(n + method, n), oracle.draws(n + method, n)
+    parents_ref = oracle.drawn_resample(method, ps[:, 6], d_o, steps)
+    out, parents = rs.resample(ps, draws=d_p.source(), want_parents=True)
+    assert len(out) == n and np.array_equal(parents, parents_ref)
+    assert np.array_equal(out, ps[parents_ref])
+    assert d_p.used() == d_o.used()
+
+
+def test_drawn_resamplers_on_the_resident_set(oracle):
+    """The node's flow with resampling_method 0 / 4 / 5: sensor update, then the resampler on the set left on the device."""
+    _, m = common.box_room()
+    e = CudaEvaluator(m)
+    ps, pts, _ = common.config_c1()
+    mine = ps.copy()
+    e.evaluate(mine, pts, syn.IDENTITY_TF)
+    n = len(mine)
+    for method, cls in DRAWN:
+        rs = cls(e)
+        d_o, d_p = oracle.draws(method, n), oracle.draws(method, n)
+        parents_ref = oracle.drawn_resample(method, mine[:, 6], d_o, 50)
+        out, parents = rs.resample_resident(n, draws=d_p.source(), want_parents=True)
+        assert len(out) == n and np.array_equal(parents, parents_ref) and np.array_equal(out, mine[parents_ref])
+    # default draws (a seeded numpy Generator through Python callbacks): a valid resampled set, reproducible by seed
+    a = WheelResampler(e, seed=3).resample_resident(n)
+    b = WheelResampler(e, seed=3).resample_resident(n)
+    assert np.array_equal(a, b) and len(a) == n
+    assert (a[:, None, :] == mine[None, :, :]).all(-1).any(-1).all()        # every output is one of the particles
+    e.close()
+
+
+def test_drawn_resampler_errors(ev):
+    ps = weighted_cloud(64, "flat", 0)
+    ps[:, 6] = -1.0                                   # the reference's rejection loop never ends on all-negative weights
+    with pytest.raises(capi.TsdflocError) as ei:
+        RejectionResampler(ev, seed=1).resample(ps, max_draws=1000)
+    assert ei.value.status == capi.E_CAPACITY
+    lib = ev._lib
+    n_out = C.c_uint64(0)
+    out = np.empty((64, 7), dtype=np.float32)
+    rc = lib.tsdfloc_resample_drawn(ev.ctx, capi.RESAMPLE_RESIDUAL, ps.ctypes.data_as(C.c_void_p), 64, C.byref(capi.Draws()),
+                                    out.ctypes.data_as(C.c_void_p), 64, C.byref(n_out), None)
+    assert rc == capi.E_BAD_ARG
 
 
 def test_resident_set_after_sensor_update(oracle):

@@ -121,6 +121,30 @@ def test_gpu_residual_resamplers_match_reference_classes(shim, small_map, n, met
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("method", [3, 4, 5], ids=["wheel", "metropolis", "rejection"])
+@pytest.mark.parametrize("n", [500, 4096, 20000])
+def test_gpu_drawn_resamplers_match_reference_classes(shim, small_map, n, method):
+    """GpuWheelResampler / GpuMetropolisResampler(steps) / GpuRejectionResampler (shim/tsdfloc_shim.h) through the reference's
+    Resampler interface against the reference's own WheelResampler (src/resampling/wheel_resampler.cpp), MetropolisResampler and
+    RejectionResampler (novel_resampling.h:106-189) — cases 0, 4 and default of src/mcl_3d.cpp:243-263 — with equal seeds:
+    identical outputs. (20,000 particles bound the reference's own O(n^2) wheel walk.)"""
+    ev = shim.eval_create(small_map)
+    rng = np.random.default_rng(n + method)
+    ps = np.zeros((n, 7), dtype=np.float32)
+    ps[:, :6] = rng.normal(size=(n, 6))
+    w = rng.exponential(size=n)
+    ps[:, 6] = (w / w.sum()).astype(np.float32)
+    shim.set_metropolis_steps(50 if n <= 4096 else 10)
+    for seed in (1, 7):
+        m_ref, out_ref, _ = shim.resample_method(method, ps, seed)
+        m_gpu, out_gpu = shim.gpu_resample_method(method, ps, seed)
+        assert m_gpu == m_ref == n
+        assert np.array_equal(out_gpu, out_ref)
+    shim.set_metropolis_steps(50)
+    shim.eval_destroy(ev)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("near", [0, 400])
 def test_reference_evaluateParticles_gpu_branch_matches_its_cpu_branch(shim, small_map, near):
     """TSDFEvaluatorB200::evaluateParticles (GPU scan reduction + evaluation, the reduced scan never leaves the device)

@@ -6,10 +6,13 @@ generators the tests and ``bench.py`` share (``synthetic.py``) and the one-proce
 There is no CPU fallback: importing works anywhere, computing needs a B200.
 """
 from .capi import LibraryNotBuilt, TsdflocError, lib_path, load_library  # noqa: F401
-from .evaluator import (CudaEvaluator, CudaSubVoxelMap, MultiGpuEvaluator, ParticleCloud, ResidualResampler,  # noqa: F401
-                        ResidualSystematicResampler, SystematicResampler, TSDFEvaluator, likelihood_init, likelihood_value)
+from .evaluator import (CudaEvaluator, CudaSubVoxelMap, DrawSource, MetropolisResampler, MultiGpuEvaluator, ParticleCloud,  # noqa: F401
+                        RejectionResampler, ResidualResampler, ResidualSystematicResampler, SystematicResampler, TSDFEvaluator,
+                        WheelResampler, likelihood_init, likelihood_value)
 
 __all__ = [
-    "CudaEvaluator", "CudaSubVoxelMap", "MultiGpuEvaluator", "ParticleCloud", "ResidualResampler", "ResidualSystematicResampler", "SystematicResampler", "TSDFEvaluator", "likelihood_init", "likelihood_value",
+    "CudaEvaluator", "CudaSubVoxelMap", "DrawSource", "MetropolisResampler", "MultiGpuEvaluator", "ParticleCloud", "RejectionResampler",
+    "ResidualResampler", "ResidualSystematicResampler", "SystematicResampler", "TSDFEvaluator", "WheelResampler", "likelihood_init",
+    "likelihood_value",
     "LibraryNotBuilt", "TsdflocError", "lib_path", "load_library",
 ]

@@ -17,7 +17,15 @@ NEG_MISS, NEG_SATURATE_LIKE_REF_GPU = range(2)
 TUNE_SPATIAL_ORDER, TUNE_EVAL_PAIRING, TUNE_DIVISION, TUNE_STAGE_TIMERS, TUNE_EVAL_REGISTERS, TUNE_GRAPHS, TUNE_EVAL_CHUNKS = range(7)
 DIV_IEEE, DIV_THREE, DIV_BRACKET = range(3)
 RESAMPLE_SYSTEMATIC, RESAMPLE_RESIDUAL, RESAMPLE_RESIDUAL_SYSTEMATIC = range(3)
+RESAMPLE_WHEEL, RESAMPLE_METROPOLIS, RESAMPLE_REJECTION = 3, 4, 5
 INDEX_DRAW_FN = C.CFUNCTYPE(C.c_uint64, C.c_void_p)
+REAL_DRAW_FN = C.CFUNCTYPE(C.c_float, C.c_void_p)
+
+
+class Draws(C.Structure):
+    """tsdfloc_draws: the random draws of the Wheel / Metropolis / Rejection resamplers, as callbacks."""
+    _fields_ = [("real", REAL_DRAW_FN), ("index", INDEX_DRAW_FN), ("user", C.c_void_p), ("metropolis_steps", C.c_uint64),
+                ("max_draws", C.c_uint64)]
 
 
 class LibraryNotBuilt(RuntimeError):
@@ -94,6 +102,10 @@ SIGNATURES = {
     "tsdfloc_resample_expand": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _u64, C.POINTER(_u64), _vp]),
     "tsdfloc_resample_expand_device": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp, C.POINTER(_vp), C.c_uint32, _vp, _vp]),
     "tsdfloc_resample": (C.c_int, [_vp, C.c_int, _vp, _u64, C.c_float, INDEX_DRAW_FN, _vp, _vp, _u64, C.POINTER(_u64), _vp]),
+    "tsdfloc_wheel_parents": (C.c_int, [_vp, _u64, _u64, REAL_DRAW_FN, _vp, _vp]),
+    "tsdfloc_metropolis_parents": (C.c_int, [_vp, _u64, _u64, _u64, REAL_DRAW_FN, INDEX_DRAW_FN, _vp, _vp]),
+    "tsdfloc_rejection_parents": (C.c_int, [_vp, _u64, _u64, REAL_DRAW_FN, INDEX_DRAW_FN, _vp, _u64, _vp, C.POINTER(_u64)]),
+    "tsdfloc_resample_drawn": (C.c_int, [_vp, C.c_int, _vp, _u64, C.POINTER(Draws), _vp, _u64, C.POINTER(_u64), _vp]),
     "tsdfloc_cdf_device": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
     "tsdfloc_debug_eval": (C.c_int, [_vp, _vp, _u64, _vp, _u64, _fp, _vp, _vp, _vp]),
     "tsdfloc_set_scan_device": (C.c_int, [_vp, _vp, _u64, _vp]),

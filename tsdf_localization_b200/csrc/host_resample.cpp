@@ -1,5 +1,5 @@
-// host_resample.cpp — the sequential halves of the reference's Residual and ResidualSystematic resamplers
-// (include/tsdf_localization/resampling/novel_resampling.h:9-36, 76-104). Both are recurrences with no exact parallel form:
+// host_resample.cpp — the host halves of the reference's resamplers other than Systematic: Residual and ResidualSystematic
+// (include/tsdf_localization/resampling/novel_resampling.h:9-36, 76-104) first, Wheel / Metropolis / Rejection below. Both are recurrences with no exact parallel form:
 // ResidualSystematic carries an fp32 remainder `u` from particle to particle (every step rounds), Residual consumes a random
 // index stream until the output is full. They run here, on the host, over the N weights (4 B per particle); what they
 // produce — how many copies of which particle, in output order — is expanded on the device (k_expand_runs), so the 28 B
@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstddef>
+#include <vector>
 
 extern "C" int tsdfloc_residual_systematic_counts(const float* weights, uint64_t stride, uint64_t n, float u0, uint32_t* counts, uint64_t* total)
 {
@@ -65,6 +66,117 @@ extern "C" int tsdfloc_residual_runs(const float* weights, uint64_t stride, uint
     filled += k;
   }
   *n_runs = runs;
+  if (n_draws) *n_draws = draws;
+  return TSDFLOC_OK;
+}
+
+// ---- Wheel / Metropolis / Rejection: the remaining choices of mcl_3d's resampling_method switch (src/mcl_3d.cpp:243-263).
+// Each output slot is decided by random draws; the draws come through callbacks from the caller's generator, the decisions
+// are made here (one parent per slot), the copies on the device.
+
+extern "C" int tsdfloc_wheel_parents(const float* weights, uint64_t stride, uint64_t n, tsdfloc_real_draw_fn real, void* user, uint32_t* parents)
+{
+  if (!weights || !real || !parents || stride == 0 || n == 0) return TSDFLOC_E_BAD_ARG;
+  if (n > (1ull << 24)) return TSDFLOC_E_BAD_ARG;
+  // wheel_resampler.cpp:16-29 restarts `FLOAT_T weight_sum = 0.0` for every output slot and adds the weights in index order,
+  // so every slot walks the same fp32 running sums; slot i takes the first index whose sum s satisfies u <= s. With
+  // reach[k] = max(s_0 .. s_k) (NaN sums never satisfy the test and are skipped) that index is the first k with
+  // u <= reach[k], and reach is non-decreasing whatever the signs of the weights.
+  std::vector<float> reach(n);
+  float sum = 0.0f;                                                    // FLOAT_T weight_sum = 0.0;               (:16)
+  float top = -INFINITY;
+  for (uint64_t k = 0; k < n; ++k)
+  {
+    sum += weights[k * stride];                                        // weight_sum += current_weight;          (:21-22)
+    if (sum > top) top = sum;
+    reach[k] = top;
+  }
+  // guide[b] = first k with reach[k] >= b / n, b = 0 .. n (n when there is none): u in [b/n, (b+1)/n) finds its index inside
+  // [guide[b], guide[b + 1]]. reach * n and u * n are exact in fp64 (24-bit significands, n <= 2^24).
+  const double nd = static_cast<double>(n);
+  std::vector<uint32_t> guide(n + 2);
+  {
+    uint64_t k = 0;
+    for (uint64_t b = 0; b <= n; ++b)
+    {
+      while (k < n && !(static_cast<double>(reach[k]) * nd >= static_cast<double>(b))) ++k;
+      guide[b] = static_cast<uint32_t>(k);
+    }
+    guide[n + 1] = static_cast<uint32_t>(n);
+  }
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    const float u = real(user);                                        // FLOAT_T random_value = uniform_distribution(gen);  (:15)
+    uint64_t lo = 0, hi = n;                                           // the answer lies in [lo, hi]; n: no sum reaches u
+    if (u != u) lo = n;                                                // a NaN draw satisfies no test (a std distribution never makes one)
+    else if (u >= 0.0f)
+    {
+      const double scaled = static_cast<double>(u) * nd;
+      const uint64_t b = scaled >= nd ? n : static_cast<uint64_t>(scaled);
+      lo = guide[b];
+      hi = guide[b + 1];
+    }
+    while (lo < hi)                                                    // first k in [lo, hi) with u <= reach[k], else hi
+    {
+      const uint64_t mid = lo + ((hi - lo) >> 1);
+      if (u <= reach[mid]) hi = mid; else lo = mid + 1;
+    }
+    // lo == hi: either reach[hi] >= (b + 1) / n > u, or hi == n and no sum reaches u: the slot keeps its own particle (:31 is
+    // commented out in the reference)
+    parents[i] = static_cast<uint32_t>(lo < n ? lo : i);
+  }
+  return TSDFLOC_OK;
+}
+
+extern "C" int tsdfloc_metropolis_parents(const float* weights, uint64_t stride, uint64_t n, uint64_t steps, tsdfloc_real_draw_fn real,
+                                          tsdfloc_index_draw_fn index, void* user, uint32_t* parents)
+{
+  if (!weights || !real || !index || !parents || stride == 0 || n == 0) return TSDFLOC_E_BAD_ARG;
+  if (n > (1ull << 24)) return TSDFLOC_E_BAD_ARG;
+  const float w_k = weights[0];                                        // auto& particle_k = particle_cloud[k] with k == 0: bound
+                                                                       // once per slot, never rebound                     (:123-125)
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    uint64_t k = 0;                                                    // auto k = 0;                                       (:123)
+    for (uint64_t s = 0; s < steps; ++s)                               // for (auto n = 0u; n < sampling_steps_; ++n)       (:127)
+    {
+      const float u = real(user);                                      // u first, then j                                   (:129-130)
+      const uint64_t j = index(user);
+      if (j >= n) return TSDFLOC_E_BAD_ARG;
+      const float ratio = weights[j * stride] / w_k;                   // float / float                                     (:133)
+      if (u <= ratio) k = j;                                           //                                                   (:133-136)
+    }
+    parents[i] = static_cast<uint32_t>(k);                             // new_particles.push_back(particle_cloud[k]);       (:139)
+  }
+  return TSDFLOC_OK;
+}
+
+extern "C" int tsdfloc_rejection_parents(const float* weights, uint64_t stride, uint64_t n, tsdfloc_real_draw_fn real, tsdfloc_index_draw_fn index,
+                                         void* user, uint64_t max_draws, uint32_t* parents, uint64_t* n_draws)
+{
+  if (!weights || !real || !index || !parents || stride == 0 || n == 0) return TSDFLOC_E_BAD_ARG;
+  if (n > (1ull << 24)) return TSDFLOC_E_BAD_ARG;
+  double sup_w = 0.0;                                                  // auto sup_w = 0.0;  — a double                     (:157)
+  for (uint64_t k = 0; k < n; ++k)
+  {
+    const float w = weights[k * stride];
+    if (sup_w < w) sup_w = w;                                          //                                                   (:163-166)
+  }
+  uint64_t draws = 0;
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    uint64_t j = i;                                                    // auto j = i;                                       (:171)
+    float u = real(user);                                              //                                                   (:172)
+    while (static_cast<double>(u) > static_cast<double>(weights[j * stride]) / sup_w)   // float / double -> double        (:174)
+    {
+      if (max_draws && draws >= max_draws) { if (n_draws) *n_draws = draws; return TSDFLOC_E_CAPACITY; }
+      j = index(user);                                                 // j first, then u                                   (:176-177)
+      ++draws;
+      if (j >= n) return TSDFLOC_E_BAD_ARG;
+      u = real(user);
+    }
+    parents[i] = static_cast<uint32_t>(j);                             //                                                   (:180)
+  }
   if (n_draws) *n_draws = draws;
   return TSDFLOC_OK;
 }

@@ -1818,19 +1818,11 @@ static int resident_weights_to_host(tsdfloc_ctx* c, std::vector<float>& w)
   return TSDFLOC_OK;
 }
 
-int tsdfloc_resample(tsdfloc_ctx* c, int method, const float* particles, uint64_t n, float u, tsdfloc_index_draw_fn draw, void* user,
-                     float* particles_out, uint64_t cap, uint64_t* n_out, uint32_t* parents)
+// The weights a host-half resampler works on: of a weighted cloud in host memory (uploaded here so that the device half finds it
+// resident), or of the set the last sensor update left on the device (4 B per particle come back).
+static int weights_for_host_half(tsdfloc_ctx* c, const float* particles, uint64_t& n, std::vector<float>& w)
 {
-  if (!c) return TSDFLOC_E_BAD_ARG;
-  if (!particles_out || !n_out) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
-  if (method == TSDFLOC_RESAMPLE_SYSTEMATIC)
-    return particles ? tsdfloc_resample_particles(c, particles, n, u, particles_out, cap, n_out, parents)
-                     : tsdfloc_resample_systematic(c, u, particles_out, cap, n_out, parents);
-  if (method != TSDFLOC_RESAMPLE_RESIDUAL && method != TSDFLOC_RESAMPLE_RESIDUAL_SYSTEMATIC) return fail(c, TSDFLOC_E_BAD_ARG, "unknown resampling method");
-  if (method == TSDFLOC_RESAMPLE_RESIDUAL && !draw) return fail(c, TSDFLOC_E_BAD_ARG, "the residual resampler needs an index draw callback");
-  DeviceGuard guard(c->device);
   int rc;
-  std::vector<float> w;
   if (particles)
   {
     // Resampler::resample(ParticleCloud&) on a weighted host cloud: upload it, keep the weights here
@@ -1846,13 +1838,27 @@ int tsdfloc_resample(tsdfloc_ctx* c, int method, const float* particles, uint64_
     w.resize(n);
     for (uint64_t i = 0; i < n; ++i) w[i] = particles[7 * i + 6];
     c->n_resident = n;
+    return TSDFLOC_OK;
   }
-  else
-  {
-    if (c->n_resident == 0) return fail(c, TSDFLOC_E_STATE, "resample needs a preceding successful sensor_update");
-    n = c->n_resident;
-    if ((rc = resident_weights_to_host(c, w))) return rc;
-  }
+  if (c->n_resident == 0) return fail(c, TSDFLOC_E_STATE, "resample needs a preceding successful sensor_update");
+  n = c->n_resident;
+  return resident_weights_to_host(c, w);
+}
+
+int tsdfloc_resample(tsdfloc_ctx* c, int method, const float* particles, uint64_t n, float u, tsdfloc_index_draw_fn draw, void* user,
+                     float* particles_out, uint64_t cap, uint64_t* n_out, uint32_t* parents)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!particles_out || !n_out) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (method == TSDFLOC_RESAMPLE_SYSTEMATIC)
+    return particles ? tsdfloc_resample_particles(c, particles, n, u, particles_out, cap, n_out, parents)
+                     : tsdfloc_resample_systematic(c, u, particles_out, cap, n_out, parents);
+  if (method != TSDFLOC_RESAMPLE_RESIDUAL && method != TSDFLOC_RESAMPLE_RESIDUAL_SYSTEMATIC) return fail(c, TSDFLOC_E_BAD_ARG, "unknown resampling method");
+  if (method == TSDFLOC_RESAMPLE_RESIDUAL && !draw) return fail(c, TSDFLOC_E_BAD_ARG, "the residual resampler needs an index draw callback");
+  DeviceGuard guard(c->device);
+  int rc;
+  std::vector<float> w;
+  if ((rc = weights_for_host_half(c, particles, n, w))) return rc;
   std::vector<uint32_t> counts, run_parent;
   uint64_t n_runs = 0;
   if (method == TSDFLOC_RESAMPLE_RESIDUAL_SYSTEMATIC)
@@ -1870,6 +1876,33 @@ int tsdfloc_resample(tsdfloc_ctx* c, int method, const float* particles, uint64_
   if (rc == TSDFLOC_E_CAPACITY) return fail(c, TSDFLOC_E_NO_VALID_PARTICLE, "residual resampling: the weights do not fill the output (all zero?)");
   if (rc != TSDFLOC_OK) return fail(c, rc, "residual resampling: bad index draw");
   return tsdfloc_resample_expand(c, run_parent.data(), counts.data(), n_runs, particles_out, cap, n_out, parents);
+}
+
+// Wheel / Metropolis / Rejection (src/mcl_3d.cpp:243-263 cases 0, 4, default): the host half picks one parent per output slot
+// from the caller's draws (host_resample.cpp), the device copies the particles — runs of length one through k_expand_runs.
+int tsdfloc_resample_drawn(tsdfloc_ctx* c, int method, const float* particles, uint64_t n, const tsdfloc_draws* draws, float* particles_out,
+                           uint64_t cap, uint64_t* n_out, uint32_t* parents)
+{
+  if (!c) return TSDFLOC_E_BAD_ARG;
+  if (!particles_out || !n_out || !draws) return fail(c, TSDFLOC_E_BAD_ARG, "NULL argument");
+  if (method != TSDFLOC_RESAMPLE_WHEEL && method != TSDFLOC_RESAMPLE_METROPOLIS && method != TSDFLOC_RESAMPLE_REJECTION)
+    return fail(c, TSDFLOC_E_BAD_ARG, "tsdfloc_resample_drawn serves the Wheel, Metropolis and Rejection resamplers (use tsdfloc_resample for the others)");
+  if (!draws->real) return fail(c, TSDFLOC_E_BAD_ARG, "the resampler needs a uniform_real draw callback");
+  if (method != TSDFLOC_RESAMPLE_WHEEL && !draws->index) return fail(c, TSDFLOC_E_BAD_ARG, "the resampler needs an index draw callback");
+  DeviceGuard guard(c->device);
+  int rc;
+  std::vector<float> w;
+  if ((rc = weights_for_host_half(c, particles, n, w))) return rc;
+  std::vector<uint32_t> parent(n), ones(n, 1u);
+  if (method == TSDFLOC_RESAMPLE_WHEEL)
+    rc = tsdfloc_wheel_parents(w.data(), 1, n, draws->real, draws->user, parent.data());
+  else if (method == TSDFLOC_RESAMPLE_METROPOLIS)
+    rc = tsdfloc_metropolis_parents(w.data(), 1, n, draws->metropolis_steps, draws->real, draws->index, draws->user, parent.data());
+  else
+    rc = tsdfloc_rejection_parents(w.data(), 1, n, draws->real, draws->index, draws->user, draws->max_draws, parent.data(), nullptr);
+  if (rc == TSDFLOC_E_CAPACITY) return fail(c, TSDFLOC_E_CAPACITY, "rejection resampling: max_draws index draws did not fill the output");
+  if (rc != TSDFLOC_OK) return fail(c, rc, "resampling: bad index draw");
+  return tsdfloc_resample_expand(c, parent.data(), ones.data(), n, particles_out, cap, n_out, parents);
 }
 
 int tsdfloc_debug_eval(tsdfloc_ctx* c, const float* particles, uint64_t n, const float* points, uint64_t p, const float tf[16],

@@ -670,3 +670,94 @@ class ResidualResampler(_RunResampler):
     def resample_resident(self, n: int, index_draws=None, want_parents: bool = False):
         return self._call(None, n, 0.0, self._draw_cb(n, index_draws), n, want_parents)
 
+
+
+class DrawSource:
+    """The random draws a drawn resampler consumes, as the C callbacks of ``tsdfloc_draws``.
+
+    ``real`` / ``index`` are either C function pointers taking ``user`` (a generator living in native code — how the C++ shim
+    hands over the reference's std::mt19937) or Python callables (wrapped here; slow, for small sets). ``DrawSource.numpy(seed,
+    n)`` draws from a seeded numpy Generator."""
+
+    def __init__(self, real, index=None, user=None, wheel_real=None):
+        self._keep = []
+        self.real = self._wrap(real, capi.REAL_DRAW_FN)
+        self.wheel_real = self._wrap(wheel_real, capi.REAL_DRAW_FN) if wheel_real is not None else self.real
+        self.index = self._wrap(index, capi.INDEX_DRAW_FN) if index is not None else C.cast(None, capi.INDEX_DRAW_FN)
+        self.user = user
+
+    def _wrap(self, fn, proto):
+        if isinstance(fn, proto):
+            return fn
+        if isinstance(fn, C._CFuncPtr):                      # a symbol of another shared library
+            return C.cast(fn, proto)
+        cb = proto(lambda _user: fn())
+        self._keep.append(cb)
+        return cb
+
+    @classmethod
+    def numpy(cls, seed, n):
+        rng = np.random.default_rng(seed)
+        return cls(real=lambda: float(np.float32(rng.random(dtype=np.float32))), index=lambda: int(rng.integers(0, n)))
+
+
+class _DrawnResampler:
+    """Shared plumbing of the resamplers that pick every output particle from random draws (tsdfloc_resample_drawn)."""
+
+    METHOD = None
+
+    def __init__(self, evaluator, seed: Optional[int] = None):
+        self._ev = evaluator.cuda_evaluator_ if isinstance(evaluator, TSDFEvaluator) else evaluator
+        self._seed = seed
+
+    def _call(self, particle_cloud, n, draws, steps, max_draws, want_parents):
+        lib = self._ev._lib
+        ps = None if particle_cloud is None else _f32(particle_cloud, 7, "particle_cloud")
+        if ps is not None:
+            n = ps.shape[0]
+        if draws is None:
+            draws = DrawSource.numpy(self._seed, n)
+        d = capi.Draws(draws.wheel_real if self.METHOD == capi.RESAMPLE_WHEEL else draws.real, draws.index, draws.user, steps, max_draws)
+        out = np.empty((n, 7), dtype=np.float32)
+        parents = np.empty(n, dtype=np.uint32) if want_parents else None
+        n_out = C.c_uint64(0)
+        rc = lib.tsdfloc_resample_drawn(self._ev.ctx, self.METHOD, ps.ctypes.data_as(C.c_void_p) if ps is not None else None, n, C.byref(d),
+                                        out.ctypes.data_as(C.c_void_p), n, C.byref(n_out),
+                                        parents.ctypes.data_as(C.c_void_p) if want_parents else None)
+        capi.check(lib, self._ev.ctx, rc)
+        m = int(n_out.value)
+        return (out[:m], parents[:m]) if want_parents else out[:m]
+
+    STEPS = 0
+
+    def resample(self, particle_cloud: np.ndarray, draws: Optional[DrawSource] = None, want_parents: bool = False, max_draws: int = 0):
+        return self._call(particle_cloud, 0, draws, self.STEPS, max_draws, want_parents)
+
+    def resample_resident(self, n: int, draws: Optional[DrawSource] = None, want_parents: bool = False, max_draws: int = 0):
+        """Resample the particle set the evaluator's last evaluate() left on the device (only the weights visit the host)."""
+        return self._call(None, n, draws, self.STEPS, max_draws, want_parents)
+
+
+class WheelResampler(_DrawnResampler):
+    """WheelResampler (src/resampling/wheel_resampler.cpp:6-34), case 0 of mcl_3d's switch (src/mcl_3d.cpp:245-247): every slot
+    draws u and takes the first particle whose fp32 running weight sum reaches it. O(n) here (one prefix + guide table) instead
+    of the reference's O(n^2) walk; same parents given the same draws."""
+
+    METHOD = capi.RESAMPLE_WHEEL
+
+
+class MetropolisResampler(_DrawnResampler):
+    """MetropolisResampler(sampling_steps) (novel_resampling.h:106-144), case 4 (the node passes 50, src/mcl_3d.cpp:257-259)."""
+
+    METHOD = capi.RESAMPLE_METROPOLIS
+
+    def __init__(self, evaluator, sampling_steps: int = 50, seed: Optional[int] = None):
+        super().__init__(evaluator, seed)
+        self.STEPS = int(sampling_steps)
+
+
+class RejectionResampler(_DrawnResampler):
+    """RejectionResampler (novel_resampling.h:146-189), the switch's default branch (src/mcl_3d.cpp:260-262). ``max_draws``
+    bounds the index draws (0 = unbounded like the reference, which spins on e.g. all-negative weights)."""
+
+    METHOD = capi.RESAMPLE_REJECTION

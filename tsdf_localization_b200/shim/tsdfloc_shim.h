@@ -167,4 +167,90 @@ private:
   tsdfloc_ctx* ctx_;
 };
 
+// The remaining three choices of the node's resampling_method switch (src/mcl_3d.cpp:243-263: case 0 Wheel, case 4
+// Metropolis(50), default Rejection). Every output slot is decided by draws on the base class's mt19937 through the very
+// distribution types the reference constructs (wheel_resampler.cpp:9, novel_resampling.h:115-116, 151-152), handed to the
+// library as callbacks; the decisions are made over the weights alone, the particles are copied on the device.
+class GpuDrawnResampler : public Resampler
+{
+public:
+  void resample(ParticleCloud& particle_cloud) override
+  {
+    tsdfloc_ctx* ctx = ctx_ ? ctx_ : tsdfloc_shim_context();
+    if (!ctx) throw std::runtime_error(std::string(name_) + ": no CudaEvaluator context alive");
+    const std::size_t n = particle_cloud.size();
+    if (n == 0) return;
+    Draw d{m_generator_ptr.get(), std::uniform_real_distribution<FLOAT_T>(0.0, 1.0), std::uniform_real_distribution<>(0.0, 1.0),
+           std::uniform_int_distribution<size_t>(0, n - 1)};
+    tsdfloc_draws draws{};
+    draws.real = method_ == TSDFLOC_RESAMPLE_WHEEL ? &Draw::next_real_wheel : &Draw::next_real;
+    draws.index = &Draw::next_index;
+    draws.user = &d;
+    draws.metropolis_steps = steps_;
+    draws.max_draws = 0;   // like the reference: the loop ends when the draws say so
+    std::vector<Particle> new_particles(n);
+    uint64_t n_out = 0;
+    const int rc = tsdfloc_resample_drawn(ctx, method_, reinterpret_cast<const float*>(particle_cloud.particles().data()), n, &draws,
+                                          reinterpret_cast<float*>(new_particles.data()), new_particles.size(), &n_out, nullptr);
+    if (rc != TSDFLOC_OK) throw std::runtime_error(std::string(name_) + ": " + tsdfloc_last_error(ctx));
+    new_particles.resize(n_out);
+    particle_cloud.particles() = std::move(new_particles);
+  }
+
+  void seed(uint32_t s) { m_generator_ptr.reset(new std::mt19937(s)); }
+
+protected:
+  GpuDrawnResampler(int method, const char* name, tsdfloc_ctx* ctx, std::size_t steps) : method_(method), name_(name), ctx_(ctx), steps_(steps) {}
+
+private:
+  struct Draw
+  {
+    std::mt19937* gen;
+    std::uniform_real_distribution<FLOAT_T> real;   // Metropolis / Rejection: auto u = uniform_real_distribution(*m_generator_ptr)
+    std::uniform_real_distribution<> real_wheel;    // Wheel: FLOAT_T random_value = uniform_distribution(*m_generator_ptr)
+    std::uniform_int_distribution<size_t> index;
+    static float next_real(void* self)
+    {
+      Draw* d = static_cast<Draw*>(self);
+      return d->real(*d->gen);
+    }
+    static float next_real_wheel(void* self)
+    {
+      Draw* d = static_cast<Draw*>(self);
+      const FLOAT_T random_value = d->real_wheel(*d->gen);
+      return random_value;
+    }
+    static uint64_t next_index(void* self)
+    {
+      Draw* d = static_cast<Draw*>(self);
+      return d->index(*d->gen);
+    }
+  };
+  int method_;
+  const char* name_;
+  tsdfloc_ctx* ctx_;
+  std::size_t steps_;
+};
+
+class GpuWheelResampler : public GpuDrawnResampler
+{
+public:
+  explicit GpuWheelResampler(tsdfloc_ctx* ctx = nullptr) : GpuDrawnResampler(TSDFLOC_RESAMPLE_WHEEL, "GpuWheelResampler", ctx, 0) {}
+};
+
+class GpuMetropolisResampler : public GpuDrawnResampler
+{
+public:
+  explicit GpuMetropolisResampler(size_t sampling_steps, tsdfloc_ctx* ctx = nullptr)
+  : GpuDrawnResampler(TSDFLOC_RESAMPLE_METROPOLIS, "GpuMetropolisResampler", ctx, sampling_steps)
+  {
+  }
+};
+
+class GpuRejectionResampler : public GpuDrawnResampler
+{
+public:
+  explicit GpuRejectionResampler(tsdfloc_ctx* ctx = nullptr) : GpuDrawnResampler(TSDFLOC_RESAMPLE_REJECTION, "GpuRejectionResampler", ctx, 0) {}
+};
+
 }  // namespace tsdf_localization
