@@ -7,6 +7,7 @@
 #include <sstream>
 #include <string>
 #include <cstdint>
+#include <cstdlib>
 #include <stdexcept>
 #include <cmath>
 #include <algorithm>
@@ -30,6 +31,25 @@ struct Time {
   }
   double toSec() const { return sec_; }
   Duration operator-(const Time& o) const { return Duration(sec_ - o.sec_); }
+};
+// Just enough of the node API for the reference's own benchmark program (src/num_particles_eval.cpp:41-62) to run unmodified:
+// private parameters come from environment variables ROSPARAM_<name>; an unset one leaves the program's default in place,
+// like an unset ROS parameter.
+inline void init(int&, char**, const std::string&) {}
+class NodeHandle {
+ public:
+  NodeHandle() = default;
+  explicit NodeHandle(const std::string&) {}
+  template <typename T>
+  bool getParam(const std::string& name, T& value) const {
+    const char* e = std::getenv(("ROSPARAM_" + name).c_str());
+    if (!e || !*e) return false;
+    std::istringstream in(e);
+    double v = 0.0;
+    if (!(in >> v)) return false;
+    value = static_cast<T>(v);
+    return true;
+  }
 };
 }  // namespace ros
 #define TSDF_STUB_LOG(x) do { std::ostringstream _s; _s << x; std::cerr << _s.str() << std::endl; } while (0)
