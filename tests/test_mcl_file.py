@@ -55,3 +55,53 @@ def test_round_trip_and_errors(tmp_path):
         MCLFile(tmp_path / "bad.mcl").read()
     with pytest.raises(OSError):
         MCLFile(tmp_path / "missing.mcl").read()
+
+
+MUTANTS = ["1e3", "+5", "-0", "0x10", "nan", "inf", "-inf", "1.5.2", "abc", "1e999", "-1e999", "1e-999", ".5", "5.", "-", "+", "1e", "1e+",
+           "3,5", "7f", "0007", "1E2", "-.25e-1", "2147483648", "-2147483649", "99999999999999999999", "3.9999999999", "", "1 2", "\t8\n",
+           "+inf", "-nan", "-0x10", "+0x1p3", "1e+5x", "-infinity", "--1", "+-1", "1..2", "1.e3", ".e3", "e3", "1e3e4", "1e-", "-.", "+.5",
+           "-5.", "0e0", "00.10", "1d5"]
+SAFE_FOR_COUNTS = ("+5", "abc", "", "-", "0x10", "1.5.2", "0007", "3,5", "1 2", "-0", "+0x1p3", "--1", "+-1", "-.")   # others make the reference resize() wildly
+
+
+@needs_ref
+def test_reader_agrees_with_reference_reader_on_mutated_files(tmp_path):
+    """Differential test of tsdfloc_mcl_read against the verbatim MCLFile::read (`istream >> size_t / int / float`,
+    src/util/mcl_file.cpp:66-113): a small valid snapshot with one token replaced, dropped, doubled, or the file truncated —
+    both readers must accept or reject alike, and where they accept, parse the same values."""
+    ref = Ref()
+    pts, ring, ps, tf, pose = snapshot(3, 2)
+    good = tmp_path / "good.mcl"
+    MCLFile(good).write(pts, ring, ps, tf, *pose)
+    tokens = good.read_text().split()
+    count_slots = {0, 1 + 3 * 3 + 3}                     # the two element counts
+    cases = []
+    for slot in range(len(tokens)):
+        for m in MUTANTS:
+            if slot in count_slots and m not in SAFE_FOR_COUNTS:
+                continue
+            t = list(tokens)
+            t[slot] = m
+            cases.append(" ".join(t))
+    for cut in range(0, len(good.read_text()), 7):
+        cases.append(good.read_text()[:cut])
+    cases.append(good.read_text() + " 1 2 3")                     # trailing tokens are ignored by both
+    cases.append(good.read_text().replace("\n", "\r\n"))
+    n_ok = 0
+    for k, text in enumerate(cases):
+        f = tmp_path / "case.mcl"
+        f.write_text(text)
+        try:
+            theirs = ref.mcl_read(f)
+        except RuntimeError:
+            theirs = None
+        try:
+            ours = MCLFile(f).read()
+        except ValueError:
+            ours = None
+        assert (ours is None) == (theirs is None), f"case {k}: product {'rejects' if ours is None else 'accepts'}, reference does not: {text[:120]!r}"
+        if ours is not None:
+            n_ok += 1
+            for a, b in zip((ours.points, ours.rings, ours.particles, ours.tf, ours.pose), theirs):
+                assert np.asarray(a).tobytes() == np.asarray(b).tobytes(), f"case {k}: {text[:120]!r}"
+    assert 0 < n_ok < len(cases)
