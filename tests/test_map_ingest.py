@@ -76,6 +76,32 @@ def test_other_sigma_and_empty_chunk():
     ref.map_destroy(h)
 
 
+@needs_ref
+@pytest.mark.parametrize("kind", ["full range", "truncation boundary", "dense band"])
+@pytest.mark.parametrize("pos", [[(-2, 1, 0), (3, -1, 2)], [(100, -100, 7)], [(-32, 5, 0), (31, 5, 0)]], ids=["apart", "far", "wide"])
+def test_random_words_match_createTSDFMap(pos, kind):
+    """Arbitrary TSDFValue words — int16 values over the whole range or sitting on the +-600 mm truncation bounds, negative
+    weights — through both ingests: same geometry, brick table, payload and free-space points."""
+    ref = Ref()
+    rng = np.random.default_rng(len(pos) + len(kind))
+    shape = (len(pos), 64, 64, 64)
+    if kind == "full range":
+        value = rng.integers(-32768, 32768, size=shape)
+        weight = np.where(rng.random(shape) < 0.02, rng.integers(-32768, 32768, size=shape), 0)
+    elif kind == "truncation boundary":
+        value = rng.choice([-601, -600, -599, -1, 0, 1, 599, 600, 601], size=shape)
+        weight = np.where(rng.random(shape) < 0.05, rng.integers(1, 5, size=shape), 0)
+    else:
+        value = rng.integers(-700, 701, size=shape)
+        weight = np.where(rng.random(shape) < 0.3, 1, 0)
+    data = value.astype(np.int16).view(np.uint16).astype(np.uint32) | (weight.astype(np.int16).view(np.uint16).astype(np.uint32) << 16)
+    h, free_ref = ref.create_tsdf_map(pos, data, 0.1)
+    m = CudaSubVoxelMap.from_chunks(pos, data, 0.1)
+    assert_same_map(ref, h, m)
+    assert m.free_map().tobytes() == free_ref.tobytes()
+    ref.map_destroy(h)
+
+
 def test_rejects_bad_input():
     with pytest.raises(ValueError):
         CudaSubVoxelMap.from_chunks([(0, 0, 0)], np.zeros((1, 10), dtype=np.uint32))
