@@ -209,3 +209,29 @@ def test_drawn_host_halves_reject_bad_input():
     it = capi.INDEX_DRAW_FN(lambda _u: next(seq))
     assert lib.tsdfloc_metropolis_parents(w0.ctypes.data_as(C.c_void_p), 1, 4, 4, half, it, None, pp) == capi.OK
     assert np.array_equal(parents, [3, 3, 3, 3])
+
+
+def test_wheel_search_equals_linear_walk_on_hostile_floats():
+    """The wheel's O(n) search (running maximum + guide table + bracketed search) against the oracle's plain walk on weights and
+    draws no sane caller produces: negative, zero, subnormal, huge, infinite and NaN weights; draws of 0, 1, > 1, < 0, NaN."""
+    lib, oracle = capi.load_library(), Oracle()
+    rng = np.random.default_rng(99)
+    specials = np.array([0.0, -0.0, 1e-45, -1e-45, 1e-38, 3.4e38, -3.4e38, np.inf, -np.inf, np.nan, 1.0, 0.5, -0.5, 2.0 ** -24], dtype=np.float32)
+    draw_specials = np.array([0.0, -0.0, 1.0, np.nextafter(np.float32(1), np.float32(0)), 1.5, -0.25, np.nan, np.inf, 1e-45, 2.0 ** -24], dtype=np.float32)
+    for trial in range(400):
+        n = int(rng.integers(1, 40))
+        w = (rng.normal(size=n) * rng.choice([1e-3, 0.1, 1.0])).astype(np.float32)
+        if trial % 2:
+            w = np.abs(w)
+        k = rng.integers(0, n, size=rng.integers(0, 4))
+        w[k] = rng.choice(specials, size=len(k))
+        u = rng.random(n).astype(np.float32)
+        j = rng.integers(0, n, size=rng.integers(0, 3))
+        u[j] = rng.choice(draw_specials, size=len(j))
+        it_o, it_p = iter(u.tolist()), iter(u.tolist())
+        cb_o, cb_p = capi.REAL_DRAW_FN(lambda _u: next(it_o)), capi.REAL_DRAW_FN(lambda _u: next(it_p))
+        want = np.empty(n, dtype=np.uint32)
+        oracle.lib.oracle_wheel_resample(w.ctypes.data_as(C.c_void_p), n, C.cast(cb_o, C.c_void_p), None, want.ctypes.data_as(C.c_void_p))
+        got = np.empty(n, dtype=np.uint32)
+        assert lib.tsdfloc_wheel_parents(w.ctypes.data_as(C.c_void_p), 1, n, cb_p, None, got.ctypes.data_as(C.c_void_p)) == capi.OK
+        assert np.array_equal(got, want), (trial, w, u, got, want)
