@@ -705,6 +705,7 @@ class _DrawnResampler:
     """Shared plumbing of the resamplers that pick every output particle from random draws (tsdfloc_resample_drawn)."""
 
     METHOD = None
+    STEPS = 0          # sampling_steps_ (Metropolis only)
 
     def __init__(self, evaluator, seed: Optional[int] = None):
         self._ev = evaluator.cuda_evaluator_ if isinstance(evaluator, TSDFEvaluator) else evaluator
@@ -727,8 +728,6 @@ class _DrawnResampler:
         capi.check(lib, self._ev.ctx, rc)
         m = int(n_out.value)
         return (out[:m], parents[:m]) if want_parents else out[:m]
-
-    STEPS = 0
 
     def resample(self, particle_cloud: np.ndarray, draws: Optional[DrawSource] = None, want_parents: bool = False, max_draws: int = 0):
         return self._call(particle_cloud, 0, draws, self.STEPS, max_draws, want_parents)
